@@ -1,0 +1,200 @@
+// Engine: tensor-map encoding and launch of the tcgen05 implicit-GEMM kernel.
+#define LDM_GEMM_IMPL
+#include "engine.h"
+#include <cstring>
+
+namespace ldm {
+
+// ------------------------------------------------------------------ arena
+void Arena::init(size_t cap) {
+  destroy();
+  CUDA_CHECK(cudaMalloc(&base_, cap));
+  cap_ = cap;
+  off_ = peak_ = 0;
+}
+void Arena::destroy() {
+  if (base_) cudaFree(base_);
+  base_ = nullptr;
+  cap_ = off_ = 0;
+}
+void* Arena::alloc(size_t bytes) {
+  const size_t a = (off_ + 1023) & ~size_t(1023);
+  const size_t end = a + bytes;
+  if (end > peak_) peak_ = end;
+  if (dry) {
+    off_ = end;
+    return reinterpret_cast<void*>(uintptr_t(0x100000) + a);  // never dereferenced
+  }
+  LDM_CHECK(end <= cap_, "activation arena exhausted: need %zu, capacity %zu", end, cap_);
+  off_ = end;
+  return base_ + a;
+}
+
+// ------------------------------------------------------------------ engine
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+Engine::Engine(int dev) : device(dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  LDM_CHECK(e == cudaSuccess && count > 0,
+            "no CUDA device available (%s): ldm_b200 has no CPU fallback", cudaGetErrorString(e));
+  LDM_CHECK(dev >= 0 && dev < count, "device %d out of range (have %d)", dev, count);
+  CUDA_CHECK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  LDM_CHECK(prop.major == 10, "ldm_b200 kernels are sm_100a only; device %d is sm_%d%d", dev, prop.major,
+            prop.minor);
+  num_sms = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
+  LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GEMM_SMEM_BYTES));
+}
+
+Engine::~Engine() {
+  arena.destroy();
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+
+void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, int box_n) {
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  dims[0] = (cuuint64_t)v.C;
+  box[0] = GEMM_BK;
+  if (!v.swap_xy) {
+    dims[1] = v.W; dims[2] = v.H;
+    strides[0] = (cuuint64_t)v.sx * 2; strides[1] = (cuuint64_t)v.sy * 2;
+    box[1] = box_x; box[2] = box_y;
+  } else {
+    dims[1] = v.H; dims[2] = v.W;
+    strides[0] = (cuuint64_t)v.sy * 2; strides[1] = (cuuint64_t)v.sx * 2;
+    box[1] = box_y; box[2] = box_x;
+  }
+  dims[3] = v.NB;
+  strides[2] = (cuuint64_t)v.sn * 2;
+  box[3] = box_n;
+  LDM_CHECK((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "TMA operand not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    LDM_CHECK(strides[i] % 16 == 0 && strides[i] > 0, "TMA stride %d = %llu not a positive multiple of 16 B", i,
+              (unsigned long long)strides[i]);
+  for (int i = 0; i < 4; ++i) LDM_CHECK(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u", i, box[i]);
+  CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
+      m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(v.ptr), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LDM_CHECK(r == CUDA_SUCCESS,
+            "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u",
+            (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+            (unsigned long long)strides[2], box[0], box[1], box[2], box[3]);
+}
+
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu) {
+  static const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+  const int step = geglu ? 32 : 16;
+  int best = 0;
+  for (int bn : cand) {
+    if (bn % step) continue;
+    if (gemm_n % bn) continue;
+    if (boundary && boundary % bn) continue;
+    if (!best) best = bn;  // largest exact divisor
+    if ((long long)m_tiles * (gemm_n / bn) >= 120) return bn;  // enough CTAs for the 148 SMs
+    if (bn <= 64) break;  // don't shrink tiles below 64 just for parallelism
+    best = bn;
+  }
+  if (best) return best;
+  // no exact divisor: one ragged tile set, TMA zero-fills the B rows past gemm_n
+  int bn = ((gemm_n + step - 1) / step) * step;
+  return bn > 256 ? 256 : bn;
+}
+
+void Engine::gemm(const GemmOp& op) {
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  LDM_CHECK(op.num_a >= 1 && op.num_a <= 3 && op.num_segs >= 1, "gemm: bad operand/segment count");
+  // ---- M tile geometry
+  int w_b = op.w_b, h_b = op.h_b, n_b = op.n_b;
+  if (!w_b) {
+    w_b = op.W >= GEMM_BM ? GEMM_BM : op.W;
+    h_b = GEMM_BM / w_b;
+    if (h_b > op.H) h_b = op.H;
+    if (h_b < 1) h_b = 1;
+    n_b = GEMM_BM / (w_b * h_b);
+    if (n_b < 1) n_b = 1;
+    if (n_b > op.NB) n_b = op.NB;
+  }
+  const int box_rows = w_b * h_b * n_b;
+  LDM_CHECK(box_rows >= 1 && box_rows <= GEMM_BM && w_b <= 256 && h_b <= 256 && n_b <= 256,
+            "gemm: bad M tile %dx%dx%d", n_b, h_b, w_b);
+  p.W = op.W; p.H = op.H; p.NB = op.NB;
+  p.w_b = w_b; p.h_b = h_b; p.n_b = n_b;
+  p.box_rows = box_rows;
+  p.tiles_x = (op.W + w_b - 1) / w_b;
+  p.tiles_y = (op.H + h_b - 1) / h_b;
+  p.tiles_img = (op.NB + n_b - 1) / n_b;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_img * op.num_phases;
+  // ---- N tiling
+  const bool geglu = op.act == ACT_GEGLU;
+  const int gemm_n = op.gemm_n ? op.gemm_n : (geglu ? 2 * op.N : op.N);
+  int bn = op.block_n ? op.block_n : choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu);
+  LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 32 == 0), "gemm: bad block_n %d", bn);
+  p.block_n = bn;
+  p.n_tiles = (gemm_n + bn - 1) / bn;
+  p.N = op.N;
+  p.num_phases = op.num_phases;
+  p.b_mode = op.b_mode;
+  // ---- K segments
+  p.num_segs = op.num_segs;
+  int total_kb = 0;
+  for (int i = 0; i < op.num_segs; ++i) {
+    p.segs[i] = op.segs[i];
+    LDM_CHECK(op.segs[i].map >= 0 && op.segs[i].map < op.num_a, "gemm: segment map index");
+    total_kb += op.segs[i].nkb;
+  }
+  p.total_kb = total_kb;
+  LDM_CHECK(total_kb >= 1, "gemm: empty K loop");
+  // ---- pipeline depth from the shared-memory budget
+  const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
+  const int a_bytes_full = GEMM_BM * GEMM_BK * 2;  // smem slot for A is always 16 KB
+  const int slot = a_bytes_full + bn * GEMM_BK * 2;
+  int stages = (GEMM_SMEM_BYTES - 2048) / slot;
+  if (stages > 8) stages = 8;
+  LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
+  p.stages = stages;
+  p.tx_bytes = stage_bytes;
+  // ---- epilogue
+  p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
+  p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;
+  p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
+  p.os_n = op.os_n; p.os_y = op.os_y; p.os_x = op.os_x; p.os_phase_y = op.os_phase_y; p.os_phase_x = op.os_phase_x;
+  p.out_tr = op.out_tr; p.tr_col0 = op.tr_col0; p.ts_n = op.ts_n; p.ts_y = op.ts_y; p.ts_c = op.ts_c;
+  LDM_CHECK(op.out_f32 || op.out_bf16 || op.out_tr, "gemm: no output");
+  launches++;
+  gemm_launches++;
+  if (dry) return;
+  // ---- tensor maps
+  for (int i = 0; i < 3; ++i) {
+    const AView& v = op.a[i < op.num_a ? i : 0];
+    encode_map(&p.amap[i], v, w_b, h_b, n_b);
+    p.a_swap[i] = v.swap_xy ? 1 : 0;
+  }
+  encode_map(&p.bmap, op.b, bn, 1, 1);
+  p.b_swap = op.b.swap_xy ? 1 : 0;
+  const int total_tiles = m_tiles * p.n_tiles;
+  int ctas = max_ctas > 0 ? max_ctas : num_sms;
+  if (ctas > total_tiles) ctas = total_tiles;
+  const int smem = stages * slot + (2 * stages + 4) * 8 + 16 + 1024;
+  LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
+  implicit_gemm_kernel<<<ctas, GEMM_THREADS, smem, stream>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ldm

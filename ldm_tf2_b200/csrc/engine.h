@@ -1,0 +1,106 @@
+// Host-side engine: device/stream ownership, bump arena for activations, TMA tensor-map
+// encoding, and the launcher of the tcgen05 implicit-GEMM kernel.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ldm {
+
+// 4-D bf16 operand view: innermost C contiguous, then (x, y, n) with element strides.
+struct AView {
+  const bf16* ptr = nullptr;
+  int C = 0, W = 1, H = 1, NB = 1;
+  long long sx = 0, sy = 0, sn = 0;
+  bool swap_xy = false;  // tensor-map dim order (C, y, x, n) instead of (C, x, y, n)
+};
+inline AView view_nhwc(const bf16* p, int nb, int h, int w, int c) {
+  AView v; v.ptr = p; v.C = c; v.W = w; v.H = h; v.NB = nb;
+  v.sx = c; v.sy = (long long)w * c; v.sn = (long long)h * w * c;
+  return v;
+}
+inline AView view_mat(const bf16* p, long long rows, int k, long long ld) {
+  AView v; v.ptr = p; v.C = k; v.W = (int)rows; v.H = 1; v.NB = 1;
+  v.sx = ld; v.sy = ld * rows; v.sn = ld * rows;
+  return v;
+}
+
+struct GemmOp {
+  AView a[3];
+  int num_a = 0;
+  AView b;            // B rows = output columns (x), K = C; batched: (y, n) follow the A tile
+  GemmSeg segs[GEMM_MAX_SEGS];
+  int num_segs = 0;
+  int W = 1, H = 1, NB = 1;        // output row geometry (img, y, x)
+  int w_b = 0, h_b = 0, n_b = 0;   // 0 = choose automatically
+  int N = 0;                        // valid output columns
+  int gemm_n = 0;                   // B rows covered by tiles (defaults to N; 2N for GEGLU)
+  int block_n = 0;                  // 0 = choose automatically
+  int n_boundary = 0;               // tiles must not straddle multiples of this (0 = none)
+  int num_phases = 1;
+  int b_mode = B_PLAIN;
+  const float* bias = nullptr;
+  const float* bias2 = nullptr;
+  int bias2_stride = 0;
+  int bias2_by_img = 0;
+  const int* step_ptr = nullptr;
+  int act = ACT_NONE;
+  float alpha = 1.0f;
+  const float* residual = nullptr;
+  float* out_f32 = nullptr;
+  bf16* out_bf16 = nullptr;
+  long long os_n = 0, os_y = 0, os_x = 0, os_phase_y = 0, os_phase_x = 0;
+  bf16* out_tr = nullptr;
+  int tr_col0 = 0;
+  long long ts_n = 0, ts_y = 0, ts_c = 0;
+
+  void add_seg(int map, int dy, int dx, int c0, int channels, int& bk) {
+    LDM_CHECK(num_segs < GEMM_MAX_SEGS, "too many K segments");
+    GemmSeg s; s.map = map; s.dy = dy; s.dx = dx; s.c0 = c0;
+    s.nkb = (channels + GEMM_BK - 1) / GEMM_BK; s.bk0 = bk;
+    segs[num_segs++] = s;
+    bk += channels;
+  }
+};
+
+class Arena {
+ public:
+  void init(size_t cap);
+  void destroy();
+  void* alloc(size_t bytes);
+  size_t mark() const { return off_; }
+  void release(size_t m) { off_ = m; }
+  void reset() { off_ = 0; }
+  size_t peak() const { return peak_; }
+  size_t capacity() const { return cap_; }
+  bool dry = false;  // dry run: only tally sizes, return fake (null-based) addresses
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0, peak_ = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(int device);
+  ~Engine();
+  int device;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  bool dry = false;            // skip launches (arena sizing pass)
+  long long launches = 0;      // kernels launched by this engine (reported as gpu_launches)
+  long long gemm_launches = 0;
+  int max_ctas = 0;            // 0 = num_sms (test hook)
+
+  void gemm(const GemmOp& op);
+  template <typename T> T* alloc(size_t n) { return reinterpret_cast<T*>(arena.alloc(n * sizeof(T))); }
+  void sync();
+
+ private:
+  void encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, int box_n);
+  void* encode_fn_ = nullptr;
+};
+
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu);
+
+}  // namespace ldm

@@ -1,0 +1,382 @@
+// Implicit-GEMM engine on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the sampling
+// path (K1 conv3x3, K3 dense, the batched QK^T / PV products):
+//   D[128 x block_n] (fp32, TMEM) += A-tile[128 x 64] (bf16, smem via TMA) * B-tile[block_n x 64]^T
+// A tiles are 4-D TMA boxes (64 channels, w_b, h_b, n_b) over an NHWC bf16 activation, so
+// a 3x3 tap is the same box shifted by (dy,dx) with TMA out-of-bounds zero fill acting as
+// SAME padding.  The K loop is a list of segments (map, dy, dx, c0, #k-blocks): 9 taps of a
+// conv, optionally followed by 1x1 "shortcut" segments reading other tensors (the ResBlock
+// shortcut Dense over the virtual concat, unet.py:393-394, is folded into conv2's K loop).
+// B is the weight matrix pre-transposed to [N, K] bf16 (K-major), or a batched activation
+// (attention K / V^T).  The epilogue (4 warps, one TMEM lane quadrant each) fuses bias,
+// per-image/per-step bias (timestep embedding add, unet.py:386-388), SiLU / exact GELU /
+// GEGLU gating (unet.py:323-324), the fp32 residual add, and writes fp32 and/or bf16,
+// optionally transposed (V^T for attention).
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+// Pipelines: smem ring full/empty (TMA<->MMA) and 2 TMEM accumulator stages (MMA<->epilogue).
+#pragma once
+#include "common.cuh"
+
+namespace ldm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_SEGS = 12;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BYTES = 227 * 1024;
+
+enum ActKind : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };
+enum BMode : int { B_PLAIN = 0, B_BATCH = 1, B_PHASE = 2 };
+
+struct GemmSeg {
+  int map;   // which A tensor map
+  int dy, dx;
+  int c0;    // first channel in that map
+  int nkb;   // number of 64-wide k-blocks
+  int bk0;   // first k index in B for this segment
+};
+
+struct GemmParams {
+  CUtensorMap amap[3];
+  CUtensorMap bmap;
+  GemmSeg segs[GEMM_MAX_SEGS];
+  int num_segs;
+  int total_kb;
+  // M geometry: rows are (img, y, x); a tile is n_b x h_b x w_b = 128 rows
+  int W, H, NB;
+  int w_b, h_b, n_b;
+  int tiles_x, tiles_y, tiles_img;
+  int n_tiles, block_n, N;  // N = valid output columns (per batch)
+  int num_phases;           // >1: NN-upsample phase-collapsed conv, grid of phases
+  int b_mode;
+  int stages;
+  int box_rows;             // rows actually loaded per A tile (<= 128)
+  int tx_bytes;             // bytes both TMA loads of a stage deliver
+  int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
+  int b_swap;
+  // epilogue
+  const float* bias;        // [N] or null
+  const float* bias2;       // [rows2, bias2_stride] or null
+  int bias2_stride;
+  int bias2_by_img;         // row index += img
+  const int* step_ptr;      // row index += *step_ptr (device-side DDIM index)
+  int act;
+  float alpha;              // scales the accumulator before bias
+  const float* residual;    // fp32, same addressing as out
+  float* out_f32;
+  bf16* out_bf16;
+  long long os_n, os_y, os_x;  // output element strides for (img, y, x)
+  long long os_phase_y, os_phase_x;  // extra offset for phase (py, px)
+  // transposed bf16 output for columns >= tr_col0 (V^T): out_tr[img*ts_n + y*ts_y + (col-tr_col0)*ts_c + x]
+  bf16* out_tr;
+  int tr_col0;
+  long long ts_n, ts_y, ts_c;
+};
+
+#if defined(__CUDACC__) && defined(LDM_GEMM_IMPL)
+
+struct TileCoord {
+  int img0, y0, x0, n0, phase, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  int ty = m % p.tiles_y;
+  m /= p.tiles_y;
+  int ti = m % p.tiles_img;
+  t.phase = m / p.tiles_img;
+  t.x0 = tx * p.w_b;
+  t.y0 = ty * p.h_b;
+  t.img0 = ti * p.n_b;
+  t.n0 = t.n_tile * p.block_n;
+  return t;
+}
+
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* acc, const float* gate,
+                                               int col0, bool row_ok, long long row_off, int img,
+                                               int xq, long long tr_row_off, const float* bias2_row) {
+  // acc[CH]: accumulator values for output columns col0 .. col0+CH-1 (already alpha-scaled).
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    int col = col0 + j;
+    float x = acc[j];
+    if (col < p.N) {
+      if (p.act == ACT_GEGLU) {
+        // value/gate biases are interleaved like the weights: handled by caller via bias ptrs
+      }
+      if (p.bias) x += __ldg(p.bias + col);
+      if (bias2_row) x += __ldg(bias2_row + col);
+      if (p.act == ACT_SILU) x = silu_f(x);
+      else if (p.act == ACT_GELU) x = gelu_erf_f(x);
+    }
+    v[j] = x;
+  }
+  (void)gate;
+  if (!row_ok) return;
+  const bool full = (col0 + CH <= p.N);
+  if (p.out_tr && col0 >= p.tr_col0) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      int col = col0 + j;
+      if (col < p.N) p.out_tr[tr_row_off + (long long)(col - p.tr_col0) * p.ts_c + xq] = __float2bfloat16(v[j]);
+    }
+    return;
+  }
+  const long long off = row_off + col0;
+  if (p.residual) {
+    if (full && ((off & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) {
+        float4 r = *reinterpret_cast<const float4*>(p.residual + off + j);
+        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < p.N) v[j] += p.residual[off + j];
+    }
+  }
+  if (p.out_f32) {
+    if (full && ((off & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4)
+        *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < p.N) p.out_f32[off + j] = v[j];
+    }
+  }
+  if (p.out_bf16) {
+    if (full && ((off & 7) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j], v[j + 1]);
+        u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]);
+        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < p.N) p.out_bf16[off + j] = __float2bfloat16(v[j]);
+    }
+  }
+  (void)img;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; barriers after.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = GEMM_BM * GEMM_BK * 2;
+  const int b_bytes = p.block_n * GEMM_BK * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tfull_bar = empty_bar + stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.bmap);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int py = t.phase >> 1, px = t.phase & 1;
+        int bz0 = 0, bz1 = 0;
+        if (p.b_mode == B_BATCH) { bz0 = t.y0; bz1 = t.img0; }
+        else if (p.b_mode == B_PHASE) { bz0 = t.phase; }
+        for (int s = 0; s < p.num_segs; ++s) {
+          const GemmSeg sg = p.segs[s];
+          const int dy = sg.dy + (p.num_phases > 1 ? py : 0);
+          const int dx = sg.dx + (p.num_phases > 1 ? px : 0);
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
+            const int ax = t.x0 + dx, ay = t.y0 + dy;
+            if (p.a_swap[sg.map])
+              tma_load_4d(sa, &p.amap[sg.map], &full_bar[stage], sg.c0 + kb * GEMM_BK, ay, ax, t.img0);
+            else
+              tma_load_4d(sa, &p.amap[sg.map], &full_bar[stage], sg.c0 + kb * GEMM_BK, ax, ay, t.img0);
+            if (p.b_swap)
+              tma_load_4d(sb, &p.bmap, &full_bar[stage], sg.bk0 + kb * GEMM_BK, bz0, t.n0, bz1);
+            else
+              tma_load_4d(sb, &p.bmap, &full_bar[stage], sg.bk0 + kb * GEMM_BK, t.n0, bz0, bz1);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, (uint32_t)p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in 16-B units
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps 2..5
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const int hw_b = p.h_b * p.w_b;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int py = t.phase >> 1, px = t.phase & 1;
+      const int img = t.img0 + r / hw_b;
+      const int yq = t.y0 + (r % hw_b) / p.w_b;
+      const int xq = t.x0 + r % p.w_b;
+      const bool row_ok = (r < p.box_rows) && (img < p.NB) && (yq < p.H) && (xq < p.W);
+      const long long row_off = (long long)img * p.os_n + (long long)yq * p.os_y + (long long)xq * p.os_x +
+                                (long long)py * p.os_phase_y + (long long)px * p.os_phase_x;
+      const long long tr_row_off = (long long)img * p.ts_n + (long long)yq * p.ts_y;
+      const float* bias2_row = nullptr;
+      if (p.bias2) {
+        long long row2 = (p.bias2_by_img ? img : 0) + (p.step_ptr ? __ldg(p.step_ptr) : 0);
+        bias2_row = p.bias2 + row2 * p.bias2_stride;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+      if (p.act == ACT_GEGLU) {
+        // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates
+        const int half = p.block_n >> 1;
+        for (int c = 0; c < half; c += 16) {
+          uint32_t rv[16], rg[16];
+          tmem_ld_x16(t_base + (uint32_t)c, rv);
+          tmem_ld_x16(t_base + (uint32_t)(half + c), rg);
+          tmem_ld_wait();
+          float v[16];
+          const int oc0 = t.n_tile * half + c;  // output column
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(rv[j]) * p.alpha;
+            float g = __uint_as_float(rg[j]) * p.alpha;
+            if (p.bias) {
+              a += __ldg(p.bias + t.n0 + c + j);
+              g += __ldg(p.bias + t.n0 + half + c + j);
+            }
+            v[j] = a * gelu_erf_f(g);
+          }
+          if (row_ok) {
+            const long long off = row_off + oc0;
+            if (p.out_bf16) {
+              if ((off & 7) == 0 && oc0 + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  uint4 u;
+                  u.x = pack_bf16(v[j], v[j + 1]);
+                  u.y = pack_bf16(v[j + 2], v[j + 3]);
+                  u.z = pack_bf16(v[j + 4], v[j + 5]);
+                  u.w = pack_bf16(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (oc0 + j < p.N) p.out_bf16[off + j] = __float2bfloat16(v[j]);
+              }
+            }
+            if (p.out_f32) {
+              for (int j = 0; j < 16; ++j)
+                if (oc0 + j < p.N) p.out_f32[off + j] = v[j];
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(t_base + (uint32_t)c, rr);
+          tmem_ld_wait();
+          float acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
+          epilogue_chunk<16>(p, acc, nullptr, t.n0 + c, row_ok, row_off, img, xq, tr_row_off, bias2_row);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+#endif  // __CUDACC__ && LDM_GEMM_IMPL
+
+}  // namespace ldm

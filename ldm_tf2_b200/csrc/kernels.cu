@@ -1,0 +1,581 @@
+// Memory-bound / small kernels of the sampling path.  See kernels.cuh for the map to the
+// reference call sites.
+#include "kernels.cuh"
+
+namespace ldm {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// =====================================================================================
+// K5: CFG combine + DDIM update.  One float4 (= one latent pixel, 4 channels) per thread
+// iteration, fully coalesced; each product/sum separately rounded (the reference runs
+// them as separate eager TF ops), so the result is bit-identical to the fp32 oracle.
+// Algorithmic bytes: 3 reads (+1 noise) + 1 write of 16 B per latent pixel.
+// =====================================================================================
+__global__ void ddim_update_kernel(const float4* __restrict__ eps_u, const float4* __restrict__ eps_c,
+                                   const float4* __restrict__ xt, const float4* __restrict__ noise,
+                                   long long noise_stride4, const float* __restrict__ coeffs, const int* __restrict__ step_ptr,
+                                   int step_host, float s, int clip, float4* __restrict__ xt_out,
+                                   float4* __restrict__ x0_out, long long n4) {
+  const int step = step_ptr ? __ldg(step_ptr) : step_host;
+  const float* c = coeffs + step * 8;
+  const float c_recip = __ldg(c + 0), c_recipm1 = __ldg(c + 1), c_x0 = __ldg(c + 2), c_eps = __ldg(c + 3),
+              sigma = __ldg(c + 4);
+  const float4* nz = noise ? noise + (long long)step * noise_stride4 : nullptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 eu = __ldg(eps_u + i), ec = __ldg(eps_c + i), x = __ldg(xt + i);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nz) z = __ldg(nz + i);
+    float o[4], p0[4];
+    const float eu_[4] = {eu.x, eu.y, eu.z, eu.w}, ec_[4] = {ec.x, ec.y, ec.z, ec.w},
+                x_[4] = {x.x, x.y, x.z, x.w}, z_[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = __fadd_rn(eu_[k], __fmul_rn(s, __fsub_rn(ec_[k], eu_[k])));
+      float x0 = __fsub_rn(__fmul_rn(c_recip, x_[k]), __fmul_rn(c_recipm1, e));
+      if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+      float m = __fadd_rn(__fmul_rn(c_x0, x0), __fmul_rn(c_eps, e));
+      if (nz) m = __fadd_rn(m, __fmul_rn(z_[k], sigma));
+      o[k] = m;
+      p0[k] = x0;
+    }
+    xt_out[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (x0_out) x0_out[i] = make_float4(p0[0], p0[1], p0[2], p0[3]);
+  }
+}
+
+void launch_ddim_update(const float* eps2, const float* xt, const float* noise, long long noise_step_stride,
+                        const float* coeffs,
+                        const int* step_ptr, int step_host, float guidance, int clip, float* xt_out,
+                        float* x0_out, long long n_per_half, cudaStream_t st) {
+  LDM_CHECK(n_per_half % 4 == 0, "ddim_update: element count must be a multiple of 4");
+  const long long n4 = n_per_half / 4;
+  const int threads = 256;
+  ddim_update_kernel<<<grid_for(n4, threads, 148 * 8), threads, 0, st>>>(
+      reinterpret_cast<const float4*>(eps2), reinterpret_cast<const float4*>(eps2 + n_per_half),
+      reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(noise), noise_step_stride / 4, coeffs,
+      step_ptr,
+      step_host, guidance, clip, reinterpret_cast<float4*>(xt_out), reinterpret_cast<float4*>(x0_out), n4);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void step_advance_kernel(int* p, int d) { *p += d; }
+void launch_step_advance(int* step_ptr, int delta, cudaStream_t st) {
+  step_advance_kernel<<<1, 1, 0, st>>>(step_ptr, delta);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// K2: GroupNorm statistics.  One CTA per (sample, group); two passes (mean, then centred
+// second moment) like Keras' moments; the second pass hits L2.  Group channels are
+// contiguous (cg = C/32).  Handles the virtual concat [a | b] along C.
+// =====================================================================================
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? sh[l] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+__global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                int hw, float eps, float* __restrict__ out) {
+  __shared__ float sh[32];
+  const int c = ca + cb, cg = c / 32;
+  const int n = blockIdx.x / 32, g = blockIdx.x % 32;
+  const long long count = (long long)hw * cg;
+  const float* pa = a + (long long)n * hw * ca;
+  const float* pb = b ? b + (long long)n * hw * cb : nullptr;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+    const int pix = (int)(i / cg), ch = g * cg + (int)(i % cg);
+    s += (ch < ca) ? pa[(long long)pix * ca + ch] : pb[(long long)pix * cb + (ch - ca)];
+  }
+  const float mean = block_sum(s, sh) / (float)count;
+  float q = 0.f;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+    const int pix = (int)(i / cg), ch = g * cg + (int)(i % cg);
+    const float v = ((ch < ca) ? pa[(long long)pix * ca + ch] : pb[(long long)pix * cb + (ch - ca)]) - mean;
+    q += v * v;
+  }
+  const float var = block_sum(q, sh) / (float)count;
+  if (threadIdx.x == 0) {
+    out[blockIdx.x * 2 + 0] = mean;
+    out[blockIdx.x * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, float eps,
+                     float* mean_rstd, cudaStream_t st) {
+  LDM_CHECK((ca + cb) % 32 == 0, "GroupNorm(32): channels %d not a multiple of 32", ca + cb);
+  const long long count = (long long)hw * ((ca + cb) / 32);
+  int threads = count >= 4096 ? 512 : (count >= 1024 ? 256 : 128);
+  gn_stats_kernel<<<n * 32, threads, 0, st>>>(a, ca, b, cb, hw, eps, mean_rstd);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                int hw, const float* __restrict__ mr, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int do_silu, bf16* __restrict__ out,
+                                long long total4) {
+  const int c = ca + cb, cg = c / 32, c4 = c / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c4) * 4;
+    const long long pixg = i / c4;  // global pixel index n*hw + pix
+    const int n = (int)(pixg / hw);
+    float4 v;
+    if (ch < ca) v = *reinterpret_cast<const float4*>(a + pixg * ca + ch);
+    else v = *reinterpret_cast<const float4*>(b + pixg * cb + (ch - ca));
+    float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (ch + k) / cg;
+      const float mean = __ldg(mr + (n * 32 + g) * 2), rstd = __ldg(mr + (n * 32 + g) * 2 + 1);
+      float y = (x[k] - mean) * rstd * __ldg(gamma + ch + k) + __ldg(beta + ch + k);
+      if (do_silu) y = silu_f(y);
+      x[k] = y;
+    }
+    uint2 u;
+    u.x = pack_bf16(x[0], x[1]);
+    u.y = pack_bf16(x[2], x[3]);
+    *reinterpret_cast<uint2*>(out + pixg * c + ch) = u;
+  }
+}
+
+void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const float* mean_rstd,
+                     const float* gamma, const float* beta, int do_silu, bf16* out, cudaStream_t st) {
+  LDM_CHECK(ca % 4 == 0 && cb % 4 == 0, "gn_apply: channel counts must be multiples of 4");
+  const long long total4 = (long long)n * hw * (ca + cb) / 4;
+  gn_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(a, ca, b, cb, hw, mean_rstd, gamma, beta, do_silu,
+                                                        out, total4);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// LayerNorm: one warp per row, two-pass in fp32, row re-read from L1/L2.
+// =====================================================================================
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, int c, float eps,
+                                 bf16* __restrict__ ob, float* __restrict__ of) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * c;
+  float s = 0.f;
+  for (int i = lane; i < c; i += 32) s += xr[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)c;
+  float q = 0.f;
+  for (int i = lane; i < c; i += 32) {
+    const float d = xr[i] - mean;
+    q += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)c + eps);
+  for (int i = lane; i < c; i += 32) {
+    const float y = (xr[i] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
+    if (ob) ob[(long long)row * c + i] = __float2bfloat16(y);
+    if (of) of[(long long)row * c + i] = y;
+  }
+}
+
+void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
+                      bf16* out_bf16, float* out_f32, cudaStream_t st) {
+  const int wpb = 8;
+  layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// softmax(scale * s) over tk valid keys of a tpad-wide row; pad columns get 0.
+// =====================================================================================
+__global__ void softmax_kernel(const float* __restrict__ s, bf16* __restrict__ p, long long rows, int tk,
+                               int tpad, float scale) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * tpad;
+  bf16* pr = p + row * tpad;
+  float m = -INFINITY;
+  for (int i = lane; i < tk; i += 32) m = fmaxf(m, sr[i] * scale);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int i = lane; i < tk; i += 32) sum += __expf(sr[i] * scale - m);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < tpad; i += 32)
+    pr[i] = __float2bfloat16(i < tk ? __expf(sr[i] * scale - m) * inv : 0.f);
+}
+
+void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, cudaStream_t st) {
+  const int wpb = 8;
+  softmax_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(s, p, rows, tk, tpad, scale);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// conv_in: direct 3x3 SAME conv with 4 input channels (K = 36: too thin for UMMA).
+// One thread per (pixel, 4 output channels).
+// =====================================================================================
+__global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
+                               const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
+                               float* __restrict__ of, bf16* __restrict__ ob) {
+  const int c4 = cout / 4;
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c4) * 4;
+    long long pix = i / c4;
+    const int xx = (int)(pix % w);
+    pix /= w;
+    const int yy = (int)(pix % h);
+    const int img = (int)(pix / h);
+    const float* src = x + (long long)(img % nsrc) * h * w * 4;
+    float acc[4] = {__ldg(bias + co), __ldg(bias + co + 1), __ldg(bias + co + 2), __ldg(bias + co + 3)};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = xx + kx - 1;
+        if (ix < 0 || ix >= w) continue;
+        const float4 v = *reinterpret_cast<const float4*>(src + ((long long)iy * w + ix) * 4);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const float4 kw = __ldg(reinterpret_cast<const float4*>(kernel + ((ky * 3 + kx) * 4 + ci) * cout + co));
+          acc[0] += in[ci] * kw.x;
+          acc[1] += in[ci] * kw.y;
+          acc[2] += in[ci] * kw.z;
+          acc[3] += in[ci] * kw.w;
+        }
+      }
+    }
+    const long long o = (((long long)img * h + yy) * w + xx) * cout + co;
+    if (of) *reinterpret_cast<float4*>(of + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (ob) {
+      uint2 u;
+      u.x = pack_bf16(acc[0], acc[1]);
+      u.y = pack_bf16(acc[2], acc[3]);
+      *reinterpret_cast<uint2*>(ob + o) = u;
+    }
+  }
+}
+
+void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel, const float* bias,
+                    int cout, float* out_f32, bf16* out_bf16, cudaStream_t st) {
+  LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
+  const long long total = (long long)n * h * w * (cout / 4);
+  conv_in_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, nsrc, n, h, w, kernel, bias, cout, out_f32, out_bf16);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// out = (x / div) @ K[4,4] + b  -- post_quant_conv (autoencoder.py:362,434), after the
+// decode_first_stage scaling (model_runners.py:426) when div != 1.
+__global__ void dense4_kernel(const float4* __restrict__ x, long long rows, float div,
+                              const float* __restrict__ k, const float* __restrict__ b, float4* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    const float in[4] = {v.x / div, v.y / div, v.z / div, v.w / div};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a += in[c] * __ldg(k + c * 4 + j);
+      o[j] = a + __ldg(b + j);
+    }
+    out[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+void launch_dense4(const float* x, long long rows, float in_div, const float* kernel, const float* bias,
+                   float* out, cudaStream_t st) {
+  dense4_kernel<<<grid_for(rows, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), rows, in_div, kernel,
+                                                    bias, reinterpret_cast<float4*>(out));
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// im2col for pad(1,1) + 3x3 stride-2 VALID: out[(n,oy,ox), tap*c + ch] = x[n, 2oy+ky-1, 2ox+kx-1, ch]
+// =====================================================================================
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, int n, int h, int w, int c8, uint4* __restrict__ out) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * 9 * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c8);
+    long long r = i / c8;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int ox = (int)(r % wo);
+    r /= wo;
+    const int oy = (int)(r % ho);
+    const int img = (int)(r / ho);
+    const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = x[(((long long)img * h + iy) * w + ix) * c8 + ch];
+    out[i] = v;
+  }
+}
+void launch_im2col_s2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st) {
+  LDM_CHECK(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_s2: bad shape");
+  const long long total = (long long)n * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
+                                                        reinterpret_cast<uint4*>(out));
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void upsample2_kernel(const uint4* __restrict__ x, int n, int h, int w, int c8, uint4* __restrict__ out) {
+  const long long total = (long long)n * (2 * h) * (2 * w) * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c8);
+    long long r = i / c8;
+    const int ox = (int)(r % (2 * w));
+    r /= (2 * w);
+    const int oy = (int)(r % (2 * h));
+    const int img = (int)(r / (2 * h));
+    out[i] = x[(((long long)img * h + (oy >> 1)) * w + (ox >> 1)) * c8 + ch];
+  }
+}
+void launch_upsample2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st) {
+  LDM_CHECK(c % 8 == 0, "upsample2: channels must be a multiple of 8");
+  const long long total = (long long)n * 4 * h * w * (c / 8);
+  upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
+                                                        reinterpret_cast<uint4*>(out));
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// misc
+// =====================================================================================
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n, int do_silu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (do_silu) v = silu_f(v);
+    y[i] = __float2bfloat16(v);
+  }
+}
+void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, cudaStream_t st) {
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, do_silu);
+  CUDA_CHECK(cudaGetLastError());
+}
+__global__ void fill_f32_kernel(float* x, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+void launch_fill_f32(float* x, long long n, float v, cudaStream_t st) {
+  fill_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, n, v);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// W[k][n] fp32 -> dst[(row0 + perm(n)) * ld + k] bf16 through a 32x32 smem transpose.
+__global__ void pack_weight_kernel(const float* __restrict__ w, int k, int n, bf16* __restrict__ dst,
+                                   long long ld, int row0, int geglu_half) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int kk = k0 + j, nn = n0 + threadIdx.x;
+    tile[j][threadIdx.x] = (kk < k && nn < n) ? w[(long long)kk * n + nn] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int nn = n0 + j, kk = k0 + threadIdx.x;
+    if (nn < n && kk < k) {
+      int r = nn;
+      if (geglu_half > 0) {
+        const int nh = n / 2;  // first nh columns = values, last nh = gates (unet.py:323)
+        const int j2 = nn < nh ? nn : nn - nh;
+        r = (j2 / geglu_half) * (2 * geglu_half) + (nn < nh ? 0 : geglu_half) + j2 % geglu_half;
+      }
+      dst[(long long)(row0 + r) * ld + kk] = __float2bfloat16(tile[threadIdx.x][j]);
+    }
+  }
+}
+void launch_pack_weight(const float* w, int k, int n, bf16* dst, long long dst_ld, int dst_row0,
+                        int geglu_half, cudaStream_t st) {
+  dim3 grid(cdiv(n, 32), cdiv(k, 32)), block(32, 8);
+  pack_weight_kernel<<<grid, block, 0, st>>>(w, k, n, dst, dst_ld, dst_row0, geglu_half);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// token + positional embedding (transformer.py:262-267)
+__global__ void embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                             const float* __restrict__ pos, int rows, int seq, int d, float* __restrict__ out) {
+  const long long total = (long long)rows * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i % d);
+    out[i] = tok[ids[r] * d + c] + pos[(long long)(r % seq) * d + c];
+  }
+}
+void launch_embed(const long long* ids, const float* tok, const float* pos, int rows, int seq, int d,
+                  float* out, cudaStream_t st) {
+  embed_kernel<<<grid_for((long long)rows * d, 256), 256, 0, st>>>(ids, tok, pos, rows, seq, d, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// get_time_embedding (unet.py:401-422): [cos | sin], freqs exp(-ln(1e4) * i / half)
+__global__ void time_embed_kernel(const int* __restrict__ t, int n, int channels, float* __restrict__ out) {
+  const int half = channels / 2;
+  const int total = n * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / half, j = i % half;
+    const float f = expf(-logf(10000.0f) * (float)j / (float)half);
+    const float a = (float)t[r] * f;
+    out[r * channels + j] = cosf(a);
+    out[r * channels + half + j] = sinf(a);
+  }
+}
+void launch_time_embed(const int* t, int n, int channels, float* out, cudaStream_t st) {
+  time_embed_kernel<<<grid_for((long long)n * channels / 2, 128), 128, 0, st>>>(t, n, channels, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// tensor_to_image (run_ldm_sampler.py:18-25): one CTA per image, min/max then scale.
+__global__ void tensor_to_image_kernel(const float* __restrict__ x, long long per, unsigned char* __restrict__ out) {
+  __shared__ float smin[32], smax[32];
+  const float* p = x + blockIdx.x * per;
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float v = p[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  mn = smin[0]; mx = smax[0];
+  for (int i = 1; i < nw; ++i) { mn = fminf(mn, smin[i]); mx = fmaxf(mx, smax[i]); }
+  const float range = __fsub_rn(mx, mn);
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float v = __fmul_rn(__fdiv_rn(__fsub_rn(p[i], mn), range), 255.0f);
+    out[blockIdx.x * per + i] = (unsigned char)v;  // truncating cast like numpy astype("uint8")
+  }
+}
+void launch_tensor_to_image(const float* x, int n, long long per, unsigned char* out, cudaStream_t st) {
+  tensor_to_image_kernel<<<n, 1024, 0, st>>>(x, per, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// K6: VQ codebook argmin (quantize.py:65-72) + gather (quantize.py:75-78).
+// A warp owns VQ_R rows; lanes stride over the codes, so every code vector fetched
+// (coalesced float4, L1/L2 resident: 16384 x 16 B = 256 KB) is reused for VQ_R rows.
+// Distances use the oracle's exact fp32 op order with no FMA contraction:
+//   A = ((z0^2+z1^2)+z2^2)+z3^2, B likewise (precomputed per code), M = ((z0e0+z1e1)+z2e2)+z3e3,
+//   d = (A+B) - 2M.  The running (d, idx) minimum and the 5-step shuffle reduction break
+//   ties towards the lower index, i.e. tf.argmin semantics.  dim is fixed to 4 here.
+// =====================================================================================
+constexpr int VQ_R = 8;
+
+__global__ void vq_code_norm_kernel(const float4* __restrict__ cb, int codes, float* __restrict__ bnorm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= codes) return;
+  const float4 e = cb[i];
+  bnorm[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(e.x, e.x), __fmul_rn(e.y, e.y)), __fmul_rn(e.z, e.z)),
+                       __fmul_rn(e.w, e.w));
+}
+
+__global__ void vq_argmin_kernel(const float4* __restrict__ z, long long rows, const float4* __restrict__ cb,
+                                 const float* __restrict__ bnorm, int codes, long long* __restrict__ idx_out,
+                                 float4* __restrict__ zq_out) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = warp * VQ_R;
+  if (row0 >= rows) return;
+  float4 zr[VQ_R];
+  float A[VQ_R], best[VQ_R];
+  int bi[VQ_R];
+#pragma unroll
+  for (int r = 0; r < VQ_R; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;
+    zr[r] = z[row];
+    A[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(zr[r].x, zr[r].x), __fmul_rn(zr[r].y, zr[r].y)),
+                               __fmul_rn(zr[r].z, zr[r].z)),
+                     __fmul_rn(zr[r].w, zr[r].w));
+    best[r] = INFINITY;
+    bi[r] = 0x7fffffff;
+  }
+  for (int c = lane; c < codes; c += 32) {
+    const float4 e = __ldg(cb + c);
+    const float B = __ldg(bnorm + c);
+#pragma unroll
+    for (int r = 0; r < VQ_R; ++r) {
+      const float M = __fadd_rn(
+          __fadd_rn(__fadd_rn(__fmul_rn(zr[r].x, e.x), __fmul_rn(zr[r].y, e.y)), __fmul_rn(zr[r].z, e.z)),
+          __fmul_rn(zr[r].w, e.w));
+      const float d = __fsub_rn(__fadd_rn(A[r], B), __fmul_rn(2.0f, M));
+      if (d < best[r]) {  // strict: codes ascend per lane, the first minimum is kept
+        best[r] = d;
+        bi[r] = c;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < VQ_R; ++r) {
+    float d = best[r];
+    int i = bi[r];
+    for (int o = 16; o > 0; o >>= 1) {
+      const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+      if (d2 < d || (d2 == d && i2 < i)) {
+        d = d2;
+        i = i2;
+      }
+    }
+    if (lane == 0 && row0 + r < rows) {
+      idx_out[row0 + r] = (long long)i;
+      if (zq_out) zq_out[row0 + r] = __ldg(cb + i);
+    }
+  }
+}
+
+// z_scaled = z / div (decode_first_stage, model_runners.py:426), IEEE division.
+__global__ void div_scalar_kernel(const float* __restrict__ x, float div, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __fdiv_rn(x[i], div);
+}
+
+void launch_vq_argmin(const float* z, long long rows, int dim, const float* codebook, int codes, float in_div,
+                      long long* idx_out, float* zq_out, cudaStream_t st) {
+  LDM_CHECK(dim == 4, "vq_argmin: latent_channels must be 4 (got %d)", dim);
+  // scratch: code norms (codes floats) live right after use; allocate per call from the async pool
+  float* bnorm = nullptr;
+  float* zs = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&bnorm, sizeof(float) * codes, st));
+  const float* zin = z;
+  if (in_div != 1.0f) {
+    CUDA_CHECK(cudaMallocAsync(&zs, sizeof(float) * rows * 4, st));
+    div_scalar_kernel<<<grid_for(rows * 4, 256), 256, 0, st>>>(z, in_div, zs, rows * 4);
+    zin = zs;
+  }
+  vq_code_norm_kernel<<<cdiv(codes, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(codebook), codes, bnorm);
+  const long long warps = (rows + VQ_R - 1) / VQ_R;
+  const int threads = 128;
+  vq_argmin_kernel<<<cdiv(warps * 32, threads), threads, 0, st>>>(
+      reinterpret_cast<const float4*>(zin), rows, reinterpret_cast<const float4*>(codebook), bnorm, codes, idx_out,
+      reinterpret_cast<float4*>(zq_out));
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaFreeAsync(bnorm, st));
+  if (zs) CUDA_CHECK(cudaFreeAsync(zs, st));
+}
+
+}  // namespace ldm

@@ -1,0 +1,1198 @@
+// Model graphs of the sampling path on the B200 engine.  See model.h.
+#include "model.h"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <algorithm>
+
+namespace ldm {
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+template <typename T>
+T* Model::dev_alloc(size_t n, bool zero) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  owned_.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+// =====================================================================================
+// Construction: slots in flat Keras order + packed destinations
+// =====================================================================================
+struct Builder {
+  Model& m;
+  int model;
+  std::vector<Slot>& s;
+  explicit Builder(Model& mm, int which) : m(mm), model(which), s(mm.slots[which]) {}
+
+  Slot* f32(const std::string& name, std::vector<int> shape) {
+    Slot sl;
+    sl.name = name;
+    sl.shape = std::move(shape);
+    sl.kind = Slot::F32;
+    s.push_back(sl);
+    return &s.back();
+  }
+  // kernel viewed as [k, n]; packed to dst[(row0+perm(n))*ld + col0 + k]
+  Slot* pack(const std::string& name, std::vector<int> shape, int k, int n, bf16* dst, long long ld, int row0,
+             int col0, int geglu_half = 0) {
+    Slot sl;
+    sl.name = name;
+    sl.shape = std::move(shape);
+    sl.kind = Slot::PACK;
+    sl.dst = dst; sl.ld = ld; sl.row0 = row0; sl.col0 = col0; sl.k = k; sl.n = n; sl.geglu_half = geglu_half;
+    s.push_back(sl);
+    return &s.back();
+  }
+  LinW lin(int n, int k) {
+    LinW w;
+    w.n = n; w.k = k; w.ld = k;
+    LDM_CHECK(k % 8 == 0, "linear K=%d must be a multiple of 8 (16-byte TMA rows)", k);
+    w.wt = m.dev_alloc<bf16>((size_t)n * k, true);
+    return w;
+  }
+  GNW gnw(const std::string& p, int c, float eps) {
+    GNW g; g.c = c; g.eps = eps;
+    g.gamma = f32(p + "/gamma", {c});
+    g.beta = f32(p + "/beta", {c});
+    return g;
+  }
+  LNW lnw(const std::string& p, int c) {
+    LNW g; g.c = c;
+    g.gamma = f32(p + "/gamma", {c});
+    g.beta = f32(p + "/beta", {c});
+    return g;
+  }
+  // Dense [k,n] + bias
+  LinW dense(const std::string& p, int k, int n, bool bias = true) {
+    LinW w = lin(n, k);
+    pack(p + "/kernel", {k, n}, k, n, w.wt, w.ld, 0, 0);
+    if (bias) w.bias = f32(p + "/bias", {n});
+    return w;
+  }
+  // ResidualBlock (unet.py:368-380 / autoencoder.py:13-41) in Keras weight order
+  ResW res(const std::string& p, int cin, int cout, int temb_dim, bool shortcut, bool ae, int* temb_cols,
+           LinW* tproj) {
+    ResW r;
+    r.cin = cin; r.cout = cout; r.shortcut = shortcut;
+    const char* n_gn1 = ae ? "/_group_norm1" : "/_group_norm_1";
+    const char* n_c1 = ae ? "/_conv1" : "/_conv2d_1";
+    const char* n_gn2 = ae ? "/_group_norm2" : "/_group_norm_2";
+    const char* n_c2 = ae ? "/_conv2" : "/_conv2d_2";
+    const float eps = ae ? 1e-6f : 1e-5f;
+    r.gn1 = gnw(p + n_gn1, cin, eps);
+    r.conv1 = lin(cout, 9 * cin);
+    pack(p + n_c1 + "/kernel", {3, 3, cin, cout}, 9 * cin, cout, r.conv1.wt, r.conv1.ld, 0, 0);
+    r.conv1.bias = f32(p + n_c1 + "/bias", {cout});
+    if (temb_dim) {
+      r.temb_off = *temb_cols;
+      pack(p + "/_dense/kernel", {temb_dim, cout}, temb_dim, cout, tproj->wt, tproj->ld, r.temb_off, 0);
+      Slot* b = f32(p + "/_dense/bias", {cout});
+      tproj_bias.push_back({b, r.temb_off});
+      *temb_cols += cout;
+    }
+    r.gn2 = gnw(p + n_gn2, cout, eps);
+    r.conv2 = lin(cout, 9 * cout + (shortcut ? cin : 0));
+    pack(p + n_c2 + "/kernel", {3, 3, cout, cout}, 9 * cout, cout, r.conv2.wt, r.conv2.ld, 0, 0);
+    r.conv2.bias = f32(p + n_c2 + "/bias", {cout});
+    if (shortcut) {
+      pack(p + "/_shortcut/kernel", {cin, cout}, cin, cout, r.conv2.wt, r.conv2.ld, 0, 9 * cout);
+      r.sc_bias = f32(p + "/_shortcut/bias", {cout});
+    }
+    return r;
+  }
+  std::vector<std::pair<Slot*, int>> tproj_bias;
+
+  // CrossAttention (unet.py:248-267): q,k,v split Projections (no bias), out merge (+bias)
+  AttnW attn(const std::string& p, int cq, int ckv, int heads, int d, int cout, bool self) {
+    AttnW a;
+    a.heads = heads; a.d = d;
+    const int inner = heads * d;
+    if (self) {
+      a.qkv = lin(3 * inner, cq);
+      pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
+      pack(p + "/_dense_layer_key/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, inner, 0);
+      pack(p + "/_dense_layer_value/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 2 * inner, 0);
+    } else {
+      a.qkv = lin(inner, cq);
+      a.kv = lin(2 * inner, ckv);
+      pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
+      pack(p + "/_dense_layer_key/kernel", {ckv, heads, d}, ckv, inner, a.kv.wt, a.kv.ld, 0, 0);
+      pack(p + "/_dense_layer_value/kernel", {ckv, heads, d}, ckv, inner, a.kv.wt, a.kv.ld, inner, 0);
+    }
+    a.out = lin(cout, inner);
+    pack(p + "/_dense_layer_output/kernel", {heads, d, cout}, inner, cout, a.out.wt, a.out.ld, 0, 0);
+    a.out.bias = f32(p + "/_dense_layer_output/bias", {cout});
+    return a;
+  }
+  // SpatialTransformer (unet.py:341-354), 26 tensors, GroupNorm last
+  void st(STW& t, const std::string& p, int c, int heads, int d, int ctx) {
+    t.c = c; t.d = d;
+    t.d1 = dense(p + "/_dense1", c, c);
+    t.a1 = attn(p + "/_block/_att_layer1", c, c, heads, d, c, true);
+    t.a2 = attn(p + "/_block/_att_layer2", c, ctx, heads, d, c, false);
+    // GEGLU Dense c -> 8c, rows permuted per tile so value/gate columns share a tile
+    t.geglu = lin(8 * c, c);
+    int bn = 256;
+    while ((8 * c) % bn) bn -= 32;
+    t.geglu_bn = bn;
+    pack(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/kernel", {c, 8 * c}, c, 8 * c, t.geglu.wt, t.geglu.ld, 0,
+         0, bn / 2);
+    t.geglu.bias = f32(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/bias", {8 * c});
+    t.ff = dense(p + "/_block/_ffn_layer/_dense_layer", 4 * c, c);
+    t.ln1 = lnw(p + "/_block/_layernorm1", c);
+    t.ln2 = lnw(p + "/_block/_layernorm2", c);
+    t.ln3 = lnw(p + "/_block/_layernorm3", c);
+    t.d2 = dense(p + "/_dense2", c, c);
+    t.gn = gnw(p + "/_groupnorm", c, 1e-6f);
+  }
+  // AE AttentionBlock (autoencoder.py:61-72): GN, then q,k,v,out Dense with bias
+  void ae_attn(AEAttnW& a, const std::string& p, int c) {
+    a.c = c;
+    a.gn = gnw(p + "/_group_norm", c, 1e-6f);
+    a.qkv = lin(3 * c, c);
+    a.qkv_bias = m.dev_alloc<float>(3 * c, true);
+    const char* nm[3] = {"/_dense_query", "/_dense_key", "/_dense_value"};
+    for (int i = 0; i < 3; ++i) {
+      pack(p + nm[i] + "/kernel", {c, c}, c, c, a.qkv.wt, a.qkv.ld, i * c, 0);
+      Slot* b = f32(p + nm[i] + "/bias", {c});
+      concat_bias.push_back({b, a.qkv_bias + i * c});
+    }
+    a.out = dense(p + "/_dense_output", c, c);
+  }
+  std::vector<std::pair<Slot*, float*>> concat_bias;
+};
+
+Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) { build(); }
+
+Model::~Model() {
+  if (step_graph_) cudaGraphExecDestroy(step_graph_);
+  for (auto& v : slots)
+    for (auto& s : v)
+      if (s.f32) cudaFree(s.f32);
+  for (void* p : owned_) cudaFree(p);
+}
+
+void Model::build() {
+  // ---------------- text transformer (transformer.py:218-252; flat order SURVEY A.3)
+  {
+    Builder b(*this, 0);
+    const int D = cfg.text_hidden, H = cfg.text_heads, S = cfg.text_head_dim, F = cfg.text_filter;
+    slots[0].reserve((size_t)cfg.text_layers * 13 + 4);
+    text_layers_.resize(cfg.text_layers);
+    for (int i = 0; i < cfg.text_layers; ++i) {
+      const std::string p = "transformer/_encoder/_stack/" + std::to_string(i);
+      TextLayer& L = text_layers_[i];
+      L.attn = b.attn(p + "/_mha", D, D, H, S, D, true);
+      L.ln_mha = b.lnw(p + "/_layernorm_mha", D);
+      L.f1 = b.dense(p + "/_ffn/_dense_layer_filter", D, F);
+      L.f2 = b.dense(p + "/_ffn/_dense_layer_output", F, D);
+      L.ln_ffn = b.lnw(p + "/_layernorm_ffn", D);
+    }
+    text_ln_ = b.lnw("transformer/_encoder/_layernorm", D);
+    tok_emb_ = b.f32("transformer/_embedding_layer/embeddings", {cfg.vocab_size, D});
+    pos_emb_ = b.f32("transformer/_positional_embedding_layer/embeddings", {cfg.max_seq_len, D});
+  }
+  // ---------------- unet (unet.py:51-116)
+  {
+    Builder b(*this, 1);
+    slots[1].reserve(4096);
+    const int mc = cfg.model_channels, td = 4 * mc, heads = cfg.num_heads, ctx = cfg.context_dim;
+    const int L = cfg.num_mult, nb = cfg.num_blocks;
+    // total columns of the stacked time projections
+    int sumc = 0;
+    {
+      for (int i = 0; i < L; ++i) sumc += nb * mc * cfg.channel_mult[i];
+      sumc += 2 * mc * cfg.channel_mult[L - 1];
+      for (int i = L - 1; i >= 0; --i) sumc += (nb + 1) * mc * cfg.channel_mult[i];
+    }
+    tproj_all_ = b.lin(sumc, td);
+    tproj_bias_ = dev_alloc<float>(sumc, true);
+    tproj_cols_ = sumc;
+    int tcols = 0;
+    conv_in_k_ = b.f32("unet/_conv_in/kernel", {3, 3, 4, mc});
+    conv_in_b_ = b.f32("unet/_conv_in/bias", {mc});
+    time1_ = b.dense("unet/_time_dense1", mc, td);
+    time2_ = b.dense("unet/_time_dense2", td, td);
+    std::vector<int> chans{mc};
+    int ch = mc;
+    in_blocks_.reserve(64);
+    out_blocks_.reserve(64);
+    for (int i = 0; i < L; ++i) {
+      const int m = cfg.channel_mult[i];
+      for (int j = 0; j < nb; ++j) {
+        const std::string p = "unet/_input_blocks/" + std::to_string(in_blocks_.size());
+        in_blocks_.emplace_back();
+        UNetBlock& blk = in_blocks_.back();
+        blk.kind = 0; blk.cin = ch; blk.cout = mc * m;
+        blk.res = b.res(p + "/_residual", ch, mc * m, td, ch != mc * m, false, &tcols, &tproj_all_);
+        blk.has_st = i < L - 1;
+        if (blk.has_st) b.st(blk.st, p + "/_spatial_transformer", mc * m, heads, cfg.head_base * m, ctx);
+        ch = mc * m;
+        chans.push_back(ch);
+      }
+      if (i < L - 1) {
+        const std::string p = "unet/_input_blocks/" + std::to_string(in_blocks_.size());
+        in_blocks_.emplace_back();
+        UNetBlock& blk = in_blocks_.back();
+        blk.kind = 1; blk.cin = blk.cout = ch;
+        blk.resample = b.lin(ch, 9 * ch);
+        b.pack(p + "/_downsample/_conv/kernel", {3, 3, ch, ch}, 9 * ch, ch, blk.resample.wt, blk.resample.ld, 0, 0);
+        blk.resample.bias = b.f32(p + "/_downsample/_conv/bias", {ch});
+        chans.push_back(ch);
+      }
+    }
+    mid_res1_ = b.res("unet/_middle_block/_residual1", ch, ch, td, false, false, &tcols, &tproj_all_);
+    b.st(mid_st_, "unet/_middle_block/_spatial_transformer", ch, heads, cfg.head_base * cfg.channel_mult[L - 1], ctx);
+    mid_res2_ = b.res("unet/_middle_block/_residual2", ch, ch, td, false, false, &tcols, &tproj_all_);
+    for (int i = L - 1; i >= 0; --i) {
+      const int m = cfg.channel_mult[i];
+      for (int j = 0; j <= nb; ++j) {
+        const std::string p = "unet/_output_blocks/" + std::to_string(out_blocks_.size());
+        const int skip = chans.back();
+        chans.pop_back();
+        out_blocks_.emplace_back();
+        UNetBlock& blk = out_blocks_.back();
+        blk.kind = 2; blk.cin = ch + skip; blk.cout = mc * m;
+        blk.res = b.res(p + "/_residual", ch + skip, mc * m, td, true, false, &tcols, &tproj_all_);
+        blk.has_st = i < L - 1;
+        if (blk.has_st) b.st(blk.st, p + "/_spatial_transformer", mc * m, heads, cfg.head_base * m, ctx);
+        blk.has_up = (i > 0 && j == nb);
+        ch = mc * m;
+        if (blk.has_up) {
+          blk.resample = b.lin(ch, 9 * ch);
+          b.pack(p + "/_upsample/_conv/kernel", {3, 3, ch, ch}, 9 * ch, ch, blk.resample.wt, blk.resample.ld, 0, 0);
+          blk.resample.bias = b.f32(p + "/_upsample/_conv/bias", {ch});
+        }
+      }
+    }
+    LDM_CHECK(tcols == sumc, "time projection column count mismatch %d vs %d", tcols, sumc);
+    out_gn_ = b.gnw("unet/_groupnorm", mc, 1e-5f);
+    conv_out_ = b.lin(cfg.out_channels, 9 * mc);
+    b.pack("unet/_conv_out/kernel", {3, 3, mc, cfg.out_channels}, 9 * mc, cfg.out_channels, conv_out_.wt,
+           conv_out_.ld, 0, 0);
+    conv_out_.bias = b.f32("unet/_conv_out/bias", {cfg.out_channels});
+    // remember where each time-Dense bias goes
+    tproj_bias_slots_.assign(b.tproj_bias.begin(), b.tproj_bias.end());
+    for (auto& blk : in_blocks_) if (blk.has_st) all_st_.push_back(&blk.st);
+    all_st_.push_back(&mid_st_);
+    for (auto& blk : out_blocks_) if (blk.has_st) all_st_.push_back(&blk.st);
+  }
+  // ---------------- autoencoder decode side (autoencoder.py:252-290,331-347,408-421)
+  {
+    Builder b(*this, 2);
+    slots[2].reserve(1024);
+    const int z = cfg.latent_channels, chn = cfg.ae_channels, L = cfg.ae_num_mult, nb = cfg.ae_num_blocks;
+    std::vector<int> chans(L);
+    for (int i = 0; i < L; ++i) chans[i] = chn * cfg.ae_mult[i];
+    const int top = chans[L - 1];
+    if (cfg.ae_kind == 1) codebook_ = b.f32("autoencoder/_quantize/kernel", {cfg.vq_vocab, z});
+    pq_k_ = b.f32("autoencoder/_post_quant_conv/kernel", {z, z});
+    pq_b_ = b.f32("autoencoder/_post_quant_conv/bias", {z});
+    const std::string d = "autoencoder/_decoder";
+    ae_conv_in_k_ = b.f32(d + "/_conv_in/kernel", {3, 3, z, top});
+    ae_conv_in_b_ = b.f32(d + "/_conv_in/bias", {top});
+    ae_mid1_ = b.res(d + "/_middle/_residual1", top, top, 0, false, true, nullptr, nullptr);
+    b.ae_attn(ae_mid_attn_, d + "/_middle/_attention", top);
+    ae_mid2_ = b.res(d + "/_middle/_residual2", top, top, 0, false, true, nullptr, nullptr);
+    ae_up_.reserve(64);
+    int hw = cfg.ae_build_hw, cur = top, idx = 0;
+    for (int i = L - 1; i >= 0; --i) {
+      for (int j = 0; j <= nb; ++j) {
+        const std::string p = d + "/_up/" + std::to_string(idx++);
+        ae_up_.emplace_back();
+        AEStage& s = ae_up_.back();
+        s.kind = 0; s.hw = hw;
+        s.res = b.res(p + "/_residual", cur, chans[i], 0, cur != chans[i], true, nullptr, nullptr);
+        s.attn = false;
+        if (cfg.ae_kind == 1)
+          for (int k = 0; k < cfg.ae_num_attn_res; ++k) s.attn |= (cfg.ae_attn_res[k] == hw);
+        if (s.attn) b.ae_attn(s.at, p + "/_attention", chans[i]);
+        cur = chans[i];
+      }
+      if (i > 0) {
+        const std::string p = d + "/_up/" + std::to_string(idx++);
+        ae_up_.emplace_back();
+        AEStage& s = ae_up_.back();
+        s.kind = 1; s.c = cur; s.hw = hw;
+        s.up = b.lin(cur, 9 * cur);
+        b.pack(p + "/_conv/kernel", {3, 3, cur, cur}, 9 * cur, cur, s.up.wt, s.up.ld, 0, 0);
+        s.up.bias = b.f32(p + "/_conv/bias", {cur});
+        hw *= 2;
+      }
+    }
+    ae_out_gn_ = b.gnw(d + "/_group_norm", chans[0], 1e-6f);
+    ae_conv_out_ = b.lin(3, 9 * chans[0]);
+    b.pack(d + "/_conv_out/kernel", {3, 3, chans[0], 3}, 9 * chans[0], 3, ae_conv_out_.wt, ae_conv_out_.ld, 0, 0);
+    ae_conv_out_.bias = b.f32(d + "/_conv_out/bias", {3});
+    ae_concat_bias_.assign(b.concat_bias.begin(), b.concat_bias.end());
+  }
+  step_dev_ = dev_alloc<int>(1, true);
+}
+
+// =====================================================================================
+// Weights
+// =====================================================================================
+void Model::set_weight(int model, int index, const float* src, const int* shape, int ndim) {
+  LDM_CHECK(model >= 0 && model < 3, "set_weight: model %d", model);
+  LDM_CHECK(index >= 0 && index < (int)slots[model].size(), "set_weight: index %d out of range (model %d has %d)",
+            index, model, (int)slots[model].size());
+  Slot& s = slots[model][index];
+  bool ok = (int)s.shape.size() == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = s.shape[i] == shape[i];
+  if (!ok) {
+    std::string want, got;
+    for (int d : s.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    throw Error(fmt("set_weight: %s (model %d index %d) expects shape [%s] got [%s]", s.name.c_str(), model, index,
+                    want.c_str(), got.c_str()));
+  }
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const size_t n = s.numel();
+  float* dev = nullptr;
+  CUDA_CHECK(cudaMalloc(&dev, n * sizeof(float)));
+  CUDA_CHECK(cudaMemcpyAsync(dev, src, n * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (s.kind == Slot::F32) {
+    eng.sync();
+    if (s.f32) cudaFree(s.f32);
+    s.f32 = dev;
+  } else {
+    launch_pack_weight(dev, s.k, s.n, s.dst + s.col0, s.ld, s.row0, s.geglu_half, eng.stream);
+    eng.sync();
+    cudaFree(dev);
+  }
+  s.set = true;
+  finalized = false;
+}
+
+void Model::finalize_weights() {
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  // Only models whose weights were all provided are usable; partially set models are an error.
+  for (int mdl = 0; mdl < 3; ++mdl) {
+    int nset = 0;
+    for (auto& s : slots[mdl]) nset += s.set ? 1 : 0;
+    model_ready_[mdl] = nset == (int)slots[mdl].size();
+    if (nset != 0 && !model_ready_[mdl]) {
+      for (auto& s : slots[mdl])
+        if (!s.set) throw Error(fmt("finalize_weights: model %d is missing %s (%d of %d set)", mdl, s.name.c_str(),
+                                    nset, (int)slots[mdl].size()));
+    }
+  }
+  if (model_ready_[1]) {
+    for (auto& pr : tproj_bias_slots_)
+      CUDA_CHECK(cudaMemcpyAsync(tproj_bias_ + pr.second, pr.first->f32, pr.first->numel() * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, eng.stream));
+    // GEGLU bias permuted like the weight rows
+    for (STW* st : all_st_) {
+      const int n = 8 * st->c, nh = n / 2, half = st->geglu_bn / 2;
+      std::vector<float> hb(n), pb(n);
+      CUDA_CHECK(cudaMemcpyAsync(hb.data(), st->geglu.bias->f32, n * sizeof(float), cudaMemcpyDeviceToHost, eng.stream));
+      eng.sync();
+      for (int c = 0; c < n; ++c) {
+        const int j2 = c < nh ? c : c - nh;
+        const int r = (j2 / half) * (2 * half) + (c < nh ? 0 : half) + j2 % half;
+        pb[r] = hb[c];
+      }
+      if (!st->geglu_bias_perm) st->geglu_bias_perm = dev_alloc<float>(n);
+      CUDA_CHECK(cudaMemcpyAsync(st->geglu_bias_perm, pb.data(), n * sizeof(float), cudaMemcpyHostToDevice, eng.stream));
+      eng.sync();
+    }
+  }
+  if (model_ready_[2]) {
+    for (auto& pr : ae_concat_bias_)
+      CUDA_CHECK(cudaMemcpyAsync(pr.second, pr.first->f32, pr.first->numel() * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, eng.stream));
+  }
+  eng.sync();
+  finalized = true;
+}
+
+void Model::ensure_arena(size_t bytes) {
+  bytes += (64u << 20);
+  if (eng.arena.capacity() >= bytes) return;
+  eng.sync();
+  CUDA_CHECK(cudaDeviceSynchronize());
+  if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+  eng.arena.init(bytes);
+}
+
+// =====================================================================================
+// Ops
+// =====================================================================================
+void Model::tap(const std::string& name, const Act& a) {
+  if (eng.dry || taps.empty()) return;
+  auto it = taps.find(name);
+  if (it == taps.end()) return;
+  LDM_CHECK(it->second.second == (size_t)a.numel(), "tap %s: buffer has %zu elements, activation %lld",
+            name.c_str(), it->second.second, a.numel());
+  CUDA_CHECK(cudaMemcpyAsync(it->second.first, a.f, (size_t)a.numel() * sizeof(float), cudaMemcpyDefault, eng.stream));
+}
+
+Act Model::alloc_act(int n, int h, int w, int c, bool f, bool b) {
+  Act a; a.n = n; a.h = h; a.w = w; a.c = c;
+  if (f) a.f = eng.alloc<float>((size_t)a.numel());
+  if (b) a.b = eng.alloc<bf16>((size_t)a.numel());
+  return a;
+}
+
+void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out) {
+  const int cb = skip ? skip->c : 0;
+  LDM_CHECK(x.c + cb == g.c, "GroupNorm channel mismatch %d+%d vs %d", x.c, cb, g.c);
+  float* mr = eng.alloc<float>((size_t)x.n * 64);
+  eng.launches += 2;
+  if (eng.dry) return;
+  launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, g.eps, mr, eng.stream);
+  launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, mr, g.gamma->f32, g.beta->f32, silu ? 1 : 0,
+                  out, eng.stream);
+}
+
+void Model::linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
+                   float* out_f32, bf16* out_bf16) {
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_mat(a, rows, w.k, w.k);
+  op.b = view_mat(w.wt, w.n, w.k, w.ld);
+  int bk = 0;
+  op.add_seg(0, 0, 0, 0, w.k, bk);
+  op.W = (int)rows; op.H = 1; op.NB = 1;
+  op.N = w.n;
+  op.bias = bias; op.act = act; op.residual = residual; op.out_f32 = out_f32; op.out_bf16 = out_bf16;
+  op.os_x = w.n; op.os_y = 0; op.os_n = 0;
+  eng.gemm(op);
+}
+
+// 3x3 SAME conv over a bf16 NHWC activation, 9 shifted TMA boxes (K = 9*cin).
+static void conv_segments(GemmOp& op, int cin) {
+  int bk = 0;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) op.add_seg(0, ky - 1, kx - 1, 0, cin, bk);
+}
+
+Act Model::conv3x3(const Act& x, const LinW& w, const float* bias) {
+  Act out = alloc_act(x.n, x.h, x.w, w.n);
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(x.b, x.n, x.h, x.w, x.c);
+  op.b = view_mat(w.wt, w.n, w.k, w.ld);
+  conv_segments(op, x.c);
+  op.W = x.w; op.H = x.h; op.NB = x.n;
+  op.N = w.n;
+  op.bias = bias;
+  op.out_f32 = out.f; op.out_bf16 = out.b;
+  op.os_x = w.n; op.os_y = (long long)x.w * w.n; op.os_n = (long long)x.h * x.w * w.n;
+  eng.gemm(op);
+  return out;
+}
+
+// ResidualBlock.call (unet.py:382-398 / autoencoder.py:43-58).  `skip` != null: the input is the
+// virtual concat [x | skip] along C (unet.py:135).
+Act Model::resblock(const ResW& r, const Act& x, const Act* skip) {
+  const int cin = x.c + (skip ? skip->c : 0);
+  LDM_CHECK(cin == r.cin, "resblock: input channels %d vs %d", cin, r.cin);
+  Act out = alloc_act(x.n, x.h, x.w, r.cout);
+  const size_t mk = eng.arena.mark();
+  // GN1 + SiLU -> bf16 (concat materialised here)
+  Act a1 = alloc_act(x.n, x.h, x.w, cin, false, true);
+  gn(r.gn1, x, skip, true, a1.b);
+  // conv1 + bias + time projection (unet.py:384-388)
+  Act h1 = alloc_act(x.n, x.h, x.w, r.cout, true, false);
+  {
+    GemmOp op;
+    op.num_a = 1;
+    op.a[0] = view_nhwc(a1.b, x.n, x.h, x.w, cin);
+    op.b = view_mat(r.conv1.wt, r.cout, r.conv1.k, r.conv1.ld);
+    conv_segments(op, cin);
+    op.W = x.w; op.H = x.h; op.NB = x.n; op.N = r.cout;
+    op.bias = r.conv1.bias->f32;
+    if (r.temb_off >= 0) {
+      LDM_CHECK(temb_table_ != nullptr, "resblock: time-embedding table not computed");
+      op.bias2 = temb_table_ + r.temb_off;
+      op.bias2_stride = tproj_cols_;
+      op.bias2_by_img = temb_by_img_ ? 1 : 0;
+      op.step_ptr = temb_use_step_ ? step_dev_ : nullptr;
+    }
+    op.out_f32 = h1.f;
+    op.os_x = r.cout; op.os_y = (long long)x.w * r.cout; op.os_n = (long long)x.h * x.w * r.cout;
+    eng.gemm(op);
+  }
+  // GN2 + SiLU
+  Act a2 = alloc_act(x.n, x.h, x.w, r.cout, false, true);
+  gn(r.gn2, h1, nullptr, true, a2.b);
+  // conv2 (+ shortcut Dense folded into the K loop) + residual
+  {
+    GemmOp op;
+    op.num_a = 1;
+    op.a[0] = view_nhwc(a2.b, x.n, x.h, x.w, r.cout);
+    op.b = view_mat(r.conv2.wt, r.cout, r.conv2.k, r.conv2.ld);
+    conv_segments(op, r.cout);
+    int bk = 9 * r.cout;
+    if (r.shortcut) {
+      op.a[op.num_a] = view_nhwc(x.b, x.n, x.h, x.w, x.c);
+      op.add_seg(op.num_a, 0, 0, 0, x.c, bk);
+      op.num_a++;
+      if (skip) {
+        op.a[op.num_a] = view_nhwc(skip->b, x.n, x.h, x.w, skip->c);
+        op.add_seg(op.num_a, 0, 0, 0, skip->c, bk);
+        op.num_a++;
+      }
+      op.bias2 = r.sc_bias->f32;
+      op.bias2_stride = 0;
+    } else {
+      op.residual = x.f;
+    }
+    op.W = x.w; op.H = x.h; op.NB = x.n; op.N = r.cout;
+    op.bias = r.conv2.bias->f32;
+    op.out_f32 = out.f; op.out_bf16 = out.b;
+    op.os_x = r.cout; op.os_y = (long long)x.w * r.cout; op.os_n = (long long)x.h * x.w * r.cout;
+    eng.gemm(op);
+  }
+  eng.arena.release(mk);
+  return out;
+}
+
+// softmax(q k^T * scale) v for all (image, head) pairs (unet.py:280-287): two batched tcgen05
+// GEMMs around a row softmax.  q [n,t,heads,d] (row stride q_ld), k [n,tk,heads,d] (row stride
+// k_ld, image stride k_sn), vt [n,heads,d,tpad], o [n,t,heads*d] (row stride o_ld).
+void Model::attention_core(const bf16* q, long long q_ld, const bf16* k, long long k_ld, long long k_sn, int tk,
+                           const bf16* vt, int tpad, int n, int t, int heads, int d, float scale, bf16* o,
+                           long long o_ld) {
+  const size_t mk = eng.arena.mark();
+  float* S = eng.alloc<float>((size_t)n * heads * t * tpad);
+  bf16* P = eng.alloc<bf16>((size_t)n * heads * t * tpad);
+  {
+    GemmOp op;
+    op.num_a = 1;
+    AView a; a.ptr = q; a.C = d; a.W = t; a.H = heads; a.NB = n; a.sx = q_ld; a.sy = d; a.sn = (long long)t * q_ld;
+    a.swap_xy = true;
+    AView b; b.ptr = k; b.C = d; b.W = tk; b.H = heads; b.NB = n; b.sx = k_ld; b.sy = d; b.sn = k_sn;
+    b.swap_xy = true;
+    op.a[0] = a; op.b = b; op.b_mode = B_BATCH;
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, d, bk);
+    op.W = t; op.H = heads; op.NB = n; op.w_b = GEMM_BM; op.h_b = 1; op.n_b = 1;
+    op.N = tk;
+    op.out_f32 = S;
+    op.os_n = (long long)heads * t * tpad; op.os_y = (long long)t * tpad; op.os_x = tpad;
+    eng.gemm(op);
+  }
+  eng.launches++;
+  if (!eng.dry) launch_softmax(S, P, (long long)n * heads * t, tk, tpad, scale, eng.stream);
+  {
+    GemmOp op;
+    op.num_a = 1;
+    AView a; a.ptr = P; a.C = tpad; a.W = t; a.H = heads; a.NB = n; a.sx = tpad; a.sy = (long long)t * tpad;
+    a.sn = (long long)heads * t * tpad;
+    AView b; b.ptr = vt; b.C = tpad; b.W = d; b.H = heads; b.NB = n; b.sx = tpad; b.sy = (long long)d * tpad;
+    b.sn = (long long)heads * d * tpad;
+    op.a[0] = a; op.b = b; op.b_mode = B_BATCH;
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, tk, bk);
+    op.W = t; op.H = heads; op.NB = n; op.w_b = GEMM_BM; op.h_b = 1; op.n_b = 1;
+    op.N = d;
+    op.out_bf16 = o;
+    op.os_n = (long long)t * o_ld; op.os_y = d; op.os_x = o_ld;
+    eng.gemm(op);
+  }
+  eng.arena.release(mk);
+}
+
+// Fused q|k|v projection: q,k row-major into qk [rows, 2*inner]; v transposed into vt
+// [n, heads, d, tpad] so that P.V reads a K-major B operand.
+static void qkv_projection(Engine& eng, const bf16* z, int n, int t, int c, const LinW& w, const float* bias, int inner,
+                           bf16* qk, bf16* vt, int tpad) {
+  GemmOp op;
+  op.num_a = 1;
+  AView a; a.ptr = z; a.C = c; a.W = t; a.H = 1; a.NB = n; a.sx = c; a.sy = (long long)t * c; a.sn = (long long)t * c;
+  op.a[0] = a;
+  op.b = view_mat(w.wt, w.n, w.k, w.ld);
+  int bk = 0;
+  op.add_seg(0, 0, 0, 0, c, bk);
+  op.W = t; op.H = 1; op.NB = n;
+  op.N = 3 * inner;
+  op.n_boundary = 2 * inner;
+  op.bias = bias;
+  op.out_bf16 = qk;
+  op.os_n = (long long)t * 2 * inner; op.os_y = 0; op.os_x = 2 * inner;
+  op.out_tr = vt; op.tr_col0 = 2 * inner;
+  op.ts_n = (long long)inner * tpad; op.ts_y = 0; op.ts_c = tpad;
+  eng.gemm(op);
+}
+
+// SpatialTransformer.call (unet.py:356-365) + BasicTransformerBlock (unet.py:308-314)
+Act Model::spatial_transformer(STW& s, const Act& x) {
+  const int n = x.n, t = x.h * x.w, c = s.c, heads = cfg.num_heads, d = s.d;
+  const long long rows = (long long)n * t;
+  LDM_CHECK(x.c == c && heads * d == c, "spatial transformer: channel mismatch");
+  LDM_CHECK(s.ctx_k != nullptr && ctx_rows_ == n, "spatial transformer: context not set for %d rows", n);
+  Act out = alloc_act(n, x.h, x.w, c);
+  const size_t mk = eng.arena.mark();
+  bf16* xn = eng.alloc<bf16>((size_t)rows * c);
+  gn(s.gn, x, nullptr, false, xn);
+  float* y = eng.alloc<float>((size_t)rows * c);
+  bf16* z = eng.alloc<bf16>((size_t)rows * c);
+  bf16* o = eng.alloc<bf16>((size_t)rows * c);
+  linear(xn, rows, s.d1, s.d1.bias->f32, ACT_NONE, nullptr, y, nullptr);
+  const float scale = 1.0f / sqrtf((float)d);
+  // ---- self attention (unet.py:309-310)
+  {
+    const size_t mk2 = eng.arena.mark();
+    eng.launches++;
+    if (!eng.dry) launch_layernorm(y, s.ln1.gamma->f32, s.ln1.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    const int tpad = round_up(t, 8);
+    bf16* qk = eng.alloc<bf16>((size_t)rows * 2 * c);
+    bf16* vt = eng.alloc<bf16>((size_t)n * c * tpad);
+    if (tpad != t && !eng.dry) CUDA_CHECK(cudaMemsetAsync(vt, 0, (size_t)n * c * tpad * 2, eng.stream));
+    qkv_projection(eng, z, n, t, c, s.a1.qkv, nullptr, c, qk, vt, tpad);
+    attention_core(qk, 2 * c, qk + c, 2 * c, (long long)t * 2 * c, t, vt, tpad, n, t, heads, d, scale, o, c);
+    linear(o, rows, s.a1.out, s.a1.out.bias->f32, ACT_NONE, y, y, nullptr);
+    eng.arena.release(mk2);
+  }
+  // ---- cross attention against the hoisted context K / V^T (unet.py:311-312)
+  {
+    const size_t mk2 = eng.arena.mark();
+    eng.launches++;
+    if (!eng.dry) launch_layernorm(y, s.ln2.gamma->f32, s.ln2.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    bf16* q = eng.alloc<bf16>((size_t)rows * c);
+    linear(z, rows, s.a2.qkv, nullptr, ACT_NONE, nullptr, nullptr, q);
+    const int tk = cfg.max_seq_len, tpad = round_up(tk, 8);
+    attention_core(q, c, s.ctx_k, c, (long long)tk * c, tk, s.ctx_vt, tpad, n, t, heads, d, scale, o, c);
+    linear(o, rows, s.a2.out, s.a2.out.bias->f32, ACT_NONE, y, y, nullptr);
+    eng.arena.release(mk2);
+  }
+  // ---- GEGLU feed-forward (unet.py:313, 322-325, 335-338)
+  {
+    const size_t mk2 = eng.arena.mark();
+    eng.launches++;
+    if (!eng.dry) launch_layernorm(y, s.ln3.gamma->f32, s.ln3.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    bf16* g = eng.alloc<bf16>((size_t)rows * 4 * c);
+    {
+      GemmOp op;
+      op.num_a = 1;
+      op.a[0] = view_mat(z, rows, c, c);
+      op.b = view_mat(s.geglu.wt, 8 * c, c, s.geglu.ld);
+      int bk = 0;
+      op.add_seg(0, 0, 0, 0, c, bk);
+      op.W = (int)rows; op.H = 1; op.NB = 1;
+      op.N = 4 * c; op.gemm_n = 8 * c; op.block_n = s.geglu_bn;
+      op.act = ACT_GEGLU;
+      op.bias = s.geglu_bias_perm;
+      op.out_bf16 = g;
+      op.os_x = 4 * c;
+      eng.gemm(op);
+    }
+    // y += ff(g); the bf16 copy feeds dense2
+    linear(g, rows, s.ff, s.ff.bias->f32, ACT_NONE, y, y, z);
+    eng.arena.release(mk2);
+  }
+  // dense2 + input residual (unet.py:363-364)
+  linear(z, rows, s.d2, s.d2.bias->f32, ACT_NONE, x.f, out.f, out.b);
+  eng.arena.release(mk);
+  return out;
+}
+
+// =====================================================================================
+// Time embedding -> per-ResBlock projection table (unet.py:126-127,386-387)
+// rows = one per distinct timestep; table [rows, tproj_cols_]
+// =====================================================================================
+void Model::compute_temb_table(const int* t_host, int rows, float* table) {
+  const int mc = cfg.model_channels, td = 4 * mc;
+  char* scratch = nullptr;
+  const size_t sz_t = 256 + (size_t)rows * sizeof(int), sz_e = (size_t)rows * mc, sz_h = (size_t)rows * td;
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t total = al(sz_t) + al(sz_e * 4) + al(sz_e * 2) + al(sz_h * 2) + al(sz_h * 4) + al(sz_h * 2);
+  CUDA_CHECK(cudaMalloc(&scratch, total));
+  char* cur = scratch;
+  int* t_dev = reinterpret_cast<int*>(cur); cur += al(sz_t);
+  float* emb = reinterpret_cast<float*>(cur); cur += al(sz_e * 4);
+  bf16* emb_b = reinterpret_cast<bf16*>(cur); cur += al(sz_e * 2);
+  bf16* h1 = reinterpret_cast<bf16*>(cur); cur += al(sz_h * 2);
+  float* temb = reinterpret_cast<float*>(cur); cur += al(sz_h * 4);
+  bf16* temb_s = reinterpret_cast<bf16*>(cur);
+  CUDA_CHECK(cudaMemcpyAsync(t_dev, t_host, rows * sizeof(int), cudaMemcpyHostToDevice, eng.stream));
+  launch_time_embed(t_dev, rows, mc, emb, eng.stream);
+  launch_f32_to_bf16(emb, emb_b, (long long)rows * mc, 0, eng.stream);
+  linear(emb_b, rows, time1_, time1_.bias->f32, ACT_SILU, nullptr, nullptr, h1);
+  linear(h1, rows, time2_, time2_.bias->f32, ACT_NONE, nullptr, temb, nullptr);
+  launch_f32_to_bf16(temb, temb_s, (long long)rows * td, 1, eng.stream);  // SiLU(temb), unet.py:386
+  linear(temb_s, rows, tproj_all_, tproj_bias_, ACT_NONE, nullptr, table, nullptr);
+  eng.launches += 3;
+  eng.sync();
+  cudaFree(scratch);
+}
+
+// =====================================================================================
+// Context: hoisted K / V^T projections of all SpatialTransformers (unet.py:276-277)
+// =====================================================================================
+void Model::set_context(const float* ctx, int n) {
+  LDM_CHECK(finalized && model_ready_[1], "set_context: unet weights not finalized");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const int tk = cfg.max_seq_len, cd = cfg.context_dim, tpad = round_up(tk, 8);
+  const size_t nel = (size_t)n * tk * cd;
+  float* cf = nullptr;
+  bf16* cb = nullptr;
+  CUDA_CHECK(cudaMalloc(&cf, nel * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&cb, nel * sizeof(bf16)));
+  CUDA_CHECK(cudaMemcpyAsync(cf, ctx, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
+  launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.stream);
+  for (STW* s : all_st_) {
+    const int c = s->c;
+    if (ctx_rows_ != n || !s->ctx_k) {
+      s->ctx_k = dev_alloc<bf16>((size_t)n * tk * c);
+      s->ctx_vt = dev_alloc<bf16>((size_t)n * c * tpad, true);
+    }
+    GemmOp op;
+    op.num_a = 1;
+    AView a; a.ptr = cb; a.C = cd; a.W = tk; a.H = 1; a.NB = n; a.sx = cd; a.sy = (long long)tk * cd; a.sn = (long long)tk * cd;
+    op.a[0] = a;
+    op.b = view_mat(s->a2.kv.wt, 2 * c, cd, s->a2.kv.ld);
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, cd, bk);
+    op.W = tk; op.H = 1; op.NB = n; op.w_b = GEMM_BM; op.h_b = 1; op.n_b = 1;
+    op.N = 2 * c; op.n_boundary = c;
+    op.out_bf16 = s->ctx_k;
+    op.os_n = (long long)tk * c; op.os_x = c;
+    op.out_tr = s->ctx_vt; op.tr_col0 = c;
+    op.ts_n = (long long)c * tpad; op.ts_c = tpad;
+    eng.gemm(op);
+  }
+  ctx_rows_ = n;
+  eng.sync();
+  cudaFree(cf);
+  cudaFree(cb);
+  if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+}
+
+// =====================================================================================
+// UNet.call (unet.py:118-138)
+// =====================================================================================
+void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out) {
+  const int mc = cfg.model_channels;
+  Act cur = alloc_act(n, h, w, mc);
+  eng.launches++;
+  if (!eng.dry) launch_conv_in(x, nsrc, n, h, w, conv_in_k_->f32, conv_in_b_->f32, mc, cur.f, cur.b, eng.stream);
+  tap("conv_in", cur);
+  std::vector<Act> hiddens{cur};
+  int bi = 0;
+  for (auto& blk : in_blocks_) {
+    if (blk.kind == 1) {
+      // Downsample: pad(1,1) + 3x3 stride-2 VALID (unet.py:22,26-27) = im2col + GEMM
+      const int ho = cur.h / 2, wo = cur.w / 2;
+      Act out = alloc_act(n, ho, wo, blk.cout);
+      const size_t mk = eng.arena.mark();
+      bf16* col = eng.alloc<bf16>((size_t)n * ho * wo * 9 * cur.c);
+      eng.launches++;
+      if (!eng.dry) launch_im2col_s2(cur.b, n, cur.h, cur.w, cur.c, col, eng.stream);
+      linear(col, (long long)n * ho * wo, blk.resample, blk.resample.bias->f32, ACT_NONE, nullptr, out.f, out.b);
+      eng.arena.release(mk);
+      cur = out;
+    } else {
+      cur = resblock(blk.res, cur, nullptr);
+      if (bi == 0) tap("in0_res", cur);
+      if (blk.has_st) cur = spatial_transformer(blk.st, cur);
+    }
+    tap("in" + std::to_string(bi++), cur);
+    hiddens.push_back(cur);
+  }
+  cur = resblock(mid_res1_, cur, nullptr);
+  cur = spatial_transformer(mid_st_, cur);
+  cur = resblock(mid_res2_, cur, nullptr);
+  tap("mid", cur);
+  bi = 0;
+  for (auto& blk : out_blocks_) {
+    Act skip = hiddens.back();
+    hiddens.pop_back();
+    cur = resblock(blk.res, cur, &skip);
+    if (blk.has_st) cur = spatial_transformer(blk.st, cur);
+    if (blk.has_up) {
+      // Upsample: nearest x2 (unet.py:44-45) then 3x3 SAME conv
+      Act up = alloc_act(n, cur.h * 2, cur.w * 2, cur.c, false, true);
+      eng.launches++;
+      if (!eng.dry) launch_upsample2(cur.b, n, cur.h, cur.w, cur.c, up.b, eng.stream);
+      cur = conv3x3(up, blk.resample, blk.resample.bias->f32);
+    }
+    tap("out" + std::to_string(bi++), cur);
+  }
+  // conv_out(silu(groupnorm(x))) (unet.py:137)
+  bf16* a = eng.alloc<bf16>((size_t)cur.numel());
+  gn(out_gn_, cur, nullptr, true, a);
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(a, n, h, w, mc);
+  op.b = view_mat(conv_out_.wt, conv_out_.n, conv_out_.k, conv_out_.ld);
+  conv_segments(op, mc);
+  op.W = w; op.H = h; op.NB = n; op.N = cfg.out_channels;
+  op.bias = conv_out_.bias->f32;
+  op.out_f32 = eps_out;
+  op.os_x = cfg.out_channels; op.os_y = (long long)w * cfg.out_channels; op.os_n = (long long)h * w * cfg.out_channels;
+  eng.gemm(op);
+}
+
+void Model::unet_forward(const float* x, const int* t_host, int n, int h, int w, float* eps_out) {
+  LDM_CHECK(finalized && model_ready_[1], "unet_forward: unet weights not finalized");
+  LDM_CHECK(ctx_rows_ == n, "unet_forward: context set for %d rows, input has %d", ctx_rows_, n);
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  if (fwd_temb_rows_ < n) {
+    fwd_temb_ = dev_alloc<float>((size_t)n * tproj_cols_);
+    fwd_temb_rows_ = n;
+  }
+  compute_temb_table(t_host, n, fwd_temb_);
+  temb_table_ = fwd_temb_;
+  temb_by_img_ = true; temb_use_step_ = false;
+  const size_t nel = (size_t)n * h * w * 4;
+  float* xd = nullptr; float* ed = nullptr;
+  CUDA_CHECK(cudaMalloc(&xd, nel * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&ed, (size_t)n * h * w * cfg.out_channels * sizeof(float)));
+  CUDA_CHECK(cudaMemcpyAsync(xd, x, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
+  // size the arena with a dry pass, then run
+  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
+  const long long l0 = eng.launches, g0 = eng.gemm_launches;
+  unet_eps(xd, n, n, h, w, ed);
+  eng.launches = l0; eng.gemm_launches = g0;
+  eng.arena.dry = false; eng.dry = false;
+  ensure_arena(eng.arena.peak());
+  eng.arena.reset();
+  unet_eps(xd, n, n, h, w, ed);
+  CUDA_CHECK(cudaMemcpyAsync(eps_out, ed, (size_t)n * h * w * cfg.out_channels * sizeof(float), cudaMemcpyDefault,
+                             eng.stream));
+  eng.sync();
+  cudaFree(xd);
+  cudaFree(ed);
+}
+
+// =====================================================================================
+// Sampler (model_runners.py:438-509)
+// =====================================================================================
+void Model::configure_sampler(int S, const int* ddim_t, const float* coeffs) {
+  LDM_CHECK(finalized && model_ready_[1], "configure_sampler: unet weights not finalized");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  S_ = S;
+  ddim_t_.assign(ddim_t, ddim_t + S);
+  coeffs_dev_ = dev_alloc<float>((size_t)S * 8);
+  CUDA_CHECK(cudaMemcpy(coeffs_dev_, coeffs, (size_t)S * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  sampler_temb_ = dev_alloc<float>((size_t)S * tproj_cols_);
+  compute_temb_table(ddim_t, S, sampler_temb_);
+  if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+}
+
+void Model::ddim_step(const float* xt, const float* eps2, const float* noise, int index, float guidance, int clip,
+                      int b, int h, int w, float* xt_out, float* x0_out) {
+  LDM_CHECK(S_ > 0 && index >= 0 && index < S_, "ddim_step: index %d outside [0,%d)", index, S_);
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const long long nh = (long long)b * h * w * 4;
+  float *dx, *de, *dn = nullptr, *dout, *d0 = nullptr;
+  CUDA_CHECK(cudaMalloc(&dx, nh * 4));
+  CUDA_CHECK(cudaMalloc(&de, 2 * nh * 4));
+  CUDA_CHECK(cudaMalloc(&dout, nh * 4));
+  CUDA_CHECK(cudaMemcpyAsync(dx, xt, nh * 4, cudaMemcpyDefault, eng.stream));
+  CUDA_CHECK(cudaMemcpyAsync(de, eps2, 2 * nh * 4, cudaMemcpyDefault, eng.stream));
+  if (noise) {
+    CUDA_CHECK(cudaMalloc(&dn, nh * 4));
+    CUDA_CHECK(cudaMemcpyAsync(dn, noise, nh * 4, cudaMemcpyDefault, eng.stream));
+  }
+  if (x0_out) CUDA_CHECK(cudaMalloc(&d0, nh * 4));
+  launch_ddim_update(de, dx, dn, 0, coeffs_dev_, nullptr, index, guidance, clip, dout, d0, nh, eng.stream);
+  eng.launches++;
+  CUDA_CHECK(cudaMemcpyAsync(xt_out, dout, nh * 4, cudaMemcpyDefault, eng.stream));
+  if (x0_out) CUDA_CHECK(cudaMemcpyAsync(x0_out, d0, nh * 4, cudaMemcpyDefault, eng.stream));
+  eng.sync();
+  cudaFree(dx); cudaFree(de); cudaFree(dout);
+  if (dn) cudaFree(dn);
+  if (d0) cudaFree(d0);
+}
+
+void Model::sample(const float* x_init, const float* noise, int b, int h, int w, float guidance, float* latents_out,
+                   float* eps_trace, int steps_limit, int use_graph) {
+  LDM_CHECK(S_ > 0, "sample: sampler not configured");
+  LDM_CHECK(ctx_rows_ == 2 * b, "sample: context has %d rows, need 2*B = %d", ctx_rows_, 2 * b);
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const long long nh = (long long)b * h * w * 4;
+  if (xt_cap_ < (size_t)nh) {
+    xt_dev_ = dev_alloc<float>(nh);
+    eps_dev_ = dev_alloc<float>(2 * nh);
+    xt_cap_ = nh;
+    if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+  }
+  if (noise && noise_cap_ < (size_t)(nh * S_)) {
+    noise_dev_ = dev_alloc<float>(nh * S_);
+    noise_cap_ = nh * S_;
+    if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+  }
+  temb_table_ = sampler_temb_;
+  temb_by_img_ = false; temb_use_step_ = true;
+  // arena sizing
+  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
+  const long long l0 = eng.launches, g0 = eng.gemm_launches;
+  unet_eps(xt_dev_, b, 2 * b, h, w, eps_dev_);
+  const long long per_step = eng.launches - l0 + 2;
+  eng.launches = l0; eng.gemm_launches = g0;
+  eng.arena.dry = false; eng.dry = false;
+  ensure_arena(eng.arena.peak());
+
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, eng.stream));
+  CUDA_CHECK(cudaMemcpyAsync(xt_dev_, x_init, nh * 4, cudaMemcpyDefault, eng.stream));
+  if (noise) CUDA_CHECK(cudaMemcpyAsync(noise_dev_, noise, nh * S_ * 4, cudaMemcpyDefault, eng.stream));
+  int start = S_ - 1;
+  CUDA_CHECK(cudaMemcpyAsync(step_dev_, &start, sizeof(int), cudaMemcpyHostToDevice, eng.stream));
+  const int nsteps = (steps_limit > 0 && steps_limit < S_) ? steps_limit : S_;
+  auto one_step = [&]() {
+    eng.arena.reset();
+    unet_eps(xt_dev_, b, 2 * b, h, w, eps_dev_);
+    launch_ddim_update(eps_dev_, xt_dev_, noise ? noise_dev_ : nullptr, nh, coeffs_dev_, step_dev_, 0, guidance, 0,
+                       xt_dev_, nullptr, nh, eng.stream);
+    launch_step_advance(step_dev_, -1, eng.stream);
+    eng.launches += 2;
+  };
+  const bool graph_ok = use_graph && !eps_trace;
+  if (graph_ok) {
+    if (!step_graph_ || graph_b_ != b || graph_h_ != h || graph_w_ != w || graph_guid_ != guidance ||
+        graph_noise_ != (noise != nullptr)) {
+      if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+      eng.sync();
+      cudaGraph_t g;
+      const long long l1 = eng.launches, g1 = eng.gemm_launches;
+      CUDA_CHECK(cudaStreamBeginCapture(eng.stream, cudaStreamCaptureModeThreadLocal));
+      one_step();
+      CUDA_CHECK(cudaStreamEndCapture(eng.stream, &g));
+      eng.launches = l1; eng.gemm_launches = g1;
+      CUDA_CHECK(cudaGraphInstantiate(&step_graph_, g, 0));
+      cudaGraphDestroy(g);
+      graph_b_ = b; graph_h_ = h; graph_w_ = w; graph_guid_ = guidance; graph_noise_ = noise != nullptr;
+    }
+    for (int i = 0; i < nsteps; ++i) CUDA_CHECK(cudaGraphLaunch(step_graph_, eng.stream));
+    eng.launches += per_step * nsteps;
+  } else {
+    for (int i = 0; i < nsteps; ++i) {
+      one_step();
+      if (eps_trace)
+        CUDA_CHECK(cudaMemcpyAsync(eps_trace + (long long)i * 2 * nh, eps_dev_, 2 * nh * 4, cudaMemcpyDefault,
+                                   eng.stream));
+    }
+  }
+  CUDA_CHECK(cudaMemcpyAsync(latents_out, xt_dev_, nh * 4, cudaMemcpyDefault, eng.stream));
+  CUDA_CHECK(cudaEventRecord(e1, eng.stream));
+  eng.sync();
+  CUDA_CHECK(cudaEventElapsedTime(&last_loop_ms, e0, e1));
+  last_step_ms = last_loop_ms / nsteps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+// =====================================================================================
+// Text encoder (transformer.py:254-272, 173-182)
+// =====================================================================================
+void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
+  LDM_CHECK(finalized && model_ready_[0], "encode_text: transformer weights not finalized");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const int T = cfg.max_seq_len, D = cfg.text_hidden, H = cfg.text_heads, S = cfg.text_head_dim, inner = H * S;
+  // de-duplicate identical sequences (run_ldm_sampler.py:42-45 tiles two distinct rows B times)
+  std::vector<int> uniq_of(rows);
+  std::vector<const long long*> uniq;
+  for (int r = 0; r < rows; ++r) {
+    int f = -1;
+    for (size_t u = 0; u < uniq.size(); ++u)
+      if (!memcmp(uniq[u], ids + (long long)r * T, T * sizeof(long long))) { f = (int)u; break; }
+    if (f < 0) { f = (int)uniq.size(); uniq.push_back(ids + (long long)r * T); }
+    uniq_of[r] = f;
+  }
+  const int n = (int)uniq.size();
+  std::vector<long long> uids((size_t)n * T);
+  for (int u = 0; u < n; ++u) {
+    memcpy(&uids[(size_t)u * T], uniq[u], T * sizeof(long long));
+    for (int i = 0; i < T; ++i)
+      LDM_CHECK(uids[(size_t)u * T + i] >= 0 && uids[(size_t)u * T + i] < cfg.vocab_size, "token id %lld out of range",
+                uids[(size_t)u * T + i]);
+  }
+  const long long R = (long long)n * T;
+  const int tpad = round_up(T, 8);
+  auto body = [&](long long* ids_dev, float* x) {
+    eng.launches++;
+    if (!eng.dry) launch_embed(ids_dev, tok_emb_->f32, pos_emb_->f32, (int)R, T, D, x, eng.stream);
+    bf16* z = eng.alloc<bf16>((size_t)R * D);
+    bf16* qk = eng.alloc<bf16>((size_t)R * 2 * inner);
+    bf16* vt = eng.alloc<bf16>((size_t)n * inner * tpad);
+    bf16* o = eng.alloc<bf16>((size_t)R * inner);
+    bf16* hbuf = eng.alloc<bf16>((size_t)R * cfg.text_filter);
+    if (!eng.dry) CUDA_CHECK(cudaMemsetAsync(vt, 0, (size_t)n * inner * tpad * 2, eng.stream));
+    const float scale = 1.0f / sqrtf((float)S);
+    for (auto& L : text_layers_) {
+      eng.launches++;
+      if (!eng.dry) launch_layernorm(x, L.ln_mha.gamma->f32, L.ln_mha.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.stream);
+      qkv_projection(eng, z, n, T, D, L.attn.qkv, nullptr, inner, qk, vt, tpad);
+      attention_core(qk, 2 * inner, qk + inner, 2 * inner, (long long)T * 2 * inner, T, vt, tpad, n, T, H, S, scale, o,
+                     inner);
+      linear(o, R, L.attn.out, L.attn.out.bias->f32, ACT_NONE, x, x, nullptr);
+      eng.launches++;
+      if (!eng.dry) launch_layernorm(x, L.ln_ffn.gamma->f32, L.ln_ffn.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.stream);
+      linear(z, R, L.f1, L.f1.bias->f32, ACT_GELU, nullptr, nullptr, hbuf);
+      linear(hbuf, R, L.f2, L.f2.bias->f32, ACT_NONE, x, x, nullptr);
+    }
+  };
+  long long* ids_dev = nullptr;
+  float *x = nullptr, *y = nullptr;
+  CUDA_CHECK(cudaMalloc(&ids_dev, uids.size() * sizeof(long long)));
+  CUDA_CHECK(cudaMalloc(&x, (size_t)R * D * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&y, (size_t)R * D * sizeof(float)));
+  CUDA_CHECK(cudaMemcpyAsync(ids_dev, uids.data(), uids.size() * sizeof(long long), cudaMemcpyHostToDevice, eng.stream));
+  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
+  const long long l0 = eng.launches, g0 = eng.gemm_launches;
+  body(ids_dev, x);
+  eng.launches = l0; eng.gemm_launches = g0;
+  eng.arena.dry = false; eng.dry = false;
+  ensure_arena(eng.arena.peak());
+  eng.arena.reset();
+  body(ids_dev, x);
+  launch_layernorm(x, text_ln_.gamma->f32, text_ln_.beta->f32, (int)R, D, 1e-5f, nullptr, y, eng.stream);
+  eng.launches++;
+  for (int r = 0; r < rows; ++r)
+    CUDA_CHECK(cudaMemcpyAsync(ctx_out + (long long)r * T * D, y + (long long)uniq_of[r] * T * D,
+                               (size_t)T * D * sizeof(float), cudaMemcpyDefault, eng.stream));
+  eng.sync();
+  cudaFree(ids_dev); cudaFree(x); cudaFree(y);
+}
+
+// =====================================================================================
+// Autoencoder decode (autoencoder.py:291-298,361-364,430-436)
+// =====================================================================================
+Act Model::ae_attention(AEAttnW& a, const Act& x) {
+  const int n = x.n, t = x.h * x.w, c = a.c;
+  const long long rows = (long long)n * t;
+  Act out = alloc_act(n, x.h, x.w, c);
+  const size_t mk = eng.arena.mark();
+  bf16* xn = eng.alloc<bf16>((size_t)rows * c);
+  gn(a.gn, x, nullptr, false, xn);
+  const int tpad = round_up(t, 8);
+  bf16* qk = eng.alloc<bf16>((size_t)rows * 2 * c);
+  bf16* vt = eng.alloc<bf16>((size_t)n * c * tpad);
+  bf16* o = eng.alloc<bf16>((size_t)rows * c);
+  if (tpad != t && !eng.dry) CUDA_CHECK(cudaMemsetAsync(vt, 0, (size_t)n * c * tpad * 2, eng.stream));
+  qkv_projection(eng, xn, n, t, c, a.qkv, a.qkv_bias, c, qk, vt, tpad);
+  attention_core(qk, 2 * c, qk + c, 2 * c, (long long)t * 2 * c, t, vt, tpad, n, t, 1, c, 1.0f / sqrtf((float)c), o, c);
+  linear(o, rows, a.out, a.out.bias->f32, ACT_NONE, x.f, out.f, out.b);
+  eng.arena.release(mk);
+  return out;
+}
+
+void Model::decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev) {
+  const int zc = cfg.latent_channels;
+  LDM_CHECK(zc == 4, "decode: latent_channels must be 4");
+  const long long rows = (long long)b * h * w;
+  const float* zin = z;
+  float pq_div = div;
+  if (cfg.ae_kind == 1) {
+    // VectorQuantizer on z/scale (quantize.py:57-78); the quantized latents feed post_quant_conv
+    float* zq = eng.alloc<float>((size_t)rows * 4);
+    eng.launches += 3;
+    if (!eng.dry) launch_vq_argmin(z, rows, 4, codebook_->f32, cfg.vq_vocab, div, idx_dev, zq, eng.stream);
+    zin = zq;
+    pq_div = 1.0f;
+  }
+  float* pq = eng.alloc<float>((size_t)rows * 4);
+  eng.launches++;
+  if (!eng.dry) launch_dense4(zin, rows, pq_div, pq_k_->f32, pq_b_->f32, pq, eng.stream);
+  const int top = cfg.ae_channels * cfg.ae_mult[cfg.ae_num_mult - 1];
+  Act cur = alloc_act(b, h, w, top);
+  eng.launches++;
+  if (!eng.dry) launch_conv_in(pq, b, b, h, w, ae_conv_in_k_->f32, ae_conv_in_b_->f32, top, cur.f, cur.b, eng.stream);
+  cur = resblock(ae_mid1_, cur, nullptr);
+  cur = ae_attention(ae_mid_attn_, cur);
+  cur = resblock(ae_mid2_, cur, nullptr);
+  for (auto& s : ae_up_) {
+    if (s.kind == 0) {
+      cur = resblock(s.res, cur, nullptr);
+      bool want = false;
+      if (cfg.ae_kind == 1)
+        for (int k = 0; k < cfg.ae_num_attn_res; ++k) want |= (cfg.ae_attn_res[k] == cur.h);
+      LDM_CHECK(!want || s.attn, "decode: attention needed at resolution %d but the autoencoder was built for latent %d",
+                cur.h, cfg.ae_build_hw);
+      if (want) cur = ae_attention(s.at, cur);
+    } else {
+      Act up = alloc_act(b, cur.h * 2, cur.w * 2, cur.c, false, true);
+      eng.launches++;
+      if (!eng.dry) launch_upsample2(cur.b, b, cur.h, cur.w, cur.c, up.b, eng.stream);
+      cur = conv3x3(up, s.up, s.up.bias->f32);
+    }
+  }
+  bf16* a = eng.alloc<bf16>((size_t)cur.numel());
+  gn(ae_out_gn_, cur, nullptr, true, a);
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(a, b, cur.h, cur.w, cur.c);
+  op.b = view_mat(ae_conv_out_.wt, 3, ae_conv_out_.k, ae_conv_out_.ld);
+  conv_segments(op, cur.c);
+  op.W = cur.w; op.H = cur.h; op.NB = b; op.N = 3;
+  op.bias = ae_conv_out_.bias->f32;
+  op.out_f32 = img_dev;
+  op.os_x = 3; op.os_y = (long long)cur.w * 3; op.os_n = (long long)cur.h * cur.w * 3;
+  eng.gemm(op);
+}
+
+void Model::decode(const float* z, int b, int h, int w, float div, float* img_out, long long* idx_out) {
+  LDM_CHECK(finalized && model_ready_[2], "decode: autoencoder weights not finalized");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const long long rows = (long long)b * h * w;
+  const long long img_el = rows * 64 * 3;
+  float *zd, *imgd;
+  long long* idxd = nullptr;
+  CUDA_CHECK(cudaMalloc(&zd, rows * 4 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&imgd, img_el * sizeof(float)));
+  if (cfg.ae_kind == 1) CUDA_CHECK(cudaMalloc(&idxd, rows * sizeof(long long)));
+  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
+  const long long l0 = eng.launches, g0 = eng.gemm_launches;
+  decode_body(zd, b, h, w, div, imgd, idxd);
+  eng.launches = l0; eng.gemm_launches = g0;
+  eng.arena.dry = false; eng.dry = false;
+  ensure_arena(eng.arena.peak());
+  eng.arena.reset();
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, eng.stream));
+  CUDA_CHECK(cudaMemcpyAsync(zd, z, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
+  decode_body(zd, b, h, w, div, imgd, idxd);
+  CUDA_CHECK(cudaMemcpyAsync(img_out, imgd, img_el * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (idx_out && idxd) CUDA_CHECK(cudaMemcpyAsync(idx_out, idxd, rows * sizeof(long long), cudaMemcpyDefault, eng.stream));
+  CUDA_CHECK(cudaEventRecord(e1, eng.stream));
+  eng.sync();
+  CUDA_CHECK(cudaEventElapsedTime(&last_decode_ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(zd); cudaFree(imgd);
+  if (idxd) cudaFree(idxd);
+}
+
+void Model::vq_argmin(const float* z, long long rows, float div, long long* idx_out, float* zq_out) {
+  LDM_CHECK(codebook_ && codebook_->set, "vq_argmin: codebook not set (autoencoder kind must be vq)");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  float *zd, *zq;
+  long long* idxd;
+  CUDA_CHECK(cudaMalloc(&zd, rows * 4 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&zq, rows * 4 * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&idxd, rows * sizeof(long long)));
+  CUDA_CHECK(cudaMemcpyAsync(zd, z, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
+  launch_vq_argmin(zd, rows, 4, codebook_->f32, cfg.vq_vocab, div, idxd, zq, eng.stream);
+  eng.launches += 3;
+  CUDA_CHECK(cudaMemcpyAsync(idx_out, idxd, rows * sizeof(long long), cudaMemcpyDefault, eng.stream));
+  if (zq_out) CUDA_CHECK(cudaMemcpyAsync(zq_out, zq, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
+  eng.sync();
+  cudaFree(zd); cudaFree(zq); cudaFree(idxd);
+}
+
+void Model::tensor_to_image(const float* img, int n, long long per, unsigned char* out) {
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  float* d;
+  unsigned char* o;
+  CUDA_CHECK(cudaMalloc(&d, (size_t)n * per * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&o, (size_t)n * per));
+  CUDA_CHECK(cudaMemcpyAsync(d, img, (size_t)n * per * sizeof(float), cudaMemcpyDefault, eng.stream));
+  launch_tensor_to_image(d, n, per, o, eng.stream);
+  eng.launches++;
+  CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * per, cudaMemcpyDefault, eng.stream));
+  eng.sync();
+  cudaFree(d); cudaFree(o);
+}
+
+}  // namespace ldm

@@ -1,0 +1,353 @@
+"""ctypes binding of libldm_b200.so (include/ldm_b200.h).  No PyTorch, no CPU fallback:
+if the CUDA library is missing or no sm_100 device is present, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldm_b200.so")
+
+
+class LdmConfig(C.Structure):
+    _fields_ = [
+        ("vocab_size", C.c_int32), ("encoder_stack_size", C.c_int32), ("hidden_size", C.c_int32),
+        ("text_num_heads", C.c_int32), ("size_per_head", C.c_int32), ("max_seq_len", C.c_int32),
+        ("filter_size", C.c_int32),
+        ("model_channels", C.c_int32), ("out_channels", C.c_int32), ("num_blocks", C.c_int32),
+        ("num_channel_mult", C.c_int32), ("channel_mult", C.c_int32 * 8), ("num_heads", C.c_int32),
+        ("head_base", C.c_int32), ("context_dim", C.c_int32),
+        ("ae_kind", C.c_int32), ("latent_channels", C.c_int32), ("ae_channels", C.c_int32),
+        ("ae_num_blocks", C.c_int32), ("ae_num_multipliers", C.c_int32), ("ae_multipliers", C.c_int32 * 8),
+        ("ae_num_attention_resolutions", C.c_int32), ("ae_attention_resolutions", C.c_int32 * 8),
+        ("vq_vocab_size", C.c_int32), ("ae_build_latent_hw", C.c_int32),
+    ]
+
+
+_P = C.c_void_p
+_F = C.c_float
+_I = C.c_int
+_L = C.c_int64
+
+_PROTOS = {
+    "ldm_version": ([], _I),
+    "ldm_create": ([C.POINTER(LdmConfig), _I, C.POINTER(_P)], _I),
+    "ldm_destroy": ([_P], _I),
+    "ldm_num_weights": ([_P, _I, C.POINTER(_I)], _I),
+    "ldm_weight_info": ([_P, _I, _I, C.POINTER(C.c_char_p), C.POINTER(_I), C.POINTER(_I * 4)], _I),
+    "ldm_set_weight": ([_P, _I, _I, _P, C.POINTER(_I), _I], _I),
+    "ldm_finalize_weights": ([_P], _I),
+    "ldm_encode_text": ([_P, _P, _I, _P], _I),
+    "ldm_set_context": ([_P, _P, _I], _I),
+    "ldm_unet_forward": ([_P, _P, _P, _I, _I, _I, _P], _I),
+    "ldm_configure_sampler": ([_P, _I, _P, _P], _I),
+    "ldm_ddim_step": ([_P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P], _I),
+    "ldm_sample": ([_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I], _I),
+    "ldm_decode": ([_P, _P, _I, _I, _I, _F, _P, _P], _I),
+    "ldm_vq_argmin": ([_P, _P, _L, _F, _P, _P], _I),
+    "ldm_tensor_to_image": ([_P, _P, _I, _L, _P], _I),
+    "ldm_get_timing": ([_P, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), C.POINTER(_L), C.POINTER(_L)], _I),
+    "ldm_bench_ddim_update": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
+    "ldm_bench_unet_step": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
+    "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
+    "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "ldm_test_attention": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
+    "ldm_test_groupnorm": ([_P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P], _I),
+    "ldm_test_layernorm": ([_P, _P, _P, _P, _I, _I, _F, _P], _I),
+}
+EXPORTS = sorted(list(_PROTOS) + ["ldm_last_error"])
+
+_lib = None
+
+
+def load():
+    """Loads the shared library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m ldm_tf2_b200.build` "
+            "(ldm_tf2_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (args, res) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    lib.ldm_last_error.argtypes = []
+    lib.ldm_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+class LdmError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise LdmError(f"ldm_b200 error {rc}: {load().ldm_last_error().decode(errors='replace')}")
+
+
+def ptr(a) -> C.c_void_p:
+    """Raw data pointer of a C-contiguous numpy array, or an int device pointer, or None."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return C.c_void_p(a.ctypes.data)
+
+
+def f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def make_config(cond_stage_model: dict, unet: dict, autoencoder: dict, ae_kind: str,
+                ae_build_latent_hw: int = 32) -> LdmConfig:
+    """Maps the all_in_one_config.yaml sections (:57-102) to the flat C struct."""
+    c = LdmConfig()
+    t = cond_stage_model
+    c.vocab_size = t["vocab_size"]
+    c.encoder_stack_size = t.get("encoder_stack_size", 6)
+    c.hidden_size = t.get("hidden_size", 512)
+    c.text_num_heads = t.get("num_heads", 8)
+    c.size_per_head = t.get("size_per_head", 64)
+    c.max_seq_len = t.get("max_seq_len", 77)
+    c.filter_size = t.get("filter_size", 2048)
+    u = unet
+    c.model_channels = u.get("model_channels", 320)
+    c.out_channels = u.get("out_channels", 4)
+    c.num_blocks = u.get("num_blocks", 2)
+    mult = list(u.get("channel_mult", [1, 2, 4, 4]))
+    c.num_channel_mult = len(mult)
+    for i, m in enumerate(mult):
+        c.channel_mult[i] = m
+    c.num_heads = u.get("num_heads", 8)
+    c.head_base = u.get("head_base", 40)          # unet.py:82 hard-wires 40*mult
+    c.context_dim = u.get("context_dim", 1280)    # unet.py:83 hard-wires 1280
+    a = autoencoder
+    c.ae_kind = {"kl": 0, "vq": 1}[ae_kind]
+    c.latent_channels = a.get("latent_channels", 4)
+    c.ae_channels = a.get("channels", 128)
+    c.ae_num_blocks = a.get("num_blocks", 2)
+    am = list(a.get("multipliers", [1, 2, 4, 4] if ae_kind == "kl" else [1, 2, 2, 4]))
+    c.ae_num_multipliers = len(am)
+    for i, m in enumerate(am):
+        c.ae_multipliers[i] = m
+    # AutoencoderKL builds its Decoder with attention_resolutions=() whatever the config says
+    # (autoencoder.py:339)
+    ar = [] if ae_kind == "kl" else list(a.get("attention_resolutions", [32]))
+    c.ae_num_attention_resolutions = len(ar)
+    for i, r in enumerate(ar):
+        c.ae_attention_resolutions[i] = r
+    c.vq_vocab_size = a.get("vocab_size", 16384)
+    c.ae_build_latent_hw = ae_build_latent_hw
+    return c
+
+
+class Handle:
+    """Owns one ldm_handle (one GPU, one stream, one weight replica)."""
+
+    TEXT, UNET, AE = 0, 1, 2
+
+    def __init__(self, config: LdmConfig, device: int = 0):
+        self.lib = load()
+        self.config = config
+        self._h = C.c_void_p()
+        check(self.lib.ldm_create(C.byref(config), device, C.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self.lib.ldm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ----------------------------------------------------------
+    def num_weights(self, model: int) -> int:
+        n = C.c_int()
+        check(self.lib.ldm_num_weights(self._h, model, C.byref(n)))
+        return n.value
+
+    def weight_info(self, model: int, index: int):
+        name = C.c_char_p()
+        nd = C.c_int()
+        shp = (C.c_int * 4)()
+        check(self.lib.ldm_weight_info(self._h, model, index, C.byref(name), C.byref(nd), C.byref(shp)))
+        return name.value.decode(), tuple(shp[i] for i in range(nd.value))
+
+    def set_weights(self, model: int, weights):
+        """layer.set_weights(flat list) (convert_ckpt_pytorch_to_tf2.py:395-424)."""
+        n = self.num_weights(model)
+        if len(weights) != n:
+            raise LdmError(f"model {model} expects {n} weight tensors, got {len(weights)}")
+        for i, w in enumerate(weights):
+            w = f32(w)
+            shp = (C.c_int * w.ndim)(*w.shape)
+            check(self.lib.ldm_set_weight(self._h, model, i, ptr(w), shp, w.ndim))
+
+    def finalize(self):
+        check(self.lib.ldm_finalize_weights(self._h))
+
+    # -- model calls --------------------------------------------------------
+    def encode_text(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty((ids.shape[0], ids.shape[1], self.config.hidden_size), np.float32)
+        check(self.lib.ldm_encode_text(self._h, ptr(ids), ids.shape[0], ptr(out)))
+        return out
+
+    def set_context(self, ctx):
+        ctx = f32(ctx)
+        check(self.lib.ldm_set_context(self._h, ptr(ctx), ctx.shape[0]))
+
+    def unet_forward(self, x, t) -> np.ndarray:
+        x = f32(x)
+        t = np.ascontiguousarray(t, dtype=np.int32)
+        n, hh, ww, _ = x.shape
+        out = np.empty((n, hh, ww, self.config.out_channels), np.float32)
+        check(self.lib.ldm_unet_forward(self._h, ptr(x), ptr(t), n, hh, ww, ptr(out)))
+        return out
+
+    def configure_sampler(self, ddim_t, coeffs):
+        ddim_t = np.ascontiguousarray(ddim_t, dtype=np.int32)
+        coeffs = f32(coeffs)
+        assert coeffs.shape == (len(ddim_t), 8)
+        check(self.lib.ldm_configure_sampler(self._h, len(ddim_t), ptr(ddim_t), ptr(coeffs)))
+
+    def ddim_step(self, xt, eps2, noise, index, guidance, clip=False, return_x0=False):
+        xt, eps2 = f32(xt), f32(eps2)
+        noise = None if noise is None else f32(noise)
+        b, hh, ww, _ = xt.shape
+        out = np.empty_like(xt)
+        x0 = np.empty_like(xt) if return_x0 else None
+        check(self.lib.ldm_ddim_step(self._h, ptr(xt), ptr(eps2), ptr(noise), index, float(guidance),
+                                     int(clip), b, hh, ww, ptr(out), ptr(x0)))
+        return (out, x0) if return_x0 else out
+
+    def sample(self, x_init, noise, guidance, trace=False, steps_limit=0, use_graph=True, num_steps=None):
+        x_init = f32(x_init)
+        noise = None if noise is None else f32(noise)
+        b, hh, ww, _ = x_init.shape
+        out = np.empty_like(x_init)
+        tr = None
+        if trace:
+            n = steps_limit if steps_limit else num_steps
+            tr = np.empty((n, 2 * b, hh, ww, 4), np.float32)
+        check(self.lib.ldm_sample(self._h, ptr(x_init), ptr(noise), b, hh, ww, float(guidance), ptr(out),
+                                  ptr(tr), steps_limit, int(use_graph)))
+        return (out, tr) if trace else out
+
+    def decode(self, z, div=1.0):
+        z = f32(z)
+        b, hh, ww, _ = z.shape
+        img = np.empty((b, hh * 8, ww * 8, 3), np.float32)
+        idx = np.empty((b * hh * ww,), np.int64) if self.config.ae_kind == 1 else None
+        check(self.lib.ldm_decode(self._h, ptr(z), b, hh, ww, float(div), ptr(img), ptr(idx)))
+        return img, idx
+
+    def vq_argmin(self, z, div=1.0):
+        z = f32(z)
+        rows = z.size // 4
+        idx = np.empty((rows,), np.int64)
+        zq = np.empty_like(z)
+        check(self.lib.ldm_vq_argmin(self._h, ptr(z), rows, float(div), ptr(idx), ptr(zq)))
+        return zq, idx
+
+    def tensor_to_image(self, images):
+        images = f32(images)
+        out = np.empty(images.shape, np.uint8)
+        check(self.lib.ldm_tensor_to_image(self._h, ptr(images), images.shape[0],
+                                           images.size // images.shape[0], ptr(out)))
+        return out
+
+    def timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        l, g = C.c_int64(), C.c_int64()
+        check(self.lib.ldm_get_timing(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(l), C.byref(g)))
+        return dict(loop_ms=a.value, step_ms=b.value, decode_ms=c.value, launches=l.value,
+                    gemm_launches=g.value)
+
+    def bench_ddim_update(self, b, hh, ww, with_noise, iters):
+        ms = C.c_float()
+        check(self.lib.ldm_bench_ddim_update(self._h, b, hh, ww, int(with_noise), iters, C.byref(ms)))
+        return ms.value
+
+    def bench_unet_step(self, b, hh, ww, iters, use_graph=True):
+        ms = C.c_float()
+        check(self.lib.ldm_bench_unet_step(self._h, b, hh, ww, iters, int(use_graph), C.byref(ms)))
+        return ms.value
+
+    # -- test hooks ---------------------------------------------------------
+    def tap(self, name, shape):
+        buf = np.zeros(shape, np.float32)
+        self._keep.append(buf)
+        check(self.lib.ldm_debug_tap(self._h, name.encode(), ptr(buf), buf.size))
+        return buf
+
+    def clear_taps(self):
+        check(self.lib.ldm_debug_tap(self._h, None, None, 0))
+        self._keep.clear()
+
+    def test_linear(self, a, w, bias=None, residual=None, act=0, block_n=0, max_ctas=0):
+        a, w = f32(a), f32(w)
+        rows, k = a.shape
+        n = w.shape[1] // 2 if act == 3 else w.shape[1]
+        out = np.empty((rows, n), np.float32)
+        bias = None if bias is None else f32(bias)
+        residual = None if residual is None else f32(residual)
+        check(self.lib.ldm_test_linear(self._h, ptr(a), ptr(w), ptr(bias), ptr(residual), rows, k, n, act,
+                                       block_n, max_ctas, ptr(out)))
+        return out
+
+    def test_conv3x3(self, x, kernel, bias=None, sc_x=None, sc_kernel=None):
+        x, kernel = f32(x), f32(kernel)
+        nb, hh, ww, cin = x.shape
+        cout = kernel.shape[-1]
+        bias = None if bias is None else f32(bias)
+        sc_cin = 0
+        if sc_x is not None:
+            sc_x, sc_kernel = f32(sc_x), f32(sc_kernel)
+            sc_cin = sc_x.shape[-1]
+        out = np.empty((nb, hh, ww, cout), np.float32)
+        check(self.lib.ldm_test_conv3x3(self._h, ptr(x), ptr(kernel), ptr(bias), ptr(sc_x), ptr(sc_kernel),
+                                        nb, hh, ww, cin, cout, sc_cin, ptr(out)))
+        return out
+
+    def test_attention(self, q, k, v, scale):
+        q, k, v = f32(q), f32(k), f32(v)
+        n, t, heads, d = q.shape
+        tk = k.shape[1]
+        out = np.empty((n, t, heads * d), np.float32)
+        check(self.lib.ldm_test_attention(self._h, ptr(q), ptr(k), ptr(v), n, t, tk, heads, d, float(scale),
+                                          ptr(out)))
+        return out
+
+    def test_groupnorm(self, xa, gamma, beta, eps, silu, xb=None):
+        xa = f32(xa)
+        n, hw, ca = xa.shape
+        cb = 0
+        if xb is not None:
+            xb = f32(xb)
+            cb = xb.shape[-1]
+        out = np.empty((n, hw, ca + cb), np.float32)
+        gamma, beta = f32(gamma), f32(beta)
+        check(self.lib.ldm_test_groupnorm(self._h, ptr(xa), ca, ptr(xb), cb, ptr(gamma), ptr(beta),
+                                          n, hw, float(eps), int(silu), ptr(out)))
+        return out
+
+    def test_layernorm(self, x, gamma, beta, eps=1e-5):
+        x = f32(x)
+        out = np.empty_like(x)
+        gamma, beta = f32(gamma), f32(beta)
+        check(self.lib.ldm_test_layernorm(self._h, ptr(x), ptr(gamma), ptr(beta), x.shape[0],
+                                          x.shape[1], float(eps), ptr(out)))
+        return out

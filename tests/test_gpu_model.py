@@ -1,0 +1,133 @@
+"""Model-level parity on the B200 (tiny config, seconds on the CPU oracle): text encoder,
+UNet with block-level taps, the full DDIM loop with an eps trace, KL and VQ decode.
+Tolerances are north_star's: per-step eps relative L2 <= 1e-2 (bf16 operands), decoded images
+PSNR >= 40 dB, VQ indices bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import ldm_oracle as O
+from tests.util import make_handle, psnr, rel_l2, sampler_tables
+
+pytestmark = pytest.mark.gpu
+
+CFG = O.TINY_CONFIG
+EPS_TOL = 1e-2   # north_star: relative L2 of per-step eps, bf16 mode
+PSNR_TOL = 40.0  # north_star: decoded images vs reference
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    hd = make_handle(CFG, "kl", ae_hw=8)
+    us = O.unet_spec(CFG["unet"])
+    ts = O.text_spec(CFG["cond_stage_model"])
+    as_ = O.ae_spec(CFG["autoencoder_kl"], "kl", 8)
+    wu, wt, wa = O.init_weights(us, 0), O.init_weights(ts, 1), O.init_weights(as_, 2)
+    hd.set_weights(hd.TEXT, wt)
+    hd.set_weights(hd.UNET, wu)
+    hd.set_weights(hd.AE, wa)
+    hd.finalize()
+    ids = np.array([O.KAT_UNCOND_IDS] * 2 + [O.KAT_COND_IDS] * 2, dtype=np.int64)
+    ctx = O.text_encode(O.as_dict(ts, wt), CFG["cond_stage_model"], ids[[0, 2]])[[0, 0, 1, 1]]
+    yield dict(h=hd, Wu=O.as_dict(us, wu), Wt=O.as_dict(ts, wt), Wa=O.as_dict(as_, wa), ids=ids, ctx=ctx)
+    hd.close()
+
+
+def test_weight_order_matches_oracle_spec(tiny):
+    h = tiny["h"]
+    for model, spec in ((h.TEXT, O.text_spec(CFG["cond_stage_model"])), (h.UNET, O.unet_spec(CFG["unet"])),
+                        (h.AE, O.ae_spec(CFG["autoencoder_kl"], "kl", 8))):
+        assert h.num_weights(model) == len(spec)
+        for i, (name, shape, _) in enumerate(spec):
+            assert h.weight_info(model, i) == (name, tuple(shape))
+
+
+def test_text_encoder(tiny):
+    got = tiny["h"].encode_text(tiny["ids"])
+    err = rel_l2(got, tiny["ctx"])
+    print("text encoder rel-L2", err)
+    assert got.shape == (4, 77, CFG["cond_stage_model"]["hidden_size"])
+    assert np.array_equal(got[0], got[1]) and np.array_equal(got[2], got[3])
+    assert err < EPS_TOL
+
+
+def test_unet_forward_with_taps(tiny):
+    h = tiny["h"]
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal((2, 8, 8, 4), dtype=np.float32)
+    x2 = np.concatenate([x, x], 0)
+    t = np.array([981, 981, 981, 981], np.int32)
+    taps_ref = {}
+    ref = O.unet_forward(tiny["Wu"], CFG["unet"], x2, t, tiny["ctx"], taps=taps_ref)
+    h.set_context(tiny["ctx"])
+    bufs = {k: h.tap(k, v.shape) for k, v in taps_ref.items() if k != "temb"}
+    got = h.unet_forward(x2, t)
+    h.clear_taps()
+    for k in taps_ref:
+        if k in bufs:
+            print(f"tap {k:8s} rel-L2 {rel_l2(bufs[k], taps_ref[k]):.3e}")
+    err = rel_l2(got, ref)
+    print("eps rel-L2", err)
+    assert err < EPS_TOL
+    # mixed timesteps per row go through the per-image time-embedding path
+    t2 = np.array([1, 21, 501, 981], np.int32)
+    err2 = rel_l2(h.unet_forward(x2, t2), O.unet_forward(tiny["Wu"], CFG["unet"], x2, t2, tiny["ctx"]))
+    print("eps rel-L2 (mixed t)", err2)
+    assert err2 < EPS_TOL
+
+
+@pytest.mark.parametrize("eta,S,graph", [(0.0, 50, False), (1.0, 20, True)])
+def test_ddim_loop_eps_trace(tiny, eta, S, graph):
+    h = tiny["h"]
+    B = 2
+    sched = O.ddim_schedule(eta=eta, num_ddim_steps=S)
+    h.configure_sampler(*sampler_tables(sched))
+    h.set_context(tiny["ctx"])
+    rng = np.random.default_rng(1234)
+    x_init = rng.standard_normal((B, 8, 8, 4), dtype=np.float32)
+    noise = np.random.default_rng(5678).standard_normal((S, B, 8, 8, 4), dtype=np.float32) if eta > 0 else None
+    trace_ref = []
+    ref = O.ddim_sample_loop(tiny["Wu"], CFG["unet"], sched, tiny["ctx"], x_init, noise, 5.0, eps_trace=trace_ref)
+    got, trace = h.sample(x_init, noise, 5.0, trace=True, use_graph=False, num_steps=S)
+    errs = [rel_l2(trace[i], trace_ref[i]) for i in range(S)]
+    print("per-step eps rel-L2: max %.3e  first %.3e  last %.3e" % (max(errs), errs[0], errs[-1]))
+    print("final latent rel-L2", rel_l2(got, ref))
+    assert max(errs) < EPS_TOL
+    assert rel_l2(got, ref) < EPS_TOL
+    if graph:  # CUDA-graph replay must give the same latents as the eager launch sequence
+        got_g = h.sample(x_init, noise, 5.0, use_graph=True)
+        assert np.array_equal(got_g, got)
+
+
+def test_decode_kl(tiny):
+    h = tiny["h"]
+    rng = np.random.default_rng(99)
+    z = rng.standard_normal((2, 8, 8, 4), dtype=np.float32) * np.float32(0.18215 * 4)
+    ref, _ = O.decode_first_stage(tiny["Wa"], CFG["autoencoder_kl"], "kl", z)
+    got, idx = h.decode(z, div=0.18215)
+    assert idx is None and got.shape == (2, 64, 64, 3)
+    p = psnr(got, ref)
+    print("KL decode PSNR", p, "rel-L2", rel_l2(got, ref))
+    assert p >= PSNR_TOL
+    u8 = h.tensor_to_image(got)
+    assert np.abs(u8.astype(int) - O.tensor_to_image(got).astype(int)).max() <= 1
+    assert np.array_equal(u8, O.tensor_to_image(got))
+
+
+def test_decode_vq():
+    hd = make_handle(CFG, "vq", ae_hw=8)
+    spec = O.ae_spec(CFG["autoencoder_vq"], "vq", 8)
+    w = O.init_weights(spec, 3)
+    # a codebook on the scale of the latents so that many different codes are hit
+    w[0] = np.random.default_rng(5).standard_normal(w[0].shape, dtype=np.float32)
+    hd.set_weights(hd.AE, w)
+    hd.finalize()
+    W = O.as_dict(spec, w)
+    z = np.random.default_rng(6).standard_normal((2, 8, 8, 4), dtype=np.float32) * np.float32(0.18215)
+    ref, idx_ref = O.decode_first_stage(W, CFG["autoencoder_vq"], "vq", z)
+    got, idx = hd.decode(z, div=0.18215)
+    assert np.array_equal(idx, idx_ref)  # bit-exact contract
+    assert len(np.unique(idx)) > 16
+    p = psnr(got, ref)
+    print("VQ decode PSNR", p)
+    assert p >= PSNR_TOL
+    hd.close()

@@ -1,0 +1,210 @@
+"""Kernel-level parity on the B200: every engine op against the NumPy oracle, through the
+C ABI (ldm_test_* hooks).  Integer/bit-defined kernels (K5 DDIM update, K6 VQ argmin) must be
+bit-exact; bf16 tensor-core ops are compared with an oracle fed the same bf16-rounded
+operands (tolerance = fp32 accumulation-order noise)."""
+import numpy as np
+import pytest
+
+from oracle import ldm_oracle as O
+from tests.util import bf16_round, make_handle, rel_l2, sampler_tables
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h():
+    hd = make_handle(O.TINY_CONFIG, "vq", ae_hw=8)
+    yield hd
+    hd.close()
+
+
+def test_library_loads_on_gpu(h):
+    assert h.lib.ldm_version() == 100
+
+
+# ----------------------------------------------------------------- K5 (bit-exact)
+@pytest.mark.parametrize("S,eta", [(50, 0.0), (200, 1.0)])
+def test_ddim_update_bit_exact(S, eta):
+    hd = make_handle(O.TINY_CONFIG, "kl", ae_hw=8)
+    us = O.unet_spec(O.TINY_CONFIG["unet"])
+    hd.set_weights(hd.UNET, O.init_weights(us, 0))
+    hd.finalize()
+    sched = O.ddim_schedule(eta=eta, num_ddim_steps=S)
+    hd.configure_sampler(*sampler_tables(sched))
+    rng = np.random.default_rng(7)
+    for (b, hh, ww), index, clip in [((1, 32, 32), S - 1, False), ((4, 32, 32), 0, False),
+                                     ((3, 8, 8), S // 2, True), ((8, 64, 64), 3, False)]:
+        xt = rng.standard_normal((b, hh, ww, 4), dtype=np.float32)
+        eps2 = rng.standard_normal((2 * b, hh, ww, 4), dtype=np.float32)
+        noise = rng.standard_normal((b, hh, ww, 4), dtype=np.float32) if eta > 0 else None
+        got, got0 = hd.ddim_step(xt, eps2, noise, index, 5.0, clip=clip, return_x0=True)
+        ref, ref0 = O.ddim_update(xt, eps2[:b], eps2[b:], noise, O.ddim_coeffs(sched, index), 5.0, clip)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(got0.view(np.uint32), ref0.view(np.uint32))
+    hd.close()
+
+
+# ----------------------------------------------------------------- K6 (bit-exact)
+def _vq_handle(vocab):
+    cfg = {k: dict(v) for k, v in O.TINY_CONFIG.items()}
+    cfg["autoencoder_vq"]["vocab_size"] = vocab
+    hd = make_handle(cfg, "vq", ae_hw=8)
+    spec = O.ae_spec(cfg["autoencoder_vq"], "vq", 8)
+    w = O.init_weights(spec, 11)
+    return hd, spec, w
+
+
+@pytest.mark.parametrize("vocab,rows", [(512, 1000), (16384, 4096), (16384, 37), (16384, 1)])
+def test_vq_argmin_bit_exact(vocab, rows):
+    hd, spec, w = _vq_handle(vocab)
+    rng = np.random.default_rng(rows)
+    cb = w[0].copy()
+    # exact ties: duplicate some codes so that the lowest index must win
+    cb[vocab // 2] = cb[3]
+    cb[vocab - 1] = cb[3]
+    w[0] = cb
+    hd.set_weights(hd.AE, w)
+    hd.finalize()
+    x = rng.standard_normal((rows, 4), dtype=np.float32)
+    x[0] = cb[3] * np.float32(0.18215)  # lands exactly on the duplicated code after the division
+    zq, idx = hd.vq_argmin(x, div=0.18215)
+    z = (x / np.float32(0.18215)).astype(np.float32)
+    zq_ref, idx_ref = O.vq_lookup(z, cb)
+    assert idx.dtype == np.int64
+    assert np.array_equal(idx, idx_ref)
+    assert np.array_equal(zq.view(np.uint32), zq_ref.view(np.uint32))
+    hd.close()
+
+
+# ----------------------------------------------------------------- K2 / LayerNorm
+@pytest.mark.parametrize("n,hw,ca,cb,silu,eps", [(2, 64, 64, 0, True, 1e-5), (3, 256, 320, 0, False, 1e-6),
+                                                 (2, 16, 1280, 640, True, 1e-5), (1, 1024, 640, 320, True, 1e-5)])
+def test_groupnorm(h, n, hw, ca, cb, silu, eps):
+    rng = np.random.default_rng(hw + ca)
+    xa = rng.standard_normal((n, hw, ca), dtype=np.float32) * 2 + 0.5
+    xb = rng.standard_normal((n, hw, cb), dtype=np.float32) if cb else None
+    c = ca + cb
+    gamma = 1 + 0.1 * rng.standard_normal(c, dtype=np.float32)
+    beta = 0.1 * rng.standard_normal(c, dtype=np.float32)
+    got = h.test_groupnorm(xa, gamma, beta, eps, silu, xb)
+    x = xa if xb is None else np.concatenate([xa, xb], -1)
+    ref = O.group_norm(x.reshape(n, hw, 1, c), gamma, beta, eps).reshape(n, hw, c)
+    if silu:
+        ref = O.silu(ref)
+    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-3  # bf16 output rounding
+
+
+@pytest.mark.parametrize("rows,c", [(77, 128), (1024, 320), (300, 1280)])
+def test_layernorm(h, rows, c):
+    rng = np.random.default_rng(rows)
+    x = rng.standard_normal((rows, c), dtype=np.float32) * 3 - 1
+    gamma = 1 + 0.1 * rng.standard_normal(c, dtype=np.float32)
+    beta = 0.1 * rng.standard_normal(c, dtype=np.float32)
+    got = h.test_layernorm(x, gamma, beta)
+    ref = O.layer_norm(x, gamma, beta)
+    assert np.abs(got - ref).max() < 1e-4
+
+
+# ----------------------------------------------------------------- tcgen05 GEMM engine
+def _lin_ref(a, w, bias, residual, act):
+    y = bf16_round(a).astype(np.float64) @ bf16_round(w).astype(np.float64)
+    if bias is not None:
+        y = y + bias
+    y = y.astype(np.float32)
+    if act == 1:
+        y = O.silu(y)
+    elif act == 2:
+        y = O.gelu_erf(y)
+    elif act == 3:
+        half = y.shape[1] // 2
+        y = (y[:, :half] * O.gelu_erf(y[:, half:])).astype(np.float32)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+@pytest.mark.parametrize("rows,k,n,act,use_bias,use_res,max_ctas", [
+    (128, 64, 64, 0, False, False, 0),      # single tile, single k-block
+    (128, 256, 64, 0, True, False, 0),      # pipeline wrap (4 k-blocks)
+    (256, 320, 320, 0, True, True, 0),      # UNet dense C=320
+    (154, 1280, 1280, 2, True, False, 0),   # text encoder, ragged M, GELU
+    (1000, 320, 960, 1, True, False, 0),    # ragged M, SiLU
+    (4096, 640, 640, 0, True, True, 3),     # persistent loop: many tiles per CTA, TMEM double buffer
+    (512, 40, 64, 0, False, False, 0),      # K smaller than a k-block: TMA zero fill
+    (300, 136, 72, 0, True, False, 0),      # ragged K and N
+    (256, 2880, 4, 0, True, False, 0),      # conv_out-like: N = 4
+    (256, 1152, 3, 0, True, True, 0),       # decoder conv_out-like: N = 3 (unaligned rows)
+    (512, 320, 1280, 3, True, False, 0),    # GEGLU (w has 2n columns)
+    (2048, 1280, 5120, 3, True, False, 0),  # GEGLU, many tiles
+])
+def test_linear(h, rows, k, n, act, use_bias, use_res, max_ctas):
+    rng = np.random.default_rng(rows * 7 + k + n)
+    a = rng.standard_normal((rows, k), dtype=np.float32)
+    wn = 2 * n if act == 3 else n
+    w = rng.standard_normal((k, wn), dtype=np.float32) / np.float32(np.sqrt(k))
+    bias = rng.standard_normal(wn, dtype=np.float32) if use_bias else None
+    res = rng.standard_normal((rows, n), dtype=np.float32) if use_res else None
+    got = h.test_linear(a, w, bias, res, act=act, max_ctas=max_ctas)
+    ref = _lin_ref(a, w, bias, res, act)
+    err = np.abs(got - ref).max()
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
+def _conv_ref(x, kern, bias, sc_x=None, sc_k=None):
+    y = O.conv3x3(bf16_round(x), bf16_round(kern), np.zeros(kern.shape[-1], np.float32) if bias is None else bias)
+    if sc_x is not None:
+        y = y + O.dense(bf16_round(sc_x), bf16_round(sc_k))
+    return y
+
+
+@pytest.mark.parametrize("nb,hh,ww,cin,cout,sc", [
+    (2, 32, 32, 64, 64, 0),      # one image row-block per tile (4 rows x 32)
+    (2, 16, 16, 128, 64, 0),     # 8 rows x 16
+    (3, 8, 8, 64, 128, 0),       # two images per tile, odd image count (tail tile)
+    (16, 4, 4, 64, 64, 0),       # eight images per tile
+    (5, 2, 2, 64, 64, 0),        # 32 images per tile, ragged
+    (2, 1, 1, 64, 32, 0),        # degenerate 1x1 latent level of the tiny config
+    (1, 64, 64, 32, 32, 0),      # 2 rows x 64; Cin < 64 (zero-filled k-block)
+    (1, 128, 128, 32, 16, 0),    # one row per tile
+    (1, 256, 256, 32, 3, 0),     # half a row per tile, N = 3 (decoder conv_out)
+    (2, 32, 32, 320, 320, 0),    # UNet level-0 conv: K = 2880
+    (2, 16, 16, 64, 128, 192),   # conv + folded shortcut Dense over another tensor
+])
+def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
+    rng = np.random.default_rng(nb * 1000 + hh + cin + cout)
+    x = rng.standard_normal((nb, hh, ww, cin), dtype=np.float32)
+    kern = rng.standard_normal((3, 3, cin, cout), dtype=np.float32) / np.float32(np.sqrt(9 * cin))
+    bias = rng.standard_normal(cout, dtype=np.float32)
+    sc_x = sc_k = None
+    if sc:
+        sc_x = rng.standard_normal((nb, hh, ww, sc), dtype=np.float32)
+        sc_k = rng.standard_normal((sc, cout), dtype=np.float32) / np.float32(np.sqrt(sc))
+    got = h.test_conv3x3(x, kern, bias, sc_x, sc_k)
+    ref = _conv_ref(x, kern, bias, sc_x, sc_k)
+    err = np.abs(got - ref).max()
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("n,t,tk,heads,d", [
+    (2, 64, 64, 8, 16),      # tiny config level 0
+    (2, 4, 4, 8, 32),        # tiny: T smaller than 8 (padded keys)
+    (1, 1, 1, 8, 32),        # tiny: single token
+    (2, 256, 77, 8, 80),     # cross attention, Tk = 77 padded to 80
+    (1, 1024, 1024, 8, 40),  # UNet level 0 self attention, d = 40 (zero-filled to 64)
+    (2, 16, 16, 8, 160),     # middle block
+    (1, 1024, 1024, 1, 512), # autoencoder attention, one head of 512
+])
+def test_attention(h, n, t, tk, heads, d):
+    rng = np.random.default_rng(t * 3 + tk + d)
+    q = rng.standard_normal((n, t, heads, d), dtype=np.float32)
+    k = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
+    v = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
+    scale = d ** -0.5
+    got = h.test_attention(q, k, v, scale)
+    qb, kb, vb = bf16_round(q), bf16_round(k), bf16_round(v)
+    logits = np.einsum("nqhs,nchs->nhqc", qb, kb).astype(np.float32) * np.float32(scale)
+    p = O.softmax_last(logits)
+    ref = np.einsum("nhqc,nchs->nqhs", bf16_round(p), vb).reshape(n, t, heads * d)
+    err = np.abs(got - ref).max()
+    assert err <= 2e-2 * max(1.0, np.abs(ref).max()), f"max abs err {err}"  # P and O are bf16
+    assert rel_l2(got, ref) < 1e-2

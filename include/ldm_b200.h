@@ -130,6 +130,9 @@ LDM_API int ldm_get_timing(ldm_handle* h, float* loop_ms, float* step_ms, float*
 /* Kernel-level hooks used by the parity tests and the roofline bench. */
 LDM_API int ldm_bench_ddim_update(ldm_handle* h, int b, int hh, int ww, int with_noise, int iters, float* avg_ms);
 LDM_API int ldm_bench_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, int use_graph, float* avg_ms);
+/* Eager run of `iters` sampler steps with CUDA events around every implicit-GEMM launch. */
+LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, float* gemm_ms_per_step,
+                                  float* step_ms, int* gemm_launches_per_step, double* gemm_flops_per_step);
 
 /* Test-only hooks: one engine op on host fp32 inputs (tests/test_gpu_ops.py), and named
  * fp32 activation taps inside the UNet (block-level parity against the oracle). */

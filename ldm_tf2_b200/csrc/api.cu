@@ -268,6 +268,37 @@ int ldm_bench_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, int use
   API_END
 }
 
+// Eager (no graph) run of `iters` sampler steps with CUDA events around every implicit-GEMM
+// launch: returns the average per-step time spent inside that kernel, the whole step time and
+// the number of GEMM launches per step.  Used by bench.py for the live roofline figure.
+extern "C" LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, float* gemm_ms_per_step,
+                                             float* step_ms, int* gemm_launches_per_step, double* gemm_flops_per_step) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(b > 0 && iters > 0, "ldm_profile_unet_step: bad argument");
+  Model& m = *h->model;
+  const long long nh = (long long)b * hh * ww * 4;
+  std::vector<float> x((size_t)nh), out((size_t)nh);
+  for (long long i = 0; i < nh; ++i) x[(size_t)i] = sinf(0.37f * (float)i);
+  m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, 2, 0);  // warm-up, eager
+  const long long g0 = m.eng.gemm_launches;
+  m.eng.profile = true;
+  m.eng.prof_flops = 0;
+  try {
+    m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, iters, 0);
+  } catch (...) {
+    m.eng.profile = false;
+    throw;
+  }
+  m.eng.profile = false;
+  const float total = m.eng.collect_profile_ms();
+  if (gemm_ms_per_step) *gemm_ms_per_step = total / iters;
+  if (step_ms) *step_ms = m.last_step_ms;
+  if (gemm_launches_per_step) *gemm_launches_per_step = (int)((m.eng.gemm_launches - g0) / iters);
+  if (gemm_flops_per_step) *gemm_flops_per_step = m.eng.prof_flops / iters;
+  API_END
+}
+
 // ------------------------------------------------------------------------------------
 // Kernel-level parity hooks (tests only): run ONE op of the engine on host fp32 inputs.
 // ------------------------------------------------------------------------------------

@@ -193,8 +193,33 @@ void Engine::gemm(const GemmOp& op) {
   if (ctas > total_tiles) ctas = total_tiles;
   const int smem = stages * slot + (2 * stages + 4) * 8 + 16 + 1024;
   LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (profile) {
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, stream));
+  }
   implicit_gemm_kernel<<<ctas, GEMM_THREADS, smem, stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
+  if (profile) {
+    CUDA_CHECK(cudaEventRecord(e1, stream));
+    prof_events.push_back({e0, e1});
+    prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
+  }
+}
+
+float Engine::collect_profile_ms() {
+  sync();
+  float total = 0.f;
+  for (auto& pr : prof_events) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  prof_events.clear();
+  return total;
 }
 
 }  // namespace ldm

@@ -91,6 +91,11 @@ class Engine {
   long long launches = 0;      // kernels launched by this engine (reported as gpu_launches)
   long long gemm_launches = 0;
   int max_ctas = 0;            // 0 = num_sms (test hook)
+  // profiling: CUDA events around every implicit-GEMM launch (eager mode only)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  double prof_flops = 0;       // 2*M*N*K of the profiled launches (incl. tile padding excluded)
+  float collect_profile_ms();  // syncs, sums and clears the recorded intervals
 
   void gemm(const GemmOp& op);
   template <typename T> T* alloc(size_t n) { return reinterpret_cast<T*>(arena.alloc(n * sizeof(T))); }

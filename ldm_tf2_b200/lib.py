@@ -51,6 +51,7 @@ _PROTOS = {
     "ldm_get_timing": ([_P, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), C.POINTER(_L), C.POINTER(_L)], _I),
     "ldm_bench_ddim_update": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
     "ldm_bench_unet_step": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
+    "ldm_profile_unet_step": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I), C.POINTER(C.c_double)], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
@@ -285,6 +286,13 @@ class Handle:
         ms = C.c_float()
         check(self.lib.ldm_bench_unet_step(self._h, b, hh, ww, iters, int(use_graph), C.byref(ms)))
         return ms.value
+
+    def profile_unet_step(self, b, hh, ww, iters):
+        g, s, n, fl = C.c_float(), C.c_float(), C.c_int(), C.c_double()
+        check(self.lib.ldm_profile_unet_step(self._h, b, hh, ww, iters, C.byref(g), C.byref(s), C.byref(n),
+                                             C.byref(fl)))
+        return dict(gemm_ms_per_step=g.value, step_ms=s.value, gemm_launches_per_step=n.value,
+                    gemm_flops_per_step=fl.value)
 
     # -- test hooks ---------------------------------------------------------
     def tap(self, name, shape):

@@ -50,6 +50,8 @@ int ldm_create(const ldm_config* c, int device, ldm_handle** out) {
   for (int i = 0; i < 8; ++i) { m.ae_mult[i] = c->ae_multipliers[i]; m.ae_attn_res[i] = c->ae_attention_resolutions[i]; }
   m.ae_num_attn_res = c->ae_num_attention_resolutions; m.vq_vocab = c->vq_vocab_size;
   m.ae_build_hw = c->ae_build_latent_hw > 0 ? c->ae_build_latent_hw : 32;
+  LDM_CHECK(c->precision == 0 || c->precision == 1, "precision must be 0 (bf16) or 1 (fp16)");
+  m.precision = c->precision;
   LDM_CHECK(m.model_channels % 32 == 0 && m.ae_channels % 32 == 0, "channels must be multiples of 32 (GroupNorm(32))");
   LDM_CHECK(m.latent_channels == 4, "latent_channels must be 4");
   LDM_CHECK(m.num_heads * m.head_base == m.model_channels, "num_heads*head_base must equal model_channels (unet.py:82)");
@@ -303,6 +305,20 @@ extern "C" LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int w
 // Kernel-level parity hooks (tests only): run ONE op of the engine on host fp32 inputs.
 // ------------------------------------------------------------------------------------
 namespace {
+static inline float widen16(uint16_t v, int fp16) {
+  if (!fp16) {
+    uint32_t u = (uint32_t)v << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  const uint32_t s = (v >> 15) & 1, ex = (v >> 10) & 31, ma = v & 1023;
+  float f;
+  if (ex == 0) f = ldexpf((float)ma, -24);
+  else if (ex == 31) f = ma ? NAN : INFINITY;
+  else f = ldexpf((float)(ma | 1024), (int)ex - 25);
+  return s ? -f : f;
+}
 struct Scratch {
   std::vector<void*> ptrs;
   template <typename T> T* get(size_t n, bool zero = false) {
@@ -322,7 +338,7 @@ float* up_f32(Scratch& s, Engine& e, const float* host, size_t n) {
 bf16* up_bf16(Scratch& s, Engine& e, const float* host, size_t n) {
   float* d = up_f32(s, e, host, n);
   bf16* b = s.get<bf16>(n);
-  launch_f32_to_bf16(d, b, (long long)n, 0, e.stream);
+  launch_f32_to_bf16(d, b, (long long)n, 0, e.fp16, e.stream);
   return b;
 }
 }  // namespace
@@ -356,7 +372,7 @@ LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const
   float* bias_d = nullptr;
   if (act == ACT_GEGLU) {
     if (!bn) { bn = 256; while (wn % bn) bn -= 32; }
-    launch_pack_weight(wf, k, wn, wt, k, 0, bn / 2, e.stream);
+    launch_pack_weight(wf, k, wn, wt, k, 0, bn / 2, e.fp16, e.stream);
     if (bias) {
       pb.resize(wn);
       const int half = bn / 2;
@@ -367,7 +383,7 @@ LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const
       bias_d = up_f32(s, e, pb.data(), wn);
     }
   } else {
-    launch_pack_weight(wf, k, wn, wt, k, 0, 0, e.stream);
+    launch_pack_weight(wf, k, wn, wt, k, 0, 0, e.fp16, e.stream);
     if (bias) bias_d = up_f32(s, e, bias, n);
   }
   float* res_d = residual ? up_f32(s, e, residual, (size_t)rows * n) : nullptr;
@@ -405,12 +421,12 @@ LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel,
   const int ktot = 9 * cin + (sc_x ? sc_cin : 0);
   bf16* wt = s.get<bf16>((size_t)cout * ktot, true);
   float* kf = up_f32(s, e, kernel, (size_t)9 * cin * cout);
-  launch_pack_weight(kf, 9 * cin, cout, wt, ktot, 0, 0, e.stream);
+  launch_pack_weight(kf, 9 * cin, cout, wt, ktot, 0, 0, e.fp16, e.stream);
   bf16* sb = nullptr;
   if (sc_x) {
     sb = up_bf16(s, e, sc_x, pix * sc_cin);
     float* sk = up_f32(s, e, sc_kernel, (size_t)sc_cin * cout);
-    launch_pack_weight(sk, sc_cin, cout, wt + 9 * cin, ktot, 0, 0, e.stream);
+    launch_pack_weight(sk, sc_cin, cout, wt + 9 * cin, ktot, 0, 0, e.fp16, e.stream);
   }
   float* bias_d = bias ? up_f32(s, e, bias, cout) : nullptr;
   float* out_d = s.get<float>(pix * cout);
@@ -464,10 +480,7 @@ LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, co
   std::vector<uint16_t> raw((size_t)n * t * c);
   CUDA_CHECK(cudaMemcpyAsync(raw.data(), ob, raw.size() * 2, cudaMemcpyDefault, e.stream));
   e.sync();
-  for (size_t i = 0; i < raw.size(); ++i) {
-    uint32_t u = (uint32_t)raw[i] << 16;
-    memcpy(&out[i], &u, 4);
-  }
+  for (size_t i = 0; i < raw.size(); ++i) out[i] = widen16(raw[i], e.fp16);
   (void)of;
   API_END
 }
@@ -488,14 +501,11 @@ LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const flo
   float* mr = s.get<float>((size_t)n * 64);
   bf16* ob = s.get<bf16>((size_t)n * hw * c);
   launch_gn_stats(a, ca, b, cb, n, hw, eps, mr, e.stream);
-  launch_gn_apply(a, ca, b, cb, n, hw, mr, g, bt, silu, ob, e.stream);
+  launch_gn_apply(a, ca, b, cb, n, hw, mr, g, bt, silu, ob, e.fp16, e.stream);
   std::vector<uint16_t> raw((size_t)n * hw * c);
   CUDA_CHECK(cudaMemcpyAsync(raw.data(), ob, raw.size() * 2, cudaMemcpyDefault, e.stream));
   e.sync();
-  for (size_t i = 0; i < raw.size(); ++i) {
-    uint32_t u = (uint32_t)raw[i] << 16;
-    memcpy(&out[i], &u, 4);
-  }
+  for (size_t i = 0; i < raw.size(); ++i) out[i] = widen16(raw[i], e.fp16);
   API_END
 }
 
@@ -510,7 +520,7 @@ LDM_API int ldm_test_layernorm(ldm_handle* h, const float* x, const float* gamma
   float* g = up_f32(s, e, gamma, c);
   float* b = up_f32(s, e, beta, c);
   float* o = s.get<float>((size_t)rows * c);
-  launch_layernorm(xd, g, b, rows, c, eps, nullptr, o, e.stream);
+  launch_layernorm(xd, g, b, rows, c, eps, nullptr, o, e.fp16, e.stream);
   CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)rows * c * sizeof(float), cudaMemcpyDefault, e.stream));
   e.sync();
   API_END

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -40,6 +41,8 @@ inline std::string fmt(const char* f, ...) {
                                     cudaGetErrorName(_e), cudaGetErrorString(_e))); \
   } while (0)
 
+// 16-bit tensor-core operand storage.  The bits are bf16 or fp16 depending on the engine's
+// precision mode (Engine::fp16); only the conversion helpers below care.
 typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------- device PTX
@@ -176,18 +179,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16: A=B=bf16 (K-major), D=fp32, M=128, N=n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// Instruction descriptor for kind::f16: A=B=bf16 (format 1) or fp16 (format 0), K-major,
+// D=fp32, M=128, N=n.
+__device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, int fp16) {
+  const uint32_t f = fp16 ? 0u : 1u;
+  return (1u << 4) | (f << 7) | (f << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+// fp32 -> 16-bit operand bits; fp16 saturates instead of overflowing to inf
+__device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
+  if (fp16) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(v));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16(v));
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
+  return (uint32_t)cvt16(a, fp16) | ((uint32_t)cvt16(b, fp16) << 16);
+}
+__device__ __forceinline__ void store16(bf16* p, float v, int fp16) {
+  *reinterpret_cast<uint16_t*>(p) = cvt16(v, fp16);
 }
 #endif  // __CUDACC__
 

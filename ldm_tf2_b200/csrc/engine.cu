@@ -87,7 +87,7 @@ void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, in
               (unsigned long long)strides[i]);
   for (int i = 0; i < 4; ++i) LDM_CHECK(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u", i, box[i]);
   CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
-      m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(v.ptr), dims, strides, box, estr,
+      m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(v.ptr), dims, strides, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LDM_CHECK(r == CUDA_SUCCESS,
@@ -170,6 +170,7 @@ void Engine::gemm(const GemmOp& op) {
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
   p.tx_bytes = stage_bytes;
+  p.fp16 = fp16;
   // ---- epilogue
   p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
   p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;

@@ -91,6 +91,7 @@ class Engine {
   long long launches = 0;      // kernels launched by this engine (reported as gpu_launches)
   long long gemm_launches = 0;
   int max_ctas = 0;            // 0 = num_sms (test hook)
+  int fp16 = 0;                // 16-bit operand format: 0 = bf16, 1 = fp16 (same tensor-core rate)
   // profiling: CUDA events around every implicit-GEMM launch (eager mode only)
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

@@ -54,6 +54,7 @@ struct GemmParams {
   int stages;
   int box_rows;             // rows actually loaded per A tile (<= 128)
   int tx_bytes;             // bytes both TMA loads of a stage deliver
+  int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
   int b_swap;
   // epilogue
@@ -126,7 +127,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       int col = col0 + j;
-      if (col < p.N) p.out_tr[tr_row_off + (long long)(col - p.tr_col0) * p.ts_c + xq] = __float2bfloat16(v[j]);
+      if (col < p.N) store16(p.out_tr + tr_row_off + (long long)(col - p.tr_col0) * p.ts_c + xq, v[j], p.fp16);
     }
     return;
   }
@@ -160,16 +161,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < CH; j += 8) {
         uint4 u;
-        u.x = pack_bf16(v[j], v[j + 1]);
-        u.y = pack_bf16(v[j + 2], v[j + 3]);
-        u.z = pack_bf16(v[j + 4], v[j + 5]);
-        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        u.x = pack16(v[j], v[j + 1], p.fp16);
+        u.y = pack16(v[j + 2], v[j + 3], p.fp16);
+        u.z = pack16(v[j + 4], v[j + 5], p.fp16);
+        u.w = pack16(v[j + 6], v[j + 7], p.fp16);
         *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < CH; ++j)
-        if (col0 + j < p.N) p.out_bf16[off + j] = __float2bfloat16(v[j]);
+        if (col0 + j < p.N) store16(p.out_bf16 + off + j, v[j], p.fp16);
     }
   }
   (void)img;
@@ -253,7 +254,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, (uint32_t)p.block_n);
+      const uint32_t idesc = umma_idesc_16(GEMM_BM, (uint32_t)p.block_n, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -334,15 +335,15 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
                   uint4 u;
-                  u.x = pack_bf16(v[j], v[j + 1]);
-                  u.y = pack_bf16(v[j + 2], v[j + 3]);
-                  u.z = pack_bf16(v[j + 4], v[j + 5]);
-                  u.w = pack_bf16(v[j + 6], v[j + 7]);
+                  u.x = pack16(v[j], v[j + 1], p.fp16);
+                  u.y = pack16(v[j + 2], v[j + 3], p.fp16);
+                  u.z = pack16(v[j + 4], v[j + 5], p.fp16);
+                  u.w = pack16(v[j + 6], v[j + 7], p.fp16);
                   *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
                 }
               } else {
                 for (int j = 0; j < 16; ++j)
-                  if (oc0 + j < p.N) p.out_bf16[off + j] = __float2bfloat16(v[j]);
+                  if (oc0 + j < p.N) store16(p.out_bf16 + off + j, v[j], p.fp16);
               }
             }
             if (p.out_f32) {

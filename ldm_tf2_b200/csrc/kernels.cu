@@ -127,7 +127,7 @@ void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int 
 __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
                                 int hw, const float* __restrict__ mr, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int do_silu, bf16* __restrict__ out,
-                                long long total4) {
+                                long long total4, int fp16) {
   const int c = ca + cb, cg = c / 32, c4 = c / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -147,18 +147,18 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
       x[k] = y;
     }
     uint2 u;
-    u.x = pack_bf16(x[0], x[1]);
-    u.y = pack_bf16(x[2], x[3]);
+    u.x = pack16(x[0], x[1], fp16);
+    u.y = pack16(x[2], x[3], fp16);
     *reinterpret_cast<uint2*>(out + pixg * c + ch) = u;
   }
 }
 
 void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const float* mean_rstd,
-                     const float* gamma, const float* beta, int do_silu, bf16* out, cudaStream_t st) {
+                     const float* gamma, const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st) {
   LDM_CHECK(ca % 4 == 0 && cb % 4 == 0, "gn_apply: channel counts must be multiples of 4");
   const long long total4 = (long long)n * hw * (ca + cb) / 4;
   gn_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(a, ca, b, cb, hw, mean_rstd, gamma, beta, do_silu,
-                                                        out, total4);
+                                                        out, total4, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -167,7 +167,7 @@ void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int 
 // =====================================================================================
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int c, float eps,
-                                 bf16* __restrict__ ob, float* __restrict__ of) {
+                                 bf16* __restrict__ ob, float* __restrict__ of, int fp16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -185,15 +185,15 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   const float rstd = rsqrtf(q / (float)c + eps);
   for (int i = lane; i < c; i += 32) {
     const float y = (xr[i] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
-    if (ob) ob[(long long)row * c + i] = __float2bfloat16(y);
+    if (ob) store16(ob + (long long)row * c + i, y, fp16);
     if (of) of[(long long)row * c + i] = y;
   }
 }
 
 void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
-                      bf16* out_bf16, float* out_f32, cudaStream_t st) {
+                      bf16* out_bf16, float* out_f32, int fp16, cudaStream_t st) {
   const int wpb = 8;
-  layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32);
+  layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -201,7 +201,7 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, int
 // softmax(scale * s) over tk valid keys of a tpad-wide row; pad columns get 0.
 // =====================================================================================
 __global__ void softmax_kernel(const float* __restrict__ s, bf16* __restrict__ p, long long rows, int tk,
-                               int tpad, float scale) {
+                               int tpad, float scale, int fp16) {
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -215,12 +215,13 @@ __global__ void softmax_kernel(const float* __restrict__ s, bf16* __restrict__ p
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.0f / sum;
   for (int i = lane; i < tpad; i += 32)
-    pr[i] = __float2bfloat16(i < tk ? __expf(sr[i] * scale - m) * inv : 0.f);
+    store16(pr + i, i < tk ? __expf(sr[i] * scale - m) * inv : 0.f, fp16);
 }
 
-void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, cudaStream_t st) {
+void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, int fp16,
+                    cudaStream_t st) {
   const int wpb = 8;
-  softmax_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(s, p, rows, tk, tpad, scale);
+  softmax_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(s, p, rows, tk, tpad, scale, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -230,7 +231,7 @@ void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, f
 // =====================================================================================
 __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
                                const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
-                               float* __restrict__ of, bf16* __restrict__ ob) {
+                               float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
   const int c4 = cout / 4;
   const long long total = (long long)n * h * w * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -267,18 +268,18 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int
     if (of) *reinterpret_cast<float4*>(of + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     if (ob) {
       uint2 u;
-      u.x = pack_bf16(acc[0], acc[1]);
-      u.y = pack_bf16(acc[2], acc[3]);
+      u.x = pack16(acc[0], acc[1], fp16);
+      u.y = pack16(acc[2], acc[3], fp16);
       *reinterpret_cast<uint2*>(ob + o) = u;
     }
   }
 }
 
 void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel, const float* bias,
-                    int cout, float* out_f32, bf16* out_bf16, cudaStream_t st) {
+                    int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st) {
   LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
   const long long total = (long long)n * h * w * (cout / 4);
-  conv_in_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, nsrc, n, h, w, kernel, bias, cout, out_f32, out_bf16);
+  conv_in_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, nsrc, n, h, w, kernel, bias, cout, out_f32, out_bf16, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -362,15 +363,16 @@ void launch_upsample2(const bf16* x, int n, int h, int w, int c, bf16* out, cuda
 // =====================================================================================
 // misc
 // =====================================================================================
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n, int do_silu) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n, int do_silu,
+                                   int fp16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
     if (do_silu) v = silu_f(v);
-    y[i] = __float2bfloat16(v);
+    store16(y + i, v, fp16);
   }
 }
-void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, cudaStream_t st) {
-  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, do_silu);
+void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, int fp16, cudaStream_t st) {
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, do_silu, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 __global__ void fill_f32_kernel(float* x, long long n, float v) {
@@ -384,7 +386,7 @@ void launch_fill_f32(float* x, long long n, float v, cudaStream_t st) {
 
 // W[k][n] fp32 -> dst[(row0 + perm(n)) * ld + k] bf16 through a 32x32 smem transpose.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int k, int n, bf16* __restrict__ dst,
-                                   long long ld, int row0, int geglu_half) {
+                                   long long ld, int row0, int geglu_half, int fp16) {
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -401,14 +403,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int k, int n, bf
         const int j2 = nn < nh ? nn : nn - nh;
         r = (j2 / geglu_half) * (2 * geglu_half) + (nn < nh ? 0 : geglu_half) + j2 % geglu_half;
       }
-      dst[(long long)(row0 + r) * ld + kk] = __float2bfloat16(tile[threadIdx.x][j]);
+      store16(dst + (long long)(row0 + r) * ld + kk, tile[threadIdx.x][j], fp16);
     }
   }
 }
 void launch_pack_weight(const float* w, int k, int n, bf16* dst, long long dst_ld, int dst_row0,
-                        int geglu_half, cudaStream_t st) {
+                        int geglu_half, int fp16, cudaStream_t st) {
   dim3 grid(cdiv(n, 32), cdiv(k, 32)), block(32, 8);
-  pack_weight_kernel<<<grid, block, 0, st>>>(w, k, n, dst, dst_ld, dst_row0, geglu_half);
+  pack_weight_kernel<<<grid, block, 0, st>>>(w, k, n, dst, dst_ld, dst_row0, geglu_half, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -442,6 +444,31 @@ __global__ void time_embed_kernel(const int* __restrict__ t, int n, int channels
 }
 void launch_time_embed(const int* t, int n, int channels, float* out, cudaStream_t st) {
   time_embed_kernel<<<grid_for((long long)n * channels / 2, 128), 128, 0, st>>>(t, n, channels, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// y[r, n] = act(sum_k x[r,k] * w[k,n] + b[n]) in fp32 for a handful of rows (time-embedding MLP,
+// unet.py:126-127,386: depends only on the timestep, so it runs once per sampler setup).
+__global__ void small_dense_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                       const float* __restrict__ b, int rows, int k, int n, int act_in_silu,
+                                       int act_out_silu, float* __restrict__ y) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (col >= n || r >= rows) return;
+  float acc = 0.f;
+  for (int i = 0; i < k; ++i) {
+    float v = x[(long long)r * k + i];
+    if (act_in_silu) v = silu_f(v);
+    acc = fmaf(v, __ldg(w + (long long)i * n + col), acc);
+  }
+  acc += b ? __ldg(b + col) : 0.f;
+  if (act_out_silu) acc = silu_f(acc);
+  y[(long long)r * n + col] = acc;
+}
+void launch_small_dense_f32(const float* x, const float* w, const float* b, int rows, int k, int n, int act_in_silu,
+                            int act_out_silu, float* y, cudaStream_t st) {
+  dim3 grid(cdiv(n, 128), rows);
+  small_dense_f32_kernel<<<grid, 128, 0, st>>>(x, w, b, rows, k, n, act_in_silu, act_out_silu, y);
   CUDA_CHECK(cudaGetLastError());
 }
 

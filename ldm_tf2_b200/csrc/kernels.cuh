@@ -21,21 +21,22 @@ void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int 
                      float* mean_rstd /*[n][32][2]*/, cudaStream_t st);
 void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw,
                      const float* mean_rstd, const float* gamma, const float* beta, int do_silu,
-                     bf16* out, cudaStream_t st);
+                     bf16* out, int fp16, cudaStream_t st);
 
 // ---- LayerNorm over the last axis (unet.py:304-306, transformer.py:165,170,209) --------
 void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
-                      bf16* out_bf16, float* out_f32, cudaStream_t st);
+                      bf16* out_bf16, float* out_f32, int fp16, cudaStream_t st);
 
 // ---- softmax over the last axis with post-dot scale and key mask (unet.py:281-284) -----
-void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, cudaStream_t st);
+void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, int fp16,
+                    cudaStream_t st);
 
 // ---- conv_in: 3x3 SAME conv with Cin = 4 (unet.py:71,125; autoencoder.py:275,292) ------
 // x [nsrc,h,w,4] fp32; output rows n read image (n % nsrc) (virtual concat([xt,xt]),
 // model_runners.py:452).  pre: optional 4x4 Dense applied first (post_quant_conv,
 // autoencoder.py:362) with input scale.
 void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel /*[3,3,4,cout]*/,
-                    const float* bias, int cout, float* out_f32, bf16* out_bf16, cudaStream_t st);
+                    const float* bias, int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st);
 void launch_dense4(const float* x, long long rows, float in_scale, const float* kernel, const float* bias,
                    float* out, cudaStream_t st);
 
@@ -45,12 +46,14 @@ void launch_im2col_s2(const bf16* x, int n, int h, int w, int c, bf16* out /*[n*
 void launch_upsample2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st);
 
 // ---- misc ---------------------------------------------------------------------------------
-void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, cudaStream_t st);
+void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, int fp16, cudaStream_t st);
+void launch_small_dense_f32(const float* x, const float* w, const float* b, int rows, int k, int n, int act_in_silu,
+                            int act_out_silu, float* y, cudaStream_t st);
 void launch_fill_f32(float* x, long long n, float v, cudaStream_t st);
 // W fp32 [K,N] (Keras Dense / reshaped conv) -> bf16 [N (dst rows), K] at dst row offset;
 // geglu_half>0 permutes rows so that value/gate columns interleave per block (see gemm.cuh).
 void launch_pack_weight(const float* w, int k, int n, bf16* dst, long long dst_ld, int dst_row0,
-                        int geglu_half, cudaStream_t st);
+                        int geglu_half, int fp16, cudaStream_t st);
 void launch_embed(const long long* ids, const float* tok, const float* pos, int rows, int seq, int d,
                   float* out, cudaStream_t st);
 void launch_time_embed(const int* t, int n, int channels, float* out, cudaStream_t st);

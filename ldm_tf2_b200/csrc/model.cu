@@ -46,6 +46,15 @@ struct Builder {
     s.push_back(sl);
     return &s.back();
   }
+  Slot* f32mat(const std::string& name, std::vector<int> shape, int k, int n, float* dst, long long ld, int col0) {
+    Slot sl;
+    sl.name = name;
+    sl.shape = std::move(shape);
+    sl.kind = Slot::F32MAT;
+    sl.k = k; sl.n = n; sl.f32_dst = dst; sl.f32_ld = ld; sl.f32_col0 = col0;
+    s.push_back(sl);
+    return &s.back();
+  }
   LinW lin(int n, int k) {
     LinW w;
     w.n = n; w.k = k; w.ld = k;
@@ -74,7 +83,7 @@ struct Builder {
   }
   // ResidualBlock (unet.py:368-380 / autoencoder.py:13-41) in Keras weight order
   ResW res(const std::string& p, int cin, int cout, int temb_dim, bool shortcut, bool ae, int* temb_cols,
-           LinW* tproj) {
+           float* tproj, int tproj_ld) {
     ResW r;
     r.cin = cin; r.cout = cout; r.shortcut = shortcut;
     const char* n_gn1 = ae ? "/_group_norm1" : "/_group_norm_1";
@@ -88,7 +97,7 @@ struct Builder {
     r.conv1.bias = f32(p + n_c1 + "/bias", {cout});
     if (temb_dim) {
       r.temb_off = *temb_cols;
-      pack(p + "/_dense/kernel", {temb_dim, cout}, temb_dim, cout, tproj->wt, tproj->ld, r.temb_off, 0);
+      f32mat(p + "/_dense/kernel", {temb_dim, cout}, temb_dim, cout, tproj, tproj_ld, r.temb_off);
       Slot* b = f32(p + "/_dense/bias", {cout});
       tproj_bias.push_back({b, r.temb_off});
       *temb_cols += cout;
@@ -165,7 +174,10 @@ struct Builder {
   std::vector<std::pair<Slot*, float*>> concat_bias;
 };
 
-Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) { build(); }
+Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) {
+  eng.fp16 = c.precision == 1 ? 1 : 0;
+  build();
+}
 
 Model::~Model() {
   if (step_graph_) cudaGraphExecDestroy(step_graph_);
@@ -208,14 +220,18 @@ void Model::build() {
       sumc += 2 * mc * cfg.channel_mult[L - 1];
       for (int i = L - 1; i >= 0; --i) sumc += (nb + 1) * mc * cfg.channel_mult[i];
     }
-    tproj_all_ = b.lin(sumc, td);
+    tproj_w_ = dev_alloc<float>((size_t)td * sumc, true);
     tproj_bias_ = dev_alloc<float>(sumc, true);
+    time1_w_ = dev_alloc<float>((size_t)mc * td, true);
+    time2_w_ = dev_alloc<float>((size_t)td * td, true);
     tproj_cols_ = sumc;
     int tcols = 0;
     conv_in_k_ = b.f32("unet/_conv_in/kernel", {3, 3, 4, mc});
     conv_in_b_ = b.f32("unet/_conv_in/bias", {mc});
-    time1_ = b.dense("unet/_time_dense1", mc, td);
-    time2_ = b.dense("unet/_time_dense2", td, td);
+    b.f32mat("unet/_time_dense1/kernel", {mc, td}, mc, td, time1_w_, td, 0);
+    time1_b_ = b.f32("unet/_time_dense1/bias", {td});
+    b.f32mat("unet/_time_dense2/kernel", {td, td}, td, td, time2_w_, td, 0);
+    time2_b_ = b.f32("unet/_time_dense2/bias", {td});
     std::vector<int> chans{mc};
     int ch = mc;
     in_blocks_.reserve(64);
@@ -227,7 +243,7 @@ void Model::build() {
         in_blocks_.emplace_back();
         UNetBlock& blk = in_blocks_.back();
         blk.kind = 0; blk.cin = ch; blk.cout = mc * m;
-        blk.res = b.res(p + "/_residual", ch, mc * m, td, ch != mc * m, false, &tcols, &tproj_all_);
+        blk.res = b.res(p + "/_residual", ch, mc * m, td, ch != mc * m, false, &tcols, tproj_w_, sumc);
         blk.has_st = i < L - 1;
         if (blk.has_st) b.st(blk.st, p + "/_spatial_transformer", mc * m, heads, cfg.head_base * m, ctx);
         ch = mc * m;
@@ -244,9 +260,9 @@ void Model::build() {
         chans.push_back(ch);
       }
     }
-    mid_res1_ = b.res("unet/_middle_block/_residual1", ch, ch, td, false, false, &tcols, &tproj_all_);
+    mid_res1_ = b.res("unet/_middle_block/_residual1", ch, ch, td, false, false, &tcols, tproj_w_, sumc);
     b.st(mid_st_, "unet/_middle_block/_spatial_transformer", ch, heads, cfg.head_base * cfg.channel_mult[L - 1], ctx);
-    mid_res2_ = b.res("unet/_middle_block/_residual2", ch, ch, td, false, false, &tcols, &tproj_all_);
+    mid_res2_ = b.res("unet/_middle_block/_residual2", ch, ch, td, false, false, &tcols, tproj_w_, sumc);
     for (int i = L - 1; i >= 0; --i) {
       const int m = cfg.channel_mult[i];
       for (int j = 0; j <= nb; ++j) {
@@ -256,7 +272,7 @@ void Model::build() {
         out_blocks_.emplace_back();
         UNetBlock& blk = out_blocks_.back();
         blk.kind = 2; blk.cin = ch + skip; blk.cout = mc * m;
-        blk.res = b.res(p + "/_residual", ch + skip, mc * m, td, true, false, &tcols, &tproj_all_);
+        blk.res = b.res(p + "/_residual", ch + skip, mc * m, td, true, false, &tcols, tproj_w_, sumc);
         blk.has_st = i < L - 1;
         if (blk.has_st) b.st(blk.st, p + "/_spatial_transformer", mc * m, heads, cfg.head_base * m, ctx);
         blk.has_up = (i > 0 && j == nb);
@@ -294,9 +310,9 @@ void Model::build() {
     const std::string d = "autoencoder/_decoder";
     ae_conv_in_k_ = b.f32(d + "/_conv_in/kernel", {3, 3, z, top});
     ae_conv_in_b_ = b.f32(d + "/_conv_in/bias", {top});
-    ae_mid1_ = b.res(d + "/_middle/_residual1", top, top, 0, false, true, nullptr, nullptr);
+    ae_mid1_ = b.res(d + "/_middle/_residual1", top, top, 0, false, true, nullptr, nullptr, 0);
     b.ae_attn(ae_mid_attn_, d + "/_middle/_attention", top);
-    ae_mid2_ = b.res(d + "/_middle/_residual2", top, top, 0, false, true, nullptr, nullptr);
+    ae_mid2_ = b.res(d + "/_middle/_residual2", top, top, 0, false, true, nullptr, nullptr, 0);
     ae_up_.reserve(64);
     int hw = cfg.ae_build_hw, cur = top, idx = 0;
     for (int i = L - 1; i >= 0; --i) {
@@ -305,7 +321,7 @@ void Model::build() {
         ae_up_.emplace_back();
         AEStage& s = ae_up_.back();
         s.kind = 0; s.hw = hw;
-        s.res = b.res(p + "/_residual", cur, chans[i], 0, cur != chans[i], true, nullptr, nullptr);
+        s.res = b.res(p + "/_residual", cur, chans[i], 0, cur != chans[i], true, nullptr, nullptr, 0);
         s.attn = false;
         if (cfg.ae_kind == 1)
           for (int k = 0; k < cfg.ae_num_attn_res; ++k) s.attn |= (cfg.ae_attn_res[k] == hw);
@@ -358,8 +374,13 @@ void Model::set_weight(int model, int index, const float* src, const int* shape,
     eng.sync();
     if (s.f32) cudaFree(s.f32);
     s.f32 = dev;
+  } else if (s.kind == Slot::F32MAT) {
+    CUDA_CHECK(cudaMemcpy2DAsync(s.f32_dst + s.f32_col0, s.f32_ld * sizeof(float), dev, s.n * sizeof(float),
+                                 s.n * sizeof(float), s.k, cudaMemcpyDeviceToDevice, eng.stream));
+    eng.sync();
+    cudaFree(dev);
   } else {
-    launch_pack_weight(dev, s.k, s.n, s.dst + s.col0, s.ld, s.row0, s.geglu_half, eng.stream);
+    launch_pack_weight(dev, s.k, s.n, s.dst + s.col0, s.ld, s.row0, s.geglu_half, eng.fp16, eng.stream);
     eng.sync();
     cudaFree(dev);
   }
@@ -445,7 +466,7 @@ void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out
   if (eng.dry) return;
   launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, g.eps, mr, eng.stream);
   launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, mr, g.gamma->f32, g.beta->f32, silu ? 1 : 0,
-                  out, eng.stream);
+                  out, eng.fp16, eng.stream);
 }
 
 void Model::linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
@@ -578,7 +599,7 @@ void Model::attention_core(const bf16* q, long long q_ld, const bf16* k, long lo
     eng.gemm(op);
   }
   eng.launches++;
-  if (!eng.dry) launch_softmax(S, P, (long long)n * heads * t, tk, tpad, scale, eng.stream);
+  if (!eng.dry) launch_softmax(S, P, (long long)n * heads * t, tk, tpad, scale, eng.fp16, eng.stream);
   {
     GemmOp op;
     op.num_a = 1;
@@ -639,7 +660,7 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
   {
     const size_t mk2 = eng.arena.mark();
     eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln1.gamma->f32, s.ln1.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    if (!eng.dry) launch_layernorm(y, s.ln1.gamma->f32, s.ln1.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     const int tpad = round_up(t, 8);
     bf16* qk = eng.alloc<bf16>((size_t)rows * 2 * c);
     bf16* vt = eng.alloc<bf16>((size_t)n * c * tpad);
@@ -653,7 +674,7 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
   {
     const size_t mk2 = eng.arena.mark();
     eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln2.gamma->f32, s.ln2.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    if (!eng.dry) launch_layernorm(y, s.ln2.gamma->f32, s.ln2.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     bf16* q = eng.alloc<bf16>((size_t)rows * c);
     linear(z, rows, s.a2.qkv, nullptr, ACT_NONE, nullptr, nullptr, q);
     const int tk = cfg.max_seq_len, tpad = round_up(tk, 8);
@@ -665,7 +686,7 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
   {
     const size_t mk2 = eng.arena.mark();
     eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln3.gamma->f32, s.ln3.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.stream);
+    if (!eng.dry) launch_layernorm(y, s.ln3.gamma->f32, s.ln3.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     bf16* g = eng.alloc<bf16>((size_t)rows * 4 * c);
     {
       GemmOp op;
@@ -697,29 +718,22 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
 // rows = one per distinct timestep; table [rows, tproj_cols_]
 // =====================================================================================
 void Model::compute_temb_table(const int* t_host, int rows, float* table) {
+  // fp32 end to end: [cos|sin] -> Dense+SiLU -> Dense -> per-ResBlock Dense(SiLU(.)) for all blocks at once
   const int mc = cfg.model_channels, td = 4 * mc;
-  char* scratch = nullptr;
-  const size_t sz_t = 256 + (size_t)rows * sizeof(int), sz_e = (size_t)rows * mc, sz_h = (size_t)rows * td;
-  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-  const size_t total = al(sz_t) + al(sz_e * 4) + al(sz_e * 2) + al(sz_h * 2) + al(sz_h * 4) + al(sz_h * 2);
-  CUDA_CHECK(cudaMalloc(&scratch, total));
-  char* cur = scratch;
-  int* t_dev = reinterpret_cast<int*>(cur); cur += al(sz_t);
-  float* emb = reinterpret_cast<float*>(cur); cur += al(sz_e * 4);
-  bf16* emb_b = reinterpret_cast<bf16*>(cur); cur += al(sz_e * 2);
-  bf16* h1 = reinterpret_cast<bf16*>(cur); cur += al(sz_h * 2);
-  float* temb = reinterpret_cast<float*>(cur); cur += al(sz_h * 4);
-  bf16* temb_s = reinterpret_cast<bf16*>(cur);
+  int* t_dev = nullptr;
+  float *emb = nullptr, *h1 = nullptr, *temb = nullptr;
+  CUDA_CHECK(cudaMalloc(&t_dev, rows * sizeof(int)));
+  CUDA_CHECK(cudaMalloc(&emb, (size_t)rows * mc * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&h1, (size_t)rows * td * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&temb, (size_t)rows * td * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(t_dev, t_host, rows * sizeof(int), cudaMemcpyHostToDevice, eng.stream));
   launch_time_embed(t_dev, rows, mc, emb, eng.stream);
-  launch_f32_to_bf16(emb, emb_b, (long long)rows * mc, 0, eng.stream);
-  linear(emb_b, rows, time1_, time1_.bias->f32, ACT_SILU, nullptr, nullptr, h1);
-  linear(h1, rows, time2_, time2_.bias->f32, ACT_NONE, nullptr, temb, nullptr);
-  launch_f32_to_bf16(temb, temb_s, (long long)rows * td, 1, eng.stream);  // SiLU(temb), unet.py:386
-  linear(temb_s, rows, tproj_all_, tproj_bias_, ACT_NONE, nullptr, table, nullptr);
-  eng.launches += 3;
+  launch_small_dense_f32(emb, time1_w_, time1_b_->f32, rows, mc, td, 0, 1, h1, eng.stream);   // unet.py:72 silu
+  launch_small_dense_f32(h1, time2_w_, time2_b_->f32, rows, td, td, 0, 0, temb, eng.stream);   // unet.py:73
+  launch_small_dense_f32(temb, tproj_w_, tproj_bias_, rows, td, tproj_cols_, 1, 0, table, eng.stream);  // unet.py:386
+  eng.launches += 4;
   eng.sync();
-  cudaFree(scratch);
+  cudaFree(t_dev); cudaFree(emb); cudaFree(h1); cudaFree(temb);
 }
 
 // =====================================================================================
@@ -735,7 +749,7 @@ void Model::set_context(const float* ctx, int n) {
   CUDA_CHECK(cudaMalloc(&cf, nel * sizeof(float)));
   CUDA_CHECK(cudaMalloc(&cb, nel * sizeof(bf16)));
   CUDA_CHECK(cudaMemcpyAsync(cf, ctx, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
-  launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.stream);
+  launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.fp16, eng.stream);
   for (STW* s : all_st_) {
     const int c = s->c;
     if (ctx_rows_ != n || !s->ctx_k) {
@@ -771,7 +785,7 @@ void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_o
   const int mc = cfg.model_channels;
   Act cur = alloc_act(n, h, w, mc);
   eng.launches++;
-  if (!eng.dry) launch_conv_in(x, nsrc, n, h, w, conv_in_k_->f32, conv_in_b_->f32, mc, cur.f, cur.b, eng.stream);
+  if (!eng.dry) launch_conv_in(x, nsrc, n, h, w, conv_in_k_->f32, conv_in_b_->f32, mc, cur.f, cur.b, eng.fp16, eng.stream);
   tap("conv_in", cur);
   std::vector<Act> hiddens{cur};
   int bi = 0;
@@ -1021,13 +1035,13 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
     const float scale = 1.0f / sqrtf((float)S);
     for (auto& L : text_layers_) {
       eng.launches++;
-      if (!eng.dry) launch_layernorm(x, L.ln_mha.gamma->f32, L.ln_mha.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.stream);
+      if (!eng.dry) launch_layernorm(x, L.ln_mha.gamma->f32, L.ln_mha.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.fp16, eng.stream);
       qkv_projection(eng, z, n, T, D, L.attn.qkv, nullptr, inner, qk, vt, tpad);
       attention_core(qk, 2 * inner, qk + inner, 2 * inner, (long long)T * 2 * inner, T, vt, tpad, n, T, H, S, scale, o,
                      inner);
       linear(o, R, L.attn.out, L.attn.out.bias->f32, ACT_NONE, x, x, nullptr);
       eng.launches++;
-      if (!eng.dry) launch_layernorm(x, L.ln_ffn.gamma->f32, L.ln_ffn.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.stream);
+      if (!eng.dry) launch_layernorm(x, L.ln_ffn.gamma->f32, L.ln_ffn.beta->f32, (int)R, D, 1e-5f, z, nullptr, eng.fp16, eng.stream);
       linear(z, R, L.f1, L.f1.bias->f32, ACT_GELU, nullptr, nullptr, hbuf);
       linear(hbuf, R, L.f2, L.f2.bias->f32, ACT_NONE, x, x, nullptr);
     }
@@ -1046,7 +1060,7 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
   body(ids_dev, x);
-  launch_layernorm(x, text_ln_.gamma->f32, text_ln_.beta->f32, (int)R, D, 1e-5f, nullptr, y, eng.stream);
+  launch_layernorm(x, text_ln_.gamma->f32, text_ln_.beta->f32, (int)R, D, 1e-5f, nullptr, y, eng.fp16, eng.stream);
   eng.launches++;
   for (int r = 0; r < rows; ++r)
     CUDA_CHECK(cudaMemcpyAsync(ctx_out + (long long)r * T * D, y + (long long)uniq_of[r] * T * D,
@@ -1097,7 +1111,7 @@ void Model::decode_body(const float* z, int b, int h, int w, float div, float* i
   const int top = cfg.ae_channels * cfg.ae_mult[cfg.ae_num_mult - 1];
   Act cur = alloc_act(b, h, w, top);
   eng.launches++;
-  if (!eng.dry) launch_conv_in(pq, b, b, h, w, ae_conv_in_k_->f32, ae_conv_in_b_->f32, top, cur.f, cur.b, eng.stream);
+  if (!eng.dry) launch_conv_in(pq, b, b, h, w, ae_conv_in_k_->f32, ae_conv_in_b_->f32, top, cur.f, cur.b, eng.fp16, eng.stream);
   cur = resblock(ae_mid1_, cur, nullptr);
   cur = ae_attention(ae_mid_attn_, cur);
   cur = resblock(ae_mid2_, cur, nullptr);

@@ -26,18 +26,20 @@ struct ModelConfig {
   int latent_channels = 4, ae_channels = 128, ae_num_blocks = 2, ae_num_mult = 4, ae_mult[8] = {1, 2, 4, 4},
       ae_num_attn_res = 0, ae_attn_res[8] = {0}, vq_vocab = 16384,
       ae_build_hw = 32;  // latent size the checkpoint's Decoder was built at (autoencoder.py:176)
+  int precision = 1;       // 16-bit tensor-core operand format: 0 = bf16, 1 = fp16
 };
 
 // One tensor of a model in flat Keras order, with how it is consumed.
 struct Slot {
   std::string name;
   std::vector<int> shape;
-  enum Kind { F32, PACK } kind = F32;
+  enum Kind { F32, PACK, F32MAT } kind = F32;  // F32MAT: fp32 [k,n] block copied into a wider fp32 matrix
   float* f32 = nullptr;     // F32: device copy
   // PACK: W viewed as [k, n] fp32 -> bf16 dst[(row0 + perm(n)) * ld + col0 + k]
   bf16* dst = nullptr;
   long long ld = 0;
   int row0 = 0, col0 = 0, k = 0, n = 0, geglu_half = 0;
+  float* f32_dst = nullptr; long long f32_ld = 0; int f32_col0 = 0;  // F32MAT destination
   bool set = false;
   size_t numel() const { size_t s = 1; for (int d : shape) s *= (size_t)d; return s; }
 };
@@ -130,7 +132,9 @@ class Model {
   LNW text_ln_; Slot* tok_emb_ = nullptr; Slot* pos_emb_ = nullptr;
   // unet
   Slot* conv_in_k_ = nullptr; Slot* conv_in_b_ = nullptr;
-  LinW time1_, time2_, tproj_all_;  // tproj_all_: all ResBlock time Dense layers stacked [sumC, 4mc]
+  // time-embedding MLP kept in fp32 (runs once per sampler setup): kernels [k,n] row-major
+  float* time1_w_ = nullptr; float* time2_w_ = nullptr; Slot* time1_b_ = nullptr; Slot* time2_b_ = nullptr;
+  float* tproj_w_ = nullptr;   // all ResBlock time Dense kernels side by side: [4mc, sumC]
   float* tproj_bias_ = nullptr; int tproj_cols_ = 0;
   std::vector<UNetBlock> in_blocks_, out_blocks_;
   ResW mid_res1_, mid_res2_; STW mid_st_;

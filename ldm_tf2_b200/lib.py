@@ -22,7 +22,7 @@ class LdmConfig(C.Structure):
         ("ae_kind", C.c_int32), ("latent_channels", C.c_int32), ("ae_channels", C.c_int32),
         ("ae_num_blocks", C.c_int32), ("ae_num_multipliers", C.c_int32), ("ae_multipliers", C.c_int32 * 8),
         ("ae_num_attention_resolutions", C.c_int32), ("ae_attention_resolutions", C.c_int32 * 8),
-        ("vq_vocab_size", C.c_int32), ("ae_build_latent_hw", C.c_int32),
+        ("vq_vocab_size", C.c_int32), ("ae_build_latent_hw", C.c_int32), ("precision", C.c_int32),
     ]
 
 
@@ -107,8 +107,12 @@ def f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+PRECISIONS = {"bf16": 0, "fp16": 1}
+DEFAULT_PRECISION = "fp16"
+
+
 def make_config(cond_stage_model: dict, unet: dict, autoencoder: dict, ae_kind: str,
-                ae_build_latent_hw: int = 32) -> LdmConfig:
+                ae_build_latent_hw: int = 32, precision: str = None) -> LdmConfig:
     """Maps the all_in_one_config.yaml sections (:57-102) to the flat C struct."""
     c = LdmConfig()
     t = cond_stage_model
@@ -147,6 +151,7 @@ def make_config(cond_stage_model: dict, unet: dict, autoencoder: dict, ae_kind: 
         c.ae_attention_resolutions[i] = r
     c.vq_vocab_size = a.get("vocab_size", 16384)
     c.ae_build_latent_hw = ae_build_latent_hw
+    c.precision = PRECISIONS[precision or os.environ.get("LDM_B200_PRECISION", DEFAULT_PRECISION)]
     return c
 
 

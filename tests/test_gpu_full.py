@@ -10,7 +10,7 @@ from tests.util import make_handle, psnr, rel_l2, sampler_tables
 pytestmark = pytest.mark.gpu
 
 CFG = O.FULL_CONFIG
-EPS_TOL = 1e-2   # per-step eps relative L2, bf16 operands (north_star)
+EPS_TOL = 1e-2   # per-step eps relative L2, 16-bit tensor-core operands (north_star)
 PSNR_TOL = 40.0  # decoded images (north_star)
 
 

@@ -6,14 +6,15 @@ import numpy as np
 import pytest
 
 from oracle import ldm_oracle as O
-from tests.util import bf16_round, make_handle, rel_l2, sampler_tables
+from tests.util import make_handle, rel_l2, round16, sampler_tables
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def h():
-    hd = make_handle(O.TINY_CONFIG, "vq", ae_hw=8)
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def h(request):
+    hd = make_handle(O.TINY_CONFIG, "vq", ae_hw=8, precision=request.param)
+    hd.precision = request.param
     yield hd
     hd.close()
 
@@ -91,7 +92,7 @@ def test_groupnorm(h, n, hw, ca, cb, silu, eps):
     ref = O.group_norm(x.reshape(n, hw, 1, c), gamma, beta, eps).reshape(n, hw, c)
     if silu:
         ref = O.silu(ref)
-    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-3  # bf16 output rounding
+    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-3  # 16-bit output rounding
 
 
 @pytest.mark.parametrize("rows,c", [(77, 128), (1024, 320), (300, 1280)])
@@ -106,8 +107,8 @@ def test_layernorm(h, rows, c):
 
 
 # ----------------------------------------------------------------- tcgen05 GEMM engine
-def _lin_ref(a, w, bias, residual, act):
-    y = bf16_round(a).astype(np.float64) @ bf16_round(w).astype(np.float64)
+def _lin_ref(a, w, bias, residual, act, prec):
+    y = round16(a, prec).astype(np.float64) @ round16(w, prec).astype(np.float64)
     if bias is not None:
         y = y + bias
     y = y.astype(np.float32)
@@ -145,15 +146,15 @@ def test_linear(h, rows, k, n, act, use_bias, use_res, max_ctas):
     bias = rng.standard_normal(wn, dtype=np.float32) if use_bias else None
     res = rng.standard_normal((rows, n), dtype=np.float32) if use_res else None
     got = h.test_linear(a, w, bias, res, act=act, max_ctas=max_ctas)
-    ref = _lin_ref(a, w, bias, res, act)
+    ref = _lin_ref(a, w, bias, res, act, h.precision)
     err = np.abs(got - ref).max()
     assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
 
 
-def _conv_ref(x, kern, bias, sc_x=None, sc_k=None):
-    y = O.conv3x3(bf16_round(x), bf16_round(kern), np.zeros(kern.shape[-1], np.float32) if bias is None else bias)
+def _conv_ref(x, kern, bias, sc_x, sc_k, prec):
+    y = O.conv3x3(round16(x, prec), round16(kern, prec), np.zeros(kern.shape[-1], np.float32) if bias is None else bias)
     if sc_x is not None:
-        y = y + O.dense(bf16_round(sc_x), bf16_round(sc_k))
+        y = y + O.dense(round16(sc_x, prec), round16(sc_k, prec))
     return y
 
 
@@ -180,7 +181,7 @@ def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
         sc_x = rng.standard_normal((nb, hh, ww, sc), dtype=np.float32)
         sc_k = rng.standard_normal((sc, cout), dtype=np.float32) / np.float32(np.sqrt(sc))
     got = h.test_conv3x3(x, kern, bias, sc_x, sc_k)
-    ref = _conv_ref(x, kern, bias, sc_x, sc_k)
+    ref = _conv_ref(x, kern, bias, sc_x, sc_k, h.precision)
     err = np.abs(got - ref).max()
     assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
 
@@ -201,10 +202,10 @@ def test_attention(h, n, t, tk, heads, d):
     v = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
     scale = d ** -0.5
     got = h.test_attention(q, k, v, scale)
-    qb, kb, vb = bf16_round(q), bf16_round(k), bf16_round(v)
+    qb, kb, vb = (round16(a, h.precision) for a in (q, k, v))
     logits = np.einsum("nqhs,nchs->nhqc", qb, kb).astype(np.float32) * np.float32(scale)
     p = O.softmax_last(logits)
-    ref = np.einsum("nhqc,nchs->nqhs", bf16_round(p), vb).reshape(n, t, heads * d)
+    ref = np.einsum("nhqc,nchs->nqhs", round16(p, h.precision), vb).reshape(n, t, heads * d)
     err = np.abs(got - ref).max()
     assert err <= 2e-2 * max(1.0, np.abs(ref).max()), f"max abs err {err}"  # P and O are bf16
     assert rel_l2(got, ref) < 1e-2

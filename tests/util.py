@@ -12,6 +12,13 @@ def bf16_round(x):
     return u.astype(np.uint32).view(np.float32).reshape(x.shape)
 
 
+def round16(x, precision="fp16"):
+    """What a 16-bit tensor-core operand holds in the given precision mode."""
+    if precision == "bf16":
+        return bf16_round(x)
+    return np.clip(np.asarray(x, np.float32), -65504, 65504).astype(np.float16).astype(np.float32)
+
+
 def rel_l2(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
@@ -26,9 +33,10 @@ def psnr(a, b):
     return float(10 * np.log10(rng * rng / max(mse, 1e-30)))
 
 
-def make_handle(cfg, ae_kind="kl", ae_hw=32, device=0):
+def make_handle(cfg, ae_kind="kl", ae_hw=32, device=0, precision=None):
     from ldm_tf2_b200 import lib
-    c = lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_" + ae_kind], ae_kind, ae_hw)
+    c = lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_" + ae_kind], ae_kind, ae_hw,
+                        precision)
     return lib.Handle(c, device)
 
 

@@ -137,6 +137,12 @@ LDM_API int ldm_bench_unet_step(ldm_handle* h, int b, int hh, int ww, int iters,
 LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, float* gemm_ms_per_step,
                                   float* step_ms, int* gemm_launches_per_step, double* gemm_flops_per_step);
 
+/* GEMM / conv microbenchmark on zero-filled device buffers (dbg: 1 no TMA, 2 no MMA, 4 no stores). */
+LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
+                           int iters, float* avg_ms);
+/* cudaProfilerStart (on=1) / cudaProfilerStop (on=0) for `ncu --profile-from-start off`. */
+LDM_API int ldm_profiler(int on);
+
 /* Test-only hooks: one engine op on host fp32 inputs (tests/test_gpu_ops.py), and named
  * fp32 activation taps inside the UNet (block-level parity against the oracle). */
 LDM_API int ldm_debug_tap(ldm_handle* h, const char* name, float* host_buf, int64_t numel);

@@ -3,6 +3,7 @@
 #include "model.h"
 #include <cmath>
 #include <cstring>
+#include <cuda_profiler_api.h>
 
 using namespace ldm;
 
@@ -298,6 +299,66 @@ extern "C" LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int w
   if (step_ms) *step_ms = m.last_step_ms;
   if (gemm_launches_per_step) *gemm_launches_per_step = (int)((m.eng.gemm_launches - g0) / iters);
   if (gemm_flops_per_step) *gemm_flops_per_step = m.eng.prof_flops / iters;
+  API_END
+}
+
+// GEMM microbenchmark: C[rows,n] (16-bit out) = A[rows,k] W[n,k]^T on zero-filled device buffers.
+// dbg: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores.  conv=1: 3x3 conv geometry instead
+// (rows = nb*hw*hw pixels, k = cin).  Returns the average launch time (CUDA events).
+extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
+                                      int iters, float* avg_ms) {
+  API_BEGIN
+  NEED(h);
+  Engine& e = h->model->eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  const int ktot = conv ? 9 * k : k;
+  bf16 *a, *w, *o;
+  CUDA_CHECK(cudaMalloc(&a, (size_t)rows * k * 2));
+  CUDA_CHECK(cudaMalloc(&w, (size_t)n * ktot * 2));
+  CUDA_CHECK(cudaMalloc(&o, (size_t)rows * n * 2));
+  CUDA_CHECK(cudaMemset(a, 0, (size_t)rows * k * 2));
+  CUDA_CHECK(cudaMemset(w, 0, (size_t)n * ktot * 2));
+  GemmOp op;
+  op.num_a = 1;
+  int bk = 0;
+  if (conv) {
+    const int nb = rows / (hw * hw);
+    op.a[0] = view_nhwc(a, nb, hw, hw, k);
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) op.add_seg(0, ky - 1, kx - 1, 0, k, bk);
+    op.W = hw; op.H = hw; op.NB = nb;
+    op.os_x = n; op.os_y = (long long)hw * n; op.os_n = (long long)hw * hw * n;
+  } else {
+    op.a[0] = view_mat(a, rows, k, k);
+    op.add_seg(0, 0, 0, 0, k, bk);
+    op.W = rows; op.H = 1; op.NB = 1;
+    op.os_x = n;
+  }
+  op.b = view_mat(w, n, ktot, ktot);
+  op.N = n; op.block_n = block_n; op.dbg = dbg;
+  op.out_bf16 = o;
+  for (int i = 0; i < 3; ++i) e.gemm(op);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  e.sync();
+  CUDA_CHECK(cudaEventRecord(e0, e.stream));
+  for (int i = 0; i < iters; ++i) e.gemm(op);
+  CUDA_CHECK(cudaEventRecord(e1, e.stream));
+  e.sync();
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  *avg_ms = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(a); cudaFree(w); cudaFree(o);
+  API_END
+}
+
+// cudaProfilerStart/Stop so that `ncu --profile-from-start off` captures exactly one region.
+extern "C" LDM_API int ldm_profiler(int on) {
+  API_BEGIN
+  if (on) CUDA_CHECK(cudaProfilerStart());
+  else CUDA_CHECK(cudaProfilerStop());
   API_END
 }
 

@@ -165,12 +165,13 @@ void Engine::gemm(const GemmOp& op) {
   const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
   const int a_bytes_full = GEMM_BM * GEMM_BK * 2;  // smem slot for A is always 16 KB
   const int slot = a_bytes_full + bn * GEMM_BK * 2;
-  int stages = (GEMM_SMEM_BYTES - 2048) / slot;
+  int stages = (GEMM_SMEM_BYTES - 3072) / slot;  // 2 KB control block + 1 KB alignment slack
   if (stages > 8) stages = 8;
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
   p.tx_bytes = stage_bytes;
   p.fp16 = fp16;
+  p.dbg = op.dbg;
   // ---- epilogue
   p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
   p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;
@@ -192,7 +193,7 @@ void Engine::gemm(const GemmOp& op) {
   const int total_tiles = m_tiles * p.n_tiles;
   int ctas = max_ctas > 0 ? max_ctas : num_sms;
   if (ctas > total_tiles) ctas = total_tiles;
-  const int smem = stages * slot + (2 * stages + 4) * 8 + 16 + 1024;
+  const int smem = stages * slot + 2048 + 1024;
   LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile) {

@@ -39,6 +39,7 @@ struct GemmOp {
   int n_boundary = 0;               // tiles must not straddle multiples of this (0 = none)
   int num_phases = 1;
   int b_mode = B_PLAIN;
+  int dbg = 0;
   const float* bias = nullptr;
   const float* bias2 = nullptr;
   int bias2_stride = 0;

@@ -54,6 +54,7 @@ struct GemmParams {
   int stages;
   int box_rows;             // rows actually loaded per A tile (<= 128)
   int tx_bytes;             // bytes both TMA loads of a stage deliver
+  int dbg;                  // microbenchmark switches: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
   int b_swap;
@@ -99,34 +100,35 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
+// One chunk of CH accumulator columns of one output row: bias (from smem) / per-image bias,
+// activation, residual, stores.  v[] holds alpha-scaled accumulators on entry.
 template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* acc, const float* gate,
-                                               int col0, bool row_ok, long long row_off, int img,
-                                               int xq, long long tr_row_off, const float* bias2_row) {
-  // acc[CH]: accumulator values for output columns col0 .. col0+CH-1 (already alpha-scaled).
-  float v[CH];
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float* v, const float* bias_s, int tc0, int col0,
+                                               bool row_ok, long long row_off, int xq, long long tr_row_off,
+                                               const float* bias2_row) {
 #pragma unroll
-  for (int j = 0; j < CH; ++j) {
-    int col = col0 + j;
-    float x = acc[j];
-    if (col < p.N) {
-      if (p.act == ACT_GEGLU) {
-        // value/gate biases are interleaved like the weights: handled by caller via bias ptrs
-      }
-      if (p.bias) x += __ldg(p.bias + col);
-      if (bias2_row) x += __ldg(bias2_row + col);
-      if (p.act == ACT_SILU) x = silu_f(x);
-      else if (p.act == ACT_GELU) x = gelu_erf_f(x);
-    }
-    v[j] = x;
+  for (int j = 0; j < CH; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + tc0 + j);
+    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
   }
-  (void)gate;
+  if (bias2_row) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (col0 + j < p.N) v[j] += __ldg(bias2_row + col0 + j);
+  }
+  if (p.act == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = silu_f(v[j]);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = gelu_erf_f(v[j]);
+  }
   if (!row_ok) return;
   const bool full = (col0 + CH <= p.N);
   if (p.out_tr && col0 >= p.tr_col0) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      int col = col0 + j;
+      const int col = col0 + j;
       if (col < p.N) store16(p.out_tr + tr_row_off + (long long)(col - p.tr_col0) * p.ts_c + xq, v[j], p.fp16);
     }
     return;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     if (full && ((off & 3) == 0)) {
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
-        float4 r = *reinterpret_cast<const float4*>(p.residual + off + j);
+        const float4 r = *reinterpret_cast<const float4*>(p.residual + off + j);
         v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
       }
     } else {
@@ -173,23 +175,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
         if (col0 + j < p.N) store16(p.out_bf16 + off + j, v[j], p.fp16);
     }
   }
-  (void)img;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; barriers after.
+  // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; control block after.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = GEMM_BM * GEMM_BK * 2;
   const int b_bytes = p.block_n * GEMM_BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
   const int stages = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* ctrl = smem + (size_t)stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,99 +219,130 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_a0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int py = t.phase >> 1, px = t.phase & 1;
-        int bz0 = 0, bz1 = 0;
-        if (p.b_mode == B_BATCH) { bz0 = t.y0; bz1 = t.img0; }
-        else if (p.b_mode == B_PHASE) { bz0 = t.phase; }
-        for (int s = 0; s < p.num_segs; ++s) {
-          const GemmSeg sg = p.segs[s];
-          const int dy = sg.dy + (p.num_phases > 1 ? py : 0);
-          const int dx = sg.dx + (p.num_phases > 1 ? px : 0);
-          for (int kb = 0; kb < sg.nkb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            uint8_t* sb = sa + a_bytes;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)p.tx_bytes);
-            const int ax = t.x0 + dx, ay = t.y0 + dy;
-            if (p.a_swap[sg.map])
-              tma_load_4d(sa, &p.amap[sg.map], &full_bar[stage], sg.c0 + kb * GEMM_BK, ay, ax, t.img0);
-            else
-              tma_load_4d(sa, &p.amap[sg.map], &full_bar[stage], sg.c0 + kb * GEMM_BK, ax, ay, t.img0);
-            if (p.b_swap)
-              tma_load_4d(sb, &p.bmap, &full_bar[stage], sg.bk0 + kb * GEMM_BK, bz0, t.n0, bz1);
-            else
-              tma_load_4d(sb, &p.bmap, &full_bar[stage], sg.bk0 + kb * GEMM_BK, t.n0, bz0, bz1);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+    // ------------------------------------------------ TMA producer: the whole warp runs the
+    // loop (warp-uniform control flow, addresses stay in uniform registers); one elected lane
+    // issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int py = t.phase >> 1, px = t.phase & 1;
+      int bz0 = 0, bz1 = 0;
+      if (p.b_mode == B_BATCH) { bz0 = t.y0; bz1 = t.img0; }
+      else if (p.b_mode == B_PHASE) { bz0 = t.phase; }
+      const int b1 = p.b_swap ? bz0 : t.n0, b2 = p.b_swap ? t.n0 : bz0;
+      for (int s = 0; s < p.num_segs; ++s) {
+        const GemmSeg sg = p.segs[s];
+        const int ax = t.x0 + sg.dx + (p.num_phases > 1 ? px : 0);
+        const int ay = t.y0 + sg.dy + (p.num_phases > 1 ? py : 0);
+        const int a1 = p.a_swap[sg.map] ? ay : ax, a2 = p.a_swap[sg.map] ? ax : ay;
+        const void* amap = &p.amap[sg.map];
+        int ca = sg.c0, cb = sg.bk0;
+        for (int kb = 0; kb < sg.nkb; ++kb) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = full0 + stage * 8;
+            if (p.dbg & 1) {
+              mbar_arrive_a(fb);
+            } else {
+              const uint32_t sa = smem_a0 + stage * stage_bytes;
+              mbar_expect_tx_a(fb, (uint32_t)p.tx_bytes);
+              tma_load_4d_a(sa, amap, fb, ca, a1, a2, t.img0);
+              tma_load_4d_a(sa + a_bytes, &p.bmap, fb, cb, b1, b2, bz1);
+            }
           }
+          __syncwarp();
+          ca += GEMM_BK;
+          cb += GEMM_BK;
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(GEMM_BM, (uint32_t)p.block_n, p.fp16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // ------------------------------------------------ MMA issuer: warp-uniform loop, one
+    // elected lane issues the four K=16 UMMAs of a k-block and the commit.
+    const uint32_t idesc = umma_idesc_16(GEMM_BM, (uint32_t)p.block_n, p.fp16);
+    const uint64_t da0 = umma_desc_sw128(smem_a0);
+    const uint64_t db0 = umma_desc_sw128(smem_a0 + a_bytes);
+    const uint32_t dstep = (uint32_t)(stage_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait_a(tempty0 + as * 8, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      for (int kb = 0; kb < p.total_kb; ++kb) {
+        mbar_wait_a(full0 + stage * 8, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-        for (int kb = 0; kb < p.total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sb);
+        if (elect_one()) {
+          if (!(p.dbg & 2)) {
+            const uint64_t da = da0 + (uint64_t)(dstep * (uint32_t)stage);
+            const uint64_t db = db0 + (uint64_t)(dstep * (uint32_t)stage);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in 16-B units
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advance 16 elements = 32 B inside the 128-B swizzle atom: +2 in 16-B units
+              umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          umma_commit_a(empty0 + stage * 8);
+          if (kb == p.total_kb - 1) umma_commit_a(tfull0 + as * 8);
         }
-        umma_commit(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     // ------------------------------------------------ epilogue warps 2..5
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
     int as = 0;
     uint32_t aphase = 0;
     const int hw_b = p.h_b * p.w_b;
+    const bool geglu = p.act == ACT_GEGLU;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int py = t.phase >> 1, px = t.phase & 1;
       const int img = t.img0 + r / hw_b;
       const int yq = t.y0 + (r % hw_b) / p.w_b;
       const int xq = t.x0 + r % p.w_b;
-      const bool row_ok = (r < p.box_rows) && (img < p.NB) && (yq < p.H) && (xq < p.W);
+      const bool row_ok = (r < p.box_rows) && (img < p.NB) && (yq < p.H) && (xq < p.W) && !(p.dbg & 4);
       const long long row_off = (long long)img * p.os_n + (long long)yq * p.os_y + (long long)xq * p.os_x +
                                 (long long)py * p.os_phase_y + (long long)px * p.os_phase_x;
       const long long tr_row_off = (long long)img * p.ts_n + (long long)yq * p.ts_y;
-      const float* bias2_row = nullptr;
+      const float* bias2_row = nullptr;   // per-thread path only when the row index depends on img
+      const float* bias2_tile = nullptr;  // folded into the smem bias vector otherwise
       if (p.bias2) {
-        long long row2 = (p.bias2_by_img ? img : 0) + (p.step_ptr ? __ldg(p.step_ptr) : 0);
-        bias2_row = p.bias2 + row2 * p.bias2_stride;
+        const long long step = p.step_ptr ? __ldg(p.step_ptr) : 0;
+        if (p.bias2_by_img) bias2_row = p.bias2 + ((long long)img + step) * p.bias2_stride;
+        else bias2_tile = p.bias2 + step * p.bias2_stride;
       }
-      mbar_wait(&tfull_bar[as], aphase);
+      // stage this tile's bias columns in smem (previous tile's readers are past the barrier below)
+      named_bar_sync(1, 128);
+      for (int c = et; c < p.block_n; c += 128) {
+        // bias / bias2 are indexed by B row (= output column, or packed GEGLU row)
+        const int col = t.n0 + c;
+        const int lim = geglu ? 2 * p.N : p.N;
+        float b = 0.f;
+        if (col < lim) {
+          if (p.bias) b += __ldg(p.bias + col);
+          if (bias2_tile) b += __ldg(bias2_tile + col);
+        }
+        bias_s[c] = b;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
-      if (p.act == ACT_GEGLU) {
+      if (geglu) {
         // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates
         const int half = p.block_n >> 1;
         for (int c = 0; c < half; c += 16) {
@@ -320,12 +354,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           const int oc0 = t.n_tile * half + c;  // output column
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(rv[j]) * p.alpha;
-            float g = __uint_as_float(rg[j]) * p.alpha;
-            if (p.bias) {
-              a += __ldg(p.bias + t.n0 + c + j);
-              g += __ldg(p.bias + t.n0 + half + c + j);
-            }
+            const float a = __uint_as_float(rv[j]) * p.alpha + bias_s[c + j];
+            const float g = __uint_as_float(rg[j]) * p.alpha + bias_s[half + c + j];
             v[j] = a * gelu_erf_f(g);
           }
           if (row_ok) {
@@ -353,19 +383,29 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       } else {
-        for (int c = 0; c < p.block_n; c += 16) {
+        int c = 0;
+        for (; c + 32 <= p.block_n; c += 32) {
+          uint32_t rr[32];
+          tmem_ld_x32(t_base + (uint32_t)c, rr);
+          tmem_ld_wait();
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
+          epilogue_chunk<32>(p, acc, bias_s, c, t.n0 + c, row_ok, row_off, xq, tr_row_off, bias2_row);
+        }
+        for (; c < p.block_n; c += 16) {
           uint32_t rr[16];
           tmem_ld_x16(t_base + (uint32_t)c, rr);
           tmem_ld_wait();
           float acc[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
-          epilogue_chunk<16>(p, acc, nullptr, t.n0 + c, row_ok, row_off, img, xq, tr_row_off, bias2_row);
+          epilogue_chunk<16>(p, acc, bias_s, c, t.n0 + c, row_ok, row_off, xq, tr_row_off, bias2_row);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive_a(tempty0 + as * 8);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }

@@ -337,13 +337,15 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.b = view_mat(w, n, ktot, ktot);
   op.N = n; op.block_n = block_n; op.dbg = dbg;
   op.out_bf16 = o;
+  h->model->ensure_arena((size_t)512 << 20);
+  e.arena.reset();
   for (int i = 0; i < 3; ++i) e.gemm(op);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   e.sync();
   CUDA_CHECK(cudaEventRecord(e0, e.stream));
-  for (int i = 0; i < iters; ++i) e.gemm(op);
+  for (int i = 0; i < iters; ++i) { e.arena.reset(); e.gemm(op); }
   CUDA_CHECK(cudaEventRecord(e1, e.stream));
   e.sync();
   float ms = 0;
@@ -458,6 +460,8 @@ LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const
   op.W = rows; op.H = 1; op.NB = 1;
   op.N = n; op.gemm_n = wn; op.block_n = bn;
   op.bias = bias_d; op.act = act; op.residual = res_d; op.out_f32 = out_d; op.os_x = n;
+  h->model->ensure_arena((size_t)256 << 20);
+  e.arena.reset();
   const int saved = e.max_ctas;
   e.max_ctas = max_ctas;
   try { e.gemm(op); } catch (...) { e.max_ctas = saved; throw; }
@@ -503,6 +507,8 @@ LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel,
     op.add_seg(1, 0, 0, 0, sc_cin, bk);
     op.num_a = 2;
   }
+  h->model->ensure_arena((size_t)256 << 20);
+  e.arena.reset();
   op.W = ww; op.H = hh; op.NB = nb; op.N = cout;
   op.bias = bias_d; op.out_f32 = out_d;
   op.os_x = cout; op.os_y = (long long)ww * cout; op.os_n = (long long)hh * ww * cout;
@@ -559,10 +565,10 @@ LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const flo
   float* b = xb ? up_f32(s, e, xb, (size_t)n * hw * cb) : nullptr;
   float* g = up_f32(s, e, gamma, c);
   float* bt = up_f32(s, e, beta, c);
-  float* mr = s.get<float>((size_t)n * 64);
+  double* mr = s.get<double>((size_t)n * 64, true);
   bf16* ob = s.get<bf16>((size_t)n * hw * c);
-  launch_gn_stats(a, ca, b, cb, n, hw, eps, mr, e.stream);
-  launch_gn_apply(a, ca, b, cb, n, hw, mr, g, bt, silu, ob, e.fp16, e.stream);
+  launch_gn_stats(a, ca, b, cb, n, hw, mr, e.stream);
+  launch_gn_apply(a, ca, b, cb, n, hw, mr, eps, g, bt, silu, ob, e.fp16, e.stream);
   std::vector<uint16_t> raw((size_t)n * hw * c);
   CUDA_CHECK(cudaMemcpyAsync(raw.data(), ob, raw.size() * 2, cudaMemcpyDefault, e.stream));
   e.sync();

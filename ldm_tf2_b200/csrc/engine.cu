@@ -144,7 +144,29 @@ void Engine::gemm(const GemmOp& op) {
   // ---- N tiling
   const bool geglu = op.act == ACT_GEGLU;
   const int gemm_n = op.gemm_n ? op.gemm_n : (geglu ? 2 * op.N : op.N);
-  int bn = op.block_n ? op.block_n : choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu);
+  // K extent first: split-K decisions need it
+  int total_kb = 0;
+  for (int i = 0; i < op.num_segs; ++i) total_kb += op.segs[i].nkb;
+  int bn = op.block_n;
+  int splits = 1;
+  const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1;
+  if (can_split && !bn) {
+    // few output tiles and a long K loop (low-resolution convs, text encoder): take the widest
+    // tile that divides N and spread the K loop over the idle SMs
+    int wide = 0;
+    for (int cand : {256, 192, 160, 128, 96, 80, 64})
+      if (gemm_n % cand == 0 && (!op.n_boundary || op.n_boundary % cand == 0)) { wide = cand; break; }
+    if (wide) {
+      const int tiles = m_tiles * (gemm_n / wide);
+      if (tiles * 2 <= num_sms && total_kb >= 8) {
+        int sp = op.splits > 1 ? op.splits : num_sms / tiles;
+        if (sp > total_kb / 4) sp = total_kb / 4;
+        if (sp > 32) sp = 32;
+        if (sp >= 2) { splits = sp; bn = wide; }
+      }
+    }
+  }
+  if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu);
   LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 32 == 0), "gemm: bad block_n %d", bn);
   p.block_n = bn;
   p.n_tiles = (gemm_n + bn - 1) / bn;
@@ -153,13 +175,19 @@ void Engine::gemm(const GemmOp& op) {
   p.b_mode = op.b_mode;
   // ---- K segments
   p.num_segs = op.num_segs;
-  int total_kb = 0;
   for (int i = 0; i < op.num_segs; ++i) {
     p.segs[i] = op.segs[i];
     LDM_CHECK(op.segs[i].map >= 0 && op.segs[i].map < op.num_a, "gemm: segment map index");
-    total_kb += op.segs[i].nkb;
   }
   p.total_kb = total_kb;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.splits = splits;
+  const long long rows_total = (long long)op.NB * op.H * op.W;
+  if (splits > 1) {
+    p.ws_split_stride = rows_total * op.N;
+    p.ws = alloc<float>((size_t)splits * rows_total * op.N);
+  }
   LDM_CHECK(total_kb >= 1, "gemm: empty K loop");
   // ---- pipeline depth from the shared-memory budget
   const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
@@ -179,7 +207,7 @@ void Engine::gemm(const GemmOp& op) {
   p.os_n = op.os_n; p.os_y = op.os_y; p.os_x = op.os_x; p.os_phase_y = op.os_phase_y; p.os_phase_x = op.os_phase_x;
   p.out_tr = op.out_tr; p.tr_col0 = op.tr_col0; p.ts_n = op.ts_n; p.ts_y = op.ts_y; p.ts_c = op.ts_c;
   LDM_CHECK(op.out_f32 || op.out_bf16 || op.out_tr, "gemm: no output");
-  launches++;
+  launches += splits > 1 ? 2 : 1;
   gemm_launches++;
   if (dry) return;
   // ---- tensor maps
@@ -190,7 +218,7 @@ void Engine::gemm(const GemmOp& op) {
   }
   encode_map(&p.bmap, op.b, bn, 1, 1);
   p.b_swap = op.b.swap_xy ? 1 : 0;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = m_tiles * p.n_tiles * splits;
   int ctas = max_ctas > 0 ? max_ctas : num_sms;
   if (ctas > total_tiles) ctas = total_tiles;
   const int smem = stages * slot + 2048 + 1024;
@@ -208,6 +236,65 @@ void Engine::gemm(const GemmOp& op) {
     prof_events.push_back({e0, e1});
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
+  if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);
+}
+
+// Sums the split-K partial tiles and applies the GEMM epilogue (bias, per-image / per-step bias,
+// activation, fp32 residual, fp32 / 16-bit stores with the op's output strides).
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, long long split_stride, int splits, long long rows,
+                                       int N, int W, int H, const float* __restrict__ bias,
+                                       const float* __restrict__ bias2, int bias2_stride, int bias2_by_img,
+                                       const int* __restrict__ step_ptr, int act, const float* residual,
+                                       float* out_f32, bf16* out_bf16, long long os_n, long long os_y, long long os_x,
+                                       int fp16) {
+  const int n4 = (N + 3) >> 2;
+  const long long total = rows * n4;
+  const long long step = (bias2 && step_ptr) ? __ldg(step_ptr) : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / n4;
+    const int col = (int)(i % n4) * 4;
+    const int x = (int)(row % W);
+    const int y = (int)((row / W) % H);
+    const int img = (int)(row / ((long long)W * H));
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec = (col + 4 <= N) && ((N & 3) == 0);
+    for (int s = 0; s < splits; ++s) {
+      const float* src = ws + (long long)s * split_stride + row * N + col;
+      if (vec) {
+        const float4 t = *reinterpret_cast<const float4*>(src);
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) v[j] += src[j];
+      }
+    }
+    const float* b2 = bias2 ? bias2 + ((bias2_by_img ? img : 0) + step) * bias2_stride : nullptr;
+    const long long off = (long long)img * os_n + (long long)y * os_y + (long long)x * os_x + col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (col + j >= N) continue;
+      float t = v[j];
+      if (bias) t += __ldg(bias + col + j);
+      if (b2) t += __ldg(b2 + col + j);
+      if (act == ACT_SILU) t = silu_f(t);
+      else if (act == ACT_GELU) t = gelu_erf_f(t);
+      if (residual) t += residual[off + j];
+      if (out_f32) out_f32[off + j] = t;
+      if (out_bf16) store16(out_bf16 + off + j, t, fp16);
+    }
+  }
+}
+
+void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cudaStream_t st) {
+  const long long total = rows * ((p.N + 3) / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_finalize_kernel<<<(int)blocks, 256, 0, st>>>(p.ws, p.ws_split_stride, splits, rows, p.N, p.W, p.H, p.bias,
+                                                     p.bias2, p.bias2_stride, p.bias2_by_img, p.step_ptr, p.act,
+                                                     p.residual, p.out_f32, p.out_bf16, p.os_n, p.os_y, p.os_x,
+                                                     p.fp16);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 float Engine::collect_profile_ms() {

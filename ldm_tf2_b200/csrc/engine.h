@@ -40,6 +40,7 @@ struct GemmOp {
   int num_phases = 1;
   int b_mode = B_PLAIN;
   int dbg = 0;
+  int splits = 0;   // 0 = choose automatically, 1 = never split K
   const float* bias = nullptr;
   const float* bias2 = nullptr;
   int bias2_stride = 0;
@@ -109,5 +110,6 @@ class Engine {
 };
 
 int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu);
+void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cudaStream_t st);
 
 }  // namespace ldm

@@ -54,6 +54,11 @@ struct GemmParams {
   int stages;
   int box_rows;             // rows actually loaded per A tile (<= 128)
   int tx_bytes;             // bytes both TMA loads of a stage deliver
+  // split-K: `splits` CTAs share one output tile, each reducing kb_per_split k-blocks into the
+  // fp32 workspace ws[split][row][N]; splitk_finalize_kernel applies the epilogue.
+  int splits, kb_per_split;
+  float* ws;
+  long long ws_split_stride;
   int dbg;                  // microbenchmark switches: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
@@ -80,11 +85,14 @@ struct GemmParams {
 #if defined(__CUDACC__) && defined(LDM_GEMM_IMPL)
 
 struct TileCoord {
-  int img0, y0, x0, n0, phase, n_tile;
+  int img0, y0, x0, n0, phase, n_tile, split;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
   TileCoord t;
+  const int base_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases;
+  t.split = tile / base_tiles;
+  tile -= t.split * base_tiles;
   t.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
   int tx = m % p.tiles_x;
@@ -196,7 +204,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -236,14 +244,18 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (p.b_mode == B_BATCH) { bz0 = t.y0; bz1 = t.img0; }
       else if (p.b_mode == B_PHASE) { bz0 = t.phase; }
       const int b1 = p.b_swap ? bz0 : t.n0, b2 = p.b_swap ? t.n0 : bz0;
-      for (int s = 0; s < p.num_segs; ++s) {
+      const int kb_begin = t.split * p.kb_per_split;
+      const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+      int s = 0, kin = kb_begin;
+      while (kin >= p.segs[s].nkb) { kin -= p.segs[s].nkb; ++s; }
+      for (int gk = kb_begin; gk < kb_end; ++s, kin = 0) {
         const GemmSeg sg = p.segs[s];
         const int ax = t.x0 + sg.dx + (p.num_phases > 1 ? px : 0);
         const int ay = t.y0 + sg.dy + (p.num_phases > 1 ? py : 0);
         const int a1 = p.a_swap[sg.map] ? ay : ax, a2 = p.a_swap[sg.map] ? ax : ay;
         const void* amap = &p.amap[sg.map];
-        int ca = sg.c0, cb = sg.bk0;
-        for (int kb = 0; kb < sg.nkb; ++kb) {
+        int ca = sg.c0 + kin * GEMM_BK, cb = sg.bk0 + kin * GEMM_BK;
+        for (; kin < sg.nkb && gk < kb_end; ++kin, ++gk) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
           if (elect_one()) {
             const uint32_t fb = full0 + stage * 8;
@@ -278,7 +290,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait_a(tempty0 + as * 8, aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-      for (int kb = 0; kb < p.total_kb; ++kb) {
+      const int split = tile / (total_tiles / p.splits);
+      const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
         tc_fence_after();
         if (elect_one()) {
@@ -292,7 +306,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             }
           }
           umma_commit_a(empty0 + stage * 8);
-          if (kb == p.total_kb - 1) umma_commit_a(tfull0 + as * 8);
+          if (kb == nkb - 1) umma_commit_a(tfull0 + as * 8);
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -342,7 +356,29 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
-      if (geglu) {
+      if (p.splits > 1) {
+        // raw fp32 partial sums -> workspace; the finalize kernel applies the epilogue
+        const long long rlin = ((long long)img * p.H + yq) * p.W + xq;
+        float* wrow = p.ws + (long long)t.split * p.ws_split_stride + rlin * p.N;
+        for (int c = 0; c < p.block_n; c += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(t_base + (uint32_t)c, rr);
+          tmem_ld_wait();
+          const int col0 = t.n0 + c;
+          if (row_ok) {
+            if (col0 + 16 <= p.N && ((p.N & 3) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(wrow + col0 + j) =
+                    make_float4(__uint_as_float(rr[j]) * p.alpha, __uint_as_float(rr[j + 1]) * p.alpha,
+                                __uint_as_float(rr[j + 2]) * p.alpha, __uint_as_float(rr[j + 3]) * p.alpha);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) wrow[col0 + j] = __uint_as_float(rr[j]) * p.alpha;
+            }
+          }
+        }
+      } else if (geglu) {
         // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates
         const int half = p.block_n >> 1;
         for (int c = 0; c < half; c += 16) {

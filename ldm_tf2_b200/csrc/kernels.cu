@@ -73,125 +73,201 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st) {
 }
 
 // =====================================================================================
-// K2: GroupNorm statistics.  One CTA per (sample, group); two passes (mean, then centred
-// second moment) like Keras' moments; the second pass hits L2.  Group channels are
-// contiguous (cg = C/32).  Handles the virtual concat [a | b] along C.
+// K2: GroupNorm(32).  Stats: one pass, fully coalesced.  A CTA owns a strip of pixels of one
+// image; thread <-> (pixel lane, channel quad) so every thread keeps fixed channels: float4
+// loads, fp32 running (sum, sumsq) per channel in registers over a short chain, then one
+// double-precision shared/global accumulation per (sample, group) -- the E[x^2]-E[x]^2
+// cancellation happens in double.  stats[n][32][2] (double) must be zero on entry.
+// Apply: same mapping; mean/rstd per group derived once per CTA, gamma/beta live in registers.
+// Handles the virtual concat [a | b] along C (unet.py:135).  HBM/L2-bound: 1 read (+1 write).
 // =====================================================================================
-__device__ __forceinline__ float block_sum(float v, float* sh) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+__global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
+                                int strip, double* __restrict__ stats) {
+  __shared__ double s_acc[64];
+  const int c = ca + cb, c4 = c >> 2, cg = c / 32;
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * strip;
+  const int pix1 = min(hw, pix0 + strip);
+  const int lanes = blockDim.x / c4;  // pixel lanes
+  const int q = threadIdx.x % c4, pl = threadIdx.x / c4;
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
-  if (l == 0) sh[w] = v;
+  if (pl < lanes) {
+    const int ch = q * 4;
+    const float* src;
+    int cs, co;
+    if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
+    else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
+      ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+    // the 4 channels of a quad fall in at most 2 groups
+    const int g0 = ch / cg, g3 = (ch + 3) / cg;
+    if (g0 == g3) {
+      atomicAdd(&s_acc[g0 * 2], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+      atomicAdd(&s_acc[g0 * 2 + 1], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = (ch + k) / cg;
+        atomicAdd(&s_acc[g * 2], (double)s[k]);
+        atomicAdd(&s_acc[g * 2 + 1], (double)ss[k]);
+      }
+    }
+  }
   __syncthreads();
-  float t = (l < nw) ? sh[l] : 0.f;
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  return t;
+  if (threadIdx.x < 64) atomicAdd(&stats[(long long)n * 64 + threadIdx.x], s_acc[threadIdx.x]);
 }
 
-__global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
-                                int hw, float eps, float* __restrict__ out) {
-  __shared__ float sh[32];
-  const int c = ca + cb, cg = c / 32;
-  const int n = blockIdx.x / 32, g = blockIdx.x % 32;
-  const long long count = (long long)hw * cg;
-  const float* pa = a + (long long)n * hw * ca;
-  const float* pb = b ? b + (long long)n * hw * cb : nullptr;
-  float s = 0.f;
-  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
-    const int pix = (int)(i / cg), ch = g * cg + (int)(i % cg);
-    s += (ch < ca) ? pa[(long long)pix * ca + ch] : pb[(long long)pix * cb + (ch - ca)];
-  }
-  const float mean = block_sum(s, sh) / (float)count;
-  float q = 0.f;
-  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
-    const int pix = (int)(i / cg), ch = g * cg + (int)(i % cg);
-    const float v = ((ch < ca) ? pa[(long long)pix * ca + ch] : pb[(long long)pix * cb + (ch - ca)]) - mean;
-    q += v * v;
-  }
-  const float var = block_sum(q, sh) / (float)count;
-  if (threadIdx.x == 0) {
-    out[blockIdx.x * 2 + 0] = mean;
-    out[blockIdx.x * 2 + 1] = rsqrtf(var + eps);
-  }
+static void gn_launch_shape(int c, int hw, int n, int* threads, int* strip, int* strips) {
+  const int c4 = c / 4;
+  int lanes = 256 / c4;
+  if (lanes < 1) lanes = 1;
+  int t = c4 * lanes;
+  *threads = (t + 31) / 32 * 32;
+  // enough CTAs to fill the chip (~4 per SM over the batch) but at least 8 pixels per lane
+  int want = (148 * 4 + n - 1) / n;
+  int st = (hw + want - 1) / want;
+  const int min_strip = lanes * 8;
+  if (st < min_strip) st = min_strip;
+  if (st > hw) st = hw;
+  *strip = st;
+  *strips = (hw + st - 1) / st;
 }
 
-void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, float eps,
-                     float* mean_rstd, cudaStream_t st) {
-  LDM_CHECK((ca + cb) % 32 == 0, "GroupNorm(32): channels %d not a multiple of 32", ca + cb);
-  const long long count = (long long)hw * ((ca + cb) / 32);
-  int threads = count >= 4096 ? 512 : (count >= 1024 ? 256 : 128);
-  gn_stats_kernel<<<n * 32, threads, 0, st>>>(a, ca, b, cb, hw, eps, mean_rstd);
+void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, double* stats,
+                     cudaStream_t st) {
+  const int c = ca + cb;
+  LDM_CHECK(c % 32 == 0 && ca % 4 == 0 && cb % 4 == 0, "GroupNorm(32): bad channel counts %d+%d", ca, cb);
+  LDM_CHECK(c / 4 <= 1024, "GroupNorm: too many channels");
+  int threads, strip, strips;
+  gn_launch_shape(c, hw, n, &threads, &strip, &strips);
+  gn_stats_kernel<<<dim3(strips, n), threads, 0, st>>>(a, ca, b, cb, hw, strip, stats);
   CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
-                                int hw, const float* __restrict__ mr, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int do_silu, bf16* __restrict__ out,
-                                long long total4, int fp16) {
-  const int c = ca + cb, cg = c / 32, c4 = c / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c4) * 4;
-    const long long pixg = i / c4;  // global pixel index n*hw + pix
-    const int n = (int)(pixg / hw);
-    float4 v;
-    if (ch < ca) v = *reinterpret_cast<const float4*>(a + pixg * ca + ch);
-    else v = *reinterpret_cast<const float4*>(b + pixg * cb + (ch - ca));
-    float x[4] = {v.x, v.y, v.z, v.w};
+__global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
+                                int strip, const double* __restrict__ stats, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                                bf16* __restrict__ out, int fp16) {
+  __shared__ float s_mr[64];
+  const int c = ca + cb, c4 = c >> 2, cg = c / 32;
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * strip;
+  const int pix1 = min(hw, pix0 + strip);
+  const int lanes = blockDim.x / c4;
+  const int q = threadIdx.x % c4, pl = threadIdx.x / c4;
+  if (threadIdx.x < 32) {
+    const double cnt = (double)hw * cg;
+    const double mean = stats[(long long)n * 64 + threadIdx.x * 2] / cnt;
+    double var = stats[(long long)n * 64 + threadIdx.x * 2 + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mr[threadIdx.x * 2] = (float)mean;
+    s_mr[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (pl >= lanes) return;
+  const int ch = q * 4;
+  const float* src;
+  int cs, co;
+  if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
+  else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
+  float sc[4], sh[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = (ch + k) / cg;
-      const float mean = __ldg(mr + (n * 32 + g) * 2), rstd = __ldg(mr + (n * 32 + g) * 2 + 1);
-      float y = (x[k] - mean) * rstd * __ldg(gamma + ch + k) + __ldg(beta + ch + k);
-      if (do_silu) y = silu_f(y);
-      x[k] = y;
+  for (int k = 0; k < 4; ++k) {
+    const int g = (ch + k) / cg;
+    const float mean = s_mr[g * 2], rstd = s_mr[g * 2 + 1];
+    sc[k] = rstd * __ldg(gamma + ch + k);
+    sh[k] = __ldg(beta + ch + k) - mean * sc[k];
+  }
+  bf16* dst = out + (long long)n * hw * c + ch;
+  for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+    const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+    float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+    if (do_silu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = silu_f(y[k]);
     }
     uint2 u;
-    u.x = pack16(x[0], x[1], fp16);
-    u.y = pack16(x[2], x[3], fp16);
-    *reinterpret_cast<uint2*>(out + pixg * c + ch) = u;
+    u.x = pack16(y[0], y[1], fp16);
+    u.y = pack16(y[2], y[3], fp16);
+    *reinterpret_cast<uint2*>(dst + (long long)pix * c) = u;
   }
 }
 
-void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const float* mean_rstd,
+void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const double* stats, float eps,
                      const float* gamma, const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st) {
-  LDM_CHECK(ca % 4 == 0 && cb % 4 == 0, "gn_apply: channel counts must be multiples of 4");
-  const long long total4 = (long long)n * hw * (ca + cb) / 4;
-  gn_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(a, ca, b, cb, hw, mean_rstd, gamma, beta, do_silu,
-                                                        out, total4, fp16);
+  const int c = ca + cb;
+  int threads, strip, strips;
+  gn_launch_shape(c, hw, n, &threads, &strip, &strips);
+  gn_apply_kernel<<<dim3(strips, n), threads, 0, st>>>(a, ca, b, cb, hw, strip, stats, eps, gamma, beta, do_silu, out,
+                                                      fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
 // =====================================================================================
-// LayerNorm: one warp per row, two-pass in fp32, row re-read from L1/L2.
+// LayerNorm: one warp per row; the row lives in registers (one global read), two-pass
+// statistics in fp32.  Rows up to 2560 channels.
 // =====================================================================================
+constexpr int LN_MAXQ = 20;  // float4 per lane
+
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int c, float eps,
                                  bf16* __restrict__ ob, float* __restrict__ of, int fp16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (long long)row * c;
+  const int c4 = c >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * c);
+  float4 v[LN_MAXQ];
   float s = 0.f;
-  for (int i = lane; i < c; i += 32) s += xr[i];
+#pragma unroll
+  for (int i = 0; i < LN_MAXQ; ++i) {
+    const int qi = lane + i * 32;
+    if (qi < c4) {
+      v[i] = xr[qi];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)c;
-  float q = 0.f;
-  for (int i = lane; i < c; i += 32) {
-    const float d = xr[i] - mean;
-    q += d * d;
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXQ; ++i) {
+    const int qi = lane + i * 32;
+    if (qi < c4) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      qq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+    }
   }
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)c + eps);
-  for (int i = lane; i < c; i += 32) {
-    const float y = (xr[i] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
-    if (ob) store16(ob + (long long)row * c + i, y, fp16);
-    if (of) of[(long long)row * c + i] = y;
+  for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  const float rstd = rsqrtf(qq / (float)c + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXQ; ++i) {
+    const int qi = lane + i * 32;
+    if (qi < c4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + qi);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + qi);
+      const float y0 = (v[i].x - mean) * rstd * g.x + bt.x, y1 = (v[i].y - mean) * rstd * g.y + bt.y;
+      const float y2 = (v[i].z - mean) * rstd * g.z + bt.z, y3 = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (ob) {
+        uint2 u;
+        u.x = pack16(y0, y1, fp16);
+        u.y = pack16(y2, y3, fp16);
+        *reinterpret_cast<uint2*>(ob + (long long)row * c + qi * 4) = u;
+      }
+      if (of) *reinterpret_cast<float4*>(of + (long long)row * c + qi * 4) = make_float4(y0, y1, y2, y3);
+    }
   }
 }
 
 void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
                       bf16* out_bf16, float* out_f32, int fp16, cudaStream_t st) {
+  LDM_CHECK(c % 4 == 0 && c / 4 <= 32 * LN_MAXQ, "layernorm: unsupported width %d", c);
   const int wpb = 8;
   layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16);
   CUDA_CHECK(cudaGetLastError());

@@ -17,11 +17,12 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st);
 
 // ---- K2: GroupNorm(32) statistics + apply (unet.py:374,377,354; autoencoder.py:31,33,68) --
 // Input is fp32 NHWC, optionally the virtual concat of two tensors along C (unet.py:135).
-void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, float eps,
-                     float* mean_rstd /*[n][32][2]*/, cudaStream_t st);
-void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw,
-                     const float* mean_rstd, const float* gamma, const float* beta, int do_silu,
-                     bf16* out, int fp16, cudaStream_t st);
+// stats[n][32][2] = per (sample, group) {sum, sum of squares} in double; zero on entry.
+void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, double* stats,
+                     cudaStream_t st);
+void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const double* stats,
+                     float eps, const float* gamma, const float* beta, int do_silu, bf16* out, int fp16,
+                     cudaStream_t st);
 
 // ---- LayerNorm over the last axis (unet.py:304-306, transformer.py:165,170,209) --------
 void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,

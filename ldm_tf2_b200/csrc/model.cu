@@ -461,12 +461,13 @@ Act Model::alloc_act(int n, int h, int w, int c, bool f, bool b) {
 void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out) {
   const int cb = skip ? skip->c : 0;
   LDM_CHECK(x.c + cb == g.c, "GroupNorm channel mismatch %d+%d vs %d", x.c, cb, g.c);
-  float* mr = eng.alloc<float>((size_t)x.n * 64);
-  eng.launches += 2;
+  double* st = eng.alloc<double>((size_t)x.n * 64);
+  eng.launches += 3;
   if (eng.dry) return;
-  launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, g.eps, mr, eng.stream);
-  launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, mr, g.gamma->f32, g.beta->f32, silu ? 1 : 0,
-                  out, eng.fp16, eng.stream);
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)x.n * 64 * sizeof(double), eng.stream));
+  launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, eng.stream);
+  launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
+                  silu ? 1 : 0, out, eng.fp16, eng.stream);
 }
 
 void Model::linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,

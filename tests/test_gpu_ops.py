@@ -137,6 +137,8 @@ def _lin_ref(a, w, bias, residual, act, prec):
     (256, 1152, 3, 0, True, True, 0),       # decoder conv_out-like: N = 3 (unaligned rows)
     (512, 320, 1280, 3, True, False, 0),    # GEGLU (w has 2n columns)
     (2048, 1280, 5120, 3, True, False, 0),  # GEGLU, many tiles
+    (64, 5120, 1280, 0, True, True, 0),     # split-K: one M tile, 80 k-blocks, bias + residual in the finalize
+    (200, 2560, 640, 1, True, False, 0),    # split-K with SiLU applied after the reduction
 ])
 def test_linear(h, rows, k, n, act, use_bias, use_res, max_ctas):
     rng = np.random.default_rng(rows * 7 + k + n)
@@ -170,6 +172,8 @@ def _conv_ref(x, kern, bias, sc_x, sc_k, prec):
     (1, 256, 256, 32, 3, 0),     # half a row per tile, N = 3 (decoder conv_out)
     (2, 32, 32, 320, 320, 0),    # UNet level-0 conv: K = 2880
     (2, 16, 16, 64, 128, 192),   # conv + folded shortcut Dense over another tensor
+    (4, 4, 4, 1280, 320, 0),     # low-resolution level: few tiles, K = 11520 -> split-K + finalize
+    (3, 8, 8, 640, 256, 320),    # split-K with a folded shortcut segment
 ])
 def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
     rng = np.random.default_rng(nb * 1000 + hh + cin + cout)

@@ -152,7 +152,7 @@ LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel,
                              const float* sc_x, const float* sc_kernel, int nb, int hh, int ww, int cin,
                              int cout, int sc_cin, float* out);
 LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, const float* v, int n, int t,
-                               int tk, int heads, int d, float scale, float* out);
+                               int tk, int heads, int d, float scale, int unfused, float* out);
 LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const float* xb, int cb,
                                const float* gamma, const float* beta, int n, int hw, float eps, int silu,
                                float* out);

@@ -520,10 +520,12 @@ LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel,
 
 // softmax(q k^T scale) v; q [n,t,heads,d], k,v [n,tk,heads,d] -> out [n,t,heads*d]
 LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, const float* v, int n, int t, int tk,
-                               int heads, int d, float scale, float* out) {
+                               int heads, int d, float scale, int unfused, float* out) {
   API_BEGIN
   NEED(h);
   Model& m = *h->model;
+  struct Restore { Model& m; bool v; ~Restore() { m.force_unfused_attention = v; } } restore{m, m.force_unfused_attention};
+  m.force_unfused_attention = unfused != 0;
   Engine& e = m.eng;
   CUDA_CHECK(cudaSetDevice(e.device));
   Scratch s;

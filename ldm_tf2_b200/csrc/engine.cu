@@ -53,6 +53,8 @@ Engine::Engine(int dev) : device(dev) {
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
   CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GEMM_SMEM_BYTES));
 }
 
 Engine::~Engine() {
@@ -160,8 +162,8 @@ void Engine::gemm(const GemmOp& op) {
       const int tiles = m_tiles * (gemm_n / wide);
       if (tiles * 2 <= num_sms && total_kb >= 8) {
         int sp = op.splits > 1 ? op.splits : num_sms / tiles;
-        if (sp > total_kb / 4) sp = total_kb / 4;
-        if (sp > 32) sp = 32;
+        if (sp > total_kb / 12) sp = total_kb / 12;  // >= 12 k-blocks per split: workspace traffic stays
+        if (sp > 8) sp = 8;                          // below the weight traffic it parallelises
         if (sp >= 2) { splits = sp; bn = wide; }
       }
     }
@@ -237,6 +239,43 @@ void Engine::gemm(const GemmOp& op) {
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);
+}
+
+void Engine::attention(const AttnOp& op) {
+  LDM_CHECK(attention_supported(op.d), "fused attention supports head dims up to 192 (got %d)", op.d);
+  LDM_CHECK(op.tk >= 1 && op.t >= 1 && op.tpad >= op.tk && op.tpad % 8 == 0, "attention: bad key length");
+  AttnParams p;
+  memset(&p, 0, sizeof p);
+  p.n = op.n; p.t = op.t; p.tk = op.tk; p.heads = op.heads; p.d = op.d;
+  p.dp_atoms = (op.d + 63) / 64;
+  p.dv = (op.d + 15) / 16 * 16;
+  p.q_tiles = (op.t + ATT_BM - 1) / ATT_BM;
+  p.kv_tiles = (op.tk + ATT_BN - 1) / ATT_BN;
+  p.scale_log2 = op.scale * 1.4426950408889634f;
+  p.o = op.o; p.o_ld = op.o_ld; p.fp16 = fp16;
+  const int atom = ATT_BM * 128;
+  const int q_bytes = p.dp_atoms * atom, kv_bytes = p.dp_atoms * atom + 2 * p.dv * 128, p_bytes = 2 * atom;
+  const int ctrl = 1024 + 1024;
+  p.kv_stages = 2; p.p_bufs = 2;
+  auto need = [&]() { return q_bytes + p.kv_stages * kv_bytes + p.p_bufs * p_bytes + ctrl; };
+  if (need() > GEMM_SMEM_BYTES || p.kv_tiles == 1) p.kv_stages = 1;
+  if (need() > GEMM_SMEM_BYTES || p.kv_tiles == 1) p.p_bufs = 1;
+  LDM_CHECK(need() <= GEMM_SMEM_BYTES, "attention: tile does not fit shared memory");
+  launches++;
+  attn_launches++;
+  if (dry) return;
+  AView q; q.ptr = op.q; q.C = op.d; q.W = op.t; q.H = op.heads; q.NB = op.n; q.sx = op.q_ld; q.sy = op.d;
+  q.sn = (long long)op.t * op.q_ld; q.swap_xy = true;
+  AView k; k.ptr = op.k; k.C = op.d; k.W = op.tk; k.H = op.heads; k.NB = op.n; k.sx = op.k_ld; k.sy = op.d;
+  k.sn = op.k_sn; k.swap_xy = true;
+  AView v; v.ptr = op.vt; v.C = op.tpad; v.W = op.d; v.H = op.heads; v.NB = op.n; v.sx = op.tpad;
+  v.sy = (long long)op.d * op.tpad; v.sn = (long long)op.heads * op.d * op.tpad;
+  encode_map(&p.qmap, q, ATT_BM, 1, 1);
+  encode_map(&p.kmap, k, ATT_BN, 1, 1);
+  encode_map(&p.vmap, v, p.dv, 1, 1);
+  const int grid = op.n * op.heads * p.q_tiles;
+  flash_attention_kernel<<<grid, ATT_THREADS, need(), stream>>>(p);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 // Sums the split-K partial tiles and applies the GEMM epilogue (bias, per-image / per-step bias,

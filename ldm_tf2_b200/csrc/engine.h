@@ -4,6 +4,7 @@
 #include <vector>
 #include "common.cuh"
 #include "gemm.cuh"
+#include "attn.cuh"
 
 namespace ldm {
 
@@ -65,6 +66,16 @@ struct GemmOp {
   }
 };
 
+// softmax(q k^T * scale) v for all (image, head) pairs, fused (attn.cuh)
+struct AttnOp {
+  const bf16* q = nullptr; long long q_ld = 0;                  // [n, t, heads, d], row stride q_ld
+  const bf16* k = nullptr; long long k_ld = 0, k_sn = 0;        // [n, tk, heads, d], row / image strides
+  const bf16* vt = nullptr; int tpad = 0;                       // [n, heads, d, tpad]
+  int n = 0, t = 0, tk = 0, heads = 0, d = 0;
+  float scale = 1.f;
+  bf16* o = nullptr; long long o_ld = 0;                        // [n, t, heads*d]
+};
+
 class Arena {
  public:
   void init(size_t cap);
@@ -101,6 +112,9 @@ class Engine {
   float collect_profile_ms();  // syncs, sums and clears the recorded intervals
 
   void gemm(const GemmOp& op);
+  static bool attention_supported(int d) { return d <= 192; }
+  void attention(const AttnOp& op);
+  long long attn_launches = 0;
   template <typename T> T* alloc(size_t n) { return reinterpret_cast<T*>(arena.alloc(n * sizeof(T))); }
   void sync();
 

@@ -99,6 +99,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float
     if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
     else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
     for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
       const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
@@ -185,6 +186,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
     sh[k] = __ldg(beta + ch + k) - mean * sc[k];
   }
   bf16* dst = out + (long long)n * hw * c + ch;
+#pragma unroll 8
   for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
     const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
     float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
@@ -215,6 +217,7 @@ void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int 
 // =====================================================================================
 constexpr int LN_MAXQ = 20;  // float4 per lane
 
+template <int NQ>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int c, float eps,
                                  bf16* __restrict__ ob, float* __restrict__ of, int fp16) {
@@ -223,10 +226,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   if (row >= rows) return;
   const int c4 = c >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * c);
-  float4 v[LN_MAXQ];
+  float4 v[NQ];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXQ; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qi = lane + i * 32;
     if (qi < c4) {
       v[i] = xr[qi];
@@ -237,7 +240,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   const float mean = s / (float)c;
   float qq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXQ; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qi = lane + i * 32;
     if (qi < c4) {
       const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
@@ -247,7 +250,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
   const float rstd = rsqrtf(qq / (float)c + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAXQ; ++i) {
+  for (int i = 0; i < NQ; ++i) {
     const int qi = lane + i * 32;
     if (qi < c4) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + qi);
@@ -269,7 +272,16 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, int
                       bf16* out_bf16, float* out_f32, int fp16, cudaStream_t st) {
   LDM_CHECK(c % 4 == 0 && c / 4 <= 32 * LN_MAXQ, "layernorm: unsupported width %d", c);
   const int wpb = 8;
-  layernorm_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16);
+  const int nq = (c / 4 + 31) / 32;
+  const dim3 grid(cdiv(rows, wpb)), block(wpb * 32);
+#define LN_CASE(N) layernorm_kernel<N><<<grid, block, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16)
+  if (nq <= 1) LN_CASE(1);
+  else if (nq <= 2) LN_CASE(2);
+  else if (nq <= 3) LN_CASE(3);
+  else if (nq <= 5) LN_CASE(5);
+  else if (nq <= 10) LN_CASE(10);
+  else LN_CASE(LN_MAXQ);
+#undef LN_CASE
   CUDA_CHECK(cudaGetLastError());
 }
 

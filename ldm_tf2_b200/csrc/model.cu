@@ -580,6 +580,15 @@ Act Model::resblock(const ResW& r, const Act& x, const Act* skip) {
 void Model::attention_core(const bf16* q, long long q_ld, const bf16* k, long long k_ld, long long k_sn, int tk,
                            const bf16* vt, int tpad, int n, int t, int heads, int d, float scale, bf16* o,
                            long long o_ld) {
+  if (Engine::attention_supported(d) && !force_unfused_attention) {
+    AttnOp op;
+    op.q = q; op.q_ld = q_ld; op.k = k; op.k_ld = k_ld; op.k_sn = k_sn; op.vt = vt; op.tpad = tpad;
+    op.n = n; op.t = t; op.tk = tk; op.heads = heads; op.d = d; op.scale = scale; op.o = o; op.o_ld = o_ld;
+    eng.attention(op);
+    return;
+  }
+  // head dims beyond the fused kernel (autoencoder AttentionBlock, d = 512): two batched tcgen05
+  // GEMMs around a row softmax
   const size_t mk = eng.arena.mark();
   float* S = eng.alloc<float>((size_t)n * heads * t * tpad);
   bf16* P = eng.alloc<bf16>((size_t)n * heads * t * tpad);

@@ -104,6 +104,7 @@ class Model {
   void set_weight(int model, int index, const float* host_or_dev, const int* shape, int ndim);
   void finalize_weights();
   bool finalized = false;
+  bool force_unfused_attention = false;  // test hook: use the GEMM + softmax + GEMM path
 
   // ---- text encoder (transformer.py:254-272)
   void encode_text(const long long* ids_host, int rows, float* ctx_out /*host or device*/);

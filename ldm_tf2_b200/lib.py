@@ -57,7 +57,7 @@ _PROTOS = {
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
-    "ldm_test_attention": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
+    "ldm_test_attention": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P], _I),
     "ldm_test_groupnorm": ([_P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P], _I),
     "ldm_test_layernorm": ([_P, _P, _P, _P, _I, _I, _F, _P], _I),
 }
@@ -342,13 +342,13 @@ class Handle:
                                         nb, hh, ww, cin, cout, sc_cin, ptr(out)))
         return out
 
-    def test_attention(self, q, k, v, scale):
+    def test_attention(self, q, k, v, scale, unfused=False):
         q, k, v = f32(q), f32(k), f32(v)
         n, t, heads, d = q.shape
         tk = k.shape[1]
         out = np.empty((n, t, heads * d), np.float32)
         check(self.lib.ldm_test_attention(self._h, ptr(q), ptr(k), ptr(v), n, t, tk, heads, d, float(scale),
-                                          ptr(out)))
+                                          int(unfused), ptr(out)))
         return out
 
     def test_groupnorm(self, xa, gamma, beta, eps, silu, xb=None):

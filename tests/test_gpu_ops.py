@@ -197,15 +197,18 @@ def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
     (2, 256, 77, 8, 80),     # cross attention, Tk = 77 padded to 80
     (1, 1024, 1024, 8, 40),  # UNet level 0 self attention, d = 40 (zero-filled to 64)
     (2, 16, 16, 8, 160),     # middle block
-    (1, 1024, 1024, 1, 512), # autoencoder attention, one head of 512
+    (1, 1024, 1024, 1, 512), # autoencoder attention, one head of 512 (always the unfused path)
+    (2, 300, 200, 8, 64),    # ragged query and key tiles
+    (1, 4096, 4096, 2, 40),  # 64x64 latents: 32 key tiles per query tile
 ])
-def test_attention(h, n, t, tk, heads, d):
+@pytest.mark.parametrize("unfused", [False, True])
+def test_attention(h, n, t, tk, heads, d, unfused):
     rng = np.random.default_rng(t * 3 + tk + d)
     q = rng.standard_normal((n, t, heads, d), dtype=np.float32)
     k = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
     v = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
     scale = d ** -0.5
-    got = h.test_attention(q, k, v, scale)
+    got = h.test_attention(q, k, v, scale, unfused=unfused)
     qb, kb, vb = (round16(a, h.precision) for a in (q, k, v))
     logits = np.einsum("nqhs,nchs->nhqc", qb, kb).astype(np.float32) * np.float32(scale)
     p = O.softmax_last(logits)

@@ -14,8 +14,10 @@
 //   Q  [n, t,  heads, d]  A of S     (head dim padded to a multiple of 64 by TMA zero fill)
 //   K  [n, tk, heads, d]  B of S
 //   Vt [n, heads, d, tpad] B of PV   (V transposed by the projection GEMM's epilogue)
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax + epilogue (one TMEM lane
-// quadrant each; thread = one query row).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax + epilogue: warp w owns TMEM lane
+// quadrant w%4 (32 query rows) and key-column half (w-2)/4 of every tile, so each scheduler has
+// two softmax warps to hide TMEM-load and MUFU latency; row max / row sum are combined through
+// shared memory.
 #pragma once
 #include "common.cuh"
 
@@ -23,7 +25,7 @@ namespace ldm {
 
 constexpr int ATT_BM = 128;   // queries per CTA
 constexpr int ATT_BN = 128;   // keys per tile
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;  // producer + MMA + 8 softmax warps (two column halves per row)
 
 struct AttnParams {
   CUtensorMap qmap, kmap, vmap;
@@ -42,7 +44,7 @@ struct AttnParams {
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // not volatile: let the scheduler batch MUFU ops
   return y;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -64,9 +66,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   uint8_t* p_s = v_s + p.kv_stages * v_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + p.p_bufs * p_bytes);
   // barrier indices
-  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13,
-         P_EMPTY = 15, O_FULL = 17, NBARS = 18 };
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 9, V_FULL = 17, V_EMPTY = 25, S_FULL = 33, S_EMPTY = 35, P_FULL = 37,
+         P_EMPTY = 39, O_FULL = 41, NBARS = 42 };  // K/V rings: up to 8 stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+  float* red_s = reinterpret_cast<float*>(bars + NBARS + 2);  // [2][128] max / sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cta = blockIdx.x;
@@ -75,14 +78,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   const int head = cta % p.heads;
   const int img = cta / p.heads;
   const int q0 = qt * ATT_BM;
+  pdl_launch();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.qmap);
     tma_prefetch_desc(&p.kmap);
     tma_prefetch_desc(&p.vmap);
     for (int i = 0; i < NBARS; ++i) {
-      const bool four = (i >= S_EMPTY && i < S_EMPTY + 2) || (i >= P_FULL && i < P_FULL + 2);
-      mbar_init(&bars[i], four ? 4 : 1);
+      const bool soft = (i >= S_EMPTY && i < S_EMPTY + 2) || (i >= P_FULL && i < P_FULL + 2);
+      mbar_init(&bars[i], soft ? 8 : 1);
     }
     mbar_fence_init();
   }
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), p_a = smem_u32(p_s);
@@ -109,14 +114,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
     uint32_t kph = 0, vph = 0;
     for (int pass = 0; pass < 2; ++pass) {
       for (int j = 0; j < p.kv_tiles; ++j) {
-        mbar_wait_a(bar(K_EMPTY + ks), kph ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx_a(bar(K_FULL + ks), (uint32_t)k_bytes);
-          for (int a = 0; a < p.dp_atoms; ++a)
-            tma_load_4d_a(k_a + ks * k_bytes + a * atom, &p.kmap, bar(K_FULL + ks), a * 64, head, j * ATT_BN, img);
+        if (pass == 0 || p.kv_tiles > 1) {   // a single key tile is multiplied once and kept in registers
+          mbar_wait_a(bar(K_EMPTY + ks), kph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(bar(K_FULL + ks), (uint32_t)k_bytes);
+            for (int a = 0; a < p.dp_atoms; ++a)
+              tma_load_4d_a(k_a + ks * k_bytes + a * atom, &p.kmap, bar(K_FULL + ks), a * 64, head, j * ATT_BN, img);
+          }
+          __syncwarp();
+          if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
         }
-        __syncwarp();
-        if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
         if (pass == 1) {
           mbar_wait_a(bar(V_EMPTY + vs), vph ^ 1);
           if (elect_one()) {
@@ -158,8 +165,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
       if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
       if (++sb == 2) { sb = 0; sph ^= 1; }
     };
+    const bool single = p.kv_tiles == 1;
     for (int j = 0; j < p.kv_tiles; ++j) issue_s();  // pass 1
-    issue_s();                                        // pass 2, tile 0
+    if (!single) issue_s();                           // pass 2, tile 0
     for (int j = 0; j < p.kv_tiles; ++j) {
       if (j + 1 < p.kv_tiles) issue_s();              // next tile's logits overlap this tile's softmax
       mbar_wait_a(bar(P_FULL + pb), pph);
@@ -182,78 +190,112 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   } else {
     // ---------------------------------------------------------------- softmax + epilogue
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;     // key columns [64*half, 64*half+64) of every tile
     const int r = quad * 32 + lane;       // query row of this thread inside the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int cbase = half * 64;
     int sb = 0, pb = 0;
     uint32_t sph = 0, pph = 0;
     float m = -INFINITY;
-    // pass 1: row max over the valid keys
-    for (int j = 0; j < p.kv_tiles; ++j) {
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t ra[32], rb[32];
+    const bool single = p.kv_tiles == 1;
+    // this warp's 64 logits of S buffer sb -> registers, then the buffer is released
+    auto load_release = [&]() {
       mbar_wait_a(bar(S_FULL + sb), sph);
       tc_fence_after();
-      const int kbase = j * ATT_BN;
-      for (int c = 0; c < ATT_BN; c += 32) {
-        if (kbase + c >= p.tk) break;
-        uint32_t rr[32];
-        tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + c), rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c + i < p.tk) m = fmaxf(m, __uint_as_float(rr[i]));
-      }
+      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + cbase), ra);
+      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + cbase + 32), rb);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar(S_EMPTY + sb));
       if (++sb == 2) { sb = 0; sph ^= 1; }
-    }
-    const float ms = m * p.scale_log2;
-    float l = 0.f;
-    // pass 2: P = exp2(S*scale*log2e - ms), written as the 16-bit A operand of the PV product
-    for (int j = 0; j < p.kv_tiles; ++j) {
-      mbar_wait_a(bar(S_FULL + sb), sph);
-      mbar_wait_a(bar(P_EMPTY + pb), pph ^ 1);
-      tc_fence_after();
-      const int kbase = j * ATT_BN;
-      uint8_t* prow = p_s + pb * p_bytes + r * 128;
-      for (int c = 0; c < ATT_BN; c += 32) {
-        uint32_t rr[32];
-        tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + c), rr);
-        tmem_ld_wait();
-        uint32_t pk[16];
+    };
+    auto tile_max = [&](int k0) {
+      if (k0 >= p.tk) return;
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      if (k0 + 64 <= p.tk) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (kbase + c + i < p.tk) p0 = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms));
-          if (kbase + c + i + 1 < p.tk) p1 = ex2_approx(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -ms));
-          l += p0 + p1;
-          pk[i >> 1] = pack16(p0, p1, p.fp16);
+          m0 = fmaxf(m0, __uint_as_float(ra[i]));
+          m1 = fmaxf(m1, __uint_as_float(ra[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(rb[i]));
+          m3 = fmaxf(m3, __uint_as_float(rb[i + 1]));
         }
-        // 32 keys = four 16-byte chunks of this row's 128-byte line in atom (c / 64)
-        uint8_t* arow = prow + (c >> 6) * atom;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (k0 + i < p.tk) m0 = fmaxf(m0, __uint_as_float(ra[i]));
+          if (k0 + 32 + i < p.tk) m2 = fmaxf(m2, __uint_as_float(rb[i]));
+        }
+      }
+      m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+    };
+    // P = exp2(S*scale*log2e - ms) for this warp's 64 keys = one 64-key swizzle atom (index = half)
+    auto emit_p = [&](int k0, float ms) {
+      mbar_wait_a(bar(P_EMPTY + pb), pph ^ 1);
+      uint8_t* arow = p_s + pb * p_bytes + half * atom + r * 128;
+      const bool fullt = (k0 + 64 <= p.tk);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t* rr = hh ? rb : ra;
+        uint32_t pk[16];
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(e[i]);
+        if (!fullt) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k0 + hh * 32 + i >= p.tk) e[i] = 0.f;
+        }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+          pk[i >> 1] = pack16(e[i], e[i + 1], p.fp16);
+          pk[(i >> 1) + 1] = pack16(e[i + 2], e[i + 3], p.fp16);
+        }
+        l0 += s0 + s1;
+        l1 += s2 + s3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 63) >> 3) + q;       // 0..7 inside the atom row
+          const int chunk = hh * 4 + q;                // 16-byte chunk 0..7 of this row's 128-byte line
           const int pos = chunk ^ (r & 7);             // 128-byte swizzle
           *reinterpret_cast<uint4*>(arow + pos * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
-      tc_fence_before();
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_a(bar(S_EMPTY + sb));
-        mbar_arrive_a(bar(P_FULL + pb));
-      }
-      if (++sb == 2) { sb = 0; sph ^= 1; }
+      if (lane == 0) mbar_arrive_a(bar(P_FULL + pb));
       if (++pb == p.p_bufs) { pb = 0; pph ^= 1; }
+    };
+    // pass 1: row max over the valid keys
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      load_release();
+      tile_max(j * ATT_BN + cbase);
     }
-    // epilogue: O / l -> 16-bit [n, t, heads*d]
+    red_s[half * 128 + r] = m;
+    named_bar_sync(1, 256);
+    m = fmaxf(red_s[r], red_s[128 + r]);
+    named_bar_sync(1, 256);
+    const float ms = m * p.scale_log2;
+    // pass 2 (a single key tile is still in registers: no second QK^T)
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      if (!single) load_release();
+      emit_p(j * ATT_BN + cbase, ms);
+    }
+    red_s[half * 128 + r] = l0 + l1;
+    named_bar_sync(1, 256);
+    const float inv = 1.0f / (red_s[r] + red_s[128 + r]);
+    // epilogue: O / l -> 16-bit [n, t, heads*d]; the two halves take alternate 16-column chunks
     mbar_wait_a(bar(O_FULL), 0);
     tc_fence_after();
-    const float inv = 1.0f / l;
     const int row = q0 + r;
     bf16* orow = p.o + ((long long)img * p.t + row) * p.o_ld + (long long)head * p.d;
-    for (int c = 0; c < p.dv; c += 16) {
+    for (int c = half * 16; c < p.dv; c += 32) {
       uint32_t rr[16];
       tmem_ld_x16(lane_base + (uint32_t)(256 + c), rr);
       tmem_ld_wait();

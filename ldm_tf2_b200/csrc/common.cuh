@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <stdexcept>
 
@@ -45,8 +47,34 @@ inline std::string fmt(const char* f, ...) {
 // precision mode (Engine::fp16); only the conversion helpers below care.
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch: every hot-path kernel is launched with the stream-serialization
+// attribute, calls pdl_launch() first (its successor may start its prologue as soon as all of
+// this grid's CTAs are resident) and pdl_wait() before touching any global data (blocks until the
+// predecessor grid has completed and flushed).  Without the attribute both are no-ops.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl_on = [] { const char* e = getenv("LDM_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_on;  // opt-in: see DESIGN.md (measured neutral)
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+#endif
+
 // ---------------------------------------------------------------- device PTX
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -256,7 +284,14 @@ __device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
   return __bfloat16_as_ushort(__float2bfloat16(v));
 }
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
-  return (uint32_t)cvt16(a, fp16) | ((uint32_t)cvt16(b, fp16) << 16);
+  if (fp16) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 __device__ __forceinline__ void store16(bf16* p, float v, int fp16) {
   *reinterpret_cast<uint16_t*>(p) = cvt16(v, fp16);

@@ -2,6 +2,7 @@
 #define LDM_GEMM_IMPL
 #include "engine.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace ldm {
 
@@ -195,13 +196,17 @@ void Engine::gemm(const GemmOp& op) {
   const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
   const int a_bytes_full = GEMM_BM * GEMM_BK * 2;  // smem slot for A is always 16 KB
   const int slot = a_bytes_full + bn * GEMM_BK * 2;
-  int stages = (GEMM_SMEM_BYTES - 3072) / slot;  // 2 KB control block + 1 KB alignment slack
+  int stages = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - 1024) / slot;  // control block + 1 KB alignment slack
   if (stages > 8) stages = 8;
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
   p.tx_bytes = stage_bytes;
   p.fp16 = fp16;
   p.dbg = op.dbg;
+  p.epi_vec = ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 3) == 0 &&
+              (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
+              (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
+              (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 7) == 0);
   // ---- epilogue
   p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
   p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;
@@ -223,7 +228,7 @@ void Engine::gemm(const GemmOp& op) {
   const int total_tiles = m_tiles * p.n_tiles * splits;
   int ctas = max_ctas > 0 ? max_ctas : num_sms;
   if (ctas > total_tiles) ctas = total_tiles;
-  const int smem = stages * slot + 2048 + 1024;
+  const int smem = stages * slot + GEMM_CTRL_BYTES + 1024;
   LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile) {
@@ -231,11 +236,13 @@ void Engine::gemm(const GemmOp& op) {
     CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream));
   }
-  implicit_gemm_kernel<<<ctas, GEMM_THREADS, smem, stream>>>(p);
+  launch_pdl(implicit_gemm_kernel, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
   CUDA_CHECK(cudaGetLastError());
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
     prof_events.push_back({e0, e1});
+    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d", rows_total * op.num_phases, gemm_n,
+                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act));
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);
@@ -256,10 +263,13 @@ void Engine::attention(const AttnOp& op) {
   const int atom = ATT_BM * 128;
   const int q_bytes = p.dp_atoms * atom, kv_bytes = p.dp_atoms * atom + 2 * p.dv * 128, p_bytes = 2 * atom;
   const int ctrl = 1024 + 1024;
-  p.kv_stages = 2; p.p_bufs = 2;
+  // K/V are L2-resident: the ring depth hides TMA latency, so take what shared memory allows
+  p.p_bufs = p.kv_tiles > 1 ? 2 : 1;
+  p.kv_stages = (GEMM_SMEM_BYTES - ctrl - q_bytes - p.p_bufs * p_bytes) / kv_bytes;
+  if (p.kv_stages > 8) p.kv_stages = 8;
+  if (p.kv_stages > p.kv_tiles) p.kv_stages = p.kv_tiles;
+  if (p.kv_stages < 1) { p.kv_stages = 1; p.p_bufs = 1; }
   auto need = [&]() { return q_bytes + p.kv_stages * kv_bytes + p.p_bufs * p_bytes + ctrl; };
-  if (need() > GEMM_SMEM_BYTES || p.kv_tiles == 1) p.kv_stages = 1;
-  if (need() > GEMM_SMEM_BYTES || p.kv_tiles == 1) p.p_bufs = 1;
   LDM_CHECK(need() <= GEMM_SMEM_BYTES, "attention: tile does not fit shared memory");
   launches++;
   attn_launches++;
@@ -274,7 +284,7 @@ void Engine::attention(const AttnOp& op) {
   encode_map(&p.kmap, k, ATT_BN, 1, 1);
   encode_map(&p.vmap, v, p.dv, 1, 1);
   const int grid = op.n * op.heads * p.q_tiles;
-  flash_attention_kernel<<<grid, ATT_THREADS, need(), stream>>>(p);
+  launch_pdl(flash_attention_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -286,6 +296,8 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, long long s
                                        const int* __restrict__ step_ptr, int act, const float* residual,
                                        float* out_f32, bf16* out_bf16, long long os_n, long long os_y, long long os_x,
                                        int fp16) {
+  pdl_launch();
+  pdl_wait();
   const int n4 = (N + 3) >> 2;
   const long long total = rows * n4;
   const long long step = (bias2 && step_ptr) ? __ldg(step_ptr) : 0;
@@ -329,24 +341,28 @@ void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cud
   const long long total = rows * ((p.N + 3) / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  splitk_finalize_kernel<<<(int)blocks, 256, 0, st>>>(p.ws, p.ws_split_stride, splits, rows, p.N, p.W, p.H, p.bias,
-                                                     p.bias2, p.bias2_stride, p.bias2_by_img, p.step_ptr, p.act,
-                                                     p.residual, p.out_f32, p.out_bf16, p.os_n, p.os_y, p.os_x,
-                                                     p.fp16);
+  launch_pdl(splitk_finalize_kernel, dim3((int)blocks), dim3(256), 0, st, (const float*)p.ws, p.ws_split_stride, splits,
+             rows, p.N, p.W, p.H, p.bias, p.bias2, p.bias2_stride, p.bias2_by_img, p.step_ptr, p.act,
+             (const float*)p.residual, p.out_f32, p.out_bf16, p.os_n, p.os_y, p.os_x, p.fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
 float Engine::collect_profile_ms() {
   sync();
   float total = 0.f;
+  const bool dump = getenv("LDM_B200_PROFILE_DUMP") != nullptr;
+  size_t idx = 0;
   for (auto& pr : prof_events) {
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    if (dump && idx < prof_labels.size()) fprintf(stderr, "GEMM %s us=%.1f\n", prof_labels[idx].c_str(), ms * 1e3f);
+    ++idx;
     total += ms;
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
   prof_events.clear();
+  prof_labels.clear();
   return total;
 }
 

@@ -108,6 +108,7 @@ class Engine {
   // profiling: CUDA events around every implicit-GEMM launch (eager mode only)
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<std::string> prof_labels;  // one per profiled launch (shape summary)
   double prof_flops = 0;       // 2*M*N*K of the profiled launches (incl. tile padding excluded)
   float collect_profile_ms();  // syncs, sums and clears the recorded intervals
 

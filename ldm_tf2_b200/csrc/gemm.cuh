@@ -14,7 +14,9 @@
 // GEGLU gating (unet.py:323-324), the fp32 residual add, and writes fp32 and/or bf16,
 // optionally transposed (V^T for attention).
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue: warp w owns TMEM
+// lane quadrant w%4 and every second column chunk; accumulators are transposed through a small
+// per-warp smem tile so that residual loads and output stores are full 128-bit, row-contiguous.
 // Pipelines: smem ring full/empty (TMA<->MMA) and 2 TMEM accumulator stages (MMA<->epilogue).
 #pragma once
 #include "common.cuh"
@@ -24,7 +26,9 @@ namespace ldm {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_SEGS = 12;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // producer + MMA + 8 epilogue warps
+constexpr int GEMM_EPI_PITCH = 36;    // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
+constexpr int GEMM_CTRL_BYTES = 2048 + 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // barriers, bias, staging
 constexpr int GEMM_SMEM_BYTES = 227 * 1024;
 
 enum ActKind : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };
@@ -60,6 +64,7 @@ struct GemmParams {
   float* ws;
   long long ws_split_stride;
   int dbg;                  // microbenchmark switches: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores
+  int epi_vec;              // 1: all output offsets are multiples of 4 elements -> coalesced vector epilogue
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
   int b_swap;
@@ -108,12 +113,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-// One chunk of CH accumulator columns of one output row: bias (from smem) / per-image bias,
-// activation, residual, stores.  v[] holds alpha-scaled accumulators on entry.
+// Bias / activation on one chunk of CH accumulator columns of this thread's row (registers).
 template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float* v, const float* bias_s, int tc0, int col0,
-                                               bool row_ok, long long row_off, int xq, long long tr_row_off,
-                                               const float* bias2_row) {
+__device__ __forceinline__ void epi_math(const GemmParams& p, float* v, const float* bias_s, int tc0, int col0,
+                                         const float* bias2_row) {
 #pragma unroll
   for (int j = 0; j < CH; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias_s + tc0 + j);
@@ -131,8 +134,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float* v, co
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = gelu_erf_f(v[j]);
   }
+}
+
+// Direct (thread-per-row) residual + stores: used for unaligned outputs and the transposed V^T.
+template <int CH>
+__device__ __forceinline__ void epi_store_direct(const GemmParams& p, float* v, int col0, bool row_ok, long long row_off,
+                                                 int xq, long long tr_row_off) {
   if (!row_ok) return;
-  const bool full = (col0 + CH <= p.N);
   if (p.out_tr && col0 >= p.tr_col0) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -142,47 +150,51 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float* v, co
     return;
   }
   const long long off = row_off + col0;
-  if (p.residual) {
-    if (full && ((off & 3) == 0)) {
 #pragma unroll
-      for (int j = 0; j < CH; j += 4) {
-        const float4 r = *reinterpret_cast<const float4*>(p.residual + off + j);
-        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+  for (int j = 0; j < CH; ++j) {
+    if (col0 + j < p.N) {
+      float x = v[j];
+      if (p.residual) x += p.residual[off + j];
+      if (p.out_f32) p.out_f32[off + j] = x;
+      if (p.out_bf16) store16(p.out_bf16 + off + j, x, p.fp16);
+    }
+  }
+}
+
+// Coalesced path: the warp's 32 rows x CH columns go through a padded smem tile; afterwards CH/4
+// lanes cover one row with float4, so each instruction moves whole 16*CH/4-byte row segments.
+template <int CH>
+__device__ __forceinline__ void epi_store_staged(const GemmParams& p, const float* v, int col0, float* stage,
+                                                 const long long* roff, int lane) {
+#pragma unroll
+  for (int j = 0; j < CH; j += 4)
+    *reinterpret_cast<float4*>(stage + lane * GEMM_EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+  constexpr int LPR = CH / 4;        // lanes per row
+  constexpr int RPI = 32 / LPR;      // rows per iteration
+  const int q = lane % LPR, rs = lane / LPR;
+  const int col = col0 + q * 4;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int row = it * RPI + rs;
+    const long long ro = roff[row];
+    if (ro >= 0 && col < p.N) {   // N % 4 == 0 on this path
+      float4 x = *reinterpret_cast<const float4*>(stage + row * GEMM_EPI_PITCH + q * 4);
+      const long long off = ro + col;
+      if (p.residual) {
+        const float4 r = *reinterpret_cast<const float4*>(p.residual + off);
+        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (col0 + j < p.N) v[j] += p.residual[off + j];
-    }
-  }
-  if (p.out_f32) {
-    if (full && ((off & 3) == 0)) {
-#pragma unroll
-      for (int j = 0; j < CH; j += 4)
-        *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (col0 + j < p.N) p.out_f32[off + j] = v[j];
-    }
-  }
-  if (p.out_bf16) {
-    if (full && ((off & 7) == 0)) {
-#pragma unroll
-      for (int j = 0; j < CH; j += 8) {
-        uint4 u;
-        u.x = pack16(v[j], v[j + 1], p.fp16);
-        u.y = pack16(v[j + 2], v[j + 3], p.fp16);
-        u.z = pack16(v[j + 4], v[j + 5], p.fp16);
-        u.w = pack16(v[j + 6], v[j + 7], p.fp16);
-        *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
+      if (p.out_bf16) {
+        uint2 u;
+        u.x = pack16(x.x, x.y, p.fp16);
+        u.y = pack16(x.z, x.w, p.fp16);
+        *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (col0 + j < p.N) store16(p.out_bf16 + off + j, v[j], p.fp16);
     }
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -201,10 +213,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
+  float* stage_all = reinterpret_cast<float*>(ctrl + 2048);                                   // 8 x [32][36] fp32
+  long long* roff_all = reinterpret_cast<long long*>(ctrl + 2048 + 8 * 32 * GEMM_EPI_PITCH * 4);  // 8 x [32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
+  pdl_launch();  // the next kernel may start its own prologue once all our CTAs are resident
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -215,7 +230,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     mbar_fence_init();
   }
@@ -226,6 +241,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();    // everything above overlapped the previous kernel's tail; global data from here on
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_a0 = smem_u32(smem);
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
@@ -314,10 +330,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ------------------------------------------------ epilogue warps 2..5
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------ epilogue warps 2..9
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // takes column chunks with (chunk index & 1) == half
+    const int ew = warp - 2;
     const int r = quad * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
+    float* stage = stage_all + ew * 32 * GEMM_EPI_PITCH;
+    long long* roff = roff_all + ew * 32;
     int as = 0;
     uint32_t aphase = 0;
     const int hw_b = p.h_b * p.w_b;
@@ -336,14 +356,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       const float* bias2_tile = nullptr;  // folded into the smem bias vector otherwise
       if (p.bias2) {
         const long long step = p.step_ptr ? __ldg(p.step_ptr) : 0;
-        if (p.bias2_by_img) bias2_row = p.bias2 + ((long long)img + step) * p.bias2_stride;
+        if (p.bias2_by_img) bias2_row = (img < p.NB) ? p.bias2 + ((long long)img + step) * p.bias2_stride : nullptr;
         else bias2_tile = p.bias2 + step * p.bias2_stride;
       }
-      // stage this tile's bias columns in smem (previous tile's readers are past the barrier below)
-      named_bar_sync(1, 128);
-      for (int c = et; c < p.block_n; c += 128) {
-        // bias / bias2 are indexed by B row (= output column, or packed GEGLU row)
-        const int col = t.n0 + c;
+      // stage this tile's bias columns and row offsets in smem (the previous tile's readers are
+      // past the first barrier)
+      named_bar_sync(1, 256);
+      for (int c = et; c < p.block_n; c += 256) {
+        const int col = t.n0 + c;        // bias / bias2 are indexed by B row (packed row for GEGLU)
         const int lim = geglu ? 2 * p.N : p.N;
         float b = 0.f;
         if (col < lim) {
@@ -352,91 +372,96 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         bias_s[c] = b;
       }
-      named_bar_sync(1, 128);
+      roff[lane] = row_ok ? row_off : -1;
+      named_bar_sync(1, 256);
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
       if (p.splits > 1) {
         // raw fp32 partial sums -> workspace; the finalize kernel applies the epilogue
         const long long rlin = ((long long)img * p.H + yq) * p.W + xq;
-        float* wrow = p.ws + (long long)t.split * p.ws_split_stride + rlin * p.N;
-        for (int c = 0; c < p.block_n; c += 16) {
+        const long long wro = (long long)t.split * p.ws_split_stride + rlin * p.N;
+        roff[lane] = row_ok ? wro : -1;
+        __syncwarp();
+        int ci = 0;
+        for (int c = 0; c < p.block_n; c += 16, ++ci) {
+          if ((ci & 1) != half) continue;
           uint32_t rr[16];
           tmem_ld_x16(t_base + (uint32_t)c, rr);
           tmem_ld_wait();
-          const int col0 = t.n0 + c;
-          if (row_ok) {
-            if (col0 + 16 <= p.N && ((p.N & 3) == 0)) {
+          float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(wrow + col0 + j) =
-                    make_float4(__uint_as_float(rr[j]) * p.alpha, __uint_as_float(rr[j + 1]) * p.alpha,
-                                __uint_as_float(rr[j + 2]) * p.alpha, __uint_as_float(rr[j + 3]) * p.alpha);
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.N) wrow[col0 + j] = __uint_as_float(rr[j]) * p.alpha;
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+          const int col0 = t.n0 + c;
+          if ((p.N & 3) == 0) {
+            // same staged store, into the workspace, without residual / 16-bit copy
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * GEMM_EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            const int q = lane & 3, rs = lane >> 2;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = it * 8 + rs;
+              const long long ro = roff[row];
+              if (ro >= 0 && col0 + q * 4 < p.N)
+                *reinterpret_cast<float4*>(p.ws + ro + col0 + q * 4) =
+                    *reinterpret_cast<const float4*>(stage + row * GEMM_EPI_PITCH + q * 4);
             }
+            __syncwarp();
+          } else if (row_ok) {
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) p.ws[wro + col0 + j] = v[j];
           }
         }
       } else if (geglu) {
         // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates
-        const int half = p.block_n >> 1;
-        for (int c = 0; c < half; c += 16) {
+        const int hcols = p.block_n >> 1;
+        int ci = 0;
+        for (int c = 0; c < hcols; c += 16, ++ci) {
+          if ((ci & 1) != half) continue;
           uint32_t rv[16], rg[16];
           tmem_ld_x16(t_base + (uint32_t)c, rv);
-          tmem_ld_x16(t_base + (uint32_t)(half + c), rg);
+          tmem_ld_x16(t_base + (uint32_t)(hcols + c), rg);
           tmem_ld_wait();
           float v[16];
-          const int oc0 = t.n_tile * half + c;  // output column
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float a = __uint_as_float(rv[j]) * p.alpha + bias_s[c + j];
-            const float g = __uint_as_float(rg[j]) * p.alpha + bias_s[half + c + j];
-            v[j] = a * gelu_erf_f(g);
+            const float gt = __uint_as_float(rg[j]) * p.alpha + bias_s[hcols + c + j];
+            v[j] = a * gelu_erf_f(gt);
           }
-          if (row_ok) {
-            const long long off = row_off + oc0;
-            if (p.out_bf16) {
-              if ((off & 7) == 0 && oc0 + 16 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                  uint4 u;
-                  u.x = pack16(v[j], v[j + 1], p.fp16);
-                  u.y = pack16(v[j + 2], v[j + 3], p.fp16);
-                  u.z = pack16(v[j + 4], v[j + 5], p.fp16);
-                  u.w = pack16(v[j + 6], v[j + 7], p.fp16);
-                  *reinterpret_cast<uint4*>(p.out_bf16 + off + j) = u;
-                }
-              } else {
-                for (int j = 0; j < 16; ++j)
-                  if (oc0 + j < p.N) store16(p.out_bf16 + off + j, v[j], p.fp16);
-              }
-            }
-            if (p.out_f32) {
-              for (int j = 0; j < 16; ++j)
-                if (oc0 + j < p.N) p.out_f32[off + j] = v[j];
-            }
-          }
+          const int oc0 = t.n_tile * hcols + c;  // output column
+          if (p.epi_vec) epi_store_staged<16>(p, v, oc0, stage, roff, lane);
+          else epi_store_direct<16>(p, v, oc0, row_ok, row_off, xq, tr_row_off);
         }
       } else {
-        int c = 0;
-        for (; c + 32 <= p.block_n; c += 32) {
+        int ci = 0, c = 0;
+        for (; c + 32 <= p.block_n; c += 32, ++ci) {
+          if ((ci & 1) != half) continue;
           uint32_t rr[32];
           tmem_ld_x32(t_base + (uint32_t)c, rr);
           tmem_ld_wait();
           float acc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
-          epilogue_chunk<32>(p, acc, bias_s, c, t.n0 + c, row_ok, row_off, xq, tr_row_off, bias2_row);
+          const int col0 = t.n0 + c;
+          epi_math<32>(p, acc, bias_s, c, col0, bias2_row);
+          if (p.epi_vec && !(p.out_tr && col0 >= p.tr_col0)) epi_store_staged<32>(p, acc, col0, stage, roff, lane);
+          else epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off);
         }
-        for (; c < p.block_n; c += 16) {
+        for (; c < p.block_n; c += 16, ++ci) {
+          if ((ci & 1) != half) continue;
           uint32_t rr[16];
           tmem_ld_x16(t_base + (uint32_t)c, rr);
           tmem_ld_wait();
           float acc[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
-          epilogue_chunk<16>(p, acc, bias_s, c, t.n0 + c, row_ok, row_off, xq, tr_row_off, bias2_row);
+          const int col0 = t.n0 + c;
+          epi_math<16>(p, acc, bias_s, c, col0, bias2_row);
+          if (p.epi_vec && !(p.out_tr && col0 >= p.tr_col0)) epi_store_staged<16>(p, acc, col0, stage, roff, lane);
+          else epi_store_direct<16>(p, acc, col0, row_ok, row_off, xq, tr_row_off);
         }
       }
       tc_fence_before();

@@ -23,6 +23,8 @@ __global__ void ddim_update_kernel(const float4* __restrict__ eps_u, const float
                                    long long noise_stride4, const float* __restrict__ coeffs, const int* __restrict__ step_ptr,
                                    int step_host, float s, int clip, float4* __restrict__ xt_out,
                                    float4* __restrict__ x0_out, long long n4) {
+  pdl_launch();
+  pdl_wait();
   const int step = step_ptr ? __ldg(step_ptr) : step_host;
   const float* c = coeffs + step * 8;
   const float c_recip = __ldg(c + 0), c_recipm1 = __ldg(c + 1), c_x0 = __ldg(c + 2), c_eps = __ldg(c + 3),
@@ -58,7 +60,7 @@ void launch_ddim_update(const float* eps2, const float* xt, const float* noise, 
   LDM_CHECK(n_per_half % 4 == 0, "ddim_update: element count must be a multiple of 4");
   const long long n4 = n_per_half / 4;
   const int threads = 256;
-  ddim_update_kernel<<<grid_for(n4, threads, 148 * 8), threads, 0, st>>>(
+  launch_pdl(ddim_update_kernel, dim3(grid_for(n4, threads, 148 * 8)), dim3(threads), 0, st, 
       reinterpret_cast<const float4*>(eps2), reinterpret_cast<const float4*>(eps2 + n_per_half),
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(noise), noise_step_stride / 4, coeffs,
       step_ptr,
@@ -66,9 +68,13 @@ void launch_ddim_update(const float* eps2, const float* xt, const float* noise, 
   CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void step_advance_kernel(int* p, int d) { *p += d; }
+__global__ void step_advance_kernel(int* p, int d) {
+  pdl_launch();
+  pdl_wait();
+  *p += d;
+}
 void launch_step_advance(int* step_ptr, int delta, cudaStream_t st) {
-  step_advance_kernel<<<1, 1, 0, st>>>(step_ptr, delta);
+  launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, st, step_ptr, delta);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -83,6 +89,8 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st) {
 // =====================================================================================
 __global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
                                 int strip, double* __restrict__ stats) {
+  pdl_launch();
+  pdl_wait();
   __shared__ double s_acc[64];
   const int c = ca + cb, c4 = c >> 2, cg = c / 32;
   const int n = blockIdx.y;
@@ -147,7 +155,7 @@ void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int 
   LDM_CHECK(c / 4 <= 1024, "GroupNorm: too many channels");
   int threads, strip, strips;
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
-  gn_stats_kernel<<<dim3(strips, n), threads, 0, st>>>(a, ca, b, cb, hw, strip, stats);
+  launch_pdl(gn_stats_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -155,6 +163,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
                                 int strip, const double* __restrict__ stats, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
                                 bf16* __restrict__ out, int fp16) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float s_mr[64];
   const int c = ca + cb, c4 = c >> 2, cg = c / 32;
   const int n = blockIdx.y;
@@ -206,7 +216,7 @@ void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int 
   const int c = ca + cb;
   int threads, strip, strips;
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
-  gn_apply_kernel<<<dim3(strips, n), threads, 0, st>>>(a, ca, b, cb, hw, strip, stats, eps, gamma, beta, do_silu, out,
+  launch_pdl(gn_apply_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, eps, gamma, beta, do_silu, out,
                                                       fp16);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -221,6 +231,8 @@ template <int NQ>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int c, float eps,
                                  bf16* __restrict__ ob, float* __restrict__ of, int fp16) {
+  pdl_launch();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -274,7 +286,7 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, int
   const int wpb = 8;
   const int nq = (c / 4 + 31) / 32;
   const dim3 grid(cdiv(rows, wpb)), block(wpb * 32);
-#define LN_CASE(N) layernorm_kernel<N><<<grid, block, 0, st>>>(x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16)
+#define LN_CASE(N) launch_pdl(layernorm_kernel<N>, dim3(grid), dim3(block), 0, st, x, gamma, beta, rows, c, eps, out_bf16, out_f32, fp16)
   if (nq <= 1) LN_CASE(1);
   else if (nq <= 2) LN_CASE(2);
   else if (nq <= 3) LN_CASE(3);
@@ -290,6 +302,8 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, int
 // =====================================================================================
 __global__ void softmax_kernel(const float* __restrict__ s, bf16* __restrict__ p, long long rows, int tk,
                                int tpad, float scale, int fp16) {
+  pdl_launch();
+  pdl_wait();
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -309,7 +323,7 @@ __global__ void softmax_kernel(const float* __restrict__ s, bf16* __restrict__ p
 void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, float scale, int fp16,
                     cudaStream_t st) {
   const int wpb = 8;
-  softmax_kernel<<<cdiv(rows, wpb), wpb * 32, 0, st>>>(s, p, rows, tk, tpad, scale, fp16);
+  launch_pdl(softmax_kernel, dim3(cdiv(rows, wpb)), dim3(wpb * 32), 0, st, s, p, rows, tk, tpad, scale, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -320,6 +334,8 @@ void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, f
 __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
                                const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
                                float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
+  pdl_launch();
+  pdl_wait();
   const int c4 = cout / 4;
   const long long total = (long long)n * h * w * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -367,7 +383,7 @@ void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* 
                     int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st) {
   LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
   const long long total = (long long)n * h * w * (cout / 4);
-  conv_in_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, nsrc, n, h, w, kernel, bias, cout, out_f32, out_bf16, fp16);
+  launch_pdl(conv_in_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32, out_bf16, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -375,6 +391,8 @@ void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* 
 // decode_first_stage scaling (model_runners.py:426) when div != 1.
 __global__ void dense4_kernel(const float4* __restrict__ x, long long rows, float div,
                               const float* __restrict__ k, const float* __restrict__ b, float4* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = x[i];
@@ -392,7 +410,7 @@ __global__ void dense4_kernel(const float4* __restrict__ x, long long rows, floa
 }
 void launch_dense4(const float* x, long long rows, float in_div, const float* kernel, const float* bias,
                    float* out, cudaStream_t st) {
-  dense4_kernel<<<grid_for(rows, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), rows, in_div, kernel,
+  launch_pdl(dense4_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(x), rows, in_div, kernel,
                                                     bias, reinterpret_cast<float4*>(out));
   CUDA_CHECK(cudaGetLastError());
 }
@@ -401,6 +419,8 @@ void launch_dense4(const float* x, long long rows, float in_div, const float* ke
 // im2col for pad(1,1) + 3x3 stride-2 VALID: out[(n,oy,ox), tap*c + ch] = x[n, 2oy+ky-1, 2ox+kx-1, ch]
 // =====================================================================================
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int n, int h, int w, int c8, uint4* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * 9 * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -422,12 +442,14 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int n, int h, int 
 void launch_im2col_s2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st) {
   LDM_CHECK(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_s2: bad shape");
   const long long total = (long long)n * (h / 2) * (w / 2) * 9 * (c / 8);
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
+  launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
                                                         reinterpret_cast<uint4*>(out));
   CUDA_CHECK(cudaGetLastError());
 }
 
 __global__ void upsample2_kernel(const uint4* __restrict__ x, int n, int h, int w, int c8, uint4* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   const long long total = (long long)n * (2 * h) * (2 * w) * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -443,7 +465,7 @@ __global__ void upsample2_kernel(const uint4* __restrict__ x, int n, int h, int 
 void launch_upsample2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st) {
   LDM_CHECK(c % 8 == 0, "upsample2: channels must be a multiple of 8");
   const long long total = (long long)n * 4 * h * w * (c / 8);
-  upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
+  launch_pdl(upsample2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(x), n, h, w, c / 8,
                                                         reinterpret_cast<uint4*>(out));
   CUDA_CHECK(cudaGetLastError());
 }
@@ -562,6 +584,8 @@ void launch_small_dense_f32(const float* x, const float* w, const float* b, int 
 
 // tensor_to_image (run_ldm_sampler.py:18-25): one CTA per image, min/max then scale.
 __global__ void tensor_to_image_kernel(const float* __restrict__ x, long long per, unsigned char* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float smin[32], smax[32];
   const float* p = x + blockIdx.x * per;
   float mn = INFINITY, mx = -INFINITY;
@@ -586,7 +610,7 @@ __global__ void tensor_to_image_kernel(const float* __restrict__ x, long long pe
   }
 }
 void launch_tensor_to_image(const float* x, int n, long long per, unsigned char* out, cudaStream_t st) {
-  tensor_to_image_kernel<<<n, 1024, 0, st>>>(x, per, out);
+  launch_pdl(tensor_to_image_kernel, dim3(n), dim3(1024), 0, st, x, per, out);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -602,6 +626,8 @@ void launch_tensor_to_image(const float* x, int n, long long per, unsigned char*
 constexpr int VQ_R = 8;
 
 __global__ void vq_code_norm_kernel(const float4* __restrict__ cb, int codes, float* __restrict__ bnorm) {
+  pdl_launch();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= codes) return;
   const float4 e = cb[i];
@@ -612,6 +638,8 @@ __global__ void vq_code_norm_kernel(const float4* __restrict__ cb, int codes, fl
 __global__ void vq_argmin_kernel(const float4* __restrict__ z, long long rows, const float4* __restrict__ cb,
                                  const float* __restrict__ bnorm, int codes, long long* __restrict__ idx_out,
                                  float4* __restrict__ zq_out) {
+  pdl_launch();
+  pdl_wait();
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long row0 = warp * VQ_R;
@@ -665,6 +693,8 @@ __global__ void vq_argmin_kernel(const float4* __restrict__ z, long long rows, c
 
 // z_scaled = z / div (decode_first_stage, model_runners.py:426), IEEE division.
 __global__ void div_scalar_kernel(const float* __restrict__ x, float div, float* __restrict__ y, long long n) {
+  pdl_launch();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __fdiv_rn(x[i], div);
 }
@@ -679,13 +709,13 @@ void launch_vq_argmin(const float* z, long long rows, int dim, const float* code
   const float* zin = z;
   if (in_div != 1.0f) {
     CUDA_CHECK(cudaMallocAsync(&zs, sizeof(float) * rows * 4, st));
-    div_scalar_kernel<<<grid_for(rows * 4, 256), 256, 0, st>>>(z, in_div, zs, rows * 4);
+    launch_pdl(div_scalar_kernel, dim3(grid_for(rows * 4, 256)), dim3(256), 0, st, z, in_div, zs, rows * 4);
     zin = zs;
   }
-  vq_code_norm_kernel<<<cdiv(codes, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(codebook), codes, bnorm);
+  launch_pdl(vq_code_norm_kernel, dim3(cdiv(codes, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(codebook), codes, bnorm);
   const long long warps = (rows + VQ_R - 1) / VQ_R;
   const int threads = 128;
-  vq_argmin_kernel<<<cdiv(warps * 32, threads), threads, 0, st>>>(
+  launch_pdl(vq_argmin_kernel, dim3(cdiv(warps * 32, threads)), dim3(threads), 0, st, 
       reinterpret_cast<const float4*>(zin), rows, reinterpret_cast<const float4*>(codebook), bnorm, codes, idx_out,
       reinterpret_cast<float4*>(zq_out));
   CUDA_CHECK(cudaGetLastError());

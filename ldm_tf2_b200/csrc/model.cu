@@ -2,6 +2,7 @@
 #include "model.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <algorithm>
 
@@ -431,6 +432,14 @@ void Model::finalize_weights() {
 }
 
 void Model::ensure_arena(size_t bytes) {
+  // called right after a dry pass: gn_pool_off_ holds the number of statistic slots it used
+  if (gn_pool_off_ > gn_pool_need_) gn_pool_need_ = gn_pool_off_;
+  if (gn_pool_need_ > gn_pool_cap_) {
+    eng.sync();
+    const size_t slack = getenv("LDM_B200_GN_SLACK") ? (size_t)atol(getenv("LDM_B200_GN_SLACK")) : 0;
+    gn_pool_ = dev_alloc<double>(gn_pool_need_ + 2 * slack, true) + slack;
+    gn_pool_cap_ = gn_pool_need_;
+  }
   bytes += (64u << 20);
   if (eng.arena.capacity() >= bytes) return;
   eng.sync();
@@ -458,13 +467,29 @@ Act Model::alloc_act(int n, int h, int w, int c, bool f, bool b) {
   return a;
 }
 
+// Called at the start of every forward graph (UNet step, decode): the dry pass measures how many
+// statistic slots the pass needs, the real pass zeroes exactly those with one memset.
+void Model::begin_pass() {
+  if (!eng.dry && gn_pool_need_)
+    CUDA_CHECK(cudaMemsetAsync(gn_pool_, 0, gn_pool_need_ * sizeof(double), eng.stream));
+  gn_pool_off_ = 0;
+}
+
 void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out) {
   const int cb = skip ? skip->c : 0;
   LDM_CHECK(x.c + cb == g.c, "GroupNorm channel mismatch %d+%d vs %d", x.c, cb, g.c);
-  double* st = eng.alloc<double>((size_t)x.n * 64);
-  eng.launches += 3;
+  static const bool no_pool = getenv("LDM_B200_GN_POOL") && getenv("LDM_B200_GN_POOL")[0] == '0';
+  double* st;
+  if (no_pool) {
+    st = eng.alloc<double>((size_t)x.n * 64);
+    if (!eng.dry) CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)x.n * 64 * sizeof(double), eng.stream));
+  } else {
+    st = gn_pool_ + gn_pool_off_;
+    gn_pool_off_ += (size_t)x.n * 64;
+  }
+  eng.launches += 2;
   if (eng.dry) return;
-  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)x.n * 64 * sizeof(double), eng.stream));
+  LDM_CHECK(no_pool || gn_pool_off_ <= gn_pool_cap_, "GroupNorm statistics pool overflow");
   launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, eng.stream);
   launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
                   silu ? 1 : 0, out, eng.fp16, eng.stream);
@@ -793,6 +818,7 @@ void Model::set_context(const float* ctx, int n) {
 // =====================================================================================
 void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out) {
   const int mc = cfg.model_channels;
+  begin_pass();
   Act cur = alloc_act(n, h, w, mc);
   eng.launches++;
   if (!eng.dry) launch_conv_in(x, nsrc, n, h, w, conv_in_k_->f32, conv_in_b_->f32, mc, cur.f, cur.b, eng.fp16, eng.stream);
@@ -1104,6 +1130,7 @@ Act Model::ae_attention(AEAttnW& a, const Act& x) {
 void Model::decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev) {
   const int zc = cfg.latent_channels;
   LDM_CHECK(zc == 4, "decode: latent_channels must be 4");
+  begin_pass();
   const long long rows = (long long)b * h * w;
   const float* zin = z;
   float pq_div = div;

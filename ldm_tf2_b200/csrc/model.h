@@ -179,6 +179,9 @@ class Model {
   void decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   Act ae_attention(AEAttnW& a, const Act& x);
   void build_ae_plan(int hw);
+  // GroupNorm statistics pool: one memset per forward pass instead of one per GroupNorm
+  double* gn_pool_ = nullptr; size_t gn_pool_cap_ = 0, gn_pool_off_ = 0, gn_pool_need_ = 0;
+  void begin_pass();
   std::vector<void*> owned_;  // cudaMalloc'ed persistent buffers
   template <typename T> T* dev_alloc(size_t n, bool zero = false);
 };

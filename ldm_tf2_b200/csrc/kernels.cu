@@ -686,7 +686,13 @@ __global__ void vq_argmin_kernel(const float4* __restrict__ z, long long rows, c
     }
     if (lane == 0 && row0 + r < rows) {
       idx_out[row0 + r] = (long long)i;
-      if (zq_out) zq_out[row0 + r] = __ldg(cb + i);
+      if (zq_out) {
+        // straight-through value path (quantize.py:88): z + (e - z), separately rounded
+        const float4 e = __ldg(cb + i);
+        const float4 zz = zr[r];
+        zq_out[row0 + r] = make_float4(__fadd_rn(zz.x, __fsub_rn(e.x, zz.x)), __fadd_rn(zz.y, __fsub_rn(e.y, zz.y)),
+                                       __fadd_rn(zz.z, __fsub_rn(e.z, zz.z)), __fadd_rn(zz.w, __fsub_rn(e.w, zz.w)));
+      }
     }
   }
 }

@@ -594,7 +594,10 @@ def vq_lookup(latents, codebook, chunk=4096):
     idx = np.empty(rows.shape[0], dtype=np.int64)
     for s in range(0, rows.shape[0], chunk):
         idx[s:s + chunk] = np.argmin(vq_distances(rows[s:s + chunk], codebook), axis=1)
-    zq = np.asarray(codebook, dtype=F32)[idx].reshape(z.shape)
+    e = np.asarray(codebook, dtype=F32)[idx].reshape(z.shape)
+    # straight-through estimator (quantize.py:88): the VALUE that flows on is z + (e - z) in fp32,
+    # which differs from e by up to one ulp
+    zq = (z + (e - z).astype(F32)).astype(F32)
     return zq, idx
 
 

@@ -1,0 +1,168 @@
+"""CPU: host-side logic of the drop-in (no GPU compute): C ABI exports, error behaviour without
+a device, schedule tables, DLPack unwrapping, reference-compatible signatures, sample sharding and
+the world-size-2 image all-gather over gloo."""
+import ast
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import ldm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from ldm_tf2_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    hdr = open(os.path.join(ROOT, "include", "ldm_b200.h")).read()
+    declared = sorted(set(re.findall(r"LDM_API\s+[\w\s\*]+?\b(ldm_\w+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(libpath)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    from ldm_tf2_b200 import lib as L
+    assert sorted(L.EXPORTS) == declared  # the ctypes prototypes cover the whole header
+
+
+def test_no_cpu_fallback_without_a_device(libpath):
+    from ldm_tf2_b200 import lib as L
+    cfg = O.TINY_CONFIG
+    c = L.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8)
+    try:
+        h = L.Handle(c, 0)
+    except L.LdmError as e:
+        assert "-2" in str(e) and ("CUDA" in str(e) or "device" in str(e))
+        return
+    h.close()
+    pytest.skip("a CUDA device is present: the no-device error path cannot be exercised here")
+
+
+def test_bad_config_is_rejected(libpath):
+    from ldm_tf2_b200 import lib as L
+    cfg = {k: dict(v) for k, v in O.TINY_CONFIG.items()}
+    cfg["unet"]["model_channels"] = 48  # not a multiple of 32
+    c = L.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8)
+    with pytest.raises(L.LdmError):
+        L.Handle(c, 0)
+
+
+@pytest.mark.parametrize("eta,S", [(0.0, 50), (1.0, 200), (0.3, 7)])
+def test_host_schedule_equals_oracle_bitwise(eta, S):
+    from ldm_tf2_b200.schedule import DDIMSchedule
+    s = DDIMSchedule(1000, 0.00085, 0.012, 0.0, eta, S)
+    o = O.ddim_schedule(eta=eta, num_ddim_steps=S, num_steps=1000, beta_start=0.00085, beta_end=0.012)
+    assert np.array_equal(s.ddim_steps, o["ddim_steps"])
+    table = s.coeff_table()
+    for i in range(S):
+        assert np.array_equal(table[i, :5], np.array(O.ddim_coeffs(o, i), np.float32))
+
+
+def test_dlpack_borrow_host_tensors():
+    import torch
+    from ldm_tf2_b200.dlpack import borrow
+    a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    x, shape, _ = borrow(a, np.float32)
+    assert x is not None and tuple(shape) == (2, 3, 4) and np.array_equal(x, a)
+    t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+    x, shape, _ = borrow(t, np.float32)
+    assert isinstance(x, np.ndarray) and np.array_equal(x, a)
+    cap = torch.utils.dlpack.to_dlpack(torch.arange(6, dtype=torch.int64).reshape(2, 3))
+    x, shape, _ = borrow(cap, np.int64)
+    assert np.array_equal(x, np.arange(6).reshape(2, 3))
+    with pytest.raises(ValueError):
+        borrow(torch.utils.dlpack.to_dlpack(torch.zeros(2, dtype=torch.float64)), np.float32)
+
+
+def _ref_args(path, cls, fn):
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f.name == fn:
+                    return [a.arg for a in f.args.args if a.arg != "self"]
+    raise KeyError((cls, fn))
+
+
+def test_signatures_mirror_the_reference():
+    """Drop-in: every argument of the reference's constructors / sampling methods exists, in the
+    same order, in ours (ours may append keyword-only extras such as device, x_init, noise)."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "model_runners.py")):
+        pytest.skip("reference sources not present on this machine")
+    import inspect
+    from ldm_tf2_b200 import sampler as S
+    pairs = [
+        ("model_runners.py", "LatentDiffusionModel", "__init__", S.LatentDiffusionModelSampler.__init__),
+        ("model_runners.py", "LatentDiffusionModelSampler", "ddim_sample", S.LatentDiffusionModelSampler.ddim_sample),
+        ("model_runners.py", "LatentDiffusionModelSampler", "ddim_p_sample_loop", S.LatentDiffusionModelSampler.ddim_p_sample_loop),
+        ("model_runners.py", "LatentDiffusionModelSampler", "ddim_p_sample_loop_progressive", S.LatentDiffusionModelSampler.ddim_p_sample_loop_progressive),
+        ("model_runners.py", "LatentDiffusionModel", "decode_first_stage", S.LatentDiffusionModelSampler.decode_first_stage),
+        ("unet.py", "UNet", "__init__", S.UNet.__init__),
+        ("transformer.py", "TransformerModel", "__init__", S.TransformerModel.__init__),
+        ("autoencoder.py", "AutoencoderKL", "__init__", S.AutoencoderKL.__init__),
+        ("autoencoder.py", "AutoencoderVQ", "__init__", S.AutoencoderVQ.__init__),
+    ]
+    for f, cls, fn, ours in pairs:
+        want = _ref_args(os.path.join(ref, f), cls, fn)
+        have = [p for p in inspect.signature(ours).parameters if p != "self"]
+        assert have[: len(want)] == want, (cls, fn, want, have)
+
+
+def test_default_token_ids_layout():
+    from ldm_tf2_b200 import tokens
+    ids = tokens.default_token_ids(3)
+    assert ids.shape == (6, 77) and ids.dtype == np.int64
+    assert (ids[:3] == np.array(tokens.UNCOND_IDS)).all() and (ids[3:] == np.array(tokens.COND_IDS)).all()
+
+
+def test_shard_ranges_cover_the_batch():
+    from ldm_tf2_b200.parallel import shard_batch, shard_range, shard_token_ids
+    for total in (1, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    x = np.arange(8 * 2).reshape(8, 2)
+    assert np.array_equal(np.concatenate([shard_batch(x, r, 4) for r in range(4)]), x)
+    ids = np.arange(16 * 3).reshape(16, 3)  # 8 uncond rows then 8 cond rows
+    s1 = shard_token_ids(ids, 1, 4)
+    assert np.array_equal(s1, np.concatenate([ids[2:4], ids[10:12]]))
+
+
+def _gloo_worker(rank, world, port, total, q):
+    import torch
+    import torch.distributed as dist
+    from ldm_tf2_b200.parallel import allgather_images, shard_batch
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = np.random.default_rng(1234).standard_normal((total, 4, 4, 3)).astype(np.float32)  # global, seeded
+    local = torch.from_numpy(shard_batch(g, rank, world) * 2.0 + 1.0)  # stand-in for sample + decode
+    out = allgather_images(local, total)
+    q.put((rank, np.array_equal(out.numpy(), g * 2.0 + 1.0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 5])
+def test_world_size_2_allgather_matches_single_process(total):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

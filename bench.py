@@ -148,15 +148,19 @@ def main():
         }))
         return
 
+    # keep stdout clean for the single JSON line: libraries (NCCL banner, ...) print to fd 1
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
-    from ldm_tf2_b200 import lib, synth, tokens
+    from ldm_tf2_b200 import lib, parallel, synth, tokens
     from ldm_tf2_b200.sampler import (AutoencoderKL, LatentDiffusionModelSampler, TransformerModel, UNet)
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = synth.FULL_CONFIG
+    precision = os.environ.get("LDM_B200_PRECISION", lib.DEFAULT_PRECISION)
     ldm_kw = dict(cfg["ldm"])
     ldm_kw["num_ddim_steps"] = args.ddim_steps
     # public API objects, exactly as run_ldm_sampler.py:56-83 builds them
@@ -174,13 +178,12 @@ def main():
     # global seeded x_T, sliced per rank: results do not depend on the GPU count
     xg = np.random.default_rng(1234).standard_normal((B * world, 32, 32, 4), dtype=np.float32)
     x_host = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
-    x_host.copy_(torch.from_numpy(xg[rank * B:(rank + 1) * B]))
+    x_host.copy_(torch.from_numpy(parallel.shard_batch(xg, rank, world)))
     x_np = x_host.numpy()
     dev = torch.device("cuda", local_rank)
     x_dev = x_host.to(dev)
     lat_dev = torch.empty_like(x_dev)
     img_dev = torch.empty((B, 256, 256, 3), dtype=torch.float32, device=dev)
-    gathered = torch.empty((B * world, 256, 256, 3), dtype=torch.float32, device=dev) if world > 1 else None
     ctx = h.encode_text(ids)
     h.set_context(ctx)
 
@@ -202,7 +205,7 @@ def main():
         ms = t["loop_ms"] + t["decode_ms"]
         if world > 1:
             ev0.record()
-            dist.all_gather_into_tensor(gathered, img_dev)
+            parallel.allgather_images(img_dev, B * world)
             ev1.record()
             torch.cuda.synchronize()
             ms += ev0.elapsed_time(ev1)
@@ -271,8 +274,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world} (sample-sharded replicas)",
+            "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": {"workload": workload, "operands": f"{precision} tensor-core operands, fp32 accumulate, fp32 residual stream", "global_batch": B * world, "parallelism": f"dp{world} (sample-sharded replicas)",
                        "l2": "not flushed explicitly: 1.75 GB of bf16 weights stream through L2 every UNet step",
                        "timing": "CUDA events on the library stream (+ torch events for the all-gather), max over ranks"},
             "ms_per_unet_step": loop_ms / args.steps / args.ddim_steps,
@@ -300,8 +303,7 @@ def main():
                                     "sample": r["sample"]}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
-        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

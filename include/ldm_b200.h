@@ -139,7 +139,7 @@ LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iter
 
 /* GEMM / conv microbenchmark on zero-filled device buffers (dbg: 1 no TMA, 2 no MMA, 4 no stores). */
 LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
-                           int iters, float* avg_ms);
+                           int iters, float* avg_ms, long long* trace_host, int with_residual);
 /* cudaProfilerStart (on=1) / cudaProfilerStop (on=0) for `ncu --profile-from-start off`. */
 LDM_API int ldm_profiler(int on);
 

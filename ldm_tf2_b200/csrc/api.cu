@@ -306,7 +306,8 @@ extern "C" LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int w
 // dbg: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores.  conv=1: 3x3 conv geometry instead
 // (rows = nb*hw*hw pixels, k = cin).  Returns the average launch time (CUDA events).
 extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
-                                      int iters, float* avg_ms) {
+                                      int iters, float* avg_ms, long long* trace_host /* [148*64*16] or null */,
+                                      int with_residual) {
   API_BEGIN
   NEED(h);
   Engine& e = h->model->eng;
@@ -337,6 +338,17 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.b = view_mat(w, n, ktot, ktot);
   op.N = n; op.block_n = block_n; op.dbg = dbg;
   op.out_bf16 = o;
+  float* of = nullptr;
+  if (with_residual) {
+    CUDA_CHECK(cudaMalloc(&of, (size_t)rows * n * 4));
+    CUDA_CHECK(cudaMemset(of, 0, (size_t)rows * n * 4));
+    op.out_f32 = of; op.residual = of;
+  }
+  long long* trace_d = nullptr;
+  if (trace_host) {
+    CUDA_CHECK(cudaMalloc(&trace_d, (size_t)148 * 64 * 16 * 8));
+    CUDA_CHECK(cudaMemset(trace_d, 0, (size_t)148 * 64 * 16 * 8));
+  }
   h->model->ensure_arena((size_t)512 << 20);
   e.arena.reset();
   for (int i = 0; i < 3; ++i) e.gemm(op);
@@ -351,8 +363,17 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   *avg_ms = ms / iters;
+  if (trace_host) {
+    op.trace = trace_d;
+    e.arena.reset();
+    e.gemm(op);
+    e.sync();
+    CUDA_CHECK(cudaMemcpy(trace_host, trace_d, (size_t)148 * 64 * 16 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(trace_d);
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(a); cudaFree(w); cudaFree(o);
+  if (of) cudaFree(of);
   API_END
 }
 
@@ -434,7 +455,7 @@ LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const
   std::vector<float> pb;
   float* bias_d = nullptr;
   if (act == ACT_GEGLU) {
-    if (!bn) { bn = 256; while (wn % bn) bn -= 32; }
+    if (!bn) { bn = 256; while (wn % bn) bn -= 64; }
     launch_pack_weight(wf, k, wn, wt, k, 0, bn / 2, e.fp16, e.stream);
     if (bias) {
       pb.resize(wn);

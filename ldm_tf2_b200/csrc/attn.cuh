@@ -53,7 +53,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const int atom = ATT_BM * 128;                 // 16 KB: 128 rows x 128 B
   const int q_bytes = p.dp_atoms * atom;
   const int k_bytes = p.dp_atoms * atom;         // per stage

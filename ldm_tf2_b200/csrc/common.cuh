@@ -272,8 +272,20 @@ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, int fp
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, branch-free: one rcp, one ex2, five FMAs);
+// exact-erf GELU of tf.nn.gelu (unet.py:324, transformer.py:169) to fp32 round-off.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float y = fmaf(1.061405429f, t, -1.453152027f);
+  y = fmaf(y, t, 1.421413741f);
+  y = fmaf(y, t, -0.284496736f);
+  y = fmaf(y, t, 0.254829592f);
+  y = y * t * exp2f(-ax * ax * 1.4426950408889634f);
+  return copysignf(1.0f - y, x);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
 }
 // fp32 -> 16-bit operand bits; fp16 saturates instead of overflowing to inf
 __device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
@@ -285,9 +297,9 @@ __device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
 }
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
   if (fp16) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    const __half2 h = __floats2half2_rn(a, b);
+    // saturate instead of overflowing to inf: clamp the converted pair (inf -> 65504)
+    const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
+    const __half2 h = __hmin2(__hmax2(__floats2half2_rn(a, b), __hneg2(lim)), lim);
     return *reinterpret_cast<const uint32_t*>(&h);
   }
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -102,7 +102,7 @@ void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, in
 
 int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu) {
   static const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
-  const int step = geglu ? 32 : 16;
+  const int step = geglu ? 64 : 16;
   int best = 0;
   for (int bn : cand) {
     if (bn % step) continue;
@@ -170,7 +170,7 @@ void Engine::gemm(const GemmOp& op) {
     }
   }
   if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu);
-  LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 32 == 0), "gemm: bad block_n %d", bn);
+  LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 64 == 0), "gemm: bad block_n %d", bn);
   p.block_n = bn;
   p.n_tiles = (gemm_n + bn - 1) / bn;
   p.N = op.N;
@@ -203,6 +203,12 @@ void Engine::gemm(const GemmOp& op) {
   p.tx_bytes = stage_bytes;
   p.fp16 = fp16;
   p.dbg = op.dbg;
+  p.trace = op.trace;
+  {
+    const long long max_off = (long long)(op.NB - 1) * op.os_n + (long long)(op.H - 1) * op.os_y +
+                              (long long)(op.W - 1) * op.os_x + op.os_phase_y + op.os_phase_x + op.N;
+    p.off32 = (max_off >= 0 && max_off < (1ll << 31) && op.os_n >= 0 && op.os_y >= 0 && op.os_x >= 0) ? 1 : 0;
+  }
   p.epi_vec = ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 3) == 0 &&
               (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
               (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&

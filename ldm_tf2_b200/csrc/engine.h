@@ -41,6 +41,7 @@ struct GemmOp {
   int num_phases = 1;
   int b_mode = B_PLAIN;
   int dbg = 0;
+  long long* trace = nullptr;
   int splits = 0;   // 0 = choose automatically, 1 = never split K
   const float* bias = nullptr;
   const float* bias2 = nullptr;

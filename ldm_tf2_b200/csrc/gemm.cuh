@@ -63,7 +63,9 @@ struct GemmParams {
   int splits, kb_per_split;
   float* ws;
   long long ws_split_stride;
+  long long* trace;         // optional [cta][tile slot][16] clock64 stamps (microbenchmark only)
   int dbg;                  // microbenchmark switches: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores
+  int off32;                // 1: every output element offset fits in 31 bits
   int epi_vec;              // 1: all output offsets are multiples of 4 elements -> coalesced vector epilogue
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
@@ -113,36 +115,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-// Bias / activation on one chunk of CH accumulator columns of this thread's row (registers).
+// Direct (thread-per-row, scalar) residual + stores: boundary tiles, unaligned outputs, V^T.
 template <int CH>
-__device__ __forceinline__ void epi_math(const GemmParams& p, float* v, const float* bias_s, int tc0, int col0,
-                                         const float* bias2_row) {
-#pragma unroll
-  for (int j = 0; j < CH; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + tc0 + j);
-    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-  }
-  if (bias2_row) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (col0 + j < p.N) v[j] += __ldg(bias2_row + col0 + j);
-  }
-  if (p.act == ACT_SILU) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = silu_f(v[j]);
-  } else if (p.act == ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = gelu_erf_f(v[j]);
-  }
-}
-
-// Direct (thread-per-row) residual + stores: used for unaligned outputs and the transposed V^T.
-template <int CH>
-__device__ __forceinline__ void epi_store_direct(const GemmParams& p, float* v, int col0, bool row_ok, long long row_off,
-                                                 int xq, long long tr_row_off) {
+__device__ __noinline__ void epi_store_direct(const GemmParams& p, const float* v, int col0, bool row_ok,
+                                              long long row_off, int xq, long long tr_row_off, float* o32, bf16* o16,
+                                              const float* resid) {
   if (!row_ok) return;
   if (p.out_tr && col0 >= p.tr_col0) {
-#pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int col = col0 + j;
       if (col < p.N) store16(p.out_tr + tr_row_off + (long long)(col - p.tr_col0) * p.ts_c + xq, v[j], p.fp16);
@@ -150,48 +129,48 @@ __device__ __forceinline__ void epi_store_direct(const GemmParams& p, float* v, 
     return;
   }
   const long long off = row_off + col0;
-#pragma unroll
   for (int j = 0; j < CH; ++j) {
     if (col0 + j < p.N) {
       float x = v[j];
-      if (p.residual) x += p.residual[off + j];
-      if (p.out_f32) p.out_f32[off + j] = x;
-      if (p.out_bf16) store16(p.out_bf16 + off + j, x, p.fp16);
+      if (resid) x += resid[off + j];
+      if (o32) o32[off + j] = x;
+      if (o16) store16(o16 + off + j, x, p.fp16);
     }
   }
 }
 
-// Coalesced path: the warp's 32 rows x CH columns go through a padded smem tile; afterwards CH/4
-// lanes cover one row with float4, so each instruction moves whole 16*CH/4-byte row segments.
-template <int CH>
-__device__ __forceinline__ void epi_store_staged(const GemmParams& p, const float* v, int col0, float* stage,
-                                                 const long long* roff, int lane) {
+// Coalesced path for a fully valid warp: its 32 rows x 32 columns are transposed through a padded
+// smem tile; afterwards 8 lanes cover one row with float4, so each instruction moves four whole
+// 128-byte row segments.  base[it] = this lane's element offset of row (4*it + lane/8), column
+// 4*(lane%8) (32-bit, precomputed once per tile).  No per-lane predicates in the loops.
+__device__ __forceinline__ void epi_store_staged32(const float* v, int col0, float* stage, const int* base, int lane,
+                                                   float* o32, bf16* o16, const float* resid, int fp16) {
 #pragma unroll
-  for (int j = 0; j < CH; j += 4)
+  for (int j = 0; j < 32; j += 4)
     *reinterpret_cast<float4*>(stage + lane * GEMM_EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   __syncwarp();
-  constexpr int LPR = CH / 4;        // lanes per row
-  constexpr int RPI = 32 / LPR;      // rows per iteration
-  const int q = lane % LPR, rs = lane / LPR;
-  const int col = col0 + q * 4;
+  const float* sp = stage + (lane >> 3) * GEMM_EPI_PITCH + (lane & 7) * 4;
+  float4 x[8];
 #pragma unroll
-  for (int it = 0; it < 32 / RPI; ++it) {
-    const int row = it * RPI + rs;
-    const long long ro = roff[row];
-    if (ro >= 0 && col < p.N) {   // N % 4 == 0 on this path
-      float4 x = *reinterpret_cast<const float4*>(stage + row * GEMM_EPI_PITCH + q * 4);
-      const long long off = ro + col;
-      if (p.residual) {
-        const float4 r = *reinterpret_cast<const float4*>(p.residual + off);
-        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-      }
-      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
-      if (p.out_bf16) {
-        uint2 u;
-        u.x = pack16(x.x, x.y, p.fp16);
-        u.y = pack16(x.z, x.w, p.fp16);
-        *reinterpret_cast<uint2*>(p.out_bf16 + off) = u;
-      }
+  for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(sp + it * 4 * GEMM_EPI_PITCH);
+  if (resid) {
+    float4 r[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) r[it] = *reinterpret_cast<const float4*>(resid + (base[it] + col0));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { x[it].x += r[it].x; x[it].y += r[it].y; x[it].z += r[it].z; x[it].w += r[it].w; }
+  }
+  if (o32) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(o32 + (base[it] + col0)) = x[it];
+  }
+  if (o16) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      uint2 u;
+      u.x = pack16(x[it].x, x[it].y, fp16);
+      u.y = pack16(x[it].z, x[it].w, fp16);
+      *reinterpret_cast<uint2*>(o16 + (base[it] + col0)) = u;
     }
   }
   __syncwarp();
@@ -201,7 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; control block after.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const int a_bytes = GEMM_BM * GEMM_BK * 2;
   const int b_bytes = p.block_n * GEMM_BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
@@ -220,6 +199,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
   pdl_launch();  // the next kernel may start its own prologue once all our CTAs are resident
+  if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 2] = clock64();  // kernel entry
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -302,15 +282,21 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int tslot = 0;
+    if (p.trace && lane == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16] = clock64();  // kernel body start
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tslot) {
+      long long* tr = (p.trace && lane == 0 && tslot < 63) ? p.trace + ((long long)blockIdx.x * 64 + tslot) * 16 : nullptr;
+      if (tr) tr[0] = clock64();
       mbar_wait_a(tempty0 + as * 8, aphase ^ 1);
       tc_fence_after();
+      if (tr) tr[1] = clock64();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       const int split = tile / (total_tiles / p.splits);
       const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
         tc_fence_after();
+        if (tr && kb == 0) tr[2] = clock64();
         if (elect_one()) {
           if (!(p.dbg & 2)) {
             const uint64_t da = da0 + (uint64_t)(dstep * (uint32_t)stage);
@@ -327,6 +313,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      if (tr) tr[3] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
@@ -337,11 +324,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
     float* stage = stage_all + ew * 32 * GEMM_EPI_PITCH;
-    long long* roff = roff_all + ew * 32;
+    int* roff = reinterpret_cast<int*>(roff_all) + ew * 32;
     int as = 0;
     uint32_t aphase = 0;
     const int hw_b = p.h_b * p.w_b;
     const bool geglu = p.act == ACT_GEGLU;
+    const bool split = p.splits > 1;
+    const int act = split ? (int)ACT_NONE : p.act;   // split-K: raw partial sums, epilogue in the finalize kernel
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int py = t.phase >> 1, px = t.phase & 1;
@@ -349,130 +338,135 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int yq = t.y0 + (r % hw_b) / p.w_b;
       const int xq = t.x0 + r % p.w_b;
       const bool row_ok = (r < p.box_rows) && (img < p.NB) && (yq < p.H) && (xq < p.W) && !(p.dbg & 4);
-      const long long row_off = (long long)img * p.os_n + (long long)yq * p.os_y + (long long)xq * p.os_x +
-                                (long long)py * p.os_phase_y + (long long)px * p.os_phase_x;
+      // output view of this tile: the real outputs, or the split-K workspace slice (raw partial sums)
+      float* o32 = p.out_f32;
+      bf16* o16 = p.out_bf16;
+      const float* resid = p.residual;
+      long long row_off = (long long)img * p.os_n + (long long)yq * p.os_y + (long long)xq * p.os_x +
+                          (long long)py * p.os_phase_y + (long long)px * p.os_phase_x;
+      if (split) {
+        o32 = p.ws + (long long)t.split * p.ws_split_stride;
+        o16 = nullptr;
+        resid = nullptr;
+        row_off = (((long long)img * p.H + yq) * p.W + xq) * p.N;
+      }
       const long long tr_row_off = (long long)img * p.ts_n + (long long)yq * p.ts_y;
       const float* bias2_row = nullptr;   // per-thread path only when the row index depends on img
       const float* bias2_tile = nullptr;  // folded into the smem bias vector otherwise
-      if (p.bias2) {
+      if (p.bias2 && !split) {
         const long long step = p.step_ptr ? __ldg(p.step_ptr) : 0;
         if (p.bias2_by_img) bias2_row = (img < p.NB) ? p.bias2 + ((long long)img + step) * p.bias2_stride : nullptr;
         else bias2_tile = p.bias2 + step * p.bias2_stride;
       }
-      // stage this tile's bias columns and row offsets in smem (the previous tile's readers are
-      // past the first barrier)
+      long long* tre = nullptr;
+      if (p.trace && warp == 2 && lane == 0) {
+        const int tslot = (tile - blockIdx.x) / gridDim.x;
+        if (tslot < 63) tre = p.trace + ((long long)blockIdx.x * 64 + tslot) * 16;
+      }
+      if (tre) tre[4] = clock64();
+      // stage this tile's bias columns (all 8 warps) and this warp's row offsets in smem; the
+      // previous tile's readers are past the first barrier
       named_bar_sync(1, 256);
+      if (tre) tre[7] = clock64();
       for (int c = et; c < p.block_n; c += 256) {
         const int col = t.n0 + c;        // bias / bias2 are indexed by B row (packed row for GEGLU)
         const int lim = geglu ? 2 * p.N : p.N;
         float b = 0.f;
-        if (col < lim) {
+        if (col < lim && !split) {
           if (p.bias) b += __ldg(p.bias + col);
           if (bias2_tile) b += __ldg(bias2_tile + col);
         }
         bias_s[c] = b;
       }
-      roff[lane] = row_ok ? row_off : -1;
+      // vector path: aligned 32-bit offsets and every row of this warp inside the tensor
+      const bool warp_rows_ok = __all_sync(0xffffffffu, row_ok) && p.epi_vec && p.off32;
+      roff[lane] = (int)row_off;
       named_bar_sync(1, 256);
+      int base[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) base[it] = roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
+      if (tre) tre[8] = clock64();
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
+      if (tre) tre[5] = clock64();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
-      if (p.splits > 1) {
-        // raw fp32 partial sums -> workspace; the finalize kernel applies the epilogue
-        const long long rlin = ((long long)img * p.H + yq) * p.W + xq;
-        const long long wro = (long long)t.split * p.ws_split_stride + rlin * p.N;
-        roff[lane] = row_ok ? wro : -1;
-        __syncwarp();
-        int ci = 0;
-        for (int c = 0; c < p.block_n; c += 16, ++ci) {
-          if ((ci & 1) != half) continue;
-          uint32_t rr[16];
-          tmem_ld_x16(t_base + (uint32_t)c, rr);
+      const int n32 = geglu ? (p.block_n >> 6) : (p.block_n >> 5);   // 32-column output chunks per tile
+      const int hcols = p.block_n >> 1;
+      for (int ci = half; ci < n32; ci += 2) {
+        const int c = ci * 32;
+        uint32_t rr[32];
+        float acc[32];
+        int col0;   // first output column of the chunk
+        tmem_ld_x32(t_base + (uint32_t)c, rr);
+        if (geglu) {
+          // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates (unet.py:323-324)
+          uint32_t rg[32];
+          tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
           tmem_ld_wait();
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-          const int col0 = t.n0 + c;
-          if ((p.N & 3) == 0) {
-            // same staged store, into the workspace, without residual / 16-bit copy
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(stage + lane * GEMM_EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            __syncwarp();
-            const int q = lane & 3, rs = lane >> 2;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int row = it * 8 + rs;
-              const long long ro = roff[row];
-              if (ro >= 0 && col0 + q * 4 < p.N)
-                *reinterpret_cast<float4*>(p.ws + ro + col0 + q * 4) =
-                    *reinterpret_cast<const float4*>(stage + row * GEMM_EPI_PITCH + q * 4);
-            }
-            __syncwarp();
-          } else if (row_ok) {
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < p.N) p.ws[wro + col0 + j] = v[j];
-          }
-        }
-      } else if (geglu) {
-        // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates
-        const int hcols = p.block_n >> 1;
-        int ci = 0;
-        for (int c = 0; c < hcols; c += 16, ++ci) {
-          if ((ci & 1) != half) continue;
-          uint32_t rv[16], rg[16];
-          tmem_ld_x16(t_base + (uint32_t)c, rv);
-          tmem_ld_x16(t_base + (uint32_t)(hcols + c), rg);
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(rv[j]) * p.alpha + bias_s[c + j];
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(rr[j]) * p.alpha + bias_s[c + j];
             const float gt = __uint_as_float(rg[j]) * p.alpha + bias_s[hcols + c + j];
-            v[j] = a * gelu_erf_f(gt);
+            acc[j] = a * gelu_erf_f(gt);
           }
-          const int oc0 = t.n_tile * hcols + c;  // output column
-          if (p.epi_vec) epi_store_staged<16>(p, v, oc0, stage, roff, lane);
-          else epi_store_direct<16>(p, v, oc0, row_ok, row_off, xq, tr_row_off);
-        }
-      } else {
-        int ci = 0, c = 0;
-        for (; c + 32 <= p.block_n; c += 32, ++ci) {
-          if ((ci & 1) != half) continue;
-          uint32_t rr[32];
-          tmem_ld_x32(t_base + (uint32_t)c, rr);
+          col0 = t.n_tile * hcols + c;
+        } else {
           tmem_ld_wait();
-          float acc[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
-          const int col0 = t.n0 + c;
-          epi_math<32>(p, acc, bias_s, c, col0, bias2_row);
-          if (p.epi_vec && !(p.out_tr && col0 >= p.tr_col0)) epi_store_staged<32>(p, acc, col0, stage, roff, lane);
-          else epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off);
-        }
-        for (; c < p.block_n; c += 16, ++ci) {
-          if ((ci & 1) != half) continue;
-          uint32_t rr[16];
-          tmem_ld_x16(t_base + (uint32_t)c, rr);
-          tmem_ld_wait();
-          float acc[16];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
+            acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, b.x);
+            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, b.y);
+            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, b.z);
+            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, b.w);
+          }
+          col0 = t.n0 + c;
+          if (bias2_row) {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) acc[j] += __ldg(bias2_row + col0 + j);
+          }
+          if (act == ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rr[j]) * p.alpha;
-          const int col0 = t.n0 + c;
-          epi_math<16>(p, acc, bias_s, c, col0, bias2_row);
-          if (p.epi_vec && !(p.out_tr && col0 >= p.tr_col0)) epi_store_staged<16>(p, acc, col0, stage, roff, lane);
-          else epi_store_direct<16>(p, acc, col0, row_ok, row_off, xq, tr_row_off);
+            for (int j = 0; j < 32; ++j) acc[j] = silu_f(acc[j]);
+          } else if (act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = gelu_erf_f(acc[j]);
+          }
         }
+        if (tre && ci < 6) tre[9 + ci] = clock64();
+        const bool to_tr = p.out_tr && col0 >= p.tr_col0;
+        if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
+          epi_store_staged32(acc, col0, stage, base, lane, o32, o16, resid, p.fp16);
+        else
+          epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
+      }
+      if (!geglu && (p.block_n & 31) && (n32 & 1) == half) {   // ragged 16-column tail chunk
+        const int c = n32 * 32;
+        uint32_t r16[16];
+        tmem_ld_x16(t_base + (uint32_t)c, r16);
+        tmem_ld_wait();
+        float acc[16];
+        const int col0 = t.n0 + c;
+        for (int j = 0; j < 16; ++j) {
+          float x = fmaf(__uint_as_float(r16[j]), p.alpha, bias_s[c + j]);
+          if (bias2_row && col0 + j < p.N) x += __ldg(bias2_row + col0 + j);
+          if (act == ACT_SILU) x = silu_f(x);
+          else if (act == ACT_GELU) x = gelu_erf_f(x);
+          acc[j] = x;
+        }
+        epi_store_direct<16>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(tempty0 + as * 8);
+      if (tre) tre[6] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 1] = clock64();  // kernel end
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -146,7 +146,8 @@ struct Builder {
     // GEGLU Dense c -> 8c, rows permuted per tile so value/gate columns share a tile
     t.geglu = lin(8 * c, c);
     int bn = 256;
-    while ((8 * c) % bn) bn -= 32;
+    while ((8 * c) % bn) bn -= 64;   // value and gate halves are processed in 32-column chunks
+    LDM_CHECK(bn >= 64, "GEGLU width %d has no tile that is a multiple of 64", 8 * c);
     t.geglu_bn = bn;
     pack(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/kernel", {c, 8 * c}, c, 8 * c, t.geglu.wt, t.geglu.ld, 0,
          0, bn / 2);

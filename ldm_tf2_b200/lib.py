@@ -53,7 +53,7 @@ _PROTOS = {
     "ldm_bench_unet_step": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
     "ldm_profile_unet_step": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I), C.POINTER(C.c_double)], _I),
     "ldm_profiler": ([_I], _I),
-    "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
+    "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P, _I], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
@@ -301,10 +301,12 @@ class Handle:
         return dict(gemm_ms_per_step=g.value, step_ms=s.value, gemm_launches_per_step=n.value,
                     gemm_flops_per_step=fl.value)
 
-    def bench_gemm(self, rows, k, n, block_n=0, dbg=0, conv=0, hw=32, iters=20):
+    def bench_gemm(self, rows, k, n, block_n=0, dbg=0, conv=0, hw=32, iters=20, trace=False, residual=False):
         ms = C.c_float()
-        check(self.lib.ldm_bench_gemm(self._h, rows, k, n, block_n, dbg, conv, hw, iters, C.byref(ms)))
-        return ms.value
+        tr = np.zeros((148, 64, 16), np.int64) if trace else None
+        check(self.lib.ldm_bench_gemm(self._h, rows, k, n, block_n, dbg, conv, hw, iters, C.byref(ms), ptr(tr),
+                                      int(residual)))
+        return (ms.value, tr) if trace else ms.value
 
     # -- test hooks ---------------------------------------------------------
     def tap(self, name, shape):

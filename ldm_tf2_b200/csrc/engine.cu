@@ -100,6 +100,28 @@ void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, in
             (unsigned long long)strides[2], box[0], box[1], box[2], box[3]);
 }
 
+// 4-D map over an output / residual tensor viewed as (N cols, W, H, NB) for the TMA epilogue: box =
+// (32 cols, w_b, h_b, n_b), 128-byte swizzle for fp32 rows (128 B), 64-byte swizzle for 16-bit rows.
+void Engine::encode_out_map(CUtensorMap* m, const void* ptr, int elem_bytes, bool is_float32, int N, int W, int H,
+                            int NB, long long sx, long long sy, long long sn, int w_b, int h_b, int n_b) {
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  // size-1 dims get packed strides (any positive multiple of 16 B is legal)
+  if (W == 1 || sx == 0) sx = N;
+  if (H == 1 || sy == 0) sy = sx * W;
+  if (NB == 1 || sn == 0) sn = sy * H;
+  cuuint64_t strides[3] = {(cuuint64_t)sx * elem_bytes, (cuuint64_t)sy * elem_bytes, (cuuint64_t)sn * elem_bytes};
+  cuuint32_t box[4] = {32, (cuuint32_t)w_b, (cuuint32_t)h_b, (cuuint32_t)n_b};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = is_float32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                            : (fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = reinterpret_cast<EncodeTiledFn>(encode_fn_)(
+      m, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      is_float32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LDM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (epilogue map) failed (%d): dims %d,%d,%d,%d strides %lld,%lld,%lld",
+            (int)r, N, W, H, NB, sx, sy, sn);
+}
+
 int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu) {
   static const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
   const int step = geglu ? 64 : 16;
@@ -196,7 +218,28 @@ void Engine::gemm(const GemmOp& op) {
   const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
   const int a_bytes_full = GEMM_BM * GEMM_BK * 2;  // smem slot for A is always 16 KB
   const int slot = a_bytes_full + bn * GEMM_BK * 2;
-  int stages = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - 1024) / slot;  // control block + 1 KB alignment slack
+  // ---- epilogue flavour: TMA tiles (outputs / residual through bulk tensor copies) when the output
+  // is a plain strided (N, W, H, NB) view with 16-byte-aligned strides, else register staging
+  const bool strides_ok = ((op.os_x | op.os_y | op.os_n) & 7) == 0 && op.os_x >= 0 && op.os_y >= 0 && op.os_n >= 0 &&
+                          (op.N & 7) == 0;
+  const bool tma_epi = !op.no_tma_epi && strides_ok && op.num_phases == 1 && splits == 1 && op.b_mode == B_PLAIN &&
+                       bn % 32 == 0 && (!geglu || bn % 64 == 0) && !(op.residual && op.out_tr) &&
+                       (op.out_f32 || op.out_bf16) &&
+                       (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
+                       (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
+                       (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0) &&
+                       getenv("LDM_B200_TMA_EPI") != nullptr;   // opt-in: measured on par with the staged path
+  p.tma_epi = tma_epi ? 1 : 0;
+  if (tma_epi) {
+    p.epi_r_off = 0;
+    p.epi_o32_off = op.residual ? 32768 : 0;
+    p.epi_o16_off = p.epi_o32_off + (op.out_f32 ? 16384 : 0);
+    p.epi_half_stride = p.epi_o16_off + (op.out_bf16 ? 8192 : 0);
+    p.epi_bytes = 2 * p.epi_half_stride;
+  } else {
+    p.epi_bytes = GEMM_EPI_LEGACY_BYTES;
+  }
+  int stages = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - p.epi_bytes - 1024) / slot;  // + 1 KB alignment slack
   if (stages > 8) stages = 8;
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
@@ -231,10 +274,15 @@ void Engine::gemm(const GemmOp& op) {
   }
   encode_map(&p.bmap, op.b, bn, 1, 1);
   p.b_swap = op.b.swap_xy ? 1 : 0;
+  if (p.tma_epi) {
+    if (op.out_f32) encode_out_map(&p.omap32, op.out_f32, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
+    if (op.out_bf16) encode_out_map(&p.omap16, op.out_bf16, 2, false, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
+    if (op.residual) encode_out_map(&p.rmap, op.residual, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
+  }
   const int total_tiles = m_tiles * p.n_tiles * splits;
   int ctas = max_ctas > 0 ? max_ctas : num_sms;
   if (ctas > total_tiles) ctas = total_tiles;
-  const int smem = stages * slot + GEMM_CTRL_BYTES + 1024;
+  const int smem = stages * slot + GEMM_CTRL_BYTES + p.epi_bytes + 1024;
   LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile) {

@@ -43,6 +43,7 @@ struct GemmOp {
   int dbg = 0;
   long long* trace = nullptr;
   int splits = 0;   // 0 = choose automatically, 1 = never split K
+  int no_tma_epi = 0;  // test hook: force the register/staged epilogue
   const float* bias = nullptr;
   const float* bias2 = nullptr;
   int bias2_stride = 0;
@@ -122,6 +123,8 @@ class Engine {
 
  private:
   void encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, int box_n);
+  void encode_out_map(CUtensorMap* m, const void* ptr, int elem_bytes, bool is_float32, int N, int W, int H, int NB,
+                      long long sx, long long sy, long long sn, int w_b, int h_b, int n_b);
   void* encode_fn_ = nullptr;
 };
 

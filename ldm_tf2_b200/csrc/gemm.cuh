@@ -28,7 +28,8 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_SEGS = 12;
 constexpr int GEMM_THREADS = 320;   // producer + MMA + 8 epilogue warps
 constexpr int GEMM_EPI_PITCH = 36;    // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
-constexpr int GEMM_CTRL_BYTES = 2048 + 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // barriers, bias, staging
+constexpr int GEMM_CTRL_BYTES = 2048;                                          // barriers, bias
+constexpr int GEMM_EPI_LEGACY_BYTES = 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // per-warp staging + row offsets
 constexpr int GEMM_SMEM_BYTES = 227 * 1024;
 
 enum ActKind : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };
@@ -45,6 +46,8 @@ struct GemmSeg {
 struct GemmParams {
   CUtensorMap amap[3];
   CUtensorMap bmap;
+  // TMA epilogue (tma_epi): fp32 / 16-bit outputs and fp32 residual as 4-D maps (32 cols, w_b, h_b, n_b)
+  CUtensorMap omap32, omap16, rmap;
   GemmSeg segs[GEMM_MAX_SEGS];
   int num_segs;
   int total_kb;
@@ -65,6 +68,9 @@ struct GemmParams {
   long long ws_split_stride;
   long long* trace;         // optional [cta][tile slot][16] clock64 stamps (microbenchmark only)
   int dbg;                  // microbenchmark switches: 1 = no TMA loads, 2 = no MMA, 4 = no epilogue stores
+  int tma_epi;              // 1: outputs / residual go through TMA (see the epilogue)
+  int epi_bytes;            // bytes of the epilogue smem area after the 2 KB control block
+  int epi_half_stride, epi_r_off, epi_o32_off, epi_o16_off;  // layout of one half's area (TMA epilogue)
   int off32;                // 1: every output element offset fits in 31 bits
   int epi_vec;              // 1: all output offsets are multiples of 4 elements -> coalesced vector epilogue
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
@@ -192,8 +198,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
-  float* stage_all = reinterpret_cast<float*>(ctrl + 2048);                                   // 8 x [32][36] fp32
-  long long* roff_all = reinterpret_cast<long long*>(ctrl + 2048 + 8 * 32 * GEMM_EPI_PITCH * 4);  // 8 x [32]
+  uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(ctrl + 1536);  // [half][slot] residual tiles landed
+  uint8_t* epi_area = ctrl + 2048;  // legacy: 8 x [32][36] fp32 staging + 8 x [32] offsets; TMA mode: per-half tiles
+  float* stage_all = reinterpret_cast<float*>(epi_area);
+  long long* roff_all = reinterpret_cast<long long*>(epi_area + 8 * 32 * GEMM_EPI_PITCH * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,6 +219,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&p.omap32);
+      tma_prefetch_desc(&p.omap16);
+      tma_prefetch_desc(&p.rmap);
     }
     mbar_fence_init();
   }
@@ -329,6 +343,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint32_t aphase = 0;
     const int hw_b = p.h_b * p.w_b;
     const bool geglu = p.act == ACT_GEGLU;
+    const bool elected = (quad == 0) && (lane == 0);   // one thread per half issues the TMA copies
+    uint8_t* e_half = epi_area + half * p.epi_half_stride;
+    uint8_t* e_r = e_half + p.epi_r_off;
+    uint8_t* e_o32 = e_half + p.epi_o32_off;
+    uint8_t* e_o16 = e_half + p.epi_o16_off;
+    const uint32_t rfull0 = smem_u32(rfull_bar);
+    int rseq = 0;   // residual tiles consumed so far by this half (slot = rseq & 1, parity = (rseq >> 1) & 1)
     const bool split = p.splits > 1;
     const int act = split ? (int)ACT_NONE : p.act;   // split-K: raw partial sums, epilogue in the finalize kernel
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -379,20 +400,37 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         bias_s[c] = b;
       }
       // vector path: aligned 32-bit offsets and every row of this warp inside the tensor
-      const bool warp_rows_ok = __all_sync(0xffffffffu, row_ok) && p.epi_vec && p.off32;
-      roff[lane] = (int)row_off;
+      const bool use_tma = p.tma_epi && !split;
+      const bool warp_rows_ok = !use_tma && __all_sync(0xffffffffu, row_ok) && p.epi_vec && p.off32;
+      if (!use_tma) roff[lane] = (int)row_off;   // (the TMA epilogue reuses this area for its tiles)
       named_bar_sync(1, 256);
       int base[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) base[it] = roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
+      for (int it = 0; it < 8; ++it) base[it] = use_tma ? 0 : roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
       if (tre) tre[8] = clock64();
+      const int n32_all = geglu ? (p.block_n >> 6) : (p.block_n >> 5);
+      const int kch_total = (n32_all - half + 1) / 2;   // chunks this half handles per tile
+      if (use_tma && resid && elected) {
+        // residual tiles of this half's first two chunks: requested before the accumulator is ready
+        const int cbase = geglu ? t.n_tile * (p.block_n >> 1) : t.n0;
+        for (int k = 0; k < 2 && k < kch_total; ++k) {
+          const int slot = (rseq + k) & 1;
+          const int ci0 = half + 2 * k;
+          const uint32_t fb = rfull0 + (uint32_t)((half * 2 + slot) * 8);
+          if (!(p.out_tr && cbase + ci0 * 32 >= p.tr_col0)) {
+            mbar_expect_tx_a(fb, (uint32_t)(p.box_rows * 128));
+            tma_load_4d_a(smem_u32(e_r + slot * 16384), &p.rmap, fb, cbase + ci0 * 32, t.x0, t.y0, t.img0);
+          }
+        }
+      }
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       if (tre) tre[5] = clock64();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
       const int n32 = geglu ? (p.block_n >> 6) : (p.block_n >> 5);   // 32-column output chunks per tile
       const int hcols = p.block_n >> 1;
-      for (int ci = half; ci < n32; ci += 2) {
+      int kch = 0;   // this half's chunk counter inside the tile
+      for (int ci = half; ci < n32; ci += 2, ++kch) {
         const int c = ci * 32;
         uint32_t rr[32];
         float acc[32];
@@ -435,11 +473,63 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         if (tre && ci < 6) tre[9 + ci] = clock64();
         const bool to_tr = p.out_tr && col0 >= p.tr_col0;
-        if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
+        if (use_tma && !to_tr) {
+          // ---- TMA epilogue: x = acc (+ residual tile from smem) -> swizzled smem tiles -> TMA stores.
+          // The 128 threads of this half own one 128-row x 32-column chunk.
+          const int slot = (rseq + kch) & 1;
+          if (resid) mbar_wait_a(rfull0 + (uint32_t)((half * 2 + slot) * 8), (uint32_t)(((rseq + kch) >> 1) & 1));
+          if (elected) tma_store_wait_read();        // previous chunk's stores have drained the staging tiles
+          named_bar_sync(2 + half, 128);
+          const uint32_t sw = (uint32_t)(r & 7);
+          if (resid) {
+            const uint8_t* rrow = e_r + slot * 16384 + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q4 = *reinterpret_cast<const float4*>(rrow + ((j ^ sw) << 4));
+              acc[4 * j] += q4.x; acc[4 * j + 1] += q4.y; acc[4 * j + 2] += q4.z; acc[4 * j + 3] += q4.w;
+            }
+          }
+          if (o32) {
+            uint8_t* orow = e_o32 + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(orow + ((j ^ sw) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+          if (o16) {
+            uint8_t* orow = e_o16 + r * 64;
+            const uint32_t sw2 = (uint32_t)((r >> 1) & 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack16(acc[8 * j], acc[8 * j + 1], p.fp16);
+              u.y = pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16);
+              u.z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
+              u.w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
+              *reinterpret_cast<uint4*>(orow + ((j ^ sw2) << 4)) = u;
+            }
+          }
+          fence_proxy_async_cta();
+          named_bar_sync(2 + half, 128);
+          if (elected) {
+            if (!(p.dbg & 4)) {
+              if (o32) tma_store_4d_a(&p.omap32, smem_u32(e_o32), col0, t.x0, t.y0, t.img0);
+              if (o16) tma_store_4d_a(&p.omap16, smem_u32(e_o16), col0, t.x0, t.y0, t.img0);
+              tma_store_commit();
+            }
+            // the residual slot just consumed is free: fetch this half's chunk after next
+            if (resid && ci + 4 < n32) {
+              const int ncol0 = col0 + 128;
+              const uint32_t fb = rfull0 + (uint32_t)((half * 2 + slot) * 8);
+              mbar_expect_tx_a(fb, (uint32_t)(p.box_rows * 128));
+              tma_load_4d_a(smem_u32(e_r + slot * 16384), &p.rmap, fb, ncol0, t.x0, t.y0, t.img0);
+            }
+          }
+        } else if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
           epi_store_staged32(acc, col0, stage, base, lane, o32, o16, resid, p.fp16);
         else
           epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
       }
+      if (use_tma && resid) rseq += kch_total;
       if (!geglu && (p.block_n & 31) && (n32 & 1) == half) {   // ragged 16-column tail chunk
         const int c = n32 * 32;
         uint32_t r16[16];
@@ -464,6 +554,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
   }
 
+  if (p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // drain this half's TMA stores
   tc_fence_before();
   __syncthreads();
   if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 1] = clock64();  // kernel end

@@ -308,17 +308,21 @@ extern "C" LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int w
 extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
                                       int iters, float* avg_ms, long long* trace_host /* [148*64*16] or null */,
                                       int with_residual) {
+  // dbg bits 8..11 carry an activation code (3 = GEGLU: n output columns from 2n weight rows)
+  const int act = (dbg >> 8) & 15;
+  dbg &= 255;
   API_BEGIN
   NEED(h);
   Engine& e = h->model->eng;
   CUDA_CHECK(cudaSetDevice(e.device));
   const int ktot = conv ? 9 * k : k;
+  const int wn = act == ACT_GEGLU ? 2 * n : n;
   bf16 *a, *w, *o;
   CUDA_CHECK(cudaMalloc(&a, (size_t)rows * k * 2));
-  CUDA_CHECK(cudaMalloc(&w, (size_t)n * ktot * 2));
+  CUDA_CHECK(cudaMalloc(&w, (size_t)wn * ktot * 2));
   CUDA_CHECK(cudaMalloc(&o, (size_t)rows * n * 2));
   CUDA_CHECK(cudaMemset(a, 0, (size_t)rows * k * 2));
-  CUDA_CHECK(cudaMemset(w, 0, (size_t)n * ktot * 2));
+  CUDA_CHECK(cudaMemset(w, 0, (size_t)wn * ktot * 2));
   GemmOp op;
   op.num_a = 1;
   int bk = 0;
@@ -335,8 +339,8 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
     op.W = rows; op.H = 1; op.NB = 1;
     op.os_x = n;
   }
-  op.b = view_mat(w, n, ktot, ktot);
-  op.N = n; op.block_n = block_n; op.dbg = dbg;
+  op.b = view_mat(w, wn, ktot, ktot);
+  op.N = n; op.gemm_n = wn; op.act = act; op.block_n = block_n; op.dbg = dbg;
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual) {

@@ -285,14 +285,24 @@ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, int fp
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, branch-free: one rcp, one ex2, five FMAs);
 // exact-erf GELU of tf.nn.gelu (unet.py:324, transformer.py:169) to fp32 round-off.
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float erf_as(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = mufu_rcp(fmaf(0.3275911f, ax, 1.0f));
   float y = fmaf(1.061405429f, t, -1.453152027f);
   y = fmaf(y, t, 1.421413741f);
   y = fmaf(y, t, -0.284496736f);
   y = fmaf(y, t, 0.254829592f);
-  y = y * t * exp2f(-ax * ax * 1.4426950408889634f);
+  y = y * t * mufu_ex2(ax * ax * -1.4426950408889634f);
   return copysignf(1.0f - y, x);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {

@@ -149,6 +149,33 @@ __device__ __noinline__ void epi_store_direct(const GemmParams& p, const float* 
 // smem tile; afterwards 8 lanes cover one row with float4, so each instruction moves four whole
 // 128-byte row segments.  base[it] = this lane's element offset of row (4*it + lane/8), column
 // 4*(lane%8) (32-bit, precomputed once per tile).  No per-lane predicates in the loops.
+// Transposed 16-bit store (V^T for attention): out_tr[(col - tr_col0) * ts_c + x] for a warp whose 32
+// rows are 32 consecutive x of one (img, y).  Through the smem tile each lane ends up owning one
+// output column and writes its 32 x-values as four 16-byte stores instead of 32 two-byte ones.
+__device__ __forceinline__ void epi_store_transposed32(const GemmParams& p, const float* v, int col0, float* stage,
+                                                       int lane, long long tr_base /* of x = first row */) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<float4*>(stage + lane * GEMM_EPI_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+  float x[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) x[t] = stage[t * GEMM_EPI_PITCH + lane];
+  if (col0 + lane < p.N) {
+    bf16* dst = p.out_tr + tr_base + (long long)(col0 + lane - p.tr_col0) * p.ts_c;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 u;
+      u.x = pack16(x[8 * g8], x[8 * g8 + 1], p.fp16);
+      u.y = pack16(x[8 * g8 + 2], x[8 * g8 + 3], p.fp16);
+      u.z = pack16(x[8 * g8 + 4], x[8 * g8 + 5], p.fp16);
+      u.w = pack16(x[8 * g8 + 6], x[8 * g8 + 7], p.fp16);
+      *reinterpret_cast<uint4*>(dst + 8 * g8) = u;
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void epi_store_staged32(const float* v, int col0, float* stage, const int* base, int lane,
                                                    float* o32, bf16* o16, const float* resid, int fp16) {
 #pragma unroll
@@ -402,6 +429,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       // vector path: aligned 32-bit offsets and every row of this warp inside the tensor
       const bool use_tma = p.tma_epi && !split;
       const bool warp_rows_ok = !use_tma && __all_sync(0xffffffffu, row_ok) && p.epi_vec && p.off32;
+      // vectorised V^T stores: the warp's rows are 32 consecutive, valid x of one (img, y), 16-byte aligned
+      const bool tr_vec_ok = p.out_tr && !use_tma && (p.w_b & 31) == 0 && __all_sync(0xffffffffu, row_ok) &&
+                             ((p.ts_c | p.ts_n | p.ts_y) & 7) == 0 && ((p.W & 7) == 0 || true) &&
+                             (((tr_row_off + xq - lane) & 7) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(p.out_tr) & 15) == 0);
       if (!use_tma) roff[lane] = (int)row_off;   // (the TMA epilogue reuses this area for its tiles)
       named_bar_sync(1, 256);
       int base[8];
@@ -442,10 +474,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(rr[j]) * p.alpha + bias_s[c + j];
-            const float gt = __uint_as_float(rg[j]) * p.alpha + bias_s[hcols + c + j];
-            acc[j] = a * gelu_erf_f(gt);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
+            const float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
+            acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, ba.x) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), p.alpha, bg.x));
+            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, ba.y) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 1]), p.alpha, bg.y));
+            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, ba.z) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 2]), p.alpha, bg.z));
+            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, ba.w) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 3]), p.alpha, bg.w));
           }
           col0 = t.n_tile * hcols + c;
         } else {
@@ -524,7 +559,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               tma_load_4d_a(smem_u32(e_r + slot * 16384), &p.rmap, fb, ncol0, t.x0, t.y0, t.img0);
             }
           }
-        } else if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
+        } else if (to_tr && tr_vec_ok)
+          epi_store_transposed32(p, acc, col0, stage, lane, tr_row_off + xq - lane);
+        else if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
           epi_store_staged32(acc, col0, stage, base, lane, o32, o16, resid, p.fp16);
         else
           epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <chrono>
 #include <map>
 #include <algorithm>
 
@@ -1186,6 +1187,9 @@ void Model::decode_body(const float* z, int b, int h, int w, float div, float* i
 void Model::decode(const float* z, int b, int h, int w, float div, float* img_out, long long* idx_out) {
   LDM_CHECK(finalized && model_ready_[2], "decode: autoencoder weights not finalized");
   CUDA_CHECK(cudaSetDevice(eng.device));
+  static const bool dbg_t = getenv("LDM_B200_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   const long long rows = (long long)b * h * w;
   const long long img_el = rows * 64 * 3;
   float *zd, *imgd;
@@ -1198,8 +1202,10 @@ void Model::decode(const float* z, int b, int h, int w, float div, float* img_ou
   decode_body(zd, b, h, w, div, imgd, idxd);
   eng.launches = l0; eng.gemm_launches = g0;
   eng.arena.dry = false; eng.dry = false;
+  const double t1 = now();
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
+  const double t2 = now();
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -1209,11 +1215,14 @@ void Model::decode(const float* z, int b, int h, int w, float div, float* img_ou
   CUDA_CHECK(cudaMemcpyAsync(img_out, imgd, img_el * sizeof(float), cudaMemcpyDefault, eng.stream));
   if (idx_out && idxd) CUDA_CHECK(cudaMemcpyAsync(idx_out, idxd, rows * sizeof(long long), cudaMemcpyDefault, eng.stream));
   CUDA_CHECK(cudaEventRecord(e1, eng.stream));
+  const double t3 = now();
   eng.sync();
+  const double t4 = now();
   CUDA_CHECK(cudaEventElapsedTime(&last_decode_ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(zd); cudaFree(imgd);
   if (idxd) cudaFree(idxd);
+  if (dbg_t) fprintf(stderr, "decode: malloc+dry %.1f ms, ensure_arena %.1f ms, enqueue %.1f ms, sync %.1f ms, free %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
 }
 
 void Model::vq_argmin(const float* z, long long rows, float div, long long* idx_out, float* zq_out) {

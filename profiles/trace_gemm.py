@@ -7,8 +7,8 @@ from oracle import ldm_oracle as O
 cfg = O.TINY_CONFIG
 h = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), 0)
 import itertools
-for (rows, k, n, conv, res), dbg in itertools.product([(16384, 320, 320, 0, 1), (16384, 320, 320, 0, 0)], [0, 4]):
-    ms, tr = h.bench_gemm(rows, k, n, 0, dbg, conv, 32, 20, trace=True, residual=bool(res))
+for (rows, k, n, conv, res), dbg in itertools.product([(16384, 320, 1280, 0, 0)], [0x300, 0x304]):
+    ms, tr = h.bench_gemm(rows, k, n, 256 if dbg >> 8 == 3 else 0, dbg, conv, 32, 20, trace=True, residual=bool(res))
     print(f"\nrows={rows} k={k} n={n} conv={conv} residual={res} dbg={dbg}: {ms*1e3:.1f} us/launch")
     for cta in (0,):
         t = tr[cta]

@@ -3,7 +3,6 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
-#include <chrono>
 #include <map>
 #include <algorithm>
 
@@ -188,6 +187,8 @@ Model::~Model() {
     for (auto& s : v)
       if (s.f32) cudaFree(s.f32);
   for (void* p : owned_) cudaFree(p);
+  for (void* p : stage_ptr_) if (p) cudaFree(p);
+  if (ev0_) { cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); }
 }
 
 void Model::build() {
@@ -773,6 +774,22 @@ void Model::compute_temb_table(const int* t_host, int rows, float* table) {
   cudaFree(t_dev); cudaFree(emb); cudaFree(h1); cudaFree(temb);
 }
 
+void* Model::stage(int slot, size_t bytes) {
+  if (stage_cap_[slot] < bytes) {
+    if (stage_ptr_[slot]) { eng.sync(); cudaFree(stage_ptr_[slot]); stage_ptr_[slot] = nullptr; stage_cap_[slot] = 0; }
+    const size_t cap = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    CUDA_CHECK(cudaMalloc(&stage_ptr_[slot], cap));
+    stage_cap_[slot] = cap;
+  }
+  return stage_ptr_[slot];
+}
+
+void Model::ensure_events() {
+  if (ev0_) return;
+  CUDA_CHECK(cudaEventCreate(&ev0_));
+  CUDA_CHECK(cudaEventCreate(&ev1_));
+}
+
 // =====================================================================================
 // Context: hoisted K / V^T projections of all SpatialTransformers (unet.py:276-277)
 // =====================================================================================
@@ -781,10 +798,9 @@ void Model::set_context(const float* ctx, int n) {
   CUDA_CHECK(cudaSetDevice(eng.device));
   const int tk = cfg.max_seq_len, cd = cfg.context_dim, tpad = round_up(tk, 8);
   const size_t nel = (size_t)n * tk * cd;
-  float* cf = nullptr;
-  bf16* cb = nullptr;
-  CUDA_CHECK(cudaMalloc(&cf, nel * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&cb, nel * sizeof(bf16)));
+  float* cf = static_cast<float*>(stage(ST_A, nel * sizeof(float)));
+  bf16* cb = static_cast<bf16*>(stage(ST_B, nel * sizeof(bf16)));
+  bool realloc_ctx = false;
   CUDA_CHECK(cudaMemcpyAsync(cf, ctx, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
   launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.fp16, eng.stream);
   for (STW* s : all_st_) {
@@ -792,6 +808,7 @@ void Model::set_context(const float* ctx, int n) {
     if (ctx_rows_ != n || !s->ctx_k) {
       s->ctx_k = dev_alloc<bf16>((size_t)n * tk * c);
       s->ctx_vt = dev_alloc<bf16>((size_t)n * c * tpad, true);
+      realloc_ctx = true;
     }
     GemmOp op;
     op.num_a = 1;
@@ -810,9 +827,8 @@ void Model::set_context(const float* ctx, int n) {
   }
   ctx_rows_ = n;
   eng.sync();
-  cudaFree(cf);
-  cudaFree(cb);
-  if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+  // the captured step reads ctx_k / ctx_vt by address: only new buffers invalidate it
+  if (realloc_ctx && step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
 }
 
 // =====================================================================================
@@ -893,9 +909,8 @@ void Model::unet_forward(const float* x, const int* t_host, int n, int h, int w,
   temb_table_ = fwd_temb_;
   temb_by_img_ = true; temb_use_step_ = false;
   const size_t nel = (size_t)n * h * w * 4;
-  float* xd = nullptr; float* ed = nullptr;
-  CUDA_CHECK(cudaMalloc(&xd, nel * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&ed, (size_t)n * h * w * cfg.out_channels * sizeof(float)));
+  float* xd = static_cast<float*>(stage(ST_A, nel * sizeof(float)));
+  float* ed = static_cast<float*>(stage(ST_B, (size_t)n * h * w * cfg.out_channels * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(xd, x, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
   // size the arena with a dry pass, then run
   eng.arena.dry = true; eng.dry = true; eng.arena.reset();
@@ -909,8 +924,6 @@ void Model::unet_forward(const float* x, const int* t_host, int n, int h, int w,
   CUDA_CHECK(cudaMemcpyAsync(eps_out, ed, (size_t)n * h * w * cfg.out_channels * sizeof(float), cudaMemcpyDefault,
                              eng.stream));
   eng.sync();
-  cudaFree(xd);
-  cudaFree(ed);
 }
 
 // =====================================================================================
@@ -933,25 +946,20 @@ void Model::ddim_step(const float* xt, const float* eps2, const float* noise, in
   LDM_CHECK(S_ > 0 && index >= 0 && index < S_, "ddim_step: index %d outside [0,%d)", index, S_);
   CUDA_CHECK(cudaSetDevice(eng.device));
   const long long nh = (long long)b * h * w * 4;
-  float *dx, *de, *dn = nullptr, *dout, *d0 = nullptr;
-  CUDA_CHECK(cudaMalloc(&dx, nh * 4));
-  CUDA_CHECK(cudaMalloc(&de, 2 * nh * 4));
-  CUDA_CHECK(cudaMalloc(&dout, nh * 4));
+  float *dx = static_cast<float*>(stage(ST_A, nh * 4)), *de = static_cast<float*>(stage(ST_B, 2 * nh * 4));
+  float *dout = static_cast<float*>(stage(ST_C, nh * 4)), *dn = nullptr, *d0 = nullptr;
   CUDA_CHECK(cudaMemcpyAsync(dx, xt, nh * 4, cudaMemcpyDefault, eng.stream));
   CUDA_CHECK(cudaMemcpyAsync(de, eps2, 2 * nh * 4, cudaMemcpyDefault, eng.stream));
   if (noise) {
-    CUDA_CHECK(cudaMalloc(&dn, nh * 4));
+    dn = static_cast<float*>(stage(ST_D, nh * 4));
     CUDA_CHECK(cudaMemcpyAsync(dn, noise, nh * 4, cudaMemcpyDefault, eng.stream));
   }
-  if (x0_out) CUDA_CHECK(cudaMalloc(&d0, nh * 4));
+  if (x0_out) d0 = static_cast<float*>(stage(ST_E, nh * 4));
   launch_ddim_update(de, dx, dn, 0, coeffs_dev_, nullptr, index, guidance, clip, dout, d0, nh, eng.stream);
   eng.launches++;
   CUDA_CHECK(cudaMemcpyAsync(xt_out, dout, nh * 4, cudaMemcpyDefault, eng.stream));
   if (x0_out) CUDA_CHECK(cudaMemcpyAsync(x0_out, d0, nh * 4, cudaMemcpyDefault, eng.stream));
   eng.sync();
-  cudaFree(dx); cudaFree(de); cudaFree(dout);
-  if (dn) cudaFree(dn);
-  if (d0) cudaFree(d0);
 }
 
 void Model::sample(const float* x_init, const float* noise, int b, int h, int w, float guidance, float* latents_out,
@@ -982,9 +990,8 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
   eng.arena.dry = false; eng.dry = false;
   ensure_arena(eng.arena.peak());
 
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0));
-  CUDA_CHECK(cudaEventCreate(&e1));
+  ensure_events();
+  cudaEvent_t e0 = ev0_, e1 = ev1_;
   CUDA_CHECK(cudaEventRecord(e0, eng.stream));
   CUDA_CHECK(cudaMemcpyAsync(xt_dev_, x_init, nh * 4, cudaMemcpyDefault, eng.stream));
   if (noise) CUDA_CHECK(cudaMemcpyAsync(noise_dev_, noise, nh * S_ * 4, cudaMemcpyDefault, eng.stream));
@@ -1030,8 +1037,6 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
   eng.sync();
   CUDA_CHECK(cudaEventElapsedTime(&last_loop_ms, e0, e1));
   last_step_ms = last_loop_ms / nsteps;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
 }
 
 // =====================================================================================
@@ -1084,11 +1089,9 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
       linear(hbuf, R, L.f2, L.f2.bias->f32, ACT_NONE, x, x, nullptr);
     }
   };
-  long long* ids_dev = nullptr;
-  float *x = nullptr, *y = nullptr;
-  CUDA_CHECK(cudaMalloc(&ids_dev, uids.size() * sizeof(long long)));
-  CUDA_CHECK(cudaMalloc(&x, (size_t)R * D * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&y, (size_t)R * D * sizeof(float)));
+  long long* ids_dev = static_cast<long long*>(stage(ST_C, uids.size() * sizeof(long long)));
+  float* x = static_cast<float*>(stage(ST_D, (size_t)R * D * sizeof(float)));
+  float* y = static_cast<float*>(stage(ST_E, (size_t)R * D * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(ids_dev, uids.data(), uids.size() * sizeof(long long), cudaMemcpyHostToDevice, eng.stream));
   eng.arena.dry = true; eng.dry = true; eng.arena.reset();
   const long long l0 = eng.launches, g0 = eng.gemm_launches;
@@ -1104,7 +1107,6 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
     CUDA_CHECK(cudaMemcpyAsync(ctx_out + (long long)r * T * D, y + (long long)uniq_of[r] * T * D,
                                (size_t)T * D * sizeof(float), cudaMemcpyDefault, eng.stream));
   eng.sync();
-  cudaFree(ids_dev); cudaFree(x); cudaFree(y);
 }
 
 // =====================================================================================
@@ -1187,73 +1189,52 @@ void Model::decode_body(const float* z, int b, int h, int w, float div, float* i
 void Model::decode(const float* z, int b, int h, int w, float div, float* img_out, long long* idx_out) {
   LDM_CHECK(finalized && model_ready_[2], "decode: autoencoder weights not finalized");
   CUDA_CHECK(cudaSetDevice(eng.device));
-  static const bool dbg_t = getenv("LDM_B200_DEBUG_TIMING") != nullptr;
-  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t0 = now();
   const long long rows = (long long)b * h * w;
   const long long img_el = rows * 64 * 3;
-  float *zd, *imgd;
-  long long* idxd = nullptr;
-  CUDA_CHECK(cudaMalloc(&zd, rows * 4 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&imgd, img_el * sizeof(float)));
-  if (cfg.ae_kind == 1) CUDA_CHECK(cudaMalloc(&idxd, rows * sizeof(long long)));
+  float* zd = static_cast<float*>(stage(ST_A, rows * 4 * sizeof(float)));
+  float* imgd = static_cast<float*>(stage(ST_B, img_el * sizeof(float)));
+  long long* idxd = cfg.ae_kind == 1 ? static_cast<long long*>(stage(ST_C, rows * sizeof(long long))) : nullptr;
   eng.arena.dry = true; eng.dry = true; eng.arena.reset();
   const long long l0 = eng.launches, g0 = eng.gemm_launches;
   decode_body(zd, b, h, w, div, imgd, idxd);
   eng.launches = l0; eng.gemm_launches = g0;
   eng.arena.dry = false; eng.dry = false;
-  const double t1 = now();
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
-  const double t2 = now();
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0));
-  CUDA_CHECK(cudaEventCreate(&e1));
-  CUDA_CHECK(cudaEventRecord(e0, eng.stream));
+  ensure_events();
+  CUDA_CHECK(cudaEventRecord(ev0_, eng.stream));
   CUDA_CHECK(cudaMemcpyAsync(zd, z, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
   decode_body(zd, b, h, w, div, imgd, idxd);
   CUDA_CHECK(cudaMemcpyAsync(img_out, imgd, img_el * sizeof(float), cudaMemcpyDefault, eng.stream));
   if (idx_out && idxd) CUDA_CHECK(cudaMemcpyAsync(idx_out, idxd, rows * sizeof(long long), cudaMemcpyDefault, eng.stream));
-  CUDA_CHECK(cudaEventRecord(e1, eng.stream));
-  const double t3 = now();
+  CUDA_CHECK(cudaEventRecord(ev1_, eng.stream));
   eng.sync();
-  const double t4 = now();
-  CUDA_CHECK(cudaEventElapsedTime(&last_decode_ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(zd); cudaFree(imgd);
-  if (idxd) cudaFree(idxd);
-  if (dbg_t) fprintf(stderr, "decode: malloc+dry %.1f ms, ensure_arena %.1f ms, enqueue %.1f ms, sync %.1f ms, free %.1f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
+  CUDA_CHECK(cudaEventElapsedTime(&last_decode_ms, ev0_, ev1_));
 }
 
 void Model::vq_argmin(const float* z, long long rows, float div, long long* idx_out, float* zq_out) {
   LDM_CHECK(codebook_ && codebook_->set, "vq_argmin: codebook not set (autoencoder kind must be vq)");
   CUDA_CHECK(cudaSetDevice(eng.device));
-  float *zd, *zq;
-  long long* idxd;
-  CUDA_CHECK(cudaMalloc(&zd, rows * 4 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&zq, rows * 4 * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&idxd, rows * sizeof(long long)));
+  float* zd = static_cast<float*>(stage(ST_A, rows * 4 * sizeof(float)));
+  float* zq = static_cast<float*>(stage(ST_B, rows * 4 * sizeof(float)));
+  long long* idxd = static_cast<long long*>(stage(ST_C, rows * sizeof(long long)));
   CUDA_CHECK(cudaMemcpyAsync(zd, z, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
   launch_vq_argmin(zd, rows, 4, codebook_->f32, cfg.vq_vocab, div, idxd, zq, eng.stream);
   eng.launches += 3;
   CUDA_CHECK(cudaMemcpyAsync(idx_out, idxd, rows * sizeof(long long), cudaMemcpyDefault, eng.stream));
   if (zq_out) CUDA_CHECK(cudaMemcpyAsync(zq_out, zq, rows * 4 * sizeof(float), cudaMemcpyDefault, eng.stream));
   eng.sync();
-  cudaFree(zd); cudaFree(zq); cudaFree(idxd);
 }
 
 void Model::tensor_to_image(const float* img, int n, long long per, unsigned char* out) {
   CUDA_CHECK(cudaSetDevice(eng.device));
-  float* d;
-  unsigned char* o;
-  CUDA_CHECK(cudaMalloc(&d, (size_t)n * per * sizeof(float)));
-  CUDA_CHECK(cudaMalloc(&o, (size_t)n * per));
+  float* d = static_cast<float*>(stage(ST_A, (size_t)n * per * sizeof(float)));
+  unsigned char* o = static_cast<unsigned char*>(stage(ST_B, (size_t)n * per));
   CUDA_CHECK(cudaMemcpyAsync(d, img, (size_t)n * per * sizeof(float), cudaMemcpyDefault, eng.stream));
   launch_tensor_to_image(d, n, per, o, eng.stream);
   eng.launches++;
   CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * per, cudaMemcpyDefault, eng.stream));
   eng.sync();
-  cudaFree(d); cudaFree(o);
 }
 
 }  // namespace ldm

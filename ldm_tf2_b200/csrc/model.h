@@ -183,6 +183,13 @@ class Model {
   double* gn_pool_ = nullptr; size_t gn_pool_cap_ = 0, gn_pool_off_ = 0, gn_pool_need_ = 0;
   void begin_pass();
   std::vector<void*> owned_;  // cudaMalloc'ed persistent buffers
+  // grow-only staging buffers for the API calls' host<->device copies: steady-state calls never
+  // touch cudaMalloc / cudaFree (both serialise on the driver and stall behind other processes)
+  enum { ST_A = 0, ST_B, ST_C, ST_D, ST_E, ST_COUNT };
+  void* stage_ptr_[ST_COUNT] = {}; size_t stage_cap_[ST_COUNT] = {};
+  void* stage(int slot, size_t bytes);
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  void ensure_events();
   template <typename T> T* dev_alloc(size_t n, bool zero = false);
 };
 

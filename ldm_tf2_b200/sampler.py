@@ -107,11 +107,14 @@ class LatentDiffusionModelSampler:
         self._ctx_key = None
 
     # -- helpers ------------------------------------------------------------
-    def _set_context(self, cond):
+    def _set_context(self, cond, force=False):
+        """Uploads the context and re-projects every cross-attention K / V.  The per-step API
+        (ddim_sample) passes the same context 50 times, so an unchanged host array is skipped there;
+        a sampling loop call always re-projects (force=True)."""
         cond, _, keep = borrow(cond, np.float32)
         if isinstance(cond, np.ndarray):
-            key = (cond.shape, hash(cond.tobytes()))
-            if key != self._ctx_key:
+            key = None if force else (cond.shape, hash(cond.tobytes()))
+            if force or key != self._ctx_key:
                 self.handle.set_context(cond)
                 self._ctx_key = key
         else:  # device pointer
@@ -167,7 +170,7 @@ class LatentDiffusionModelSampler:
             noise = self._rng.standard_normal((S,) + shape, dtype=np.float32)
         if self._eta == 0:
             noise = None
-        self._set_context(context)
+        self._set_context(context, force=True)
         x_final = self.handle.sample(x_init, noise, guidance_scale, use_graph=self._use_graph)
         print(f"[INFO] Done running denoising for {self._num_ddim_steps} steps with eta {self._eta}")
         sys.stdout.flush()

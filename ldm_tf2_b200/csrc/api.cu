@@ -310,6 +310,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
                                       int with_residual) {
   // dbg bits 8..11 carry an activation code (3 = GEGLU: n output columns from 2n weight rows)
   const int act = (dbg >> 8) & 15;
+  const int force_splits = (dbg >> 12) & 15;   // bits 12..15: split-K override (0 = engine heuristic)
   dbg &= 255;
   API_BEGIN
   NEED(h);
@@ -341,6 +342,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   }
   op.b = view_mat(w, wn, ktot, ktot);
   op.N = n; op.gemm_n = wn; op.act = act; op.block_n = block_n; op.dbg = dbg;
+  if (force_splits) op.splits = force_splits;
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual) {

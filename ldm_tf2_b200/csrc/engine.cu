@@ -122,22 +122,31 @@ void Engine::encode_out_map(CUtensorMap* m, const void* ptr, int elem_bytes, boo
             (int)r, N, W, H, NB, sx, sy, sn);
 }
 
-int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu) {
-  static const int cand[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
-  const int step = geglu ? 64 : 16;
+// Tile width from a small cost model fitted to profiles/sweep_gemm.py (cycles per CTA):
+//   k-block  = max(MMA issue 2*bn, operand feed (16 KB + bn*128 B) / ~58 B/clk)   [single-CTA UMMA]
+//   epilogue = ~40 cycles per output column of a 128-row tile (fp32 + 16-bit stores, residual read)
+// A persistent CTA overlaps the epilogue of one tile with the main loop of the next.
+// Widths are multiples of 32 (the epilogue's vector chunk); narrower only when N itself is.
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms) {
+  static const int cand[] = {256, 192, 160, 128, 96, 64, 32};
+  const int step = geglu ? 64 : 32;
   int best = 0;
+  double best_t = 0;
   for (int bn : cand) {
     if (bn % step) continue;
     if (gemm_n % bn) continue;
     if (boundary && boundary % bn) continue;
-    if (!best) best = bn;  // largest exact divisor
-    if ((long long)m_tiles * (gemm_n / bn) >= 120) return bn;  // enough CTAs for the 148 SMs
-    if (bn <= 64) break;  // don't shrink tiles below 64 just for parallelism
-    best = bn;
+    const long long tiles = (long long)m_tiles * (gemm_n / bn);
+    const double waves = (double)((tiles + num_sms - 1) / num_sms);
+    const double kb = std::max(2.0 * bn, (16384.0 + bn * 128.0) / 58.0);
+    const double main_t = kb * total_kb, epi_t = 40.0 * bn * (geglu ? 0.75 : 1.0);
+    const double t = 2500.0 + (waves > 1 ? waves * std::max(main_t, epi_t) + std::min(main_t, epi_t) : main_t + epi_t);
+    if (!best || t < best_t) { best = bn; best_t = t; }
   }
   if (best) return best;
   // no exact divisor: one ragged tile set, TMA zero-fills the B rows past gemm_n
-  int bn = ((gemm_n + step - 1) / step) * step;
+  const int s16 = geglu ? 64 : 16;
+  int bn = ((gemm_n + s16 - 1) / s16) * s16;
   return bn > 256 ? 256 : bn;
 }
 
@@ -175,6 +184,7 @@ void Engine::gemm(const GemmOp& op) {
   int bn = op.block_n;
   int splits = 1;
   const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1;
+  if (can_split && bn && op.splits > 1 && total_kb >= 2 * op.splits) splits = op.splits;   // explicit tile + split (tuning hook)
   if (can_split && !bn) {
     // few output tiles and a long K loop (low-resolution convs, text encoder): take the widest
     // tile that divides N and spread the K loop over the idle SMs
@@ -191,7 +201,7 @@ void Engine::gemm(const GemmOp& op) {
       }
     }
   }
-  if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu);
+  if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu, total_kb, num_sms);
   LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 64 == 0), "gemm: bad block_n %d", bn);
   p.block_n = bn;
   p.n_tiles = (gemm_n + bn - 1) / bn;

@@ -128,7 +128,7 @@ class Engine {
   void* encode_fn_ = nullptr;
 };
 
-int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu);
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms);
 void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cudaStream_t st);
 
 }  // namespace ldm

@@ -343,6 +343,8 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.b = view_mat(w, wn, ktot, ktot);
   op.N = n; op.gemm_n = wn; op.act = act; op.block_n = block_n; op.dbg = dbg;
   if (force_splits) op.splits = force_splits;
+  op.pair = (dbg & 16) ? -1 : ((dbg & 32) ? 1 : 0);   // bit 4: single-CTA kernel, bit 5: CTA-pair kernel
+  op.dbg = dbg & 15;
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual) {

@@ -52,8 +52,11 @@ Engine::Engine(int dev) : device(dev) {
   cudaDriverEntryPointQueryResult qres;
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GEMM_SMEM_BYTES));
+  { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
   CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
 }
@@ -123,11 +126,11 @@ void Engine::encode_out_map(CUtensorMap* m, const void* ptr, int elem_bytes, boo
 }
 
 // Tile width from a small cost model fitted to profiles/sweep_gemm.py (cycles per CTA):
-//   k-block  = max(MMA issue 2*bn, operand feed (16 KB + bn*128 B) / ~58 B/clk)   [single-CTA UMMA]
+//   k-block  = max(MMA issue 2*bn, operand feed (16 KB + bn*128 B [pair: bn*64 B]) / ~58 B/clk)
 //   epilogue = ~40 cycles per output column of a 128-row tile (fp32 + 16-bit stores, residual read)
 // A persistent CTA overlaps the epilogue of one tile with the main loop of the next.
 // Widths are multiples of 32 (the epilogue's vector chunk); narrower only when N itself is.
-int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms) {
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms, bool pair) {
   static const int cand[] = {256, 192, 160, 128, 96, 64, 32};
   const int step = geglu ? 64 : 32;
   int best = 0;
@@ -136,11 +139,15 @@ int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_
     if (bn % step) continue;
     if (gemm_n % bn) continue;
     if (boundary && boundary % bn) continue;
-    const long long tiles = (long long)m_tiles * (gemm_n / bn);
-    const double waves = (double)((tiles + num_sms - 1) / num_sms);
-    const double kb = std::max(2.0 * bn, (16384.0 + bn * 128.0) / 58.0);
+    if (bn < 64 && best) continue;   // narrower than 64 only when nothing else divides N
+    // CTA pairs: half as many workers, each taking two M tiles; a CTA pulls only half of the B tile
+    const int workers = pair ? num_sms / 2 : num_sms;
+    const long long tiles = (long long)(pair ? (m_tiles + 1) / 2 : m_tiles) * (gemm_n / bn);
+    const double waves = (double)((tiles + workers - 1) / workers);
+    const double kb = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / 58.0);
     const double main_t = kb * total_kb, epi_t = 40.0 * bn * (geglu ? 0.75 : 1.0);
-    const double t = 2500.0 + (waves > 1 ? waves * std::max(main_t, epi_t) + std::min(main_t, epi_t) : main_t + epi_t);
+    const double t = 2500.0 + 1500.0 * waves +   // launch / prologue, per-tile scheduling + bias staging
+                     (waves > 1 ? waves * std::max(main_t, epi_t) + std::min(main_t, epi_t) : main_t + epi_t);
     if (!best || t < best_t) { best = bn; best_t = t; }
   }
   if (best) return best;
@@ -183,6 +190,9 @@ void Engine::gemm(const GemmOp& op) {
   for (int i = 0; i < op.num_segs; ++i) total_kb += op.segs[i].nkb;
   int bn = op.block_n;
   int splits = 1;
+  // CTA pairs (cta_group::2): plain weights, one phase, at least one full pair of M tiles
+  const bool pair_ok = op.num_phases == 1 && op.b_mode == B_PLAIN && !op.b.swap_xy && m_tiles >= 2;
+  const bool pair = pair_ok && (op.pair > 0 || (op.pair == 0 && pair_default));
   const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1;
   if (can_split && bn && op.splits > 1 && total_kb >= 2 * op.splits) splits = op.splits;   // explicit tile + split (tuning hook)
   if (can_split && !bn) {
@@ -201,10 +211,11 @@ void Engine::gemm(const GemmOp& op) {
       }
     }
   }
-  if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu, total_kb, num_sms);
+  if (!bn) bn = choose_block_n(gemm_n, op.n_boundary, m_tiles, geglu, total_kb, num_sms, pair);
   LDM_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && (!geglu || bn % 64 == 0), "gemm: bad block_n %d", bn);
   p.block_n = bn;
   p.n_tiles = (gemm_n + bn - 1) / bn;
+  p.pm_tiles = (m_tiles + 1) / 2;
   p.N = op.N;
   p.num_phases = op.num_phases;
   p.b_mode = op.b_mode;
@@ -225,15 +236,16 @@ void Engine::gemm(const GemmOp& op) {
   }
   LDM_CHECK(total_kb >= 1, "gemm: empty K loop");
   // ---- pipeline depth from the shared-memory budget
-  const int stage_bytes = box_rows * GEMM_BK * 2 + bn * GEMM_BK * 2;
+  const int b_rows = pair ? bn / 2 : bn;            // B rows each CTA loads per k-block
+  const int stage_bytes = box_rows * GEMM_BK * 2 + b_rows * GEMM_BK * 2;
   const int a_bytes_full = GEMM_BM * GEMM_BK * 2;  // smem slot for A is always 16 KB
-  const int slot = a_bytes_full + bn * GEMM_BK * 2;
+  const int slot = a_bytes_full + b_rows * GEMM_BK * 2;
   // ---- epilogue flavour: TMA tiles (outputs / residual through bulk tensor copies) when the output
   // is a plain strided (N, W, H, NB) view with 16-byte-aligned strides, else register staging
   const bool strides_ok = ((op.os_x | op.os_y | op.os_n) & 7) == 0 && op.os_x >= 0 && op.os_y >= 0 && op.os_n >= 0 &&
                           (op.N & 7) == 0;
   const bool tma_epi = !op.no_tma_epi && strides_ok && op.num_phases == 1 && splits == 1 && op.b_mode == B_PLAIN &&
-                       bn % 32 == 0 && (!geglu || bn % 64 == 0) && !(op.residual && op.out_tr) &&
+                       !pair && bn % 32 == 0 && (!geglu || bn % 64 == 0) && !(op.residual && op.out_tr) &&
                        (op.out_f32 || op.out_bf16) &&
                        (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
                        (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
@@ -282,16 +294,19 @@ void Engine::gemm(const GemmOp& op) {
     encode_map(&p.amap[i], v, w_b, h_b, n_b);
     p.a_swap[i] = v.swap_xy ? 1 : 0;
   }
-  encode_map(&p.bmap, op.b, bn, 1, 1);
+  encode_map(&p.bmap, op.b, b_rows, 1, 1);
   p.b_swap = op.b.swap_xy ? 1 : 0;
   if (p.tma_epi) {
     if (op.out_f32) encode_out_map(&p.omap32, op.out_f32, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
     if (op.out_bf16) encode_out_map(&p.omap16, op.out_bf16, 2, false, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
     if (op.residual) encode_out_map(&p.rmap, op.residual, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
   }
-  const int total_tiles = m_tiles * p.n_tiles * splits;
+  const int total_tiles = (pair ? p.pm_tiles : m_tiles) * p.n_tiles * splits;
   int ctas = max_ctas > 0 ? max_ctas : num_sms;
+  if (pair) ctas /= 2;
+  if (ctas < 1) ctas = 1;
   if (ctas > total_tiles) ctas = total_tiles;
+  if (pair) ctas *= 2;
   const int smem = stages * slot + GEMM_CTRL_BYTES + p.epi_bytes + 1024;
   LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -300,13 +315,14 @@ void Engine::gemm(const GemmOp& op) {
     CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream));
   }
-  launch_pdl(implicit_gemm_kernel, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+  if (pair) launch_pair(implicit_gemm_kernel<1>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+  else launch_pdl(implicit_gemm_kernel<0>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
   CUDA_CHECK(cudaGetLastError());
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
     prof_events.push_back({e0, e1});
-    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d", rows_total * op.num_phases, gemm_n,
-                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act));
+    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d", rows_total * op.num_phases, gemm_n,
+                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0));
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);

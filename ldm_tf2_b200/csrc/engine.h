@@ -44,6 +44,7 @@ struct GemmOp {
   long long* trace = nullptr;
   int splits = 0;   // 0 = choose automatically, 1 = never split K
   int no_tma_epi = 0;  // test hook: force the register/staged epilogue
+  int pair = 0;        // CTA-pair (cta_group::2) kernel: 0 = engine decides, 1 = force, -1 = never
   const float* bias = nullptr;
   const float* bias2 = nullptr;
   int bias2_stride = 0;
@@ -100,6 +101,7 @@ class Engine {
   ~Engine();
   int device;
   int num_sms = 148;
+  bool pair_default = true;   // LDM_B200_PAIR=0 turns the CTA-pair GEMM kernel off
   cudaStream_t stream = nullptr;
   Arena arena;
   bool dry = false;            // skip launches (arena sizing pass)
@@ -128,7 +130,7 @@ class Engine {
   void* encode_fn_ = nullptr;
 };
 
-int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms);
+int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms, bool pair);
 void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cudaStream_t st);
 
 }  // namespace ldm

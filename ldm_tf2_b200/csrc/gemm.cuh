@@ -64,6 +64,7 @@ struct GemmParams {
   // split-K: `splits` CTAs share one output tile, each reducing kb_per_split k-blocks into the
   // fp32 workspace ws[split][row][N]; splitk_finalize_kernel applies the epilogue.
   int splits, kb_per_split;
+  int pm_tiles;             // CTA-pair kernel: pairs of M tiles (ceil(m_tiles / 2))
   float* ws;
   long long ws_split_stride;
   long long* trace;         // optional [cta][tile slot][16] clock64 stamps (microbenchmark only)
@@ -114,6 +115,28 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   m /= p.tiles_y;
   int ti = m % p.tiles_img;
   t.phase = m / p.tiles_img;
+  t.x0 = tx * p.w_b;
+  t.y0 = ty * p.h_b;
+  t.img0 = ti * p.n_b;
+  t.n0 = t.n_tile * p.block_n;
+  return t;
+}
+
+// CTA-pair kernel: pair tile `pt` covers M tiles (2*pm, 2*pm+1) of one N tile; CTA `rank` owns M tile
+// 2*pm + rank.  An odd tile count leaves the last peer with an all-out-of-range box (img0 >= NB: TMA
+// zero-fills, the epilogue's row_ok is false).  num_phases == 1 only.
+__device__ __forceinline__ TileCoord decode_pair_tile(const GemmParams& p, int pt, int rank) {
+  TileCoord t;
+  const int base = p.pm_tiles * p.n_tiles;
+  t.split = pt / base;
+  pt -= t.split * base;
+  t.n_tile = pt % p.n_tiles;
+  int m = (pt / p.n_tiles) * 2 + rank;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  const int ti = m / p.tiles_y;
+  t.phase = 0;
   t.x0 = tx * p.w_b;
   t.y0 = ty * p.h_b;
   t.img0 = ti * p.n_b;
@@ -209,13 +232,18 @@ __device__ __forceinline__ void epi_store_staged32(const float* v, int col0, flo
   __syncwarp();
 }
 
+// PAIR = 1: launched as (2,1,1) clusters; the two CTAs of a pair each load their own 128 A rows and half
+// of the B tile, the leader (cluster rank 0) issues M=256 cta_group::2 UMMAs that read both CTAs'
+// shared memory and write both CTAs' TMEM, and each CTA runs the epilogue of its own 128 rows.  Halves
+// the B bytes every SM has to pull from L2 and feed to its tensor core per k-block.
+template <int PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; control block after.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
   const int a_bytes = GEMM_BM * GEMM_BK * 2;
-  const int b_bytes = p.block_n * GEMM_BK * 2;
+  const int b_bytes = (PAIR ? p.block_n >> 1 : p.block_n) * GEMM_BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
   const int stages = p.stages;
   uint8_t* ctrl = smem + (size_t)stages * stage_bytes;
@@ -232,7 +260,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // tile-loop worker index
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = PAIR ? p.pm_tiles * p.n_tiles * p.splits
+                               : p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
   pdl_launch();  // the next kernel may start its own prologue once all our CTAs are resident
   if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 2] = clock64();  // kernel entry
 
@@ -245,7 +277,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
     if (p.tma_epi) {
@@ -256,11 +288,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   pdl_wait();    // everything above overlapped the previous kernel's tail; global data from here on
   const uint32_t tmem_base = *tmem_slot;
@@ -274,8 +307,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     // issues the copies.
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = cta_id; tile < total_tiles; tile += n_workers) {
+      TileCoord t = PAIR ? decode_pair_tile(p, tile, rank) : decode_tile(p, tile);
+      if (PAIR) t.n0 += rank * (p.block_n >> 1);   // this CTA's half of the B tile
       const int py = t.phase >> 1, px = t.phase & 1;
       int bz0 = 0, bz1 = 0;
       if (p.b_mode == B_BATCH) { bz0 = t.y0; bz1 = t.img0; }
@@ -296,10 +330,15 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
           if (elect_one()) {
             const uint32_t fb = full0 + stage * 8;
+            const uint32_t sa = smem_a0 + stage * stage_bytes;
             if (p.dbg & 1) {
-              mbar_arrive_a(fb);
+              if (rank == 0) mbar_arrive_a(fb);
+            } else if (PAIR) {
+              // both CTAs' copies complete on the leader's barrier, which expects the bytes of both
+              if (rank == 0) mbar_expect_tx_a(fb, (uint32_t)p.tx_bytes * 2u);
+              tma_load_4d_pair(sa, amap, fb, ca, a1, a2, t.img0);
+              tma_load_4d_pair(sa + a_bytes, &p.bmap, fb, cb, b1, b2, bz1);
             } else {
-              const uint32_t sa = smem_a0 + stage * stage_bytes;
               mbar_expect_tx_a(fb, (uint32_t)p.tx_bytes);
               tma_load_4d_a(sa, amap, fb, ca, a1, a2, t.img0);
               tma_load_4d_a(sa + a_bytes, &p.bmap, fb, cb, b1, b2, bz1);
@@ -312,10 +351,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer: warp-uniform loop, one
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------ MMA issuer (pair kernel: the leader CTA only): warp-uniform loop, one
     // elected lane issues the four K=16 UMMAs of a k-block and the commit.
-    const uint32_t idesc = umma_idesc_16(GEMM_BM, (uint32_t)p.block_n, p.fp16);
+    const uint32_t idesc = umma_idesc_16(PAIR ? 2 * GEMM_BM : GEMM_BM, (uint32_t)p.block_n, p.fp16);
     const uint64_t da0 = umma_desc_sw128(smem_a0);
     const uint64_t db0 = umma_desc_sw128(smem_a0 + a_bytes);
     const uint32_t dstep = (uint32_t)(stage_bytes >> 4);
@@ -325,7 +364,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint32_t aphase = 0;
     int tslot = 0;
     if (p.trace && lane == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16] = clock64();  // kernel body start
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tslot) {
+    for (int tile = cta_id; tile < total_tiles; tile += n_workers, ++tslot) {
       long long* tr = (p.trace && lane == 0 && tslot < 63) ? p.trace + ((long long)blockIdx.x * 64 + tslot) * 16 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait_a(tempty0 + as * 8, aphase ^ 1);
@@ -345,11 +384,17 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
               // advance 16 elements = 32 B inside the 128-B swizzle atom: +2 in 16-B units
-              umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              if (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
             }
           }
-          umma_commit_a(empty0 + stage * 8);
-          if (kb == nkb - 1) umma_commit_a(tfull0 + as * 8);
+          if (PAIR) {
+            umma_commit_pair(empty0 + stage * 8);     // frees the stage in both CTAs
+            if (kb == nkb - 1) umma_commit_pair(tfull0 + as * 8);
+          } else {
+            umma_commit_a(empty0 + stage * 8);
+            if (kb == nkb - 1) umma_commit_a(tfull0 + as * 8);
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -357,7 +402,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (tr) tr[3] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------------------------ epilogue warps 2..9
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // takes column chunks with (chunk index & 1) == half
@@ -379,8 +424,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     int rseq = 0;   // residual tiles consumed so far by this half (slot = rseq & 1, parity = (rseq >> 1) & 1)
     const bool split = p.splits > 1;
     const int act = split ? (int)ACT_NONE : p.act;   // split-K: raw partial sums, epilogue in the finalize kernel
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = cta_id; tile < total_tiles; tile += n_workers) {
+      const TileCoord t = PAIR ? decode_pair_tile(p, tile, rank) : decode_tile(p, tile);
       const int py = t.phase >> 1, px = t.phase & 1;
       const int img = t.img0 + r / hw_b;
       const int yq = t.y0 + (r % hw_b) / p.w_b;
@@ -408,7 +453,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       long long* tre = nullptr;
       if (p.trace && warp == 2 && lane == 0) {
-        const int tslot = (tile - blockIdx.x) / gridDim.x;
+        const int tslot = (tile - cta_id) / n_workers;
         if (tslot < 63) tre = p.trace + ((long long)blockIdx.x * 64 + tslot) * 16;
       }
       if (tre) tre[4] = clock64();
@@ -585,7 +630,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(tempty0 + as * 8);
+      if (lane == 0) {
+        if (PAIR && rank) mbar_arrive_cluster(tempty0 + as * 8, 0);   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive_a(tempty0 + as * 8);
+      }
       if (tre) tre[6] = clock64();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -593,11 +641,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 
   if (p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // drain this half's TMA stores
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal / read it
+  else __syncthreads();
   if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 1] = clock64();  // kernel end
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 

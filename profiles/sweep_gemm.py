@@ -17,8 +17,10 @@ CONV = [(16384, 320, 320, 32), (16384, 640, 320, 32), (16384, 960, 320, 32), (16
         (256, 1280, 1280, 4), (256, 2560, 1280, 4)]
 BNS = (64, 96, 128, 160, 192, 256)
 def run(rows, k, n, conv, hw, act, res, label):
-    ktot = 9 * k if conv else k
-    base = h.bench_gemm(rows, k, n, 0, act << 8, conv, hw, 30, residual=bool(res))
+  ktot = 9 * k if conv else k
+  base = h.bench_gemm(rows, k, n, 0, act << 8, conv, hw, 30, residual=bool(res))
+  line = f"{label} rows={rows} K={ktot} N={n}: engine {base*1e3:6.1f} us"
+  for pair_bits, pname in ((16, "single"), (32, "pair")):
     out = []
     for bn in BNS:
         gn = 2 * n if act == 3 else n
@@ -29,12 +31,12 @@ def run(rows, k, n, conv, hw, act, res, label):
         if act != 3 and tiles * 2 <= 148:
             cands += [s for s in (2, 3, 4, 6, 8) if s * tiles <= 160 and ktot // 64 >= 4 * s]
         for sp in cands:
-            ms = h.bench_gemm(rows, k, n, bn, (act << 8) | ((sp if sp > 1 else 0) << 12), conv, hw, 30, residual=bool(res))
+            ms = h.bench_gemm(rows, k, n, bn, pair_bits | (act << 8) | ((sp if sp > 1 else 0) << 12), conv, hw, 30, residual=bool(res))
             out.append((ms * 1e3, bn, sp))
     out.sort()
     gf = 2.0 * rows * ktot * (2 * n if act == 3 else n) / 1e9
-    print(f"{label} rows={rows} K={ktot} N={n}: engine {base*1e3:6.1f} us | best " +
-          ", ".join(f"bn{b}/s{s} {t:.1f}" for t, b, s in out[:4]) + f" | {gf/out[0][0]/1e3:.2f} PF/s best")
+    line += f" | {pname}: " + ", ".join(f"bn{b}/s{s} {t:.1f}" for t, b, s in out[:3]) + f" ({gf/out[0][0]/1e3:.2f} PF/s)"
+  print(line)
 for (rows, k, n, res) in LIN: run(rows, k, n, 0, 32, 0, res, "lin  ")
 for (rows, k, n) in GEGLU: run(rows, k, n, 0, 32, 3, 0, "geglu")
 for (rows, k, n, hw) in CONV: run(rows, k, n, 1, hw, 0, 0, "conv ")

@@ -137,9 +137,14 @@ LDM_API int ldm_bench_unet_step(ldm_handle* h, int b, int hh, int ww, int iters,
 LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, float* gemm_ms_per_step,
                                   float* step_ms, int* gemm_launches_per_step, double* gemm_flops_per_step);
 
-/* GEMM / conv microbenchmark on zero-filled device buffers (dbg: 1 no TMA, 2 no MMA, 4 no stores). */
+/* GEMM / conv microbenchmark on zero-filled device buffers (dbg bits: 1 no TMA, 2 no MMA,
+ * 4 no stores, 16 single-CTA kernel, 32 CTA-pair kernel, 8..11 activation, 12..15 split-K override). */
 LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
                            int iters, float* avg_ms, long long* trace_host, int with_residual);
+/* Fused-attention microbenchmark on zero-filled operands; trace_host (optional) receives
+ * [n*heads*ceil(t/128)][32] clock64 stamps of one launch. */
+LDM_API int ldm_bench_attention(ldm_handle* h, int n, int t, int tk, int heads, int d, int iters, float* avg_ms,
+                                long long* trace_host);
 /* cudaProfilerStart (on=1) / cudaProfilerStop (on=0) for `ncu --profile-from-start off`. */
 LDM_API int ldm_profiler(int on);
 

@@ -583,6 +583,46 @@ LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, co
   API_END
 }
 
+// Fused-attention microbenchmark on zero-filled operands: average launch time and, optionally, the
+// per-CTA clock64 stamps of one launch (trace_host [n*heads*q_tiles][32]).
+LDM_API int ldm_bench_attention(ldm_handle* h, int n, int t, int tk, int heads, int d, int iters, float* avg_ms,
+                                long long* trace_host) {
+  API_BEGIN
+  NEED(h);
+  Engine& e = h->model->eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  Scratch s;
+  const int c = heads * d, tpad = (tk + 7) / 8 * 8;
+  AttnOp op;
+  op.q = s.get<bf16>((size_t)n * t * c, true); op.q_ld = c;
+  op.k = s.get<bf16>((size_t)n * tk * c, true); op.k_ld = c; op.k_sn = (long long)tk * c;
+  op.vt = s.get<bf16>((size_t)n * c * tpad, true); op.tpad = tpad;
+  op.n = n; op.t = t; op.tk = tk; op.heads = heads; op.d = d; op.scale = 1.0f / sqrtf((float)d);
+  op.o = s.get<bf16>((size_t)n * t * c); op.o_ld = c;
+  for (int i = 0; i < 3; ++i) e.attention(op);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  e.sync();
+  CUDA_CHECK(cudaEventRecord(e0, e.stream));
+  for (int i = 0; i < iters; ++i) e.attention(op);
+  CUDA_CHECK(cudaEventRecord(e1, e.stream));
+  e.sync();
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  *avg_ms = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (trace_host) {
+    const size_t ctas = (size_t)n * heads * ((t + 127) / 128);
+    long long* td = s.get<long long>(ctas * 32, true);
+    op.trace = td;
+    e.attention(op);
+    e.sync();
+    CUDA_CHECK(cudaMemcpy(trace_host, td, ctas * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  API_END
+}
+
 // GroupNorm(32) (+SiLU) over x [n,hw,ca] (++ optional xb [n,hw,cb]) -> bf16 widened to f32
 LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const float* xb, int cb, const float* gamma,
                                const float* beta, int n, int hw, float eps, int silu, float* out) {

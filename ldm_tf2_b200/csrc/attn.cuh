@@ -1,31 +1,34 @@
 // Fused multi-head attention on tcgen05: softmax(q k^T * scale) v without ever
 // materialising the [N,H,T,Tk] logits the reference builds (unet.py:280-287).
 //
-// One CTA per (image, head, 128-query tile).  Two passes over the keys, both on tensor cores:
-//   pass 1: S = Q K_j^T (TMEM) -> running row max m           (no exponentials)
-//   pass 2: S = Q K_j^T again  -> P = exp2((S - m) * scale*log2e) -> 16-bit, written to shared
-//           memory in the UMMA K-major 128B-swizzled layout -> O += P V_j (TMEM accumulator)
-// then O / rowsum(P) is written as 16-bit [n, t, heads*d].  Recomputing the cheap QK^T product
-// replaces the usual online-softmax rescale of O, so O only ever accumulates.
-// S is double-buffered in TMEM (2 x 128 columns) and P in smem, so the softmax warps, the QK^T
-// MMAs of the next tile and the PV MMAs of the previous tile overlap.
+// One CTA per (image, head, 128-query tile); small enough (192 threads, <= 256 TMEM columns,
+// ~105 KB of shared memory at head dim 40) that two CTAs share an SM and fill each other's
+// barrier / TMEM-load / prologue gaps.  One pass over 64-key tiles, both products on tensor cores:
+//   S = Q K_j^T (TMEM) -> tile row max -> P = exp2(S*scale*log2e - m) -> 16-bit, written to shared
+//   memory in the UMMA K-major 128B-swizzled layout -> O += P V_j (TMEM accumulator)
+// with a LAZY running max: m is raised (and O, l rescaled by exp2(m_old - m_new) through a TMEM
+// load/store) only when a tile's max exceeds it by more than 2^8, so P stays <= 256 (exact in
+// fp16 / bf16 range) and the rescale happens on the first tiles only.  Finally O / rowsum(P) is
+// written as 16-bit [n, t, heads*d].
+// S is double-buffered in TMEM (2 x 64 columns) and P in smem, so the softmax warps, the QK^T MMA
+// of the next tile and the PV MMA of the previous tile overlap.  The MUFU.EX2 pipe (16/clk/SM)
+// bounds the kernel at 512 cycles per 128x64 tile.
 //
 // Operands (all 16-bit, K-major through TMA, zero-filled out of bounds):
 //   Q  [n, t,  heads, d]  A of S     (head dim padded to a multiple of 64 by TMA zero fill)
 //   K  [n, tk, heads, d]  B of S
 //   Vt [n, heads, d, tpad] B of PV   (V transposed by the projection GEMM's epilogue)
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax + epilogue: warp w owns TMEM lane
-// quadrant w%4 (32 query rows) and key-column half (w-2)/4 of every tile, so each scheduler has
-// two softmax warps to hide TMEM-load and MUFU latency; row max / row sum are combined through
-// shared memory.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax + epilogue: warp w owns TMEM lane
+// quadrant w%4, i.e. thread (w%4)*32+lane owns one query row and sees all of its logits -- row max
+// and row sum need no exchange between threads.
 #pragma once
 #include "common.cuh"
 
 namespace ldm {
 
 constexpr int ATT_BM = 128;   // queries per CTA
-constexpr int ATT_BN = 128;   // keys per tile
-constexpr int ATT_THREADS = 320;  // producer + MMA + 8 softmax warps (two column halves per row)
+constexpr int ATT_BN = 64;    // keys per tile (one 128-byte swizzle atom of P / V^T)
+constexpr int ATT_THREADS = 192;  // producer + MMA + 4 softmax warps
 
 struct AttnParams {
   CUtensorMap qmap, kmap, vmap;
@@ -34,10 +37,12 @@ struct AttnParams {
   int dv;           // d rounded up to 16: N of the PV product
   int q_tiles, kv_tiles;
   int kv_stages, p_bufs;
+  int tmem_cols;    // 256 (two CTAs per SM) or 512
   float scale_log2; // scale * log2(e)
   bf16* o;
   long long o_ld;
   int fp16;
+  long long* trace;   // optional [cta][32] clock64 stamps (microbenchmark only)
 };
 
 #if defined(__CUDACC__) && defined(LDM_GEMM_IMPL)
@@ -50,26 +55,37 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// 16-bit pair without the fp16 saturation of pack16(): probabilities are in [0, 1]
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_prob(float a, float b) {
+  if (FP16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const __grid_constant__ AttnParams p) {
+template <bool FP16>
+__global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
-  const int atom = ATT_BM * 128;                 // 16 KB: 128 rows x 128 B
-  const int q_bytes = p.dp_atoms * atom;
-  const int k_bytes = p.dp_atoms * atom;         // per stage
-  const int v_atom = p.dv * 128;                 // dv rows x 64 keys
-  const int v_bytes = 2 * v_atom;                // per stage
-  const int p_bytes = 2 * atom;                  // per buffer: 128 rows x 128 keys
+  const int q_atom = ATT_BM * 128;               // 16 KB: 128 query rows x 128 B
+  const int k_atom = ATT_BN * 128;               // 8 KB: 64 key rows x 128 B
+  const int q_bytes = p.dp_atoms * q_atom;
+  const int k_bytes = p.dp_atoms * k_atom;       // per stage
+  const int v_bytes = p.dv * 128;                // per stage: dv rows x 64 keys
+  const int v_stride = (v_bytes + 1023) & ~1023; // stages stay 1024-aligned (swizzle atoms)
+  const int p_bytes = ATT_BM * 128;              // per buffer: 128 rows x 64 keys
   uint8_t* q_s = smem;
   uint8_t* k_s = q_s + q_bytes;
   uint8_t* v_s = k_s + p.kv_stages * k_bytes;
-  uint8_t* p_s = v_s + p.kv_stages * v_bytes;
+  uint8_t* p_s = v_s + p.kv_stages * v_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + p.p_bufs * p_bytes);
   // barrier indices
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 9, V_FULL = 17, V_EMPTY = 25, S_FULL = 33, S_EMPTY = 35, P_FULL = 37,
          P_EMPTY = 39, O_FULL = 41, NBARS = 42 };  // K/V rings: up to 8 stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
-  float* red_s = reinterpret_cast<float*>(bars + NBARS + 2);  // [2][128] max / sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cta = blockIdx.x;
@@ -79,6 +95,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   const int img = cta / p.heads;
   const int q0 = qt * ATT_BM;
   pdl_launch();
+  long long* tr = (p.trace && warp == 2 && lane == 0) ? p.trace + (long long)blockIdx.x * 32 : nullptr;
+  if (tr) tr[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.qmap);
@@ -86,51 +104,49 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
     tma_prefetch_desc(&p.vmap);
     for (int i = 0; i < NBARS; ++i) {
       const bool soft = (i >= S_EMPTY && i < S_EMPTY + 2) || (i >= P_FULL && i < P_FULL + 2);
-      mbar_init(&bars[i], soft ? 8 : 1);
+      mbar_init(&bars[i], soft ? 4 : 1);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();
+  if (tr) tr[1] = clock64();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), p_a = smem_u32(p_s);
   auto bar = [&](int idx) { return bar0 + (uint32_t)idx * 8u; };
+  const uint32_t o_col = 2 * ATT_BN;   // O accumulator after the two S buffers
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
       mbar_expect_tx_a(bar(Q_FULL), (uint32_t)q_bytes);
-      for (int a = 0; a < p.dp_atoms; ++a) tma_load_4d_a(q_a + a * atom, &p.qmap, bar(Q_FULL), a * 64, head, q0, img);
+      for (int a = 0; a < p.dp_atoms; ++a) tma_load_4d_a(q_a + a * q_atom, &p.qmap, bar(Q_FULL), a * 64, head, q0, img);
     }
     __syncwarp();
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    {
       for (int j = 0; j < p.kv_tiles; ++j) {
-        if (pass == 0 || p.kv_tiles > 1) {   // a single key tile is multiplied once and kept in registers
-          mbar_wait_a(bar(K_EMPTY + ks), kph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx_a(bar(K_FULL + ks), (uint32_t)k_bytes);
-            for (int a = 0; a < p.dp_atoms; ++a)
-              tma_load_4d_a(k_a + ks * k_bytes + a * atom, &p.kmap, bar(K_FULL + ks), a * 64, head, j * ATT_BN, img);
-          }
-          __syncwarp();
-          if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
+        mbar_wait_a(bar(K_EMPTY + ks), kph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(bar(K_FULL + ks), (uint32_t)k_bytes);
+          for (int a = 0; a < p.dp_atoms; ++a)
+            tma_load_4d_a(k_a + ks * k_bytes + a * k_atom, &p.kmap, bar(K_FULL + ks), a * 64, head, j * ATT_BN, img);
         }
-        if (pass == 1) {
+        __syncwarp();
+        if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
+        {
           mbar_wait_a(bar(V_EMPTY + vs), vph ^ 1);
           if (elect_one()) {
             mbar_expect_tx_a(bar(V_FULL + vs), (uint32_t)v_bytes);
-            for (int a = 0; a < 2; ++a)
-              tma_load_4d_a(v_a + vs * v_bytes + a * v_atom, &p.vmap, bar(V_FULL + vs), j * ATT_BN + a * 64, 0, head,
-                            img);
+            tma_load_4d_a(v_a + vs * v_stride, &p.vmap, bar(V_FULL + vs), j * ATT_BN, 0, head, img);
           }
           __syncwarp();
           if (++vs == p.kv_stages) { vs = 0; vph ^= 1; }
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc_s = umma_idesc_16(ATT_BM, ATT_BN, p.fp16);
     const uint32_t idesc_o = umma_idesc_16(ATT_BM, (uint32_t)p.dv, p.fp16);
-    const uint32_t o_tmem = tmem_base + 256;
+    const uint32_t o_tmem = tmem_base + o_col;
     int ks = 0, vs = 0, sb = 0, pb = 0;
     uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
     const int nk16 = p.dp_atoms * 4;
@@ -154,8 +170,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
       if (elect_one()) {
         const uint32_t s_tmem = tmem_base + (uint32_t)(sb * ATT_BN);
         for (int kk = 0; kk < nk16; ++kk) {
-          const uint32_t off = (uint32_t)((kk >> 2) * atom + (kk & 3) * 32);
-          umma_bf16(s_tmem, umma_desc_sw128(q_a + off), umma_desc_sw128(k_a + ks * k_bytes + off), idesc_s,
+          const uint32_t offq = (uint32_t)((kk >> 2) * q_atom + (kk & 3) * 32);
+          const uint32_t offk = (uint32_t)((kk >> 2) * k_atom + (kk & 3) * 32);
+          umma_bf16(s_tmem, umma_desc_sw128(q_a + offq), umma_desc_sw128(k_a + ks * k_bytes + offk), idesc_s,
                     kk ? 1u : 0u);
         }
         umma_commit_a(bar(K_EMPTY + ks));
@@ -165,18 +182,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
       if (++ks == p.kv_stages) { ks = 0; kph ^= 1; }
       if (++sb == 2) { sb = 0; sph ^= 1; }
     };
-    const bool single = p.kv_tiles == 1;
-    for (int j = 0; j < p.kv_tiles; ++j) issue_s();  // pass 1
-    if (!single) issue_s();                           // pass 2, tile 0
+    issue_s();                                        // tile 0
     for (int j = 0; j < p.kv_tiles; ++j) {
       if (j + 1 < p.kv_tiles) issue_s();              // next tile's logits overlap this tile's softmax
       mbar_wait_a(bar(P_FULL + pb), pph);
       mbar_wait_a(bar(V_FULL + vs), vph);
       tc_fence_after();
       if (elect_one()) {
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t pa = p_a + pb * p_bytes + (kk >> 2) * atom + (kk & 3) * 32;
-          const uint32_t va = v_a + vs * v_bytes + (kk >> 2) * v_atom + (kk & 3) * 32;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t pa = p_a + pb * p_bytes + kk * 32;
+          const uint32_t va = v_a + vs * v_stride + kk * 32;
           umma_bf16(o_tmem, umma_desc_sw128(pa), umma_desc_sw128(va), idesc_o, (j | kk) ? 1u : 0u);
         }
         umma_commit_a(bar(P_EMPTY + pb));
@@ -190,114 +206,129 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
   } else {
     // ---------------------------------------------------------------- softmax + epilogue
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;     // key columns [64*half, 64*half+64) of every tile
     const int r = quad * 32 + lane;       // query row of this thread inside the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int cbase = half * 64;
     int sb = 0, pb = 0;
     uint32_t sph = 0, pph = 0;
-    float m = -INFINITY;
-    float l0 = 0.f, l1 = 0.f;
     uint32_t ra[32], rb[32];
-    const bool single = p.kv_tiles == 1;
-    // this warp's 64 logits of S buffer sb -> registers, then the buffer is released
-    auto load_release = [&]() {
+    float ms = -INFINITY;           // running (lazy) row max, already multiplied by scale*log2e
+    float l0 = 0.f, l1 = 0.f;
+    int prev_pb = 0;
+    uint32_t prev_pph = 0;
+    bool have_o = false;            // O holds at least one tile's P V
+    const uint32_t o_lane = lane_base + o_col;
+    // scaled max of one 32-key half; `v` = valid keys in it (may be <= 0 on the last tile)
+    auto half_max = [&](const uint32_t* rr, int v) {
+      float m0 = -INFINITY, m1 = -INFINITY;
+      if (v >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m0 = fmaxf(m0, __uint_as_float(rr[i]));
+          m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < v) m0 = fmaxf(m0, __uint_as_float(rr[i]));
+      }
+      return fmaxf(m0, m1) * p.scale_log2;   // scale > 0
+    };
+    // Lazy max update: raise the running max only when this half would push P above 2^8 (always on
+    // the very first half); rescales l and, through a TMEM load/store, this row of O.  Returns
+    // whether any row of the warp raised its max.
+    auto raise_to = [&](float mt) {
+      const bool raise = mt > ms + 8.0f;
+      if (!__any_sync(0xffffffffu, raise)) return false;
+      const float new_ms = raise ? mt : ms;
+      const float f = ex2_approx(ms - new_ms);   // 1 for rows that keep their max, 0 on the first half
+      if (have_o) {
+        // O holds P V of the previous tiles: wait for the last of those MMAs, then rescale
+        mbar_wait_a(bar(P_EMPTY + prev_pb), prev_pph);
+        tc_fence_after();
+        for (int c = 0; c < p.dv; c += 16) {
+          uint32_t ro[16];
+          tmem_ld_x16(o_lane + (uint32_t)c, ro);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * f);
+          tmem_st_x16(o_lane + (uint32_t)c, ro);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      l0 *= f;
+      l1 *= f;
+      ms = new_ms;
+      return true;
+    };
+    // P = exp2(S*scale*log2e - ms) of one half as 16-bit into the swizzled smem tile; row sum in fp32
+    auto emit = [&](const uint32_t* rr, int v, int hh, uint8_t* arow, bool add) {
+      float e[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms));
+      if (v < 32) {   // last, partial tile only (warp-uniform branch)
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= v) e[i] = 0.f;
+      }
+      uint32_t pk[16];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+        pk[i >> 1] = pack_prob<FP16>(e[i], e[i + 1]);
+        pk[(i >> 1) + 1] = pack_prob<FP16>(e[i + 2], e[i + 3]);
+      }
+      if (add) {
+        l0 += s0 + s1;
+        l1 += s2 + s3;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = hh * 4 + q;                // 16-byte chunk 0..7 of this row's 128-byte line
+        const int pos = chunk ^ (r & 7);             // 128-byte swizzle
+        *reinterpret_cast<uint4*>(arow + pos * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      }
+    };
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence (>= 1)
+      // both 32-column halves of S buffer sb -> registers; the buffer is released for the next QK^T
       mbar_wait_a(bar(S_FULL + sb), sph);
       tc_fence_after();
-      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + cbase), ra);
-      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + cbase + 32), rb);
+      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN), ra);
+      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + 32), rb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar(S_EMPTY + sb));
       if (++sb == 2) { sb = 0; sph ^= 1; }
-    };
-    auto tile_max = [&](int k0) {
-      if (k0 >= p.tk) return;
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      if (k0 + 64 <= p.tk) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = fmaxf(m0, __uint_as_float(ra[i]));
-          m1 = fmaxf(m1, __uint_as_float(ra[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(rb[i]));
-          m3 = fmaxf(m3, __uint_as_float(rb[i + 1]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (k0 + i < p.tk) m0 = fmaxf(m0, __uint_as_float(ra[i]));
-          if (k0 + 32 + i < p.tk) m2 = fmaxf(m2, __uint_as_float(rb[i]));
-        }
-      }
-      m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-    };
-    // P = exp2(S*scale*log2e - ms) for this warp's 64 keys = one 64-key swizzle atom (index = half)
-    auto emit_p = [&](int k0, float ms) {
+      if (tr && j == 0) tr[2] = clock64();
+      if (tr && j < 8) tr[8 + 2 * j] = clock64();
+      raise_to(fmaxf(half_max(ra, valid), half_max(rb, valid - 32)));
+      uint8_t* arow = p_s + pb * p_bytes + r * 128;
       mbar_wait_a(bar(P_EMPTY + pb), pph ^ 1);
-      uint8_t* arow = p_s + pb * p_bytes + half * atom + r * 128;
-      const bool fullt = (k0 + 64 <= p.tk);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const uint32_t* rr = hh ? rb : ra;
-        uint32_t pk[16];
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(e[i]);
-        if (!fullt) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + hh * 32 + i >= p.tk) e[i] = 0.f;
-        }
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
-          pk[i >> 1] = pack16(e[i], e[i + 1], p.fp16);
-          pk[(i >> 1) + 1] = pack16(e[i + 2], e[i + 3], p.fp16);
-        }
-        l0 += s0 + s1;
-        l1 += s2 + s3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = hh * 4 + q;                // 16-byte chunk 0..7 of this row's 128-byte line
-          const int pos = chunk ^ (r & 7);             // 128-byte swizzle
-          *reinterpret_cast<uint4*>(arow + pos * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-      }
+      emit(ra, valid, 0, arow, true);
+      emit(rb, valid - 32, 1, arow, true);
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar(P_FULL + pb));
+      prev_pb = pb;
+      prev_pph = pph;
+      have_o = true;
       if (++pb == p.p_bufs) { pb = 0; pph ^= 1; }
-    };
-    // pass 1: row max over the valid keys
-    for (int j = 0; j < p.kv_tiles; ++j) {
-      load_release();
-      tile_max(j * ATT_BN + cbase);
+      if (tr && j < 8) tr[9 + 2 * j] = clock64();
     }
-    red_s[half * 128 + r] = m;
-    named_bar_sync(1, 256);
-    m = fmaxf(red_s[r], red_s[128 + r]);
-    named_bar_sync(1, 256);
-    const float ms = m * p.scale_log2;
-    // pass 2 (a single key tile is still in registers: no second QK^T)
-    for (int j = 0; j < p.kv_tiles; ++j) {
-      if (!single) load_release();
-      emit_p(j * ATT_BN + cbase, ms);
-    }
-    red_s[half * 128 + r] = l0 + l1;
-    named_bar_sync(1, 256);
-    const float inv = 1.0f / (red_s[r] + red_s[128 + r]);
-    // epilogue: O / l -> 16-bit [n, t, heads*d]; the two halves take alternate 16-column chunks
+    if (tr) tr[5] = clock64();
+    const float inv = 1.0f / (l0 + l1);
+    // ---- epilogue: O / l -> 16-bit [n, t, heads*d]
     mbar_wait_a(bar(O_FULL), 0);
     tc_fence_after();
+    if (tr) tr[6] = clock64();
     const int row = q0 + r;
     bf16* orow = p.o + ((long long)img * p.t + row) * p.o_ld + (long long)head * p.d;
-    for (int c = half * 16; c < p.dv; c += 32) {
+    for (int c = 0; c < p.dv; c += 16) {
       uint32_t rr[16];
-      tmem_ld_x16(lane_base + (uint32_t)(256 + c), rr);
+      tmem_ld_x16(lane_base + o_col + (uint32_t)c, rr);
       tmem_ld_wait();
       if (row < p.t) {
         if (c + 16 <= p.d && (((reinterpret_cast<uintptr_t>(orow + c)) & 15) == 0)) {
@@ -321,9 +352,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) flash_attention_kernel(const _
 
   tc_fence_before();
   __syncthreads();
+  if (tr) tr[7] = clock64();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 

@@ -57,7 +57,9 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
   { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
-  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
 }
 
@@ -340,14 +342,20 @@ void Engine::attention(const AttnOp& op) {
   p.kv_tiles = (op.tk + ATT_BN - 1) / ATT_BN;
   p.scale_log2 = op.scale * 1.4426950408889634f;
   p.o = op.o; p.o_ld = op.o_ld; p.fp16 = fp16;
-  const int atom = ATT_BM * 128;
-  const int q_bytes = p.dp_atoms * atom, kv_bytes = p.dp_atoms * atom + 2 * p.dv * 128, p_bytes = 2 * atom;
-  const int ctrl = 1024 + 1024;
-  // K/V are L2-resident: the ring depth hides TMA latency, so take what shared memory allows
-  p.p_bufs = p.kv_tiles > 1 ? 2 : 1;
-  p.kv_stages = (GEMM_SMEM_BYTES - ctrl - q_bytes - p.p_bufs * p_bytes) / kv_bytes;
+  p.trace = op.trace;
+  const int q_bytes = p.dp_atoms * ATT_BM * 128;
+  const int kv_bytes = p.dp_atoms * ATT_BN * 128 + ((p.dv * 128 + 1023) & ~1023), p_bytes = ATT_BM * 128;
+  const int ctrl = 1024 + 1024;   // barriers + alignment slack
+  // Two CTAs per SM when the tiles allow it (<= 256 TMEM columns, ~112 KB of shared memory each):
+  // the K/V ring is L2-fed, 3-4 stages hide the TMA latency.
+  const int half_budget = 112 * 1024;
+  const bool two = (2 * ATT_BN + p.dv <= 256) && (q_bytes + 2 * kv_bytes + p_bytes + ctrl <= half_budget);
+  const int budget = two ? half_budget : GEMM_SMEM_BYTES;
+  p.tmem_cols = two ? 256 : 512;
+  p.p_bufs = (p.kv_tiles > 1 && q_bytes + 2 * kv_bytes + 2 * p_bytes + ctrl <= budget) ? 2 : 1;
+  p.kv_stages = (budget - ctrl - q_bytes - p.p_bufs * p_bytes) / kv_bytes;
   if (p.kv_stages > 8) p.kv_stages = 8;
-  if (p.kv_stages > p.kv_tiles) p.kv_stages = p.kv_tiles;
+  if (p.kv_stages > 2 * p.kv_tiles) p.kv_stages = 2 * p.kv_tiles;
   if (p.kv_stages < 1) { p.kv_stages = 1; p.p_bufs = 1; }
   auto need = [&]() { return q_bytes + p.kv_stages * kv_bytes + p.p_bufs * p_bytes + ctrl; };
   LDM_CHECK(need() <= GEMM_SMEM_BYTES, "attention: tile does not fit shared memory");
@@ -364,7 +372,8 @@ void Engine::attention(const AttnOp& op) {
   encode_map(&p.kmap, k, ATT_BN, 1, 1);
   encode_map(&p.vmap, v, p.dv, 1, 1);
   const int grid = op.n * op.heads * p.q_tiles;
-  launch_pdl(flash_attention_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
+  if (fp16) launch_pdl(flash_attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
+  else launch_pdl(flash_attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
   CUDA_CHECK(cudaGetLastError());
 }
 

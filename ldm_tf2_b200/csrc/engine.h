@@ -77,6 +77,7 @@ struct AttnOp {
   int n = 0, t = 0, tk = 0, heads = 0, d = 0;
   float scale = 1.f;
   bf16* o = nullptr; long long o_ld = 0;                        // [n, t, heads*d]
+  long long* trace = nullptr;                                   // microbenchmark: [cta][32] clock64 stamps
 };
 
 class Arena {

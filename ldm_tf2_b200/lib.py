@@ -54,6 +54,7 @@ _PROTOS = {
     "ldm_profile_unet_step": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I), C.POINTER(C.c_double)], _I),
     "ldm_profiler": ([_I], _I),
     "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P, _I], _I),
+    "ldm_bench_attention": ([_P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
@@ -306,6 +307,12 @@ class Handle:
         tr = np.zeros((148, 64, 16), np.int64) if trace else None
         check(self.lib.ldm_bench_gemm(self._h, rows, k, n, block_n, dbg, conv, hw, iters, C.byref(ms), ptr(tr),
                                       int(residual)))
+        return (ms.value, tr) if trace else ms.value
+
+    def bench_attention(self, n, t, tk, heads, d, iters=20, trace=False):
+        ms = C.c_float()
+        tr = np.zeros((n * heads * ((t + 127) // 128), 32), np.int64) if trace else None
+        check(self.lib.ldm_bench_attention(self._h, n, t, tk, heads, d, iters, C.byref(ms), ptr(tr)))
         return (ms.value, tr) if trace else ms.value
 
     # -- test hooks ---------------------------------------------------------

@@ -190,6 +190,29 @@ def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
     assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("n,t,tk,heads,d", [(1, 512, 1024, 4, 40), (2, 200, 333, 2, 80), (1, 128, 77, 8, 40)])
+@pytest.mark.parametrize("gain", [6.0, 16.0])
+def test_attention_peaky_logits(h, n, t, tk, heads, d, gain):
+    """Large, growing logits: the lazy running max must be raised (and O / l rescaled through TMEM) in
+    later key tiles and in the second half of a tile, not only on the first one."""
+    rng = np.random.default_rng(tk + d + int(gain))
+    q = rng.standard_normal((n, t, heads, d), dtype=np.float32) * np.float32(gain ** 0.5)
+    k = rng.standard_normal((n, tk, heads, d), dtype=np.float32) * np.float32(gain ** 0.5)
+    # keys grow along the sequence, so the row max keeps moving to later tiles
+    k *= np.linspace(0.25, 1.5, tk, dtype=np.float32)[None, :, None, None]
+    v = rng.standard_normal((n, tk, heads, d), dtype=np.float32)
+    scale = d ** -0.5
+    got = h.test_attention(q, k, v, scale, unfused=False)
+    qb, kb, vb = (round16(a, h.precision) for a in (q, k, v))
+    logits = np.einsum("nqhs,nchs->nhqc", qb, kb).astype(np.float32) * np.float32(scale)
+    p = O.softmax_last(logits)
+    ref = np.einsum("nhqc,nchs->nqhs", p, vb).reshape(n, t, heads * d)
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-2 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+    assert rel_l2(got, ref) < 1e-2
+
+
 @pytest.mark.parametrize("n,t,tk,heads,d", [
     (2, 64, 64, 8, 16),      # tiny config level 0
     (2, 4, 4, 8, 32),        # tiny: T smaller than 8 (padded keys)

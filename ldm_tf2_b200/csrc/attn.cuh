@@ -4,15 +4,16 @@
 // One CTA per (image, head, 128-query tile); small enough (192 threads, <= 256 TMEM columns,
 // ~105 KB of shared memory at head dim 40) that two CTAs share an SM and fill each other's
 // barrier / TMEM-load / prologue gaps.  One pass over 64-key tiles, both products on tensor cores:
-//   S = Q K_j^T (TMEM) -> tile row max -> P = exp2(S*scale*log2e - m) -> 16-bit, written to shared
-//   memory in the UMMA K-major 128B-swizzled layout -> O += P V_j (TMEM accumulator)
+//   S = Q K_j^T (TMEM) -> tile row max -> P = exp2(S*scale*log2e - m) -> 16-bit, stored back into
+//   the first 32 columns of the same TMEM buffer -> O += P V_j with P as the TMEM A operand
 // with a LAZY running max: m is raised (and O, l rescaled by exp2(m_old - m_new) through a TMEM
 // load/store) only when a tile's max exceeds it by more than 2^8, so P stays <= 256 (exact in
 // fp16 / bf16 range) and the rescale happens on the first tiles only.  Finally O / rowsum(P) is
 // written as 16-bit [n, t, heads*d].
-// S is double-buffered in TMEM (2 x 64 columns) and P in smem, so the softmax warps, the QK^T MMA
-// of the next tile and the PV MMA of the previous tile overlap.  The MUFU.EX2 pipe (16/clk/SM)
-// bounds the kernel at 512 cycles per 128x64 tile.
+// S / P is double-buffered in TMEM (2 x 64 columns), so the softmax warps, the QK^T MMA of the next
+// tile and the PV MMA of the previous tile overlap; P never touches shared memory, which leaves the
+// tensor core's 64 B/clk operand path to Q, K and V^T.  The MUFU.EX2 pipe (16/clk/SM) bounds the
+// kernel at 512 cycles per 128x64 tile.
 //
 // Operands (all 16-bit, K-major through TMA, zero-filled out of bounds):
 //   Q  [n, t,  heads, d]  A of S     (head dim padded to a multiple of 64 by TMA zero fill)
@@ -36,8 +37,9 @@ struct AttnParams {
   int dp_atoms;     // ceil(d / 64): 64-wide K atoms of the QK^T product
   int dv;           // d rounded up to 16: N of the PV product
   int q_tiles, kv_tiles;
-  int kv_stages, p_bufs;
+  int kv_stages;
   int tmem_cols;    // 256 (two CTAs per SM) or 512
+  int q_tmem;       // 1: Q (d <= 64) is copied to TMEM once and QK^T takes it as the TMEM A operand
   float scale_log2; // scale * log2(e)
   bf16* o;
   long long o_ld;
@@ -76,15 +78,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
   const int k_bytes = p.dp_atoms * k_atom;       // per stage
   const int v_bytes = p.dv * 128;                // per stage: dv rows x 64 keys
   const int v_stride = (v_bytes + 1023) & ~1023; // stages stay 1024-aligned (swizzle atoms)
-  const int p_bytes = ATT_BM * 128;              // per buffer: 128 rows x 64 keys
   uint8_t* q_s = smem;
   uint8_t* k_s = q_s + q_bytes;
   uint8_t* v_s = k_s + p.kv_stages * k_bytes;
-  uint8_t* p_s = v_s + p.kv_stages * v_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + p.p_bufs * p_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + p.kv_stages * v_stride);
   // barrier indices
+  // S_FULL: QK^T landed in S buffer b.  P_FULL: the softmax warps stored P into it (4 arrivals).
+  // S_EMPTY: the PV MMA that read P from buffer b is done -> the buffer may take the next QK^T.
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 9, V_FULL = 17, V_EMPTY = 25, S_FULL = 33, S_EMPTY = 35, P_FULL = 37,
-         P_EMPTY = 39, O_FULL = 41, NBARS = 42 };  // K/V rings: up to 8 stages
+         O_FULL = 39, QT_FULL = 40, NBARS = 41 };  // K/V rings: up to 8 stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
     tma_prefetch_desc(&p.kmap);
     tma_prefetch_desc(&p.vmap);
     for (int i = 0; i < NBARS; ++i) {
-      const bool soft = (i >= S_EMPTY && i < S_EMPTY + 2) || (i >= P_FULL && i < P_FULL + 2);
+      const bool soft = (i >= P_FULL && i < P_FULL + 2) || i == QT_FULL;
       mbar_init(&bars[i], soft ? 4 : 1);
     }
     mbar_fence_init();
@@ -119,9 +121,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
   if (tr) tr[1] = clock64();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s), p_a = smem_u32(p_s);
+  const uint32_t q_a = smem_u32(q_s), k_a = smem_u32(k_s), v_a = smem_u32(v_s);
   auto bar = [&](int idx) { return bar0 + (uint32_t)idx * 8u; };
   const uint32_t o_col = 2 * ATT_BN;   // O accumulator after the two S buffers
+  const uint32_t q_col = o_col + (uint32_t)p.dv;   // Q as TMEM A operand (q_tmem): 32 packed columns
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -158,10 +161,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
     const uint32_t idesc_s = umma_idesc_16(ATT_BM, ATT_BN, p.fp16);
     const uint32_t idesc_o = umma_idesc_16(ATT_BM, (uint32_t)p.dv, p.fp16);
     const uint32_t o_tmem = tmem_base + o_col;
-    int ks = 0, vs = 0, sb = 0, pb = 0;
-    uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
+    int ks = 0, vs = 0, sb = 0;
+    uint32_t kph = 0, vph = 0, sph = 0;
     const int nk16 = p.dp_atoms * 4;
-    mbar_wait_a(bar(Q_FULL), 0);
+    mbar_wait_a(bar(p.q_tmem ? QT_FULL : Q_FULL), 0);
+    tc_fence_after();
     // S = Q K_j^T into S buffer sb
     auto issue_s = [&]() {
       mbar_wait_a(bar(K_FULL + ks), kph);
@@ -172,8 +176,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
         for (int kk = 0; kk < nk16; ++kk) {
           const uint32_t offq = (uint32_t)((kk >> 2) * q_atom + (kk & 3) * 32);
           const uint32_t offk = (uint32_t)((kk >> 2) * k_atom + (kk & 3) * 32);
-          umma_bf16(s_tmem, umma_desc_sw128(q_a + offq), umma_desc_sw128(k_a + ks * k_bytes + offk), idesc_s,
-                    kk ? 1u : 0u);
+          if (p.q_tmem)
+            umma_bf16_ts(s_tmem, tmem_base + q_col + (uint32_t)(kk * 8), umma_desc_sw128(k_a + ks * k_bytes + offk),
+                         idesc_s, kk ? 1u : 0u);
+          else
+            umma_bf16(s_tmem, umma_desc_sw128(q_a + offq), umma_desc_sw128(k_a + ks * k_bytes + offk), idesc_s,
+                      kk ? 1u : 0u);
         }
         umma_commit_a(bar(K_EMPTY + ks));
         umma_commit_a(bar(S_FULL + sb));
@@ -183,24 +191,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       if (++sb == 2) { sb = 0; sph ^= 1; }
     };
     issue_s();                                        // tile 0
+    int pb = 0;                                       // S buffer holding P of tile j
+    uint32_t pph = 0;
     for (int j = 0; j < p.kv_tiles; ++j) {
       if (j + 1 < p.kv_tiles) issue_s();              // next tile's logits overlap this tile's softmax
       mbar_wait_a(bar(P_FULL + pb), pph);
       mbar_wait_a(bar(V_FULL + vs), vph);
       tc_fence_after();
       if (elect_one()) {
+        const uint32_t p_tmem = tmem_base + (uint32_t)(pb * ATT_BN);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t pa = p_a + pb * p_bytes + kk * 32;
+          // 16 keys = 8 packed TMEM columns of P, 32 bytes inside V^T's 128-byte swizzle atom
           const uint32_t va = v_a + vs * v_stride + kk * 32;
-          umma_bf16(o_tmem, umma_desc_sw128(pa), umma_desc_sw128(va), idesc_o, (j | kk) ? 1u : 0u);
+          umma_bf16_ts(o_tmem, p_tmem + (uint32_t)(kk * 8), umma_desc_sw128(va), idesc_o, (j | kk) ? 1u : 0u);
         }
-        umma_commit_a(bar(P_EMPTY + pb));
+        umma_commit_a(bar(S_EMPTY + pb));
         umma_commit_a(bar(V_EMPTY + vs));
         if (j == p.kv_tiles - 1) umma_commit_a(bar(O_FULL));
       }
       __syncwarp();
-      if (++pb == p.p_bufs) { pb = 0; pph ^= 1; }
+      if (++pb == 2) { pb = 0; pph ^= 1; }
       if (++vs == p.kv_stages) { vs = 0; vph ^= 1; }
     }
   } else {
@@ -208,13 +219,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
     const int quad = warp & 3;
     const int r = quad * 32 + lane;       // query row of this thread inside the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    int sb = 0, pb = 0;
-    uint32_t sph = 0, pph = 0;
+    int sb = 0;
+    uint32_t sph = 0;
     uint32_t ra[32], rb[32];
     float ms = -INFINITY;           // running (lazy) row max, already multiplied by scale*log2e
     float l0 = 0.f, l1 = 0.f;
-    int prev_pb = 0;
-    uint32_t prev_pph = 0;
+    int prev_sb = 0;
+    uint32_t prev_sph = 0;
     bool have_o = false;            // O holds at least one tile's P V
     const uint32_t o_lane = lane_base + o_col;
     // scaled max of one 32-key half; `v` = valid keys in it (may be <= 0 on the last tile)
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       const float f = ex2_approx(ms - new_ms);   // 1 for rows that keep their max, 0 on the first half
       if (have_o) {
         // O holds P V of the previous tiles: wait for the last of those MMAs, then rescale
-        mbar_wait_a(bar(P_EMPTY + prev_pb), prev_pph);
+        mbar_wait_a(bar(S_EMPTY + prev_sb), prev_sph);
         tc_fence_after();
         for (int c = 0; c < p.dv; c += 16) {
           uint32_t ro[16];
@@ -261,8 +272,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       ms = new_ms;
       return true;
     };
-    // P = exp2(S*scale*log2e - ms) of one half as 16-bit into the swizzled smem tile; row sum in fp32
-    auto emit = [&](const uint32_t* rr, int v, int hh, uint8_t* arow, bool add) {
+    // P = exp2(S*scale*log2e - ms) of one 32-key half as 16 packed 16-bit pairs, stored to TMEM
+    // columns [taddr, taddr + 16) of this thread's lane; row sum in fp32
+    auto emit = [&](const uint32_t* rr, int v, uint32_t taddr) {
       float e[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms));
@@ -279,43 +291,48 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
         pk[i >> 1] = pack_prob<FP16>(e[i], e[i + 1]);
         pk[(i >> 1) + 1] = pack_prob<FP16>(e[i + 2], e[i + 3]);
       }
-      if (add) {
-        l0 += s0 + s1;
-        l1 += s2 + s3;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = hh * 4 + q;                // 16-byte chunk 0..7 of this row's 128-byte line
-        const int pos = chunk ^ (r & 7);             // 128-byte swizzle
-        *reinterpret_cast<uint4*>(arow + pos * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-      }
+      l0 += s0 + s1;
+      l1 += s2 + s3;
+      tmem_st_x16(taddr, pk);
     };
-    for (int j = 0; j < p.kv_tiles; ++j) {
-      const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence (>= 1)
-      // both 32-column halves of S buffer sb -> registers; the buffer is released for the next QK^T
-      mbar_wait_a(bar(S_FULL + sb), sph);
-      tc_fence_after();
-      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN), ra);
-      tmem_ld_x32(lane_base + (uint32_t)(sb * ATT_BN + 32), rb);
-      tmem_ld_wait();
+    if (p.q_tmem) {
+      // this thread's Q row (64 x 16 bit, 128-byte swizzled in smem) -> 32 packed TMEM columns
+      mbar_wait_a(bar(Q_FULL), 0);
+      const uint8_t* qrow = q_s + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+        ra[4 * c] = u.x; ra[4 * c + 1] = u.y; ra[4 * c + 2] = u.z; ra[4 * c + 3] = u.w;
+      }
+      tmem_st_x32(lane_base + q_col, ra);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(bar(S_EMPTY + sb));
-      if (++sb == 2) { sb = 0; sph ^= 1; }
+      if (lane == 0) mbar_arrive_a(bar(QT_FULL));
+    }
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence (>= 1)
+      // both 32-column halves of S buffer sb -> registers
+      mbar_wait_a(bar(S_FULL + sb), sph);
+      tc_fence_after();
+      const uint32_t s_lane = lane_base + (uint32_t)(sb * ATT_BN);
+      tmem_ld_x32(s_lane, ra);
+      tmem_ld_x32(s_lane + 32, rb);
+      tmem_ld_wait();
       if (tr && j == 0) tr[2] = clock64();
       if (tr && j < 8) tr[8 + 2 * j] = clock64();
       raise_to(fmaxf(half_max(ra, valid), half_max(rb, valid - 32)));
-      uint8_t* arow = p_s + pb * p_bytes + r * 128;
-      mbar_wait_a(bar(P_EMPTY + pb), pph ^ 1);
-      emit(ra, valid, 0, arow, true);
-      emit(rb, valid - 32, 1, arow, true);
-      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      // P overwrites the first 32 columns of this thread's own S lane (already in registers)
+      emit(ra, valid, s_lane);
+      emit(rb, valid - 32, s_lane + 16);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(bar(P_FULL + pb));
-      prev_pb = pb;
-      prev_pph = pph;
+      if (lane == 0) mbar_arrive_a(bar(P_FULL + sb));
+      prev_sb = sb;
+      prev_sph = sph;
       have_o = true;
-      if (++pb == p.p_bufs) { pb = 0; pph ^= 1; }
+      if (++sb == 2) { sb = 0; sph ^= 1; }
       if (tr && j < 8) tr[9 + 2 * j] = clock64();
     }
     if (tr) tr[5] = clock64();

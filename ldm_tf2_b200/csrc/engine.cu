@@ -344,20 +344,20 @@ void Engine::attention(const AttnOp& op) {
   p.o = op.o; p.o_ld = op.o_ld; p.fp16 = fp16;
   p.trace = op.trace;
   const int q_bytes = p.dp_atoms * ATT_BM * 128;
-  const int kv_bytes = p.dp_atoms * ATT_BN * 128 + ((p.dv * 128 + 1023) & ~1023), p_bytes = ATT_BM * 128;
+  const int kv_bytes = p.dp_atoms * ATT_BN * 128 + ((p.dv * 128 + 1023) & ~1023);
   const int ctrl = 1024 + 1024;   // barriers + alignment slack
   // Two CTAs per SM when the tiles allow it (<= 256 TMEM columns, ~112 KB of shared memory each):
-  // the K/V ring is L2-fed, 3-4 stages hide the TMA latency.
+  // the K/V ring is L2-fed, a few stages hide the TMA latency.
   const int half_budget = 112 * 1024;
-  const bool two = (2 * ATT_BN + p.dv <= 256) && (q_bytes + 2 * kv_bytes + p_bytes + ctrl <= half_budget);
+  p.q_tmem = (p.dp_atoms == 1 && 2 * ATT_BN + p.dv + 32 <= 256) ? 1 : 0;
+  const bool two = (2 * ATT_BN + p.dv + (p.q_tmem ? 32 : 0) <= 256) && (q_bytes + 2 * kv_bytes + ctrl <= half_budget);
   const int budget = two ? half_budget : GEMM_SMEM_BYTES;
   p.tmem_cols = two ? 256 : 512;
-  p.p_bufs = (p.kv_tiles > 1 && q_bytes + 2 * kv_bytes + 2 * p_bytes + ctrl <= budget) ? 2 : 1;
-  p.kv_stages = (budget - ctrl - q_bytes - p.p_bufs * p_bytes) / kv_bytes;
+  p.kv_stages = (budget - ctrl - q_bytes) / kv_bytes;
   if (p.kv_stages > 8) p.kv_stages = 8;
-  if (p.kv_stages > 2 * p.kv_tiles) p.kv_stages = 2 * p.kv_tiles;
-  if (p.kv_stages < 1) { p.kv_stages = 1; p.p_bufs = 1; }
-  auto need = [&]() { return q_bytes + p.kv_stages * kv_bytes + p.p_bufs * p_bytes + ctrl; };
+  if (p.kv_stages > p.kv_tiles) p.kv_stages = p.kv_tiles;
+  if (p.kv_stages < 1) p.kv_stages = 1;
+  auto need = [&]() { return q_bytes + p.kv_stages * kv_bytes + ctrl; };
   LDM_CHECK(need() <= GEMM_SMEM_BYTES, "attention: tile does not fit shared memory");
   launches++;
   attn_launches++;

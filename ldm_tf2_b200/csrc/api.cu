@@ -638,8 +638,15 @@ LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const flo
   float* bt = up_f32(s, e, beta, c);
   double* mr = s.get<double>((size_t)n * 64, true);
   bf16* ob = s.get<bf16>((size_t)n * hw * c);
-  launch_gn_stats(a, ca, b, cb, n, hw, mr, e.stream);
-  launch_gn_apply(a, ca, b, cb, n, hw, mr, eps, g, bt, silu, ob, e.fp16, e.stream);
+  // silu bit 1 (value 2) forces the two-kernel path so both flavours are testable on any shape
+  const bool two_kernels = (silu & 2) || !gn_fused_supported(c, hw, n);
+  silu &= 1;
+  if (two_kernels) {
+    launch_gn_stats(a, ca, b, cb, n, hw, mr, e.stream);
+    launch_gn_apply(a, ca, b, cb, n, hw, mr, eps, g, bt, silu, ob, e.fp16, e.stream);
+  } else {
+    launch_gn_fused(a, ca, b, cb, n, hw, eps, g, bt, silu, ob, e.fp16, e.stream);
+  }
   std::vector<uint16_t> raw((size_t)n * hw * c);
   CUDA_CHECK(cudaMemcpyAsync(raw.data(), ob, raw.size() * 2, cudaMemcpyDefault, e.stream));
   e.sync();

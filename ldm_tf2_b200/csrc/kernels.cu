@@ -221,6 +221,159 @@ void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int 
   CUDA_CHECK(cudaGetLastError());
 }
 
+// Fused GroupNorm: statistics + apply in ONE launch.  The P CTAs of a thread-block cluster split the
+// pixels of one image; each reduces its strip (fp32 per thread, double per CTA), the cluster exchanges
+// the 64 partial sums through distributed shared memory, and every CTA then normalises its own strip
+// (a second read of x, served by L2).  No statistics buffer, no memset, half the launches of the
+// two-kernel path -- used whenever a CTA's strip is small enough to stream twice.
+__device__ __forceinline__ double dsmem_ld_f64(const double* p, uint32_t rank) {
+  double v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.f64 %0, [ra];\n\t}\n"
+      : "=d"(v)
+      : "r"(smem_u32(p)), "r"(rank)
+      : "memory");
+  return v;
+}
+
+__global__ void gn_fused_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
+                                int strip, int parts, int gpc, float eps, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int do_silu, bf16* __restrict__ out, int fp16) {
+  // grid (pixel part [= cluster rank], group chunk, image): this cluster owns groups [g_lo, g_lo + gpc)
+  __shared__ double s_acc[64];
+  __shared__ double s_tot[64];
+  __shared__ float s_mr[64];
+  const int c = ca + cb, cg = c / 32;
+  const int g_lo = blockIdx.y * gpc;
+  const int cw4 = (gpc * cg) >> 2;          // float4 columns of this chunk
+  const int n = blockIdx.z;
+  const int pix0 = blockIdx.x * strip;
+  const int pix1 = min(hw, pix0 + strip);
+  const int lanes = blockDim.x / cw4;  // pixel lanes
+  const int q = threadIdx.x % cw4, pl = threadIdx.x / cw4;
+  const bool active = pl < lanes;
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int ch = g_lo * cg + q * 4;
+  const float* src;
+  int cs, co;
+  if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
+  else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
+  if (active) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
+      ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+    const int g0 = ch / cg - g_lo, g3 = (ch + 3) / cg - g_lo;   // a quad's 4 channels fall in at most 2 groups
+    if (g0 == g3) {
+      atomicAdd(&s_acc[g0 * 2], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+      atomicAdd(&s_acc[g0 * 2 + 1], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = (ch + k) / cg - g_lo;
+        atomicAdd(&s_acc[g * 2], (double)s[k]);
+        atomicAdd(&s_acc[g * 2 + 1], (double)ss[k]);
+      }
+    }
+  }
+  cluster_sync_all();   // every CTA's partial sums are complete and visible cluster-wide
+  if (threadIdx.x < 2 * gpc) {
+    double t = 0.0;
+    for (int r = 0; r < parts; ++r) t += dsmem_ld_f64(&s_acc[threadIdx.x], (uint32_t)r);   // fixed order: deterministic
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading the peers' shared memory
+  if (threadIdx.x < gpc) {
+    const double cnt = (double)hw * cg;
+    const double mean = s_tot[threadIdx.x * 2] / cnt;
+    double var = s_tot[threadIdx.x * 2 + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mr[threadIdx.x * 2] = (float)mean;
+    s_mr[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (active) {
+    float sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (ch + k) / cg - g_lo;
+      const float mean = s_mr[g * 2], rstd = s_mr[g * 2 + 1];
+      sc[k] = rstd * __ldg(gamma + ch + k);
+      sh[k] = __ldg(beta + ch + k) - mean * sc[k];
+    }
+    bf16* dst = out + (long long)n * hw * c + ch;
+#pragma unroll 8
+    for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+      float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+      if (do_silu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] = silu_f(y[k]);
+      }
+      uint2 u;
+      u.x = pack16(y[0], y[1], fp16);
+      u.y = pack16(y[2], y[3], fp16);
+      *reinterpret_cast<uint2*>(dst + (long long)pix * c) = u;
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers are done with this CTA's partial sums
+}
+
+// Shape of the fused launch; false when a CTA's strip would be too large to stream twice.
+static bool gn_fused_shape(int c, int hw, int n, int* threads, int* strip, int* parts, int* chunks) {
+  const int cg = c / 32;
+  int p = 8;
+  while (p > 1 && hw / p < 4) p >>= 1;   // at least four pixels per CTA
+  // split the 32 groups over clusters until the grid fills the chip (>= ~3 CTAs per SM) or a
+  // pixel's channel segment would drop below 128 bytes
+  int ch = 1;
+  while (ch < 8 && (long long)n * p * ch < 448 && ((32 / (ch * 2)) * cg * 4) >= 128) ch *= 2;
+  const int cw4 = (32 / ch) * cg / 4;
+  if (cw4 > 1024 || ((32 / ch) * cg) % 4) return false;
+  int lanes = 256 / cw4;
+  if (lanes < 1) lanes = 1;
+  *threads = (cw4 * lanes + 31) / 32 * 32;
+  *parts = p;
+  *chunks = ch;
+  *strip = (hw + p - 1) / p;
+  return (long long)(*strip) * (32 / ch) * cg <= 64 * 1024;
+}
+
+bool gn_fused_supported(int c, int hw, int n) {
+  int t, s, p, ch;
+  return gn_fused_shape(c, hw, n, &t, &s, &p, &ch);
+}
+
+void launch_gn_fused(const float* a, int ca, const float* b, int cb, int n, int hw, float eps, const float* gamma,
+                     const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st) {
+  const int c = ca + cb;
+  LDM_CHECK(c % 32 == 0 && ca % 4 == 0 && cb % 4 == 0, "GroupNorm(32): bad channel counts %d+%d", ca, cb);
+  int threads, strip, parts, chunks;
+  LDM_CHECK(gn_fused_shape(c, hw, n, &threads, &strip, &parts, &chunks), "GroupNorm: fused kernel does not fit");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(parts, chunks, n);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = parts;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, a, ca, b, cb, hw, strip, parts, 32 / chunks, eps, gamma, beta,
+                                do_silu, out, fp16));
+}
+
 // =====================================================================================
 // LayerNorm: one warp per row; the row lives in registers (one global read), two-pass
 // statistics in fp32.  Rows up to 2560 channels.

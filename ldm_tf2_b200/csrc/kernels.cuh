@@ -23,6 +23,10 @@ void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int 
 void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const double* stats,
                      float eps, const float* gamma, const float* beta, int do_silu, bf16* out, int fp16,
                      cudaStream_t st);
+// one-launch GroupNorm (cluster + distributed shared memory); gn_fused_supported says when it applies
+bool gn_fused_supported(int c, int hw, int n);
+void launch_gn_fused(const float* a, int ca, const float* b, int cb, int n, int hw, float eps, const float* gamma,
+                     const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st);
 
 // ---- LayerNorm over the last axis (unet.py:304-306, transformer.py:165,170,209) --------
 void launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,

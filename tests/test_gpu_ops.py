@@ -78,16 +78,19 @@ def test_vq_argmin_bit_exact(vocab, rows):
 
 
 # ----------------------------------------------------------------- K2 / LayerNorm
+@pytest.mark.parametrize("two_kernels", [False, True])   # fused cluster kernel / statistics + apply kernels
 @pytest.mark.parametrize("n,hw,ca,cb,silu,eps", [(2, 64, 64, 0, True, 1e-5), (3, 256, 320, 0, False, 1e-6),
-                                                 (2, 16, 1280, 640, True, 1e-5), (1, 1024, 640, 320, True, 1e-5)])
-def test_groupnorm(h, n, hw, ca, cb, silu, eps):
+                                                 (2, 16, 1280, 640, True, 1e-5), (1, 1024, 640, 320, True, 1e-5),
+                                                 (16, 1024, 320, 0, True, 1e-5), (2, 4, 2560, 0, True, 1e-5),
+                                                 (1, 16384, 128, 0, True, 1e-6)])
+def test_groupnorm(h, n, hw, ca, cb, silu, eps, two_kernels):
     rng = np.random.default_rng(hw + ca)
     xa = rng.standard_normal((n, hw, ca), dtype=np.float32) * 2 + 0.5
     xb = rng.standard_normal((n, hw, cb), dtype=np.float32) if cb else None
     c = ca + cb
     gamma = 1 + 0.1 * rng.standard_normal(c, dtype=np.float32)
     beta = 0.1 * rng.standard_normal(c, dtype=np.float32)
-    got = h.test_groupnorm(xa, gamma, beta, eps, silu, xb)
+    got = h.test_groupnorm(xa, gamma, beta, eps, int(silu) | (2 if two_kernels else 0), xb)
     x = xa if xb is None else np.concatenate([xa, xb], -1)
     ref = O.group_norm(x.reshape(n, hw, 1, c), gamma, beta, eps).reshape(n, hw, c)
     if silu:

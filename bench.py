@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 # Algorithmic work (SURVEY 8d / BASELINE.md section 2), 2*MAC, unpadded dims
 GFLOP_UNET_STEP_PER_IMAGE = 364.15      # one CFG step (2 UNet passes), 32x32 latent
 GFLOP_CTX_KV_PER_IMAGE = 9.84           # loop-invariant context K/V projections, hoisted
+GEMM_DRAM_BYTES_PER_UNET_STEP_B8 = 3.925e9  # profiles/r1_dram_unet_step.csv (3898.4 MB read + 26.8 MB written)
 GFLOP_KL_DECODE_PER_IMAGE = 622.19
 METRIC = "images_per_s_256x256_ddim50_cfg"
 UNIT = "images/s"
@@ -289,7 +290,11 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "implicit_gemm_kernel (tcgen05)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                         # DRAM bytes of the 179 GEMM launches of one UNet step (ncu, cold-cache replays):
+                         # profiles/r1_dram_unet_step.csv; only valid for the default 8-image workload
+                         "traffic": GEMM_DRAM_BYTES_PER_UNET_STEP_B8 if B == 8 else None,
+                         "traffic_unit": "bytes per UNet step (all GEMM launches)",
+                         "peak_source": peaks["source"] + ", sustained bf16",
                          "launches_per_unet_step": prof["gemm_launches_per_step"],
                          "kernel_ms_per_unet_step": prof["gemm_ms_per_step"], "eager_step_ms": prof["step_ms"],
                          "algorithmic_gflop_per_unet_step": step_gflop},

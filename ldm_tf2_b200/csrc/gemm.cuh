@@ -609,7 +609,17 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         else if (warp_rows_ok && !to_tr && col0 + 32 <= p.N)
           epi_store_staged32(acc, col0, stage, base, lane, o32, o16, resid, p.fp16);
         else
-          epi_store_direct<32>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
+        {
+          // slow path: hand the row over through this warp's smem tile, so `acc` never has its address
+          // taken (a pointer to it would put the array in local memory on the fast paths too)
+          float* srow = stage + lane * GEMM_EPI_PITCH;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(srow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          __syncwarp();
+          epi_store_direct<32>(p, srow, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
+          __syncwarp();
+        }
       }
       if (use_tma && resid) rseq += kch_total;
       if (!geglu && (p.block_n & 31) && (n32 & 1) == half) {   // ragged 16-column tail chunk
@@ -626,7 +636,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           else if (act == ACT_GELU) x = gelu_erf_f(x);
           acc[j] = x;
         }
-        epi_store_direct<16>(p, acc, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
+        float* srow = stage + lane * GEMM_EPI_PITCH;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(srow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        __syncwarp();
+        epi_store_direct<16>(p, srow, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -259,7 +259,7 @@ void Engine::gemm(const GemmOp& op) {
     p.epi_o32_off = op.residual ? 32768 : 0;
     p.epi_o16_off = p.epi_o32_off + (op.out_f32 ? 16384 : 0);
     p.epi_half_stride = p.epi_o16_off + (op.out_bf16 ? 8192 : 0);
-    p.epi_bytes = 2 * p.epi_half_stride;
+    p.epi_bytes = 2 * p.epi_half_stride + GEMM_EPI_LEGACY_BYTES;   // TMA tiles, then the register-staging tiles
   } else {
     p.epi_bytes = GEMM_EPI_LEGACY_BYTES;
   }

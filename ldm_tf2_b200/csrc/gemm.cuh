@@ -255,8 +255,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
   uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(ctrl + 1536);  // [half][slot] residual tiles landed
   uint8_t* epi_area = ctrl + 2048;  // legacy: 8 x [32][36] fp32 staging + 8 x [32] offsets; TMA mode: per-half tiles
-  float* stage_all = reinterpret_cast<float*>(epi_area);
-  long long* roff_all = reinterpret_cast<long long*>(epi_area + 8 * 32 * GEMM_EPI_PITCH * 4);
+  // register-staging tiles (and row offsets) of the 8 epilogue warps; the TMA epilogue keeps its own
+  // tiles in front of them (boundary / V^T chunks still take the register paths)
+  uint8_t* stage_area = epi_area + (p.tma_epi ? 2 * p.epi_half_stride : 0);
+  float* stage_all = reinterpret_cast<float*>(stage_area);
+  long long* roff_all = reinterpret_cast<long long*>(stage_area + 8 * 32 * GEMM_EPI_PITCH * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -69,6 +69,12 @@ LDM_API int ldm_version(void);
 /* Constructors of UNet / TransformerModel / Autoencoder* (run_ldm_sampler.py:56-68). */
 LDM_API int ldm_create(const ldm_config* cfg, int device, ldm_handle** out);
 LDM_API int ldm_destroy(ldm_handle* h);
+/* ldm_create with device = -1 makes a describe-only handle: ldm_num_weights / ldm_weight_info work
+ * without a GPU (flat Keras order, names = TF2 checkpoint attribute paths, App. A.4); every compute
+ * entry point refuses it. */
+/* CRC-32C (Castagnoli) of a host buffer, continuing from crc (0 to start): TensorBundle checksums
+ * for the checkpoint reader (replaces tf.train.Checkpoint.restore, run_ldm_sampler.py:70-75). */
+LDM_API int ldm_crc32c(const void* data, unsigned long long n, unsigned int crc, unsigned int* out);
 
 /* Weights.  model: 0 = text transformer, 1 = unet, 2 = autoencoder (decode side).
  * index = position in the flat Keras weight list (layer.weights order; the order

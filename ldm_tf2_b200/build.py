@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libldm_b200.so")
 SOURCES = ["kernels.cu", "engine.cu", "model.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-msse4.2", "--expt-relaxed-constexpr",
          "-I", os.path.join(ROOT, "include")]
 
 

@@ -1,6 +1,7 @@
 // C ABI of libldm_b200.so (include/ldm_b200.h).
 #include "../../include/ldm_b200.h"
 #include "model.h"
+#include <nmmintrin.h>
 #include <cmath>
 #include <cstring>
 #include <cuda_profiler_api.h>
@@ -31,7 +32,12 @@ int ldm_version(void) { return 100; }
     return LDM_ERR_INTERNAL;                   \
   }
 
-#define NEED(h) LDM_CHECK((h) && (h)->model, "null handle")
+#define NEED_ANY(h) LDM_CHECK((h) && (h)->model, "null handle")
+#define NEED(h)                                   \
+  do {                                            \
+    NEED_ANY(h);                                  \
+    LDM_CHECK((h)->model->eng.device >= 0, "describe-only handle (device -1): only weight names and shapes"); \
+  } while (0)
 
 int ldm_create(const ldm_config* c, int device, ldm_handle** out) {
   API_BEGIN
@@ -68,6 +74,20 @@ int ldm_create(const ldm_config* c, int device, ldm_handle** out) {
   API_END
 }
 
+// CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum of the
+// TensorBundle index blocks and tensor payloads (ldm_tf2_b200/tf_checkpoint.py).  SSE4.2 crc32 instruction.
+int ldm_crc32c(const void* data, unsigned long long n, unsigned int crc, unsigned int* out) {
+  API_BEGIN
+  LDM_CHECK((data || n == 0) && out, "ldm_crc32c: null argument");
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  unsigned long long c = crc ^ 0xffffffffu;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = _mm_crc32_u8((unsigned int)c, *p++); --n; }
+  while (n >= 8) { c = _mm_crc32_u64(c, *reinterpret_cast<const unsigned long long*>(p)); p += 8; n -= 8; }
+  while (n) { c = _mm_crc32_u8((unsigned int)c, *p++); --n; }
+  *out = (unsigned int)c ^ 0xffffffffu;
+  API_END
+}
+
 int ldm_destroy(ldm_handle* h) {
   API_BEGIN
   if (h) {
@@ -79,7 +99,7 @@ int ldm_destroy(ldm_handle* h) {
 
 int ldm_num_weights(ldm_handle* h, int model, int* count) {
   API_BEGIN
-  NEED(h);
+  NEED_ANY(h);
   LDM_CHECK(model >= 0 && model < 3 && count, "ldm_num_weights: bad argument");
   *count = h->model->num_weights(model);
   API_END
@@ -87,7 +107,7 @@ int ldm_num_weights(ldm_handle* h, int model, int* count) {
 
 int ldm_weight_info(ldm_handle* h, int model, int index, const char** name, int* ndim, int shape[4]) {
   API_BEGIN
-  NEED(h);
+  NEED_ANY(h);
   LDM_CHECK(model >= 0 && model < 3, "ldm_weight_info: model");
   LDM_CHECK(index >= 0 && index < h->model->num_weights(model), "ldm_weight_info: index");
   const Slot& s = h->model->slots[model][index];

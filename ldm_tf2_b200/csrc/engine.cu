@@ -37,6 +37,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 Engine::Engine(int dev) : device(dev) {
+  if (dev == -1) return;   // describe-only engine: weight names / shapes without a device
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   LDM_CHECK(e == cudaSuccess && count > 0,

@@ -12,6 +12,7 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 template <typename T>
 T* Model::dev_alloc(size_t n, bool zero) {
+  if (eng.device < 0) return nullptr;   // describe-only model (ldm_create with device -1)
   void* p = nullptr;
   CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
   if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));

@@ -55,6 +55,7 @@ _PROTOS = {
     "ldm_profiler": ([_I], _I),
     "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P, _I], _I),
     "ldm_bench_attention": ([_P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P], _I),
+    "ldm_crc32c": ([_P, C.c_ulonglong, C.c_uint, C.POINTER(C.c_uint)], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),

@@ -4,9 +4,11 @@
     python -m ldm_tf2_b200.run_ldm_sampler --config_path all_in_one_config.yaml
 
 Differences forced by the environment (no TensorFlow here):
-  * pre_ckpt_paths entries may be TF2 object checkpoints (restored through TensorFlow when it is
-    importable), `.npz` files holding the flat Keras weight list as arr_0..arr_N, or
-    `random:<seed>` for random-init weights of the configured architecture;
+  * pre_ckpt_paths entries are TF2 object checkpoints as in the reference (`unet-1` -> `unet-1.index`
+    + `unet-1.data-00000-of-00001`), read by the standalone TensorBundle reader
+    `ldm_tf2_b200.tf_checkpoint` (no TensorFlow needed); `.npz` files holding the flat Keras weight
+    list as arr_0..arr_N and `random:<seed>` (random-init weights of the configured architecture)
+    are accepted as well;
   * x_T and the per-step noise come from a seeded NumPy generator (ldm_sampling.seed, default 0)
     instead of tf.random.normal.
 """
@@ -18,21 +20,19 @@ import sys
 import numpy as np
 import yaml
 
-from . import synth, tokens
+from . import synth, tf_checkpoint, tokens
 from .sampler import AutoencoderKL, AutoencoderVQ, LatentDiffusionModelSampler, TransformerModel, UNet
 
 
-def _load_flat_weights(path, handle, model, tf_builder):
+def _load_weights(path, handle, model):
+    """tf.train.Checkpoint(...).restore(path) of run_ldm_sampler.py:70-75, without TensorFlow."""
     if path.startswith("random:"):
-        return synth.random_weights(handle, model, int(path.split(":", 1)[1]))
-    if path.endswith(".npz"):
+        handle.set_weights(model, synth.random_weights(handle, model, int(path.split(":", 1)[1])))
+    elif path.endswith(".npz"):
         z = np.load(path)
-        return [z[f"arr_{i}"] for i in range(len(z.files))]
-    try:
-        import tensorflow as tf  # noqa: F401
-    except ImportError as e:
-        raise RuntimeError(f"{path}: TF2 checkpoints need TensorFlow to restore; use .npz or random:<seed>") from e
-    return tf_builder(path)
+        handle.set_weights(model, [z[f"arr_{i}"] for i in range(len(z.files))])
+    else:
+        tf_checkpoint.restore(handle, model, path)
 
 
 def main(argv=None):
@@ -58,14 +58,8 @@ def main(argv=None):
     h = sampler.handle
     paths = config["pre_ckpt_paths"]
 
-    def tf_restore(layer_name):
-        def go(path):
-            raise RuntimeError("TF checkpoint restore requires the reference's Keras layers; "
-                               "convert with convert_ckpt_pytorch_to_tf2.py and export layer.get_weights() to .npz")
-        return go
-
     for model, key in ((h.TEXT, "cond_stage_model"), (h.UNET, "unet"), (h.AE, "autoencoder")):
-        h.set_weights(model, _load_flat_weights(paths[key], h, model, tf_restore(key)))
+        _load_weights(paths[key], h, model)
     h.finalize()
     h.configure_sampler(sampler.schedule.ddim_steps, sampler.schedule.coeff_table())
 

@@ -150,3 +150,37 @@ def test_decode_vq():
     print("VQ decode PSNR", p)
     assert p >= PSNR_TOL
     hd.close()
+
+
+def test_restore_from_tf2_checkpoint_files(tiny, tmp_path):
+    """run_ldm_sampler.py:70-75: the three models restored from `<name>-1.index/.data-*` bundles by the
+    standalone reader produce exactly the outputs of the handle whose weights were set directly."""
+    from ldm_tf2_b200 import tf_checkpoint as T
+    h = tiny["h"]
+    us, ts = O.unet_spec(CFG["unet"]), O.text_spec(CFG["cond_stage_model"])
+    as_ = O.ae_spec(CFG["autoencoder_kl"], "kl", 8)
+    flat = {h.TEXT: O.init_weights(ts, 1), h.UNET: O.init_weights(us, 0), h.AE: O.init_weights(as_, 2)}
+    h2 = make_handle(CFG, "kl", ae_hw=8)
+    try:
+        for model, name in ((h.TEXT, "transformer"), (h.UNET, "unet"), (h.AE, "autoencoder")):
+            prefix = str(tmp_path / f"{name}-1")
+            T.save(h2, flat[model], prefix, model=model)
+            assert T.restore(h2, model, prefix) == len(flat[model])
+        h2.finalize()
+        ctx = h.encode_text(tiny["ids"])
+        assert np.array_equal(ctx, h2.encode_text(tiny["ids"]))
+        x = np.random.default_rng(4).standard_normal((4, 8, 8, 4), dtype=np.float32)
+        t = np.array([981, 981, 21, 21], np.int32)
+        h.set_context(ctx)
+        h2.set_context(ctx)
+        assert np.array_equal(h.unet_forward(x, t), h2.unet_forward(x, t))
+        assert np.array_equal(h.decode(x[:2], div=0.18215)[0], h2.decode(x[:2], div=0.18215)[0])
+        # a checkpoint of another architecture is refused with the offending key
+        bad = dict(T.load_checkpoint(str(tmp_path / "unet-1")))
+        k0 = T.variable_keys(h2, h.UNET)[0]
+        bad[k0] = bad[k0][..., :-1]
+        T.write_checkpoint(str(tmp_path / "bad-1"), bad)
+        with pytest.raises(T.CheckpointError, match="_conv_in/kernel"):
+            T.restore(h2, h.UNET, str(tmp_path / "bad-1"))
+    finally:
+        h2.close()

@@ -1,0 +1,146 @@
+"""TF2 checkpoint (TensorBundle) reader / writer -- SURVEY 8(f) row 1.  CPU-only tests.
+
+No TensorFlow-written checkpoint exists in this environment (parity against real TF is unpinned);
+what is pinned: the CRC-32C known answers, the table format against a hand-assembled index with
+prefix-compressed keys and several data blocks, corruption detection, and the variable keys against
+the reference's own objects (tests/golden/ckpt_keys_small.json, made by make_ckpt_keys.py)."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from ldm_tf2_b200 import lib, tf_checkpoint as T
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = {
+    "cond_stage_model": dict(vocab_size=30522, encoder_stack_size=2, hidden_size=1280, num_heads=8, size_per_head=64,
+                             max_seq_len=77, filter_size=512),
+    "unet": dict(model_channels=160, out_channels=4, num_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=4,
+                 head_base=40, context_dim=1280),
+    "autoencoder_kl": dict(latent_channels=4, channels=32, num_blocks=2, attention_resolutions=[],
+                           multipliers=[1, 2, 4, 4]),
+    "autoencoder_vq": dict(latent_channels=4, channels=32, num_blocks=2, attention_resolutions=[8],
+                           multipliers=[1, 2, 2, 4], vocab_size=512),
+}
+
+
+def test_crc32c_known_answers():
+    # RFC 3720 B.4 test vectors
+    assert T._crc32c_py(b"123456789") == 0xE3069283
+    assert T._crc32c_py(bytes(32)) == 0x8A9136AA
+    assert T._crc32c_py(bytes([0xFF] * 32)) == 0x62A8AB43
+    assert T._crc32c_py(bytes(range(32))) == 0x46DD794E
+    big = np.random.default_rng(0).integers(0, 256, 100003, dtype=np.uint8)
+    assert T.crc32c(big) == T._crc32c_py(big.tobytes())             # SSE4.2 routine of the library
+    assert T.crc32c(big[5:], T.crc32c(big[:5])) == T.crc32c(big)      # continuation
+    # leveldb's mask: rotate right by 15, add a constant
+    assert T.mask_crc(0) == 0xA282EAD8
+
+
+def test_roundtrip_many_blocks_and_prefix_compression(tmp_path):
+    rng = np.random.default_rng(1)
+    tensors = {f"unet/_input_blocks/{i}/_residual/_conv1/kernel{T.SUFFIX}": rng.standard_normal((3, 3, 4, 5), dtype=np.float32)
+               for i in range(40)}
+    tensors["save_counter" + T.SUFFIX] = np.array(1, np.int64)
+    tensors["unet/empty" + T.SUFFIX] = np.zeros((0, 7), np.float32)
+    tensors["unet/scalar" + T.SUFFIX] = np.float32(3.5)
+    prefix = str(tmp_path / "ckpt-1")
+    T.write_checkpoint(prefix, tensors, block_size=512, restart_interval=4)   # many blocks, shared prefixes
+    header, entries = T.read_index(prefix)
+    assert header["num_shards"] == 1 and sorted(entries) == sorted(tensors)
+    got = T.load_checkpoint(prefix)
+    for k, v in tensors.items():
+        assert got[k].dtype == np.asarray(v).dtype and got[k].shape == np.asarray(v).shape
+        assert np.array_equal(got[k], v)
+    one = T.load_checkpoint(prefix, ["unet/scalar" + T.SUFFIX])
+    assert list(one) == ["unet/scalar" + T.SUFFIX]
+    with pytest.raises(T.CheckpointError):
+        T.load_checkpoint(prefix, ["unet/missing" + T.SUFFIX])
+
+
+def test_hand_assembled_index_is_parsed(tmp_path):
+    """An index built byte by byte from the format description (independent of write_checkpoint)."""
+    payload = np.arange(6, dtype=np.float32).reshape(2, 3)
+    raw = payload.tobytes()
+    entry = (b"\x08\x01" + b"\x12\x08" + b"\x12\x02\x08\x02" + b"\x12\x02\x08\x03" + b"\x28" + bytes([len(raw)]) +
+             b"\x35" + struct.pack("<I", T.mask_crc(T._crc32c_py(raw))))
+    header = b"\x08\x01\x1a\x02\x08\x01"
+    k1, k2 = b"a/kernel", b"a/kernel2"           # k2 shares 8 bytes with k1
+    block = (b"\x00\x00" + bytes([len(header)]) + header +
+             b"\x00" + bytes([len(k1), len(entry)]) + k1 + entry +
+             bytes([8, 1, len(entry)]) + b"2" + entry +
+             struct.pack("<II", 0, 1))
+
+    def with_trailer(b):
+        return b + b"\x00" + struct.pack("<I", T.mask_crc(T._crc32c_py(b + b"\x00")))
+    out = with_trailer(block)
+    meta_off = len(out)
+    meta = struct.pack("<II", 0, 1)
+    out += with_trailer(meta)
+    idx_off = len(out)
+    handle = bytes([0, len(block)])
+    idx = b"\x00" + bytes([len(k2), len(handle)]) + k2 + handle + struct.pack("<II", 0, 1)
+    out += with_trailer(idx)
+    footer = bytes([meta_off, len(meta), idx_off, len(idx)])
+    out += footer + bytes(40 - len(footer)) + struct.pack("<Q", T.MAGIC)
+    prefix = str(tmp_path / "hand")
+    open(prefix + ".index", "wb").write(out)
+    open(prefix + ".data-00000-of-00001", "wb").write(raw)
+    got = T.load_checkpoint(prefix)
+    assert sorted(got) == ["a/kernel", "a/kernel2"]
+    assert np.array_equal(got["a/kernel2"], payload)
+
+
+def test_corruption_is_detected(tmp_path):
+    prefix = str(tmp_path / "c")
+    T.write_checkpoint(prefix, {"w" + T.SUFFIX: np.ones((64, 64), np.float32)})
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[100] ^= 1
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(T.CheckpointError, match="payload checksum"):
+        T.load_checkpoint(prefix)
+    assert T.load_checkpoint(prefix, verify=False)["w" + T.SUFFIX].shape == (64, 64)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[3] ^= 0x40
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(T.CheckpointError):
+        T.read_index(prefix)
+    open(prefix + ".index", "wb").write(b"not a table")
+    with pytest.raises(T.CheckpointError):
+        T.read_index(prefix)
+
+
+@pytest.mark.parametrize("kind", ["kl", "vq"])
+def test_variable_keys_match_the_reference_objects(kind):
+    """The library's weight names (describe-only handle: no GPU needed) are the attribute paths of
+    the reference's own layers, in flat Keras order."""
+    gold = json.load(open(os.path.join(GOLD, "ckpt_keys_small.json")))
+    cfg = lib.make_config(SMALL["cond_stage_model"], SMALL["unet"], SMALL["autoencoder_" + kind], kind, 8)
+    h = lib.Handle(cfg, -1)
+    try:
+        for model, name in ((h.TEXT, "transformer"), (h.UNET, "unet"), (h.AE, "autoencoder_" + kind)):
+            assert T.variable_keys(h, model) == gold[name]
+        with pytest.raises(lib.LdmError, match="describe-only"):
+            h.finalize()
+    finally:
+        h.close()
+
+
+def test_save_and_reload_flat_weight_list(tmp_path):
+    """save() under the reference's keys, then the keyed read restore() performs (shape-checked)."""
+    cfg = lib.make_config(SMALL["cond_stage_model"], SMALL["unet"], SMALL["autoencoder_kl"], "kl", 8)
+    h = lib.Handle(cfg, -1)
+    try:
+        rng = np.random.default_rng(2)
+        shapes = [h.weight_info(h.AE, i)[1] for i in range(h.num_weights(h.AE))]
+        weights = [rng.standard_normal(s, dtype=np.float32) for s in shapes]
+        prefix = str(tmp_path / "autoencoder-1")
+        T.save(h, weights, prefix, model=h.AE)
+        keys = T.variable_keys(h, h.AE)
+        got = T.load_checkpoint(prefix, keys)
+        assert all(np.array_equal(got[k], w) for k, w in zip(keys, weights))
+        assert keys[0] == "autoencoder/_post_quant_conv/kernel" + T.SUFFIX
+    finally:
+        h.close()

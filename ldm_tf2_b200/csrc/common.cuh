@@ -332,6 +332,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// 16 lanes x 32 consecutive fp32 columns in the m16n8 accumulator-fragment layout: for column group
+// k (8 columns), thread t holds r[4k..4k+3] = (lane t/4, cols 8k+2(t%4)+{0,1}), (lane t/4+8, same
+// cols).  Four neighbouring threads own 32 contiguous bytes of a row, so global stores of these
+// registers are sector-complete without a transposition through shared memory.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 // TMEM store of 32 lanes x 16 consecutive fp32 columns (thread i writes lane base+i), and its wait.
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
   asm volatile(

@@ -232,6 +232,78 @@ __device__ __forceinline__ void epi_store_staged32(const float* v, int col0, flo
   __syncwarp();
 }
 
+// Fragment-layout epilogue of one 32-column chunk for a fully valid warp (the common case): the
+// accumulator is read as two 16-lane m16n8 fragments, so thread t holds rows t/4 + 8j (j = 0..3) and
+// the column pairs 8k + 2(t%4) (k = 0..3) of the chunk.  Bias / activation / GEGLU / residual are
+// applied in that layout and every global access of a warp covers 8 rows x 32 contiguous bytes (whole
+// sectors) -- no shared-memory transposition (which cost ~1400 cycles of smem bandwidth per tile).
+template <bool GEGLU>
+__device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t t_lane0, int c, int hcols, int col0,
+                                                   const float* bias_s, const int* rowoff4, int lane, int act,
+                                                   float* o32, bf16* o16, const float* resid) {
+  uint32_t ra[16], rb[16], ga[16], gb[16];
+  tmem_ld_16x256b_x4(t_lane0 + (uint32_t)c, ra);                      // lanes +0..15
+  tmem_ld_16x256b_x4(t_lane0 + (16u << 16) + (uint32_t)c, rb);        // lanes +16..31
+  if (GEGLU) {
+    tmem_ld_16x256b_x4(t_lane0 + (uint32_t)(hcols + c), ga);
+    tmem_ld_16x256b_x4(t_lane0 + (16u << 16) + (uint32_t)(hcols + c), gb);
+  }
+  tmem_ld_wait();
+  const int cq = 2 * (lane & 3);
+  float2 v[4][4];   // [row j][column group k]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 b = *reinterpret_cast<const float2*>(bias_s + c + 8 * k + cq);
+    float x[8] = {__uint_as_float(ra[4 * k]), __uint_as_float(ra[4 * k + 1]), __uint_as_float(ra[4 * k + 2]),
+                  __uint_as_float(ra[4 * k + 3]), __uint_as_float(rb[4 * k]), __uint_as_float(rb[4 * k + 1]),
+                  __uint_as_float(rb[4 * k + 2]), __uint_as_float(rb[4 * k + 3])};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], p.alpha, (i & 1) ? b.y : b.x);
+    if (GEGLU) {
+      const float2 bg = *reinterpret_cast<const float2*>(bias_s + hcols + c + 8 * k + cq);
+      const float g[8] = {__uint_as_float(ga[4 * k]), __uint_as_float(ga[4 * k + 1]), __uint_as_float(ga[4 * k + 2]),
+                          __uint_as_float(ga[4 * k + 3]), __uint_as_float(gb[4 * k]), __uint_as_float(gb[4 * k + 1]),
+                          __uint_as_float(gb[4 * k + 2]), __uint_as_float(gb[4 * k + 3])};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= gelu_erf_f(fmaf(g[i], p.alpha, (i & 1) ? bg.y : bg.x));
+    } else if (act == ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = silu_f(x[i]);
+    } else if (act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = gelu_erf_f(x[i]);
+    }
+    v[0][k] = make_float2(x[0], x[1]);   // row t/4
+    v[1][k] = make_float2(x[2], x[3]);   // row t/4 + 8
+    v[2][k] = make_float2(x[4], x[5]);   // row t/4 + 16
+    v[3][k] = make_float2(x[6], x[7]);   // row t/4 + 24
+  }
+  if (resid) {
+    float2 r[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[j][k] = *reinterpret_cast<const float2*>(resid + (rowoff4[j] + col0 + 8 * k + cq));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[j][k].x += r[j][k].x; v[j][k].y += r[j][k].y; }
+  }
+  if (o32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(o32 + (rowoff4[j] + col0 + 8 * k + cq)) = v[j][k];
+  }
+  if (o16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<uint32_t*>(o16 + (rowoff4[j] + col0 + 8 * k + cq)) = pack16(v[j][k].x, v[j][k].y, p.fp16);
+  }
+}
+
 // PAIR = 1: launched as (2,1,1) clusters; the two CTAs of a pair each load their own 128 A rows and half
 // of the B tile, the leader (cluster rank 0) issues M=256 cta_group::2 UMMAs that read both CTAs'
 // shared memory and write both CTAs' TMEM, and each CTA runs the epilogue of its own 128 rows.  Halves
@@ -487,6 +559,15 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       int base[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) base[it] = use_tma ? 0 : roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
+      // fragment-layout path: whole tile goes through it when this warp's rows are all valid, nothing is
+      // transposed (V^T) and the tile's columns are whole 32-column chunks inside N
+      // (measured: a win for the GEGLU epilogue -- 16-bit output only, two accumulator reads per value --
+      // and a loss for fp32 + residual outputs, whose 8-byte accesses cost more than the transposition)
+      const bool frag = geglu && warp_rows_ok && !p.out_tr && !(p.block_n & 31) && !bias2_row &&
+                        (geglu ? (t.n_tile + 1) * (p.block_n >> 1) <= p.N : t.n0 + p.block_n <= p.N) && !(p.dbg & 8);
+      int rowoff4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rowoff4[j] = frag ? roff[(lane >> 2) + 8 * j] : 0;
       if (tre) tre[8] = clock64();
       const int n32_all = geglu ? (p.block_n >> 6) : (p.block_n >> 5);
       const int kch_total = (n32_all - half + 1) / 2;   // chunks this half handles per tile
@@ -512,6 +593,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       int kch = 0;   // this half's chunk counter inside the tile
       for (int ci = half; ci < n32; ci += 2, ++kch) {
         const int c = ci * 32;
+        if (frag) {
+          epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, rowoff4, lane, act, o32, o16, resid);
+          if (tre && ci < 6) tre[9 + ci] = clock64();
+          continue;
+        }
         uint32_t rr[32];
         float acc[32];
         int col0;   // first output column of the chunk

@@ -269,6 +269,10 @@ def main():
         achieved = step_gflop / prof["gemm_ms_per_step"]  # GFLOP/ms == TFLOP/s
         k5_ms = h.bench_ddim_update(B, 32, 32, False, 200)
         k5_bytes = 4 * 4 * B * 32 * 32 * 4  # 3 reads + 1 write of fp32 [B,32,32,4]
+        # K2 GroupNorm at the decoder's largest activation [B, 256*256, 128] (HBM-resident: 268 MB fp32)
+        gn_n, gn_hw, gn_c = B, 256 * 256, 128
+        gn_stats_ms, gn_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10)
+        gn_el = gn_n * gn_hw * gn_c
         total_images = B * world * args.steps
         value = total_images / (dev_ms / 1e3)
         gflop_per_image = args.ddim_steps * GFLOP_UNET_STEP_PER_IMAGE + GFLOP_KL_DECODE_PER_IMAGE
@@ -302,6 +306,16 @@ def main():
                             "peak": peaks["hbm"], "unit": "GB/s", "frac": k5_bytes / (k5_ms * 1e-3) / 1e9 / peaks["hbm"],
                             "traffic": None, "bytes_per_launch": k5_bytes, "ms_per_launch": k5_ms},
         }
+        line["roofline_k2"] = {
+            "bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel (GroupNorm(32)+SiLU -> 16-bit operand)",
+            "shape": [gn_n, gn_hw, gn_c], "unit": "GB/s", "peak": peaks["hbm"],
+            "stats": {"bytes_per_launch": gn_el * 4, "ms_per_launch": gn_stats_ms,
+                      "achieved": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9,
+                      "frac": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9 / peaks["hbm"]},
+            "apply": {"bytes_per_launch": gn_el * 6, "ms_per_launch": gn_apply_ms,
+                      "achieved": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9,
+                      "frac": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9 / peaks["hbm"]},
+            "traffic": None}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(2, 1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -147,6 +147,9 @@ LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iter
  * 4 no stores, 16 single-CTA kernel, 32 CTA-pair kernel, 8..11 activation, 12..15 split-K override). */
 LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
                            int iters, float* avg_ms, long long* trace_host, int with_residual);
+/* GroupNorm(32)+SiLU microbenchmark over more distinct [n, hw, c] fp32 buffers than fit in L2:
+ * average time of the statistics kernel and of the apply kernel (K2's HBM roofline). */
+LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms);
 /* Fused-attention microbenchmark on zero-filled operands; trace_host (optional) receives
  * [n*heads*ceil(t/128)][32] clock64 stamps of one launch. */
 LDM_API int ldm_bench_attention(ldm_handle* h, int n, int t, int tk, int heads, int d, int iters, float* avg_ms,

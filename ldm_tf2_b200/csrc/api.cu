@@ -603,6 +603,50 @@ LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, co
   API_END
 }
 
+// GroupNorm(32)+SiLU microbenchmark: statistics and apply kernels timed separately over enough
+// distinct [n, hw, c] buffers to exceed the L2, so the numbers are HBM numbers (K2 roofline).
+LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(n > 0 && hw > 0 && c > 0 && c % 32 == 0 && iters > 0 && stats_ms && apply_ms, "ldm_bench_groupnorm: bad argument");
+  Engine& e = h->model->eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  const size_t el = (size_t)n * hw * c;
+  int nbuf = (int)(((size_t)256 << 20) / (el * 4)) + 1;
+  if (nbuf < 2) nbuf = 2;
+  Scratch s;
+  float* x = s.get<float>(el * nbuf);
+  bf16* out = s.get<bf16>(el * nbuf);
+  float* gamma = s.get<float>(c);
+  float* beta = s.get<float>(c, true);
+  double* st = s.get<double>((size_t)n * 64 * nbuf, true);
+  launch_fill_f32(x, (long long)(el * nbuf), 0.5f, e.stream);
+  launch_fill_f32(gamma, c, 1.0f, e.stream);
+  cudaEvent_t e0, e1, e2;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventCreate(&e2));
+  float ts = 0.f, ta = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {   // pass 0 = warm-up
+    e.sync();
+    CUDA_CHECK(cudaEventRecord(e0, e.stream));
+    for (int i = 0; i < iters; ++i) launch_gn_stats(x + el * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), e.stream);
+    CUDA_CHECK(cudaEventRecord(e1, e.stream));
+    for (int i = 0; i < iters; ++i)
+      launch_gn_apply(x + el * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), 1e-5f, gamma, beta, 1,
+                      out + el * (i % nbuf), e.fp16, e.stream);
+    CUDA_CHECK(cudaEventRecord(e2, e.stream));
+    e.sync();
+    CUDA_CHECK(cudaEventElapsedTime(&ts, e0, e1));
+    CUDA_CHECK(cudaEventElapsedTime(&ta, e1, e2));
+  }
+  *stats_ms = ts / iters;
+  *apply_ms = ta / iters;
+  e.launches += 4 * iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  API_END
+}
+
 // Fused-attention microbenchmark on zero-filled operands: average launch time and, optionally, the
 // per-CTA clock64 stamps of one launch (trace_host [n*heads*q_tiles][32]).
 LDM_API int ldm_bench_attention(ldm_handle* h, int n, int t, int tk, int heads, int d, int iters, float* avg_ms,

@@ -56,6 +56,7 @@ _PROTOS = {
     "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P, _I], _I),
     "ldm_bench_attention": ([_P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P], _I),
     "ldm_crc32c": ([_P, C.c_ulonglong, C.c_uint, C.POINTER(C.c_uint)], _I),
+    "ldm_bench_groupnorm": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F)], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
@@ -290,6 +291,11 @@ class Handle:
         ms = C.c_float()
         check(self.lib.ldm_bench_ddim_update(self._h, b, hh, ww, int(with_noise), iters, C.byref(ms)))
         return ms.value
+
+    def bench_groupnorm(self, n, hw, c, iters=20):
+        a, b = C.c_float(), C.c_float()
+        check(self.lib.ldm_bench_groupnorm(self._h, n, hw, c, iters, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def bench_unet_step(self, b, hh, ww, iters, use_graph=True):
         ms = C.c_float()

@@ -278,29 +278,54 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
     v[2][k] = make_float2(x[4], x[5]);   // row t/4 + 16
     v[3][k] = make_float2(x[6], x[7]);   // row t/4 + 24
   }
+  // Neighbouring lanes (t, t^1) swap one column pair per two column groups, so every lane ends up with
+  // four consecutive columns (16 bytes): even lanes of group k, odd lanes of group k+1.
+  const bool odd = lane & 1;
+  float4 w[4][2];
+  int wcol[2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int k = 2 * h2;
+    wcol[h2] = col0 + (odd ? 8 * (k + 1) + cq - 2 : 8 * k + cq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 send = odd ? v[j][k] : v[j][k + 1];
+      float2 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+      w[j][h2] = odd ? make_float4(recv.x, recv.y, v[j][k + 1].x, v[j][k + 1].y)
+                     : make_float4(v[j][k].x, v[j][k].y, recv.x, recv.y);
+    }
+  }
   if (resid) {
-    float2 r[4][4];
+    float4 r[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) r[j][k] = *reinterpret_cast<const float2*>(resid + (rowoff4[j] + col0 + 8 * k + cq));
+      for (int h2 = 0; h2 < 2; ++h2) r[j][h2] = *reinterpret_cast<const float4*>(resid + (rowoff4[j] + wcol[h2]));
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { v[j][k].x += r[j][k].x; v[j][k].y += r[j][k].y; }
+      for (int h2 = 0; h2 < 2; ++h2) {
+        w[j][h2].x += r[j][h2].x; w[j][h2].y += r[j][h2].y; w[j][h2].z += r[j][h2].z; w[j][h2].w += r[j][h2].w;
+      }
   }
   if (o32) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(o32 + (rowoff4[j] + col0 + 8 * k + cq)) = v[j][k];
+      for (int h2 = 0; h2 < 2; ++h2) *reinterpret_cast<float4*>(o32 + (rowoff4[j] + wcol[h2])) = w[j][h2];
   }
   if (o16) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<uint32_t*>(o16 + (rowoff4[j] + col0 + 8 * k + cq)) = pack16(v[j][k].x, v[j][k].y, p.fp16);
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint2 u;
+        u.x = pack16(w[j][h2].x, w[j][h2].y, p.fp16);
+        u.y = pack16(w[j][h2].z, w[j][h2].w, p.fp16);
+        *reinterpret_cast<uint2*>(o16 + (rowoff4[j] + wcol[h2])) = u;
+      }
   }
 }
 
@@ -561,9 +586,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int it = 0; it < 8; ++it) base[it] = use_tma ? 0 : roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
       // fragment-layout path: whole tile goes through it when this warp's rows are all valid, nothing is
       // transposed (V^T) and the tile's columns are whole 32-column chunks inside N
-      // (measured: a win for the GEGLU epilogue -- 16-bit output only, two accumulator reads per value --
-      // and a loss for fp32 + residual outputs, whose 8-byte accesses cost more than the transposition)
-      const bool frag = geglu && warp_rows_ok && !p.out_tr && !(p.block_n & 31) && !bias2_row &&
+      // (measured: 15 % faster for the GEGLU epilogue -- 16-bit output only, two accumulator reads per
+      // value -- and 5-10 % slower for fp32 + residual outputs, whose 32-byte row pieces cost more L2
+      // transactions than the transposition costs shared-memory bandwidth; dbg bit 3 forces it for A/B runs)
+      const bool frag = (geglu || (p.dbg & 8)) && warp_rows_ok && !p.out_tr && !(p.block_n & 31) && !bias2_row &&
                         (geglu ? (t.n_tile + 1) * (p.block_n >> 1) <= p.N : t.n0 + p.block_n <= p.N) && !(p.dbg & 8);
       int rowoff4[4];
 #pragma unroll
@@ -594,7 +620,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int ci = half; ci < n32; ci += 2, ++kch) {
         const int c = ci * 32;
         if (frag) {
-          epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, rowoff4, lane, act, o32, o16, resid);
+          if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, rowoff4, lane, act, o32, o16, resid);
+          else epi_chunk_fragment<false>(p, t_base, c, hcols, t.n0 + c, bias_s, rowoff4, lane, act, o32, o16, resid);
           if (tre && ci < 6) tre[9 + ci] = clock64();
           continue;
         }

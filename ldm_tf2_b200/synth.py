@@ -51,3 +51,14 @@ FULL_CONFIG = {
     "ldm": dict(num_steps=1000, beta_start=0.00085, beta_end=0.012, v_posterior=0.0, scale_factor=0.18215,
                 eta=0.0, num_ddim_steps=50),
 }
+
+
+# A few-MB architecture of the same structure: microbenchmark scripts only need *a* handle.
+TINY_CONFIG = {
+    "cond_stage_model": dict(vocab_size=30522, encoder_stack_size=2, hidden_size=128, num_heads=8, size_per_head=16,
+                             max_seq_len=77, filter_size=256),
+    "unet": dict(model_channels=64, out_channels=4, num_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8,
+                 head_base=8, context_dim=128),
+    "autoencoder_kl": dict(latent_channels=4, channels=32, num_blocks=2, attention_resolutions=[],
+                           multipliers=[1, 2, 4, 4]),
+}

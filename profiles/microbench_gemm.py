@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ldm_tf2_b200 import lib
-from oracle import ldm_oracle as O  # tiny config only to build a small handle
+from ldm_tf2_b200 import synth as O  # tiny config only to build a small handle
 
 cfg = O.TINY_CONFIG
 h = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), 0)

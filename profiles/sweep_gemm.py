@@ -3,7 +3,7 @@ Prints, per shape, the time of every (block_n, splits) candidate and the engine'
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ldm_tf2_b200 import lib
-from oracle import ldm_oracle as O
+from ldm_tf2_b200 import synth as O
 cfg = O.TINY_CONFIG
 h = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), 0)
 # (rows, k_in, n, conv, hw, act, residual)

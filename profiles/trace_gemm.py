@@ -3,7 +3,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ldm_tf2_b200 import lib
-from oracle import ldm_oracle as O
+from ldm_tf2_b200 import synth as O
 cfg = O.TINY_CONFIG
 h = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), 0)
 import itertools

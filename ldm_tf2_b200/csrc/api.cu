@@ -284,9 +284,21 @@ int ldm_bench_unet_step(ldm_handle* h, int b, int hh, int ww, int iters, int use
   const long long nh = (long long)b * hh * ww * 4;
   std::vector<float> x((size_t)nh), out((size_t)nh);
   for (long long i = 0; i < nh; ++i) x[(size_t)i] = sinf(0.37f * (float)i);
-  // warm-up (also builds the graph), then timed run; both include the tiny H2D/D2H of the latents
-  m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, 3, use_graph);
-  m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, iters, use_graph);
+  // use_graph bit 1 (value 2): the same step with the implicit-GEMM launches (and their split-K
+  // finalize) left out -- attention, norms, K5 ... all stay; the difference to the full step is the
+  // time the GEMM kernel costs inside the replayed graph.  The captured graph is rebuilt around the switch.
+  const bool skip = (use_graph & 2) != 0;
+  use_graph &= 1;
+  if (skip) { m.invalidate_graph(); m.eng.skip_gemm_launches = true; }
+  try {
+    // warm-up (also builds the graph), then timed run; both include the tiny H2D/D2H of the latents
+    m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, 3, use_graph);
+    m.sample(x.data(), nullptr, b, hh, ww, 5.0f, out.data(), nullptr, iters, use_graph);
+  } catch (...) {
+    if (skip) { m.eng.skip_gemm_launches = false; m.invalidate_graph(); }
+    throw;
+  }
+  if (skip) { m.eng.skip_gemm_launches = false; m.invalidate_graph(); }
   *avg_ms = m.last_step_ms;
   API_END
 }

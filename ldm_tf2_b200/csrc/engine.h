@@ -102,6 +102,7 @@ class Engine {
   ~Engine();
   int device;
   int num_sms = 148;
+  bool skip_gemm_launches = false;   // measurement only: everything but the implicit-GEMM launch itself
   bool pair_default = true;   // LDM_B200_PAIR=0 turns the CTA-pair GEMM kernel off
   cudaStream_t stream = nullptr;
   Arena arena;

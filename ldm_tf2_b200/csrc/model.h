@@ -91,6 +91,7 @@ struct UNetBlock {
 class Model {
  public:
   Model(const ModelConfig& cfg, int device);
+  void invalidate_graph() { if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; } }
   ~Model();
   ModelConfig cfg;
   Engine eng;

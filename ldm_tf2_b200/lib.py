@@ -297,9 +297,11 @@ class Handle:
         check(self.lib.ldm_bench_groupnorm(self._h, n, hw, c, iters, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def bench_unet_step(self, b, hh, ww, iters, use_graph=True):
+    def bench_unet_step(self, b, hh, ww, iters, use_graph=True, skip_gemm=False):
+        """ms per sampler step; skip_gemm leaves the implicit-GEMM launches out (measurement only)."""
         ms = C.c_float()
-        check(self.lib.ldm_bench_unet_step(self._h, b, hh, ww, iters, int(use_graph), C.byref(ms)))
+        check(self.lib.ldm_bench_unet_step(self._h, b, hh, ww, iters, int(bool(use_graph)) | (2 if skip_gemm else 0),
+                                           C.byref(ms)))
         return ms.value
 
     def profile_unet_step(self, b, hh, ww, iters):

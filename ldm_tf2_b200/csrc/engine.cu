@@ -318,9 +318,19 @@ void Engine::gemm(const GemmOp& op) {
     CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, stream));
   }
-  if (skip_gemm_launches) return;   // bench.py: step time without this kernel (in-graph GEMM time by difference)
+  if (skip_gemm_launches) {   // bench.py: step time without this kernel (in-graph GEMM time by difference)
+    static const char* only = getenv("LDM_B200_EXPERIMENT_SKIP_ONLY");   // "lin" / "conv" / "geglu" / "res": subsets
+    if (!only) return;
+    const bool is_conv = op.num_segs >= 9;
+    const std::string o(only);
+    if (o == "conv" && is_conv) return;
+    if (o == "lin" && !is_conv) return;
+    if (o == "geglu" && op.act == ACT_GEGLU) return;
+    if (o == "res" && !is_conv && op.residual) return;
+    if (o == "split" && splits > 1) return;
+  }
   if (pair) launch_pair(implicit_gemm_kernel<1>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
-  else launch_pdl(implicit_gemm_kernel<0>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+  else launch_pdl_kind(2, implicit_gemm_kernel<0>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
   CUDA_CHECK(cudaGetLastError());
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
@@ -374,8 +384,8 @@ void Engine::attention(const AttnOp& op) {
   encode_map(&p.kmap, k, ATT_BN, 1, 1);
   encode_map(&p.vmap, v, p.dv, 1, 1);
   const int grid = op.n * op.heads * p.q_tiles;
-  if (fp16) launch_pdl(flash_attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
-  else launch_pdl(flash_attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
+  if (fp16) launch_pdl_kind(4, flash_attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
+  else launch_pdl_kind(4, flash_attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
   CUDA_CHECK(cudaGetLastError());
 }
 

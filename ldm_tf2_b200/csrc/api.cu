@@ -376,6 +376,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.N = n; op.gemm_n = wn; op.act = act; op.block_n = block_n; op.dbg = dbg;
   if (force_splits) op.splits = force_splits;
   op.pair = (dbg & 16) ? -1 : ((dbg & 32) ? 1 : 0);   // bit 4: single-CTA kernel, bit 5: CTA-pair kernel
+  op.ew = (dbg & 64) ? 4 : ((dbg & 128) ? 8 : 0);   // bit 6: two CTAs per SM (4 epilogue warps), bit 7: one (8)
   op.dbg = dbg & 15;
   op.out_bf16 = o;
   float* of = nullptr;

@@ -53,10 +53,16 @@ Engine::Engine(int dev) : device(dev) {
   cudaDriverEntryPointQueryResult qres;
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  110 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  110 * 1024));
+  // opt-in: measured -14 % on the 16384-row projections in isolation but only -0.3 % per UNet step
+  { const char* e = getenv("LDM_B200_EW4"); ew4_default = (e && e[0] == '1'); }
   { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
   CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));
@@ -254,8 +260,19 @@ void Engine::gemm(const GemmOp& op) {
                        (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
                        (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0) &&
                        getenv("LDM_B200_TMA_EPI") != nullptr;   // opt-in: measured on par with the staged path
+  // ---- one CTA per SM with 8 epilogue warps, or two per SM with 4 (gemm.cuh): the latter when the
+  // epilogue outlasts the main loop (short K), so that two tiles' epilogues overlap on every SM
+  const double kb_cyc = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / 58.0);
+  const bool short_k = kb_cyc * (total_kb / splits) < 60.0 * bn * (geglu ? 0.75 : 1.0);
+  // ... and only when every SM gets at least two tiles: a lone tile just sees half the epilogue warps
+  const long long work_tiles = (long long)(pair ? (m_tiles + 1) / 2 : m_tiles) * ((gemm_n + bn - 1) / bn) * splits;
+  const bool many_tiles = work_tiles * 2 >= 3 * (pair ? num_sms / 2 : num_sms);
+  const bool fits_half = 3 * slot + GEMM_CTRL_BYTES + GEMM_EPI_EW4_BYTES + 1024 <= 110 * 1024;   // >= 3 stages in half an SM
+  const bool ew4 = !tma_epi && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
   p.tma_epi = tma_epi ? 1 : 0;
-  if (tma_epi) {
+  if (ew4) {
+    p.epi_bytes = GEMM_EPI_EW4_BYTES;
+  } else if (tma_epi) {
     p.epi_r_off = 0;
     p.epi_o32_off = op.residual ? 32768 : 0;
     p.epi_o16_off = p.epi_o32_off + (op.out_f32 ? 16384 : 0);
@@ -264,8 +281,14 @@ void Engine::gemm(const GemmOp& op) {
   } else {
     p.epi_bytes = GEMM_EPI_LEGACY_BYTES;
   }
-  int stages = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - p.epi_bytes - 1024) / slot;  // + 1 KB alignment slack
+  const int smem_budget = ew4 ? 110 * 1024 : GEMM_SMEM_BYTES;   // two CTAs per SM: (228 KB - 2 x (1 KB reserved + 1 KB static)) / 2
+  int stages = (smem_budget - GEMM_CTRL_BYTES - p.epi_bytes - 1024) / slot;  // + 1 KB alignment slack
   if (stages > 8) stages = 8;
+  // accumulator ring in TMEM: 2 x 256 columns normally; with 256 columns per CTA two stages only
+  // for tiles up to 128 wide, else a single stage (the co-resident CTA fills the gap)
+  p.tmem_cols = ew4 ? 256 : 512;
+  p.acc_stages = (!ew4 || bn <= 128) ? 2 : 1;
+  p.acc_stride = ew4 ? 128 : 256;
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
   p.tx_bytes = stage_bytes;
@@ -305,13 +328,13 @@ void Engine::gemm(const GemmOp& op) {
     if (op.residual) encode_out_map(&p.rmap, op.residual, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
   }
   const int total_tiles = (pair ? p.pm_tiles : m_tiles) * p.n_tiles * splits;
-  int ctas = max_ctas > 0 ? max_ctas : num_sms;
+  int ctas = max_ctas > 0 ? max_ctas : (ew4 ? 2 * num_sms : num_sms);
   if (pair) ctas /= 2;
   if (ctas < 1) ctas = 1;
   if (ctas > total_tiles) ctas = total_tiles;
   if (pair) ctas *= 2;
   const int smem = stages * slot + GEMM_CTRL_BYTES + p.epi_bytes + 1024;
-  LDM_CHECK(smem <= GEMM_SMEM_BYTES, "gemm: smem %d over budget", smem);
+  LDM_CHECK(smem <= smem_budget, "gemm: smem %d over budget", smem);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile) {
     CUDA_CHECK(cudaEventCreate(&e0));
@@ -329,14 +352,19 @@ void Engine::gemm(const GemmOp& op) {
     if (o == "res" && !is_conv && op.residual) return;
     if (o == "split" && splits > 1) return;
   }
-  if (pair) launch_pair(implicit_gemm_kernel<1>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
-  else launch_pdl_kind(2, implicit_gemm_kernel<0>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+  if (ew4) {
+    if (pair) launch_pair(implicit_gemm_kernel<1, 4>, dim3(ctas), dim3(GEMM_THREADS_EW4), (size_t)smem, stream, p);
+    else launch_pdl_kind(2, implicit_gemm_kernel<0, 4>, dim3(ctas), dim3(GEMM_THREADS_EW4), (size_t)smem, stream, p);
+  } else {
+    if (pair) launch_pair(implicit_gemm_kernel<1, 8>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+    else launch_pdl_kind(2, implicit_gemm_kernel<0, 8>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
+  }
   CUDA_CHECK(cudaGetLastError());
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
     prof_events.push_back({e0, e1});
-    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d", rows_total * op.num_phases, gemm_n,
-                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0));
+    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d ew=%d", rows_total * op.num_phases, gemm_n,
+                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0, ew4 ? 4 : 8));
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);

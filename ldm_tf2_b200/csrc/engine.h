@@ -45,6 +45,7 @@ struct GemmOp {
   int splits = 0;   // 0 = choose automatically, 1 = never split K
   int no_tma_epi = 0;  // test hook: force the register/staged epilogue
   int pair = 0;        // CTA-pair (cta_group::2) kernel: 0 = engine decides, 1 = force, -1 = never
+  int ew = 0;          // epilogue warps per CTA: 0 = engine decides, 4 (two CTAs per SM) or 8
   const float* bias = nullptr;
   const float* bias2 = nullptr;
   int bias2_stride = 0;
@@ -103,6 +104,7 @@ class Engine {
   int device;
   int num_sms = 148;
   bool skip_gemm_launches = false;   // measurement only: everything but the implicit-GEMM launch itself
+  bool ew4_default = false;   // LDM_B200_EW4=1: short-K GEMMs with many tiles run two CTAs per SM (4 epilogue warps each)
   bool pair_default = true;   // LDM_B200_PAIR=0 turns the CTA-pair GEMM kernel off
   cudaStream_t stream = nullptr;
   Arena arena;

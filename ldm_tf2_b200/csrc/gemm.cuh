@@ -26,10 +26,12 @@ namespace ldm {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_SEGS = 12;
-constexpr int GEMM_THREADS = 320;   // producer + MMA + 8 epilogue warps
+constexpr int GEMM_THREADS = 320;   // producer + MMA + 8 epilogue warps (EW = 8: one CTA per SM)
+constexpr int GEMM_THREADS_EW4 = 192;  // producer + MMA + 4 epilogue warps (EW = 4: two CTAs per SM)
 constexpr int GEMM_EPI_PITCH = 36;    // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
 constexpr int GEMM_CTRL_BYTES = 2048;                                          // barriers, bias
 constexpr int GEMM_EPI_LEGACY_BYTES = 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // per-warp staging + row offsets
+constexpr int GEMM_EPI_EW4_BYTES = 4 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);
 constexpr int GEMM_SMEM_BYTES = 227 * 1024;
 
 enum ActKind : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };
@@ -65,6 +67,8 @@ struct GemmParams {
   // fp32 workspace ws[split][row][N]; splitk_finalize_kernel applies the epilogue.
   int splits, kb_per_split;
   int pm_tiles;             // CTA-pair kernel: pairs of M tiles (ceil(m_tiles / 2))
+  int tmem_cols;            // TMEM columns allocated per CTA: 512 (one CTA per SM) or 256 (two per SM)
+  int acc_stages, acc_stride;  // accumulator ring in TMEM: stages (1 or 2) and columns between them
   float* ws;
   long long ws_split_stride;
   long long* trace;         // optional [cta][tile slot][16] clock64 stamps (microbenchmark only)
@@ -333,9 +337,17 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 // of the B tile, the leader (cluster rank 0) issues M=256 cta_group::2 UMMAs that read both CTAs'
 // shared memory and write both CTAs' TMEM, and each CTA runs the epilogue of its own 128 rows.  Halves
 // the B bytes every SM has to pull from L2 and feed to its tensor core per k-block.
-template <int PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = epilogue warps per CTA.  8: 320 threads, 512 TMEM columns, all of the SM's shared memory -- the
+// long-K convolutions, whose main loop hides the epilogue.  4: 192 threads, 256 TMEM columns, half
+// the shared memory, so TWO CTAs (or CTA pairs) share an SM and one's latency-bound epilogue runs
+// under the other's -- the short-K projections of the transformers, whose epilogue (5-8 k cycles
+// per tile) outlasts the 2-3 k-cycle main loop.
+template <int PAIR, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int NHALF = EW / 4;          // column-chunk interleave between the warps of a TMEM lane quadrant
+  constexpr int ETHREADS = 32 * EW;      // epilogue threads
+  long long* const trace_base = blockIdx.x < 148 ? p.trace : nullptr;   // the trace buffer has 148 CTA slots
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: stages x (A 16 KB + B block_n*128 B), all 1024-aligned; control block after.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
@@ -356,7 +368,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   // tiles in front of them (boundary / V^T chunks still take the register paths)
   uint8_t* stage_area = epi_area + (p.tma_epi ? 2 * p.epi_half_stride : 0);
   float* stage_all = reinterpret_cast<float*>(stage_area);
-  long long* roff_all = reinterpret_cast<long long*>(stage_area + 8 * 32 * GEMM_EPI_PITCH * 4);
+  long long* roff_all = reinterpret_cast<long long*>(stage_area + EW * 32 * GEMM_EPI_PITCH * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -366,7 +378,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int total_tiles = PAIR ? p.pm_tiles * p.n_tiles * p.splits
                                : p.tiles_x * p.tiles_y * p.tiles_img * p.n_tiles * p.num_phases * p.splits;
   pdl_launch();  // the next kernel may start its own prologue once all our CTAs are resident
-  if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 2] = clock64();  // kernel entry
+  if (trace_base && threadIdx.x == 0) trace_base[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 2] = clock64();  // kernel entry
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -377,7 +389,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs)
+      mbar_init(&tempty_bar[i], PAIR ? 2 * EW : EW);   // one arrival per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
     if (p.tma_epi) {
@@ -388,8 +400,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     mbar_fence_init();
   }
   if (warp == 1) {
-    if (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
-    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (PAIR) { tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything signals them
@@ -463,14 +475,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     int as = 0;
     uint32_t aphase = 0;
     int tslot = 0;
-    if (p.trace && lane == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16] = clock64();  // kernel body start
+    if (trace_base && lane == 0) trace_base[(long long)blockIdx.x * 64 * 16 + 63 * 16] = clock64();  // kernel body start
     for (int tile = cta_id; tile < total_tiles; tile += n_workers, ++tslot) {
-      long long* tr = (p.trace && lane == 0 && tslot < 63) ? p.trace + ((long long)blockIdx.x * 64 + tslot) * 16 : nullptr;
+      long long* tr = (trace_base && lane == 0 && tslot < 63) ? trace_base + ((long long)blockIdx.x * 64 + tslot) * 16 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait_a(tempty0 + as * 8, aphase ^ 1);
       tc_fence_after();
       if (tr) tr[1] = clock64();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
       const int split = tile / (total_tiles / p.splits);
       const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -500,12 +512,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (tr) tr[3] = clock64();
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 2) {
     // ------------------------------------------------ epilogue warps 2..9
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // takes column chunks with (chunk index & 1) == half
+    const int half = (warp - 2) >> 2;   // takes column chunks with (chunk index % NHALF) == half (EW = 4: always 0)
     const int ew = warp - 2;
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
@@ -552,16 +564,16 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         else bias2_tile = p.bias2 + step * p.bias2_stride;
       }
       long long* tre = nullptr;
-      if (p.trace && warp == 2 && lane == 0) {
+      if (trace_base && warp == 2 && lane == 0) {
         const int tslot = (tile - cta_id) / n_workers;
-        if (tslot < 63) tre = p.trace + ((long long)blockIdx.x * 64 + tslot) * 16;
+        if (tslot < 63) tre = trace_base + ((long long)blockIdx.x * 64 + tslot) * 16;
       }
       if (tre) tre[4] = clock64();
       // stage this tile's bias columns (all 8 warps) and this warp's row offsets in smem; the
       // previous tile's readers are past the first barrier
-      named_bar_sync(1, 256);
+      named_bar_sync(1, ETHREADS);
       if (tre) tre[7] = clock64();
-      for (int c = et; c < p.block_n; c += 256) {
+      for (int c = et; c < p.block_n; c += ETHREADS) {
         const int col = t.n0 + c;        // bias / bias2 are indexed by B row (packed row for GEGLU)
         const int lim = geglu ? 2 * p.N : p.N;
         float b = 0.f;
@@ -580,7 +592,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
                              (((tr_row_off + xq - lane) & 7) == 0) &&
                              ((reinterpret_cast<uintptr_t>(p.out_tr) & 15) == 0);
       if (!use_tma) roff[lane] = (int)row_off;   // (the TMA epilogue reuses this area for its tiles)
-      named_bar_sync(1, 256);
+      named_bar_sync(1, ETHREADS);
       int base[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) base[it] = use_tma ? 0 : roff[it * 4 + (lane >> 3)] + (lane & 7) * 4;
@@ -613,11 +625,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       if (tre) tre[5] = clock64();
-      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+      const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
       const int n32 = geglu ? (p.block_n >> 6) : (p.block_n >> 5);   // 32-column output chunks per tile
       const int hcols = p.block_n >> 1;
       int kch = 0;   // this half's chunk counter inside the tile
-      for (int ci = half; ci < n32; ci += 2, ++kch) {
+      for (int ci = half; ci < n32; ci += NHALF, ++kch) {
         const int c = ci * 32;
         if (frag) {
           if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, rowoff4, lane, act, o32, o16, resid);
@@ -738,7 +750,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
       }
       if (use_tma && resid) rseq += kch_total;
-      if (!geglu && (p.block_n & 31) && (n32 & 1) == half) {   // ragged 16-column tail chunk
+      if (!geglu && (p.block_n & 31) && (n32 % NHALF) == half) {   // ragged 16-column tail chunk
         const int c = n32 * 32;
         uint32_t r16[16];
         tmem_ld_x16(t_base + (uint32_t)c, r16);
@@ -767,7 +779,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         else mbar_arrive_a(tempty0 + as * 8);
       }
       if (tre) tre[6] = clock64();
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -775,11 +787,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal / read it
   else __syncthreads();
-  if (p.trace && threadIdx.x == 0) p.trace[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 1] = clock64();  // kernel end
+  if (trace_base && threadIdx.x == 0) trace_base[(long long)blockIdx.x * 64 * 16 + 63 * 16 + 1] = clock64();  // kernel end
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
-    else tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 

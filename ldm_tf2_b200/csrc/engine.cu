@@ -61,8 +61,8 @@ Engine::Engine(int dev) : device(dev) {
                                   110 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   110 * 1024));
-  // opt-in: measured -14 % on the 16384-row projections in isolation but only -0.3 % per UNet step
-  { const char* e = getenv("LDM_B200_EW4"); ew4_default = (e && e[0] == '1'); }
+  // measured -14 % on the 16384-row projections in isolation, -0.7 % per UNet step (profiles/ab_step.py)
+  { const char* e = getenv("LDM_B200_EW4"); ew4_default = !(e && e[0] == '0'); }
   { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
   CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GEMM_SMEM_BYTES));

@@ -104,7 +104,7 @@ class Engine {
   int device;
   int num_sms = 148;
   bool skip_gemm_launches = false;   // measurement only: everything but the implicit-GEMM launch itself
-  bool ew4_default = false;   // LDM_B200_EW4=1: short-K GEMMs with many tiles run two CTAs per SM (4 epilogue warps each)
+  bool ew4_default = true;    // short-K GEMMs with many tiles run two CTAs per SM (4 epilogue warps each); LDM_B200_EW4=0 disables
   bool pair_default = true;   // LDM_B200_PAIR=0 turns the CTA-pair GEMM kernel off
   cudaStream_t stream = nullptr;
   Arena arena;

@@ -482,56 +482,54 @@ void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, f
 
 // =====================================================================================
 // conv_in: direct 3x3 SAME conv with 4 input channels (K = 36: too thin for UMMA).
-// A thread owns 4 output channels, keeps their 36 x 4 weights in registers and walks over pixels:
-// per pixel 9 (L1-resident) input loads and 144 FMAs; a pixel's outputs are written by consecutive
-// threads (contiguous cout), so the kernel is bound by its fp32 + 16-bit output stores.
+// One thread per (pixel, 4 output channels); the 36 x 4 weights are re-read through L1 for every
+// pixel (LSU-bound, ~38 us for 16 x 32 x 32 pixels -> 320 channels).  A variant that kept the
+// weights in registers and walked over pixels (186 registers, one CTA per SM) measured 29 us SLOWER
+// inside the step graph and was dropped.
 // =====================================================================================
-__global__ void __launch_bounds__(256, 1)
-conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w, const float* __restrict__ kernel,
-               const float* __restrict__ bias, int cout, float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
+__global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
+                               const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
+                               float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
   pdl_launch();
   pdl_wait();
   const int c4 = cout / 4;
-  const int lanes = blockDim.x / c4;            // pixel lanes per CTA
-  const int q = threadIdx.x % c4, pl = threadIdx.x / c4;
-  if (pl >= lanes) return;
-  const int co = q * 4;
-  float4 kw[36];
-#pragma unroll
-  for (int t = 0; t < 36; ++t) kw[t] = __ldg(reinterpret_cast<const float4*>(kernel + (long long)t * cout + co));
-  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + co));
-  const long long npix = (long long)n * h * w;
-  for (long long pix = (long long)blockIdx.x * lanes + pl; pix < npix; pix += (long long)gridDim.x * lanes) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c4) * 4;
+    long long pix = i / c4;
     const int xx = (int)(pix % w);
-    const int yy = (int)((pix / w) % h);
-    const int img = (int)(pix / ((long long)w * h));
+    pix /= w;
+    const int yy = (int)(pix % h);
+    const int img = (int)(pix / h);
     const float* src = x + (long long)(img % nsrc) * h * w * 4;
-    float4 acc = bv;
+    float acc[4] = {__ldg(bias + co), __ldg(bias + co + 1), __ldg(bias + co + 2), __ldg(bias + co + 3)};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = xx + kx - 1;
-        if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+        if (ix < 0 || ix >= w) continue;
         const float4 v = *reinterpret_cast<const float4*>(src + ((long long)iy * w + ix) * 4);
         const float in[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          const float4 k4 = kw[(ky * 3 + kx) * 4 + ci];
-          acc.x += in[ci] * k4.x;
-          acc.y += in[ci] * k4.y;
-          acc.z += in[ci] * k4.z;
-          acc.w += in[ci] * k4.w;
+          const float4 kw = __ldg(reinterpret_cast<const float4*>(kernel + ((ky * 3 + kx) * 4 + ci) * cout + co));
+          acc[0] += in[ci] * kw.x;
+          acc[1] += in[ci] * kw.y;
+          acc[2] += in[ci] * kw.z;
+          acc[3] += in[ci] * kw.w;
         }
       }
     }
-    const long long o = pix * cout + co;
-    if (of) *reinterpret_cast<float4*>(of + o) = acc;
+    const long long o = (((long long)img * h + yy) * w + xx) * cout + co;
+    if (of) *reinterpret_cast<float4*>(of + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     if (ob) {
       uint2 u;
-      u.x = pack16(acc.x, acc.y, fp16);
-      u.y = pack16(acc.z, acc.w, fp16);
+      u.x = pack16(acc[0], acc[1], fp16);
+      u.y = pack16(acc[2], acc[3], fp16);
       *reinterpret_cast<uint2*>(ob + o) = u;
     }
   }
@@ -539,13 +537,9 @@ conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w, const
 
 void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel, const float* bias,
                     int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st) {
-  LDM_CHECK(cout % 4 == 0 && cout / 4 <= 256, "conv_in: cout must be a multiple of 4 and at most 1024");
-  const int c4 = cout / 4;
-  const int lanes = 256 / c4;
-  const long long npix = (long long)n * h * w;
-  long long blocks = (npix + lanes - 1) / lanes;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  launch_pdl(conv_in_kernel, dim3((int)blocks), dim3(c4 * lanes), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
+  LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
+  const long long total = (long long)n * h * w * (cout / 4);
+  launch_pdl(conv_in_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
              out_bf16, fp16);
   CUDA_CHECK(cudaGetLastError());
 }

@@ -52,6 +52,8 @@ typedef __nv_bfloat16 bf16;
 // are resident) and pdl_wait() before touching any global data (blocks until the predecessor grid
 // has completed and flushed).  Without the attribute both are no-ops.
 #ifdef __CUDACC__
+// Tuning knob: integer from the environment (read once per call site), used by profiles/ab_step.py sweeps.
+#define LDM_TUNE(name, dflt) ([] { static const int v = [] { const char* e = getenv(name); return e ? atoi(e) : (dflt); }(); return v; }())
 // Programmatic dependent launch (PDL): which kernel classes may start their prologue while the
 // previous kernel in the stream is still draining.  LDM_B200_PDL_MASK: bit 0 = the small kernels
 // (norms, K5, ...), bit 1 = the CTA-pair GEMM, bit 2 = attention.  Default 2: measured 5 % faster per

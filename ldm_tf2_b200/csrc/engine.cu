@@ -155,7 +155,7 @@ int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_
     const double waves = (double)((tiles + workers - 1) / workers);
     const double kb = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / 58.0);
     const double main_t = kb * total_kb, epi_t = 40.0 * bn * (geglu ? 0.75 : 1.0);
-    const double t = 2500.0 + 1500.0 * waves +   // launch / prologue, per-tile scheduling + bias staging
+    const double t = 2500.0 + (double)LDM_TUNE("LDM_B200_T_TILE_OVH", 1500) * waves +   // launch / prologue, per-tile scheduling + bias staging
                      (waves > 1 ? waves * std::max(main_t, epi_t) + std::min(main_t, epi_t) : main_t + epi_t);
     if (!best || t < best_t) { best = bn; best_t = t; }
   }
@@ -214,8 +214,9 @@ void Engine::gemm(const GemmOp& op) {
       const int tiles = m_tiles * (gemm_n / wide);
       if (tiles * 2 <= num_sms && total_kb >= 8) {
         int sp = op.splits > 1 ? op.splits : num_sms / tiles;
-        if (sp > total_kb / 12) sp = total_kb / 12;  // >= 12 k-blocks per split: workspace traffic stays
-        if (sp > 8) sp = 8;                          // below the weight traffic it parallelises
+        const int min_kb = LDM_TUNE("LDM_B200_T_SPLIT_MINKB", 12);
+        if (sp > total_kb / min_kb) sp = total_kb / min_kb;  // >= 12 k-blocks per split: workspace traffic stays
+        if (sp > LDM_TUNE("LDM_B200_T_SPLIT_MAX", 12)) sp = LDM_TUNE("LDM_B200_T_SPLIT_MAX", 12);                          // below the weight traffic it parallelises
         if (sp >= 2) { splits = sp; bn = wide; }
       }
     }
@@ -261,12 +262,14 @@ void Engine::gemm(const GemmOp& op) {
                        (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0) &&
                        getenv("LDM_B200_TMA_EPI") != nullptr;   // opt-in: measured on par with the staged path
   // ---- one CTA per SM with 8 epilogue warps, or two per SM with 4 (gemm.cuh): the latter when the
-  // epilogue outlasts the main loop (short K), so that two tiles' epilogues overlap on every SM
+  // main loop is not many times longer than the epilogue (tuned in-graph with profiles/ab_step.py: the
+  // threshold ended up high enough to take every GEMM that has >= 1.5 tiles per SM and fits), so that
+  // two tiles' epilogues overlap on every SM
   const double kb_cyc = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / 58.0);
-  const bool short_k = kb_cyc * (total_kb / splits) < 60.0 * bn * (geglu ? 0.75 : 1.0);
+  const bool short_k = kb_cyc * (total_kb / splits) < (double)LDM_TUNE("LDM_B200_T_EW4_K", 800) * bn * (geglu ? 0.75 : 1.0);
   // ... and only when every SM gets at least two tiles: a lone tile just sees half the epilogue warps
   const long long work_tiles = (long long)(pair ? (m_tiles + 1) / 2 : m_tiles) * ((gemm_n + bn - 1) / bn) * splits;
-  const bool many_tiles = work_tiles * 2 >= 3 * (pair ? num_sms / 2 : num_sms);
+  const bool many_tiles = work_tiles * 20 >= LDM_TUNE("LDM_B200_T_EW4_TILES", 30) * (pair ? num_sms / 2 : num_sms);
   const bool fits_half = 3 * slot + GEMM_CTRL_BYTES + GEMM_EPI_EW4_BYTES + 1024 <= 110 * 1024;   // >= 3 stages in half an SM
   const bool ew4 = !tma_epi && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
   p.tma_epi = tma_epi ? 1 : 0;

@@ -139,7 +139,7 @@ static void gn_launch_shape(int c, int hw, int n, int* threads, int* strip, int*
   int t = c4 * lanes;
   *threads = (t + 31) / 32 * 32;
   // enough CTAs to fill the chip (~4 per SM over the batch) but at least 8 pixels per lane
-  int want = (148 * 4 + n - 1) / n;
+  int want = (148 * LDM_TUNE("LDM_B200_T_GN_WANT", 4) + n - 1) / n;
   int st = (hw + want - 1) / want;
   const int min_strip = lanes * 8;
   if (st < min_strip) st = min_strip;

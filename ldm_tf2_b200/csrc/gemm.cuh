@@ -8,16 +8,19 @@
 // SAME padding.  The K loop is a list of segments (map, dy, dx, c0, #k-blocks): 9 taps of a
 // conv, optionally followed by 1x1 "shortcut" segments reading other tensors (the ResBlock
 // shortcut Dense over the virtual concat, unet.py:393-394, is folded into conv2's K loop).
-// B is the weight matrix pre-transposed to [N, K] bf16 (K-major), or a batched activation
-// (attention K / V^T).  The epilogue (4 warps, one TMEM lane quadrant each) fuses bias,
-// per-image/per-step bias (timestep embedding add, unet.py:386-388), SiLU / exact GELU /
-// GEGLU gating (unet.py:323-324), the fp32 residual add, and writes fp32 and/or bf16,
-// optionally transposed (V^T for attention).
+// B is the weight matrix pre-transposed to [N, K] 16-bit (K-major), or a batched activation
+// (attention K / V^T of the unfused path).  The epilogue fuses bias, per-image/per-step bias
+// (timestep embedding add, unet.py:386-388), SiLU / exact GELU / GEGLU gating (unet.py:323-324), the
+// fp32 residual add, and writes fp32 and/or 16-bit, optionally transposed (V^T for attention).
 //
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue: warp w owns TMEM
-// lane quadrant w%4 and every second column chunk; accumulators are transposed through a small
-// per-warp smem tile so that residual loads and output stores are full 128-bit, row-contiguous.
-// Pipelines: smem ring full/empty (TMA<->MMA) and 2 TMEM accumulator stages (MMA<->epilogue).
+// Template flavours: PAIR = 1 runs (2,1,1) clusters whose two CTAs share one M = 256 cta_group::2
+// UMMA (each loads its own 128 A rows and half of B); EW = 8 / 4 epilogue warps = one / two CTAs
+// per SM (512 / 256 TMEM columns, all / half of the shared memory).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2.. = epilogue: warp w owns TMEM lane
+// quadrant w%4 (EW = 8: and every second column chunk); accumulators are transposed through a small
+// per-warp smem tile so that residual loads and output stores are full 128-bit, row-contiguous
+// (GEGLU: read in the m16n8 fragment layout and stored sector-complete without the transposition).
+// Pipelines: smem ring full/empty (TMA<->MMA) and a TMEM accumulator ring (MMA<->epilogue).
 #pragma once
 #include "common.cuh"
 

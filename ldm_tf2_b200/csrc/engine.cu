@@ -153,8 +153,8 @@ int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_
     const int workers = pair ? num_sms / 2 : num_sms;
     const long long tiles = (long long)(pair ? (m_tiles + 1) / 2 : m_tiles) * (gemm_n / bn);
     const double waves = (double)((tiles + workers - 1) / workers);
-    const double kb = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / 58.0);
-    const double main_t = kb * total_kb, epi_t = 40.0 * bn * (geglu ? 0.75 : 1.0);
+    const double kb = std::max(2.0 * bn, (16384.0 + bn * (pair ? 64.0 : 128.0)) / (double)LDM_TUNE("LDM_B200_T_FEED", 58));
+    const double main_t = kb * total_kb, epi_t = (double)LDM_TUNE("LDM_B200_T_EPI_COST", 40) * bn * (geglu ? 0.75 : 1.0);
     const double t = 2500.0 + (double)LDM_TUNE("LDM_B200_T_TILE_OVH", 1500) * waves +   // launch / prologue, per-tile scheduling + bias staging
                      (waves > 1 ? waves * std::max(main_t, epi_t) + std::min(main_t, epi_t) : main_t + epi_t);
     if (!best || t < best_t) { best = bn; best_t = t; }

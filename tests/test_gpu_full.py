@@ -69,6 +69,25 @@ def test_full_unet_eps_and_three_steps(full):
     assert np.array_equal(got_g, got)
 
 
+def test_full_loop_batch8_deterministic(full):
+    """BASELINE.json configs[2] per-GPU shape (8 images, 16 CFG rows, 50 steps): the graph-replayed loop
+    is bit-reproducible run to run (split-K partials are summed in a fixed order, no atomics on the
+    data path), its latents are finite, and the decoded images are in a sane range."""
+    h = full["h"]
+    sched = O.ddim_schedule(**CFG["ldm"])
+    h.configure_sampler(*sampler_tables(sched))
+    ctx16 = np.concatenate([np.repeat(full["ctx"][:1], 8, 0), np.repeat(full["ctx"][1:], 8, 0)], 0)
+    h.set_context(ctx16)
+    x = np.random.default_rng(1234).standard_normal((8, 32, 32, 4), dtype=np.float32)
+    a = h.sample(x, None, 5.0, use_graph=True)
+    b = h.sample(x, None, 5.0, use_graph=True)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.isfinite(a).all() and a.shape == x.shape
+    img, _ = h.decode(a, div=0.18215)
+    assert img.shape == (8, 256, 256, 3) and np.isfinite(img).all()
+    h.set_context(full["ctx"])   # restore the 2-row context for the tests that follow
+
+
 def test_full_decode_kl(full):
     z = np.random.default_rng(99).standard_normal((1, 32, 32, 4), dtype=np.float32)
     ref, _ = O.decode_first_stage(full["Wa"], CFG["autoencoder_kl"], "kl", z)

@@ -1,7 +1,6 @@
 """Tokenizer known-answer ids of the reference's default prompt and of the empty prompt
-(convert_ckpt_pytorch_to_tf2.py:384-392): BERT-uncased WordPiece, max_length 77.  Tokenisation
-itself stays in Python/HF (run_ldm_sampler.py:28-46); these constants let benchmarks and tests
-run where neither the vocab file nor a network is available."""
+(convert_ckpt_pytorch_to_tf2.py:384-392): BERT-uncased WordPiece, max_length 77.  These constants let
+benchmarks and tests run where the vocab file is not available; get_token_ids tokenises any prompt."""
 import numpy as np
 
 DEFAULT_PROMPT = "a virus monster is playing guitar, oil on canvas"
@@ -15,10 +14,7 @@ def default_token_ids(batch_size: int) -> np.ndarray:
 
 
 def get_token_ids(prompt: str, vocab_dir: str, batch_size: int, max_length: int = 77) -> np.ndarray:
-    """run_ldm_sampler.py:28-46 with the HF tokenizer (numpy tensors instead of "pt")."""
-    from transformers import BertTokenizerFast
-    tok = BertTokenizerFast.from_pretrained(vocab_dir)
-    kw = dict(truncation=True, max_length=max_length, padding="max_length", return_tensors="np")
-    cond = tok(prompt, **kw)["input_ids"]
-    uncond = tok("", **kw)["input_ids"]
-    return np.concatenate([np.tile(uncond, [batch_size, 1]), np.tile(cond, [batch_size, 1])], 0).astype(np.int64)
+    """run_ldm_sampler.py:28-46 over the same vocab.txt, with the standalone WordPiece tokenizer
+    (ldm_tf2_b200/wordpiece.py; pinned against HF's BertTokenizerFast by tests/golden/wordpiece_small.json)."""
+    from . import wordpiece
+    return wordpiece.get_token_ids(prompt, vocab_dir, batch_size, max_length)

@@ -166,3 +166,28 @@ def test_world_size_2_allgather_matches_single_process(total):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_wordpiece_matches_hf_golden(tmp_path):
+    """run_ldm_sampler.py:28-46 without `transformers`: ids of 15 prompts (accents, CJK, emoji -> [UNK],
+    punctuation, >77 tokens, a 120-character word) generated by HF's BertTokenizerFast on the reference's
+    vocab.txt, including the two known-answer vectors of convert_ckpt_pytorch_to_tf2.py:384-392."""
+    import json
+    from ldm_tf2_b200 import tokens, wordpiece
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "wordpiece_small.json"), encoding="utf-8"))
+    for prompt, ids in zip(g["prompts"], g["ids"]):
+        assert wordpiece.encode(prompt, g["vocab"]) == ids, prompt[:40]
+    assert wordpiece.encode(tokens.DEFAULT_PROMPT, g["vocab"]) == tokens.COND_IDS
+    assert wordpiece.encode("", g["vocab"]) == tokens.UNCOND_IDS
+    # vocab.txt on disk, the (uncond rows, cond rows) layout of get_token_ids
+    inv = sorted(g["vocab"].items(), key=lambda kv: kv[1])
+    lines = [""] * (inv[-1][1] + 1)
+    for t, i in inv:
+        lines[i] = t
+    for i, t in enumerate(lines):
+        if not t:
+            lines[i] = f"[unused{i}]"
+    (tmp_path / "vocab.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    ids = tokens.get_token_ids(tokens.DEFAULT_PROMPT, str(tmp_path), 3)
+    assert ids.dtype == np.int64 and ids.shape == (6, 77)
+    assert (ids[:3] == np.array(tokens.UNCOND_IDS)).all() and (ids[3:] == np.array(tokens.COND_IDS)).all()

@@ -224,3 +224,50 @@ def test_public_sampler_api_loop_and_progressive(tiny):
         assert np.isfinite(xp).all()
     finally:
         s.close()
+
+
+def test_drop_in_cli_from_checkpoint_files(tmp_path, monkeypatch):
+    """python -m ldm_tf2_b200.run_ldm_sampler --config_path <yaml> (run_ldm_sampler.py:49-99): same YAML
+    layout, weights restored from TF2 checkpoint files, prompt tokenised from vocab.txt, images.npy
+    written as uint8 -- and equal to what the classes produce when driven directly."""
+    import json
+    import os
+    import yaml
+    from ldm_tf2_b200 import lib, run_ldm_sampler, tf_checkpoint as T, tokens
+    from ldm_tf2_b200.sampler import AutoencoderKL, LatentDiffusionModelSampler, TransformerModel, UNet
+    us, ts = O.unet_spec(CFG["unet"]), O.text_spec(CFG["cond_stage_model"])
+    as_ = O.ae_spec(CFG["autoencoder_kl"], "kl", 8)
+    flat = {"cond_stage_model": O.init_weights(ts, 1), "unet": O.init_weights(us, 0), "autoencoder": O.init_weights(as_, 2)}
+    d = lib.Handle(lib.make_config(CFG["cond_stage_model"], CFG["unet"], CFG["autoencoder_kl"], "kl", 8), -1)
+    for model, key in ((d.TEXT, "cond_stage_model"), (d.UNET, "unet"), (d.AE, "autoencoder")):
+        T.save(d, flat[key], str(tmp_path / f"{key}-1"), model=model)
+    d.close()
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wordpiece_small.json"), encoding="utf-8"))
+    lines = [f"[unused{i}]" for i in range(max(g["vocab"].values()) + 1)]
+    for t, i in g["vocab"].items():
+        lines[i] = t
+    (tmp_path / "vocab.txt").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    ldm = dict(CFG["ldm"], num_ddim_steps=5, v_posterior=0.0)
+    config = {
+        "cond_stage_model": CFG["cond_stage_model"], "unet": CFG["unet"], "autoencoder_kl": CFG["autoencoder_kl"],
+        "ldm": ldm,
+        "pre_ckpt_paths": {k: str(tmp_path / f"{k}-1") for k in flat},
+        "ldm_sampling": dict(autoencoder_type="kl", latent_shape=[2, 8, 8, 4], guidance_scale=5.0,
+                             text_prompt=tokens.DEFAULT_PROMPT, vocab_dir=str(tmp_path), sample_save_progress=False,
+                             seed=3, ae_build_latent_hw=8),
+    }
+    (tmp_path / "cfg.yaml").write_text(yaml.safe_dump(config))
+    monkeypatch.chdir(tmp_path)
+    run_ldm_sampler.main(["--config_path", str(tmp_path / "cfg.yaml")])
+    images = np.load(tmp_path / "images.npy")
+    assert images.dtype == np.uint8 and images.shape == (2, 64, 64, 3)
+    text, unet, ae = TransformerModel(**CFG["cond_stage_model"]), UNet(**CFG["unet"]), AutoencoderKL(**CFG["autoencoder_kl"])
+    text.set_weights(flat["cond_stage_model"])
+    unet.set_weights(flat["unet"])
+    ae.set_weights(flat["autoencoder"])
+    s = LatentDiffusionModelSampler(unet, ae, text, device=0, seed=3, ae_build_latent_hw=8, **ldm)
+    try:
+        direct = s.tensor_to_image(s.ddim_p_sample_loop(tokens.default_token_ids(2), (2, 8, 8, 4), 5.0))
+    finally:
+        s.close()
+    assert np.array_equal(images, direct)

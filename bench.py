@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 # Algorithmic work (SURVEY 8d / BASELINE.md section 2), 2*MAC, unpadded dims
 GFLOP_UNET_STEP_PER_IMAGE = 364.15      # one CFG step (2 UNet passes), 32x32 latent
 GFLOP_CTX_KV_PER_IMAGE = 9.84           # loop-invariant context K/V projections, hoisted
-GEMM_DRAM_BYTES_PER_UNET_STEP_B8 = 3.925e9  # profiles/r1_dram_unet_step.csv (3898.4 MB read + 26.8 MB written)
+GEMM_DRAM_BYTES_PER_UNET_STEP_B8 = 3.904e9  # profiles/r1_dram_unet_step.csv (3893.3 MB read + 10.4 MB written, 179 launches)
 GFLOP_KL_DECODE_PER_IMAGE = 622.19
 METRIC = "images_per_s_256x256_ddim50_cfg"
 UNIT = "images/s"

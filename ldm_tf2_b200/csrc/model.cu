@@ -816,7 +816,7 @@ void Model::set_context(const float* ctx, int n) {
   launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.fp16, eng.stream);
   for (STW* s : all_st_) {
     const int c = s->c;
-    if (ctx_rows_ != n || !s->ctx_k) {
+    if (n > ctx_cap_rows_ || !s->ctx_k) {   // grow-only: a smaller batch reuses a prefix of the buffers
       s->ctx_k = dev_alloc<bf16>((size_t)n * tk * c);
       s->ctx_vt = dev_alloc<bf16>((size_t)n * c * tpad, true);
       realloc_ctx = true;
@@ -837,6 +837,7 @@ void Model::set_context(const float* ctx, int n) {
     eng.gemm(op);
   }
   ctx_rows_ = n;
+  if (n > ctx_cap_rows_) ctx_cap_rows_ = n;
   eng.sync();
   // the captured step reads ctx_k / ctx_vt by address: only new buffers invalidate it
   if (realloc_ctx && step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }

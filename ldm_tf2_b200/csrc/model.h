@@ -146,6 +146,7 @@ class Model {
   std::vector<std::pair<Slot*, float*>> ae_concat_bias_;
   bool model_ready_[3] = {false, false, false};
   int ctx_rows_ = 0;
+  int ctx_cap_rows_ = 0;   // rows the hoisted context K / V^T buffers were allocated for (grow-only)
   // ae
   Slot* codebook_ = nullptr; Slot* pq_k_ = nullptr; Slot* pq_b_ = nullptr;
   Slot* ae_conv_in_k_ = nullptr; Slot* ae_conv_in_b_ = nullptr;

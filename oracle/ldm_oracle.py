@@ -666,6 +666,104 @@ def ae_decode(W, cfg, kind, z, taps=None):
 
 
 # --------------------------------------------------------------------------
+# Autoencoder ENCODE side (groundwork, no CUDA path yet)
+# --------------------------------------------------------------------------
+def ae_encoder_plan(cfg, image_hw):
+    """Encoder.__init__/call walk (autoencoder.py:198-249): DownBlocks (ResidualBlock [+ AttentionBlock when
+    the feature map side is in attention_resolutions]) and Downsample stages with their spatial size."""
+    ch, mults, nb = cfg["channels"], cfg["multipliers"], cfg["num_blocks"]
+    chans = [ch * m for m in mults]
+    attn_res = list(cfg["attention_resolutions"])
+    plan, h, cur, idx = [], image_hw, ch, 0
+    for i in range(len(mults)):
+        for _ in range(nb):
+            plan.append(dict(kind="down", idx=idx, cin=cur, cout=chans[i], attn=(h in attn_res), hw=h))
+            cur = chans[i]
+            idx += 1
+        if i < len(mults) - 1:
+            plan.append(dict(kind="downsample", idx=idx, c=cur, hw=h))
+            h //= 2
+            idx += 1
+    return chans, plan
+
+
+def ae_encoder_spec(cfg, kind, image_hw=256):
+    """Encode-side weights in flat Keras order when ONLY encode() has been called on a fresh
+    AutoencoderKL / AutoencoderVQ (attribute order: `_encoder`, then `_quant_conv`;
+    autoencoder.py:322-331,395-405).  KL builds its Encoder with attention_resolutions=() and
+    2*latent_channels outputs (autoencoder.py:322-330)."""
+    cfg = dict(cfg)
+    if kind == "kl":
+        cfg["attention_resolutions"] = []
+    z = cfg["latent_channels"] * (2 if kind == "kl" else 1)
+    chans, plan = ae_encoder_plan(cfg, image_hw)
+    e = "autoencoder/_encoder"
+    s = [(f"{e}/_conv_in/kernel", (3, 3, 3, cfg["channels"]), "kernel"), (f"{e}/_conv_in/bias", (cfg["channels"],), "bias")]
+    for st in plan:
+        p = f"{e}/_down/{st['idx']}"
+        if st["kind"] == "down":
+            s += _res_spec(f"{p}/_residual", st["cin"], st["cout"], 0, st["cin"] != st["cout"], _AE_RES)
+            if st["attn"]:
+                s += _ae_attn_spec(f"{p}/_attention", st["cout"])
+        else:
+            s += [(f"{p}/_conv/kernel", (3, 3, st["c"], st["c"]), "kernel"), (f"{p}/_conv/bias", (st["c"],), "bias")]
+    top = chans[-1]
+    s += _res_spec(f"{e}/_middle/_residual1", top, top, 0, False, _AE_RES)
+    s += _ae_attn_spec(f"{e}/_middle/_attention", top)
+    s += _res_spec(f"{e}/_middle/_residual2", top, top, 0, False, _AE_RES)
+    s += [(f"{e}/_group_norm/gamma", (top,), "gamma"), (f"{e}/_group_norm/beta", (top,), "beta"),
+          (f"{e}/_conv_out/kernel", (3, 3, top, z), "kernel"), (f"{e}/_conv_out/bias", (z,), "bias"),
+          ("autoencoder/_quant_conv/kernel", (z, z), "kernel"), ("autoencoder/_quant_conv/bias", (z,), "bias")]
+    return s
+
+
+def conv3x3_down_ae(x, kernel, bias):
+    """AE Downsample (autoencoder.py:131-135): zero pad (0,1),(0,1) -- bottom / right only -- then 3x3
+    stride-2 VALID cross-correlation."""
+    n, h, w, c = x.shape
+    xp = np.zeros((n, h + 1, w + 1, c), dtype=F32)
+    xp[:, :h, :w] = x
+    ho, wo = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1
+    out = np.zeros((n * ho * wo, kernel.shape[-1]), dtype=F32)
+    for ky in range(3):
+        for kx in range(3):
+            patch = xp[:, ky:ky + 2 * ho:2, kx:kx + 2 * wo:2, :]
+            out += np.ascontiguousarray(patch).reshape(-1, c) @ kernel[ky, kx]
+    out += bias
+    return out.reshape(n, ho, wo, -1)
+
+
+def ae_encode(W, cfg, kind, images):
+    """AutoencoderKL.encode (autoencoder.py:354-359) -> (mean, logvar) of the diagonal Gaussian;
+    AutoencoderVQ.encode(only_encode=True) (autoencoder.py:421-425) -> pre-quantisation latents."""
+    cfg = dict(cfg)
+    if kind == "kl":
+        cfg["attention_resolutions"] = []
+    x = np.asarray(images, dtype=F32)
+    e = "autoencoder/_encoder"
+    h = conv3x3(x, W[f"{e}/_conv_in/kernel"], W[f"{e}/_conv_in/bias"])
+    _, plan = ae_encoder_plan(cfg, x.shape[1])
+    for st in plan:
+        p = f"{e}/_down/{st['idx']}"
+        if st["kind"] == "down":
+            h = ae_resblock(W, f"{p}/_residual", h)
+            if st["attn"]:
+                h = ae_attention(W, f"{p}/_attention", h)
+        else:
+            h = conv3x3_down_ae(h, W[f"{p}/_conv/kernel"], W[f"{p}/_conv/bias"])
+    h = ae_resblock(W, f"{e}/_middle/_residual1", h)
+    h = ae_attention(W, f"{e}/_middle/_attention", h)
+    h = ae_resblock(W, f"{e}/_middle/_residual2", h)
+    h = silu(group_norm(h, W[f"{e}/_group_norm/gamma"], W[f"{e}/_group_norm/beta"], 1e-6))
+    h = conv3x3(h, W[f"{e}/_conv_out/kernel"], W[f"{e}/_conv_out/bias"])
+    h = dense(h, W["autoencoder/_quant_conv/kernel"], W["autoencoder/_quant_conv/bias"])
+    if kind == "kl":
+        z = h.shape[-1] // 2
+        return h[..., :z], h[..., z:]
+    return h
+
+
+# --------------------------------------------------------------------------
 # Sampler (model_runners.py:425-509) and host glue (run_ldm_sampler.py:18-46)
 # --------------------------------------------------------------------------
 def ddim_sample_loop(Wu, cfg_unet, sched, context, x_init, noise, guidance_scale,

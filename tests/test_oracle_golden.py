@@ -164,3 +164,22 @@ def test_tensor_to_image():
     x = np.random.default_rng(0).standard_normal((2, 4, 4, 3)).astype(np.float32)
     u = O.tensor_to_image(x)
     assert u.dtype == np.uint8 and u.min() == 0 and u.max() == 255
+
+
+def test_ae_encoder_oracle_matches_reference_code():
+    """SURVEY 8(f) row 4 groundwork: the oracle's encode side against the reference's own
+    AutoencoderKL.encode / AutoencoderVQ.encode(only_encode=True) run on the TensorFlow stand-in
+    (tests/golden/make_encoder_golden.py): asymmetric (0,1) stride-2 padding, encoder attention at
+    16x16 for the VQ flavour, quant_conv, the mean / logvar split."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_encoder_small.npz"))
+    small_kl = dict(latent_channels=4, channels=32, num_blocks=2, attention_resolutions=[], multipliers=[1, 2, 4, 4])
+    small_vq = dict(latent_channels=4, channels=32, num_blocks=2, attention_resolutions=[16], multipliers=[1, 2, 2, 4],
+                    vocab_size=512)
+    x = g["images"]
+    spec = O.ae_encoder_spec(small_kl, "kl", 32)
+    mean, logvar = O.ae_encode(O.as_dict(spec, O.init_weights(spec, 31)), small_kl, "kl", x)
+    assert mean.shape == g["kl_mean"].shape == (2, 4, 4, 4)
+    assert rel_l2(mean, g["kl_mean"]) < 2e-4 and rel_l2(logvar, g["kl_logvar"]) < 2e-4
+    spec_v = O.ae_encoder_spec(small_vq, "vq", 32)
+    lat = O.ae_encode(O.as_dict(spec_v, O.init_weights(spec_v, 32)), small_vq, "vq", x)
+    assert rel_l2(lat, g["vq_latents"]) < 2e-4

@@ -191,3 +191,26 @@ def test_wordpiece_matches_hf_golden(tmp_path):
     ids = tokens.get_token_ids(tokens.DEFAULT_PROMPT, str(tmp_path), 3)
     assert ids.dtype == np.int64 and ids.shape == (6, 77)
     assert (ids[:3] == np.array(tokens.UNCOND_IDS)).all() and (ids[3:] == np.array(tokens.COND_IDS)).all()
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/r1_bench_n1.json is a bench.py line as the driver reads it: the base contract's keys plus
+    roofline / cpu_baseline / e2e / gpu_launches / clocks, with consistent arithmetic."""
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["algorithmic_gflop_per_unet_step"] / r["kernel_ms_per_unet_step"]) < 1e-6
+    assert r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
+    assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == []
+    images = d["config"]["global_batch"] * d["steps"]
+    assert abs(d["value"] - images / (d["ms_per_step"] * d["steps"] / 1e3)) / d["value"] < 1e-6

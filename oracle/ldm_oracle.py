@@ -763,6 +763,19 @@ def ae_encode(W, cfg, kind, images):
     return h
 
 
+def get_latents(W, cfg, kind, images, noise=None, scale_factor=0.18215):
+    """LatentDiffusionModel.get_latents (model_runners.py:602-625).  KL: posterior.sample() =
+    mean + exp(0.5 * logvar) * N(0,1) (distribution.py:18,23-25 -- the standard deviation is taken from
+    the UNclipped logvar; only the stored `_logvar` is clipped to [-30, 20], distribution.py:16); VQ:
+    encode(only_encode=True).  Both times scale_factor.  `noise` injects the normal draw (None = 0)."""
+    if kind == "kl":
+        mean, logvar = ae_encode(W, cfg, kind, images)
+        lat = mean if noise is None else (mean + np.exp(F32(0.5) * logvar, dtype=F32) * np.asarray(noise, F32)).astype(F32)
+    else:
+        lat = ae_encode(W, cfg, kind, images)
+    return (F32(scale_factor) * lat).astype(F32)
+
+
 # --------------------------------------------------------------------------
 # Sampler (model_runners.py:425-509) and host glue (run_ldm_sampler.py:18-46)
 # --------------------------------------------------------------------------

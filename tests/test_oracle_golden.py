@@ -183,3 +183,11 @@ def test_ae_encoder_oracle_matches_reference_code():
     spec_v = O.ae_encoder_spec(small_vq, "vq", 32)
     lat = O.ae_encode(O.as_dict(spec_v, O.init_weights(spec_v, 32)), small_vq, "vq", x)
     assert rel_l2(lat, g["vq_latents"]) < 2e-4
+    # get_latents (model_runners.py:602-625): scale_factor * posterior sample with an injected draw
+    W = O.as_dict(spec, O.init_weights(spec, 31))
+    nz = np.random.default_rng(5).standard_normal(mean.shape).astype(np.float32)
+    got = O.get_latents(W, small_kl, "kl", x, nz)
+    want = np.float32(0.18215) * (g["kl_mean"] + np.exp(np.float32(0.5) * g["kl_logvar"]) * nz)
+    assert rel_l2(got, want) < 2e-4
+    assert rel_l2(O.get_latents(W, small_kl, "kl", x), np.float32(0.18215) * g["kl_mean"]) < 2e-4
+

@@ -3,15 +3,26 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+    python bench.py --config c2|c4|c5                        # the other BASELINE.json configs
 
-One "step" = one full sampling job of the per-GPU batch: 50 DDIM steps (each = CFG-doubled UNet
-+ fused CFG/DDIM update) + KL decode to 256x256 (+ NCCL all-gather of the images when N > 1).
-Weak scaling: 8 images per GPU, so N = 8 is BASELINE.json configs[2] (latent [64,32,32,4]).
+One "step" = one full sampling job of this rank's shard of the global batch: S DDIM steps (each = one
+CFG-doubled UNet forward + the fused CFG/DDIM update) + decode (+ the all-gather of the images when
+N > 1).  Workloads (SURVEY 8a legend; BASELINE.json `configs` index in brackets):
+
+    c3 [2] (default)  latent [64,32,32,4], 50 steps eta 0, guidance 5, KL decode  -- the config the
+                      metric is quoted on.  STRONG scaling: the 64 images shard over the N GPUs
+                      (64/32/16/8 per GPU).  --weak B keeps B images per GPU instead.
+    c2 [1]            latent [4,32,32,4], 200 steps eta 1 (per-step noise), guidance 5, KL decode
+    c4 [3]            latent [8,64,64,4] (4096-token self-attention), 50 steps, KL decode to 512x512
+    c5 [4]            decode only, batch 32 at 256x256: KL decode and VQ decode (codebook argmin);
+                      `index_match` = fraction of VQ indices equal to the CPU oracle's
+
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -24,12 +35,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic work (SURVEY 8d / BASELINE.md section 2), 2*MAC, unpadded dims
-GFLOP_UNET_STEP_PER_IMAGE = 364.15      # one CFG step (2 UNet passes), 32x32 latent
-GFLOP_CTX_KV_PER_IMAGE = 9.84           # loop-invariant context K/V projections, hoisted
-GEMM_DRAM_BYTES_PER_UNET_STEP_B8 = 3.904e9  # profiles/r1_dram_unet_step.csv (3893.3 MB read + 10.4 MB written, 179 launches)
-GFLOP_KL_DECODE_PER_IMAGE = 622.19
-METRIC = "images_per_s_256x256_ddim50_cfg"
+# Algorithmic work (SURVEY 8d / BASELINE.md section 2), 2*MAC, unpadded dims, per image
+GFLOP_UNET_STEP = {32: 364.15, 64: 1610.48}   # one CFG step (2 UNet passes) incl. the context K/V projections
+GFLOP_CTX_KV = 9.84                           # ... of which loop-invariant (hoisted into set_context)
+# the part of a CFG step the implicit-GEMM kernel executes (conv3x3 + dense; attention products excluded):
+# conv 55.0 % + dense 37.6 % of 364.15 at 32x32 minus the hoisted 9.84 (the library's own count of
+# 2*M*N*K over one step's launches gives the same: profiles/r1_gemm_shapes.txt, 2696.5 GFLOP for 8 images)
+GFLOP_GEMM_STEP = {32: 337.06, 64: None}
+GFLOP_KL_DECODE = {32: 622.19, 64: 2514.52}
+GFLOP_VQ_DECODE = 472.53
+SCALE_FACTOR = 0.18215
+
+CONFIGS = {
+    "c2": dict(index=1, B=4, hw=32, steps=200, eta=1.0, metric="images_per_s_256x256_ddim200_eta1_cfg"),
+    "c3": dict(index=2, B=64, hw=32, steps=50, eta=0.0, metric="images_per_s_256x256_ddim50_cfg"),
+    "c4": dict(index=3, B=8, hw=64, steps=50, eta=0.0, metric="images_per_s_512x512_ddim50_cfg"),
+    "c5": dict(index=4, B=32, hw=32, steps=0, eta=0.0, metric="images_per_s_256x256_decode_only"),
+}
 UNIT = "images/s"
 
 
@@ -80,41 +102,95 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def workload_text(name, c, world, per_gpu, weak):
+    if name == "c5":
+        return (f"BASELINE configs[4]: decode only, batch {c['B']} at 256x256: KL decode + VQ decode with the "
+                f"quantize.py codebook argmin (16384 codes), txt2img-f8-large random-init autoencoders")
+    out = 8 * c["hw"]
+    return (f"BASELINE configs[{c['index']}]: txt2img-f8-large random-init, latent [{per_gpu * world if weak else c['B']},"
+            f"{c['hw']},{c['hw']},4] ({per_gpu}/GPU, {'weak' if weak else 'strong'} scaling), {c['steps']} DDIM steps "
+            f"eta={c['eta']:g} + CFG (guidance 5), KL decode to {out}x{out}"
+            + (", all-gather of the images" if world > 1 else ""))
+
+
 # --------------------------------------------------------------------------------------
 # CPU arm: the NumPy restatement of the reference (oracle/), the only place bench.py runs it
 # --------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, quiet=False):
+def cpu_threads():
+    """Pins the BLAS pool to every core this process may use (torchrun exports OMP_NUM_THREADS=1) and
+    returns the count actually in effect."""
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        got = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(got)) if got else want
+    except Exception:
+        return want
+
+
+def cpu_reference(name, steps, warmup):
+    """A bounded sample of the workload on the host cores with the oracle (kind = "port": TensorFlow
+    cannot be installed here).  Sampling configs: `steps` CFG UNet steps at B = 1 + one decode,
+    extrapolated to S steps + decode per image.  c5: KL + VQ decode of ONE image."""
     from oracle import ldm_oracle as O
+    threads = cpu_threads()
+    c = CONFIGS[name]
     cfg = O.FULL_CONFIG
-    us = O.unet_spec(cfg["unet"])
-    Wu = O.as_dict(us, O.init_weights(us, 0))
+    hw = c["hw"]
     as_ = O.ae_spec(cfg["autoencoder_kl"], "kl")
     Wa = O.as_dict(as_, O.init_weights(as_, 2))
-    sched = O.ddim_schedule(**cfg["ldm"])
     rng = np.random.default_rng(1234)
-    xt = rng.standard_normal((1, 32, 32, 4), dtype=np.float32)
+    if name == "c5":
+        vs = O.ae_spec(cfg["autoencoder_vq"], "vq")
+        Wv = O.as_dict(vs, O.init_weights(vs, 3))
+        z = np.random.default_rng(6).standard_normal((c["B"], hw, hw, 4), dtype=np.float32)
+        t0 = time.perf_counter()
+        O.decode_first_stage(Wa, cfg["autoencoder_kl"], "kl", z[:1])
+        t_kl = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        _, idx = O.vq_lookup((z / np.float32(SCALE_FACTOR)).astype(np.float32), Wv["autoencoder/_quantize/kernel"])
+        t_idx = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.decode_first_stage(Wv, cfg["autoencoder_vq"], "vq", z[:1])
+        t_vq = time.perf_counter() - t0
+        per_image = t_kl + t_vq   # one KL decode + one VQ decode (argmin of its rows included)
+        return dict(value=1.0 / per_image, cores=threads, vq_indices=idx,
+                    sample=f"1 of {c['B']} images: KL decode {t_kl:.2f} s + VQ decode incl. argmin {t_vq:.2f} s "
+                           f"(argmin of all {idx.size} rows: {t_idx:.2f} s); NumPy fp32 + OpenBLAS, {threads} threads")
+    us = O.unet_spec(cfg["unet"])
+    Wu = O.as_dict(us, O.init_weights(us, 0))
+    sched = O.ddim_schedule(**dict(cfg["ldm"], eta=c["eta"], num_ddim_steps=c["steps"]))
+    S = c["steps"]
+    xt = rng.standard_normal((1, hw, hw, 4), dtype=np.float32)
     ctx = np.random.default_rng(3).standard_normal((2, 77, 1280), dtype=np.float32)
+    nz = rng.standard_normal((1, hw, hw, 4), dtype=np.float32) if c["eta"] > 0 else None
 
     def one_step(x, index):
         t = np.full([2], sched["ddim_steps"][index], np.int32)
         e = O.unet_forward(Wu, cfg["unet"], np.concatenate([x, x]), t, ctx)
-        return O.ddim_update(x, e[:1], e[1:], None, O.ddim_coeffs(sched, index), 5.0)[0]
+        return O.ddim_update(x, e[:1], e[1:], nz, O.ddim_coeffs(sched, index), 5.0)[0]
 
     t0 = time.perf_counter()
-    O.decode_first_stage(Wa, cfg["autoencoder_kl"], "kl", xt * np.float32(0.18215))
+    O.decode_first_stage(Wa, cfg["autoencoder_kl"], "kl", xt * np.float32(SCALE_FACTOR))
     t_dec = time.perf_counter() - t0
     for i in range(warmup):
-        xt = one_step(xt, 49 - i % 50)
+        xt = one_step(xt, S - 1 - i % S)
     ts = []
     for i in range(steps):
         t0 = time.perf_counter()
-        xt = one_step(xt, 49 - (warmup + i) % 50)
+        xt = one_step(xt, S - 1 - (warmup + i) % S)
         ts.append(time.perf_counter() - t0)
     t_step = float(np.mean(ts))
-    per_image = 50 * t_step + t_dec
-    return dict(value=1.0 / per_image, t_step=t_step, t_dec=t_dec, cores=os.cpu_count(),
-                sample=f"B=1: {steps} CFG UNet steps ({t_step:.2f} s each) + 1 KL decode ({t_dec:.2f} s), "
-                       f"extrapolated to 50 steps + decode per image; NumPy fp32 + OpenBLAS, all host threads")
+    per_image = S * t_step + t_dec
+    return dict(value=1.0 / per_image, cores=threads,
+                sample=f"B=1 at {hw}x{hw} latents: {steps} CFG UNet steps ({t_step:.2f} s each) + 1 KL decode "
+                       f"({t_dec:.2f} s), extrapolated to {S} steps + decode per image; NumPy fp32 + OpenBLAS, "
+                       f"{threads} threads")
+
+
+def sha16(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
 
 def main():
@@ -123,27 +199,41 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=8)
-    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--weak", type=int, default=0, metavar="B",
+                    help="weak scaling: B images per GPU (round-1 line: --weak 8) instead of sharding the config's batch")
+    ap.add_argument("--verify", action="store_true",
+                    help="multi-GPU invariance: rank 0 recomputes every shard locally and compares it bit for bit "
+                         "with the gathered images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rooflines", action="store_true", help="skip the microbenchmarks behind the roofline keys")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    B = args.batch_per_gpu
-    workload = (f"txt2img-f8-large random-init, latent [{B * world},32,32,4] ({B}/GPU), {args.ddim_steps} DDIM steps "
-                f"eta=0 + CFG (guidance 5), KL decode to 256x256" + (", NCCL all-gather of images" if world > 1 else ""))
+    name = args.config
+    c = CONFIGS[name]
+    weak = args.weak > 0
+    if weak:
+        per_gpu, global_b = args.weak, args.weak * world
+    else:
+        global_b = c["B"]
+        if global_b % world:
+            raise SystemExit(f"config {name}: global batch {global_b} does not shard over {world} GPUs")
+        per_gpu = global_b // world
+    workload = workload_text(name, c, world, per_gpu, weak)
+    scaling = "weak" if weak else "strong"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference(max(args.steps, 1), min(args.warmup, 1))
+        r = cpu_reference(name, max(args.steps, 1), min(args.warmup, 1))
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "impl": "reference", "metric": c["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU restatement of the reference (oracle/, NumPy fp32); "
-                       "TensorFlow is not installable here, so this is kind=port, not the TF2 sampler itself"},
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "note": "CPU restatement of the reference (oracle/, NumPy fp32) on a bounded "
+                       "sample of this workload; TensorFlow is not installable here, so kind=port, not the TF2 sampler"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -155,97 +245,24 @@ def main():
     import torch
     import torch.distributed as dist
     from ldm_tf2_b200 import lib, parallel, synth, tokens
-    from ldm_tf2_b200.sampler import (AutoencoderKL, LatentDiffusionModelSampler, TransformerModel, UNet)
+    from ldm_tf2_b200.sampler import (AutoencoderKL, AutoencoderVQ, LatentDiffusionModelSampler, TransformerModel,
+                                      UNet)
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     cfg = synth.FULL_CONFIG
     precision = os.environ.get("LDM_B200_PRECISION", lib.DEFAULT_PRECISION)
-    ldm_kw = dict(cfg["ldm"])
-    ldm_kw["num_ddim_steps"] = args.ddim_steps
-    # public API objects, exactly as run_ldm_sampler.py:56-83 builds them
-    text = TransformerModel(**cfg["cond_stage_model"])
-    unet = UNet(**cfg["unet"])
-    ae = AutoencoderKL(**{k: v for k, v in cfg["autoencoder_kl"].items()})
-    sampler = LatentDiffusionModelSampler(unet, ae, text, device=local_rank, **ldm_kw)
-    h = sampler.handle
-    for model, seed in ((h.TEXT, 1), (h.UNET, 0), (h.AE, 2)):
-        h.set_weights(model, synth.random_weights(h, model, seed))
-    h.finalize()
-    h.configure_sampler(sampler.schedule.ddim_steps, sampler.schedule.coeff_table())
-
-    ids = tokens.default_token_ids(B)
-    # global seeded x_T, sliced per rank: results do not depend on the GPU count
-    xg = np.random.default_rng(1234).standard_normal((B * world, 32, 32, 4), dtype=np.float32)
-    x_host = torch.empty((B, 32, 32, 4), dtype=torch.float32, pin_memory=True)
-    x_host.copy_(torch.from_numpy(parallel.shard_batch(xg, rank, world)))
-    x_np = x_host.numpy()
-    dev = torch.device("cuda", local_rank)
-    x_dev = x_host.to(dev)
-    lat_dev = torch.empty_like(x_dev)
-    img_dev = torch.empty((B, 256, 256, 3), dtype=torch.float32, device=dev)
-    ctx = h.encode_text(ids)
-    h.set_context(ctx)
+    peaks = measured_peaks()
+    B, hw, S = per_gpu, c["hw"], c["steps"]
+    out_hw = 8 * hw
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def device_step():
-        """inputs resident in HBM: sample + decode (+ all-gather); returns device ms"""
-        lib.check(h.lib.ldm_sample(h._h, lib.ptr(x_dev.data_ptr()), None, B, 32, 32, 5.0, lib.ptr(lat_dev.data_ptr()),
-                                   None, 0, 1))
-        lib.check(h.lib.ldm_decode(h._h, lib.ptr(lat_dev.data_ptr()), B, 32, 32, 0.18215,
-                                   lib.ptr(img_dev.data_ptr()), None))
-        t = h.timing()
-        ms = t["loop_ms"] + t["decode_ms"]
-        if world > 1:
-            ev0.record()
-            parallel.allgather_images(img_dev, B * world)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms += ev0.elapsed_time(ev1)
-        return ms, t
-
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    l0 = h.timing()["launches"]
-    w0 = time.perf_counter()
-    dev_ms, loop_ms, dec_ms = 0.0, 0.0, 0.0
-    for _ in range(args.steps):
-        ms, t = device_step()
-        dev_ms += ms
-        loop_ms += t["loop_ms"]
-        dec_ms += t["decode_ms"]
-    barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3
-    launches = h.timing()["launches"] - l0
-    clk = clocks.stop()
-
-    # end to end through the public API: host x_T in, host images out, every call
-    def e2e_step():
-        return sampler.ddim_p_sample_loop(ids, (B, 32, 32, 4), 5.0, x_init=x_np)
-
-    import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()):
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
-        barrier()
-        e0 = time.perf_counter()
-        for _ in range(args.steps):
-            images = e2e_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - e0) * 1e3
-    h2d = x_np.nbytes + ids.nbytes + ctx.nbytes
-    d2h = images.nbytes + ctx.nbytes + x_np.nbytes  # images + context + final latents read back
 
     def allmax(v):
         if world == 1:
@@ -254,89 +271,295 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dev_ms, wall_ms, e2e_ms = allmax(dev_ms), allmax(wall_ms), allmax(e2e_ms)
-    launches_total = launches
-    if world > 1:
-        t = torch.tensor([launches], dtype=torch.int64, device=dev)
+    def allsum_int(v):
+        if world == 1:
+            return int(v)
+        t = torch.tensor([v], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
-        launches_total = int(t.item())
+        return int(t.item())
 
-    line = None
+    ldm_kw = dict(cfg["ldm"], eta=c["eta"], num_ddim_steps=max(S, 1))
+    text = TransformerModel(**cfg["cond_stage_model"])
+    unet = UNet(**cfg["unet"])
+    ae = AutoencoderKL(**cfg["autoencoder_kl"])
+    # public API objects, exactly as run_ldm_sampler.py:56-83 builds them
+    sampler = LatentDiffusionModelSampler(unet, ae, text, device=local_rank, **ldm_kw)
+    h = sampler.handle
+    models = ((h.AE, 2),) if name == "c5" else ((h.TEXT, 1), (h.UNET, 0), (h.AE, 2))
+    for model, seed in models:
+        h.set_weights(model, synth.random_weights(h, model, seed))
+    h.finalize()
+    hv = None
+    if name == "c5" or (rank == 0 and not args.no_rooflines):
+        # VQ autoencoder (decode side + codebook) on its own handle: K6 lives there
+        vq = AutoencoderVQ(**cfg["autoencoder_vq"])
+        hv = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], vq.kwargs, "vq", 32), local_rank)
+        hv.set_weights(hv.AE, synth.random_weights(hv, hv.AE, 3))
+        hv.finalize()
+
+    extra = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gathered = None
+
+    def gather(img_dev):
+        """The one collective of the path: all ranks' decoded images; returns (tensor, ms)."""
+        if world == 1:
+            return img_dev, 0.0
+        ev0.record()
+        out = parallel.allgather_images(img_dev, global_b)
+        ev1.record()
+        torch.cuda.synchronize()
+        return out, ev0.elapsed_time(ev1)
+
+    if name == "c5":
+        # ------------------------------------------------------------------ decode-only workload
+        zg = np.random.default_rng(6).standard_normal((global_b, hw, hw, 4), dtype=np.float32)
+        z_np = parallel.shard_batch(zg, rank, world)
+        z_dev = torch.from_numpy(z_np).to(dev)
+        img_kl = torch.empty((B, out_hw, out_hw, 3), dtype=torch.float32, device=dev)
+        img_vq = torch.empty_like(img_kl)
+        idx_dev = torch.empty((B * hw * hw,), dtype=torch.int64, device=dev)
+
+        def device_step():
+            lib.check(h.lib.ldm_decode(h._h, lib.ptr(z_dev.data_ptr()), B, hw, hw, SCALE_FACTOR,
+                                       lib.ptr(img_kl.data_ptr()), None))
+            t_kl = h.timing()["decode_ms"]
+            lib.check(hv.lib.ldm_decode(hv._h, lib.ptr(z_dev.data_ptr()), B, hw, hw, SCALE_FACTOR,
+                                        lib.ptr(img_vq.data_ptr()), lib.ptr(idx_dev.data_ptr())))
+            t_vq = hv.timing()["decode_ms"]
+            _, g_ms = gather(img_kl)
+            return t_kl + t_vq + g_ms, dict(loop_ms=0.0, decode_ms=t_kl, vq_ms=t_vq)
+
+        def e2e_step():
+            a = sampler.decode_first_stage(z_np)
+            b_, idx = hv.decode(z_np, div=SCALE_FACTOR)
+            return a, b_, idx
+
+        h2d, d2h = 2 * z_np.nbytes, 2 * B * out_hw * out_hw * 3 * 4 + B * hw * hw * 8
+        gflop_per_image = GFLOP_KL_DECODE[hw] + GFLOP_VQ_DECODE
+    else:
+        # ------------------------------------------------------------------ sampling workloads
+        h.configure_sampler(sampler.schedule.ddim_steps, sampler.schedule.coeff_table())
+        ids_g = tokens.default_token_ids(global_b)
+        ids = parallel.shard_token_ids(ids_g, rank, world)
+        # globally seeded x_T / noise, sliced per rank: results do not depend on the GPU count
+        xg = np.random.default_rng(1234).standard_normal((global_b, hw, hw, 4), dtype=np.float32)
+        x_host = torch.empty((B, hw, hw, 4), dtype=torch.float32).pin_memory()
+        x_host.copy_(torch.from_numpy(parallel.shard_batch(xg, rank, world)))
+        x_np = x_host.numpy()
+        x_dev = x_host.to(dev)
+        nz_np, nz_dev = None, None
+        if c["eta"] > 0:
+            ng = np.random.default_rng(5678).standard_normal((S, global_b, hw, hw, 4), dtype=np.float32)
+            nz_np = parallel.shard_batch(ng, rank, world, axis=1)
+            nz_dev = torch.from_numpy(nz_np).to(dev)
+        img_dev = torch.empty((B, out_hw, out_hw, 3), dtype=torch.float32, device=dev)
+        ctx = h.encode_text(ids)
+        h.set_context(ctx)
+
+        def device_step():
+            """inputs resident in HBM: loop + decode of the device-resident latents (+ all-gather); device ms"""
+            lib.check(h.lib.ldm_sample(h._h, lib.ptr(x_dev.data_ptr()), lib.ptr(None if nz_dev is None else nz_dev.data_ptr()),
+                                       B, hw, hw, 5.0, None, None, 0, 1))
+            lib.check(h.lib.ldm_decode(h._h, None, B, hw, hw, SCALE_FACTOR, lib.ptr(img_dev.data_ptr()), None))
+            t = h.timing()
+            nonlocal gathered
+            gathered, g_ms = gather(img_dev)
+            return t["loop_ms"] + t["decode_ms"] + g_ms, t
+
+        def e2e_step():
+            # the call a user makes: host token ids + host x_T (+ host noise) in, host images out
+            return sampler.ddim_p_sample_loop(ids, (B, hw, hw, 4), 5.0, x_init=x_np, noise=nz_np)
+
+        h2d = x_np.nbytes + ids.nbytes + ctx.nbytes + (nz_np.nbytes if nz_np is not None else 0)
+        d2h = B * out_hw * out_hw * 3 * 4 + ctx.nbytes   # images + the text context (returned, then re-uploaded)
+        gflop_per_image = S * (GFLOP_UNET_STEP[hw] - GFLOP_CTX_KV) + GFLOP_KL_DECODE[hw]
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = h.timing()["launches"] + (hv.timing()["launches"] if hv else 0)
+    w0 = time.perf_counter()
+    dev_ms, acc = 0.0, {}
+    for _ in range(args.steps):
+        ms, t = device_step()
+        dev_ms += ms
+        for k, v in t.items():
+            if k.endswith("_ms"):
+                acc[k] = acc.get(k, 0.0) + v
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    launches = h.timing()["launches"] + (hv.timing()["launches"] if hv else 0) - l0
+    clk = clocks.stop()
+
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_out = e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - e0) * 1e3
+
+    dev_ms, wall_ms, e2e_ms = allmax(dev_ms), allmax(wall_ms), allmax(e2e_ms)
+    launches_total = allsum_int(launches)
+
+    # ---- multi-GPU invariance (SURVEY 4): gathered == every shard recomputed on this GPU, bit for bit
+    if name != "c5":
+        img_all = gathered if world > 1 else img_dev
+        extra["images_sha256_16"] = sha16(img_all.cpu().numpy())
+        if args.verify and rank == 0 and world > 1:
+            ok = True
+            all_np = img_all.cpu().numpy()
+            chk = torch.empty_like(img_dev)
+            for r in range(world):
+                ids_r = parallel.shard_token_ids(ids_g, r, world)
+                h.set_context(h.encode_text(ids_r))
+                xr = np.ascontiguousarray(parallel.shard_batch(xg, r, world))
+                nr = None if c["eta"] == 0 else np.ascontiguousarray(parallel.shard_batch(ng, r, world, axis=1))
+                lib.check(h.lib.ldm_sample(h._h, lib.ptr(xr), lib.ptr(nr), B, hw, hw, 5.0, None, None, 0, 1))
+                lib.check(h.lib.ldm_decode(h._h, None, B, hw, hw, SCALE_FACTOR, lib.ptr(chk.data_ptr()), None))
+                lo, hi = parallel.shard_range(global_b, r, world)
+                ok = ok and np.array_equal(all_np[lo:hi].view(np.uint32), chk.cpu().numpy().view(np.uint32))
+            extra["verify"] = {"gathered_equals_local_recompute_bitwise": bool(ok), "shards": world}
+            h.set_context(ctx)
+
     if rank == 0:
-        peaks = measured_peaks()
-        prof = h.profile_unet_step(B, 32, 32, 3)
-        step_gflop = B * (GFLOP_UNET_STEP_PER_IMAGE - GFLOP_CTX_KV_PER_IMAGE)
-        # Time of the GEMM kernel inside the replayed step graph = full step - the same graph without
-        # its GEMM launches (CUDA events around 20 graph replays each).  Events around every single
-        # launch of an eager step (prof) add ~4 us of launch latency to each of the 179 launches and
-        # overstate the kernel's share (81 % against ncu's 62 %); that figure is kept as a cross-check.
-        t_full = h.bench_unet_step(B, 32, 32, 20, True)
-        t_rest = h.bench_unet_step(B, 32, 32, 20, True, skip_gemm=True)
-        gemm_ms = t_full - t_rest
-        achieved = step_gflop / gemm_ms  # GFLOP/ms == TFLOP/s
-        k5_ms = h.bench_ddim_update(B, 32, 32, False, 200)
-        k5_bytes = 4 * 4 * B * 32 * 32 * 4  # 3 reads + 1 write of fp32 [B,32,32,4]
-        # K2 GroupNorm at the decoder's largest activation [B, 256*256, 128] (HBM-resident: 268 MB fp32)
-        gn_n, gn_hw, gn_c = B, 256 * 256, 128
-        gn_stats_ms, gn_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10)
-        gn_el = gn_n * gn_hw * gn_c
-        total_images = B * world * args.steps
+        total_images = global_b * args.steps
         value = total_images / (dev_ms / 1e3)
-        gflop_per_image = args.ddim_steps * GFLOP_UNET_STEP_PER_IMAGE + GFLOP_KL_DECODE_PER_IMAGE
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
-            "config": {"workload": workload, "operands": f"{precision} tensor-core operands, fp32 accumulate, fp32 residual stream", "global_batch": B * world, "parallelism": f"dp{world} (sample-sharded replicas)",
-                       "l2": "not flushed explicitly: 1.75 GB of bf16 weights stream through L2 every UNet step",
+            "scaling": scaling, "vs_baseline": None, "dtype": precision, "data": "synthetic",
+            "config": {"workload": workload, "baseline_config_index": c["index"],
+                       "operands": f"{precision} tensor-core operands, fp32 accumulate, fp32 residual stream at block boundaries",
+                       "global_batch": global_b, "per_gpu_batch": B,
+                       "parallelism": f"dp{world} (sample-sharded weight replicas, no collective inside the loop)",
+                       "l2": "not flushed explicitly: every UNet step streams 1.75 GB of 16-bit weights plus "
+                             "activations far larger than the 126 MB L2",
                        "timing": "CUDA events on the library stream (+ torch events for the all-gather), max over ranks"},
-            "ms_per_unet_step": loop_ms / args.steps / args.ddim_steps,
-            "ms_decode": dec_ms / args.steps,
             "wall_ms_per_step": wall_ms / args.steps,
-            "model_tflops": value * gflop_per_image / 1e3 / world,
+            "model_tflops_per_gpu": value * gflop_per_image / 1e3 / world,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h),
-                    "api": "LatentDiffusionModelSampler.ddim_p_sample_loop(ids, shape, guidance) incl. text encoder"},
+                    "api": ("LatentDiffusionModelSampler.decode_first_stage (KL) + Handle.decode (VQ), host latents in, host images out"
+                            if name == "c5" else
+                            "LatentDiffusionModelSampler.ddim_p_sample_loop(ids, shape, guidance) incl. text encoder, host x_T in, host images out")},
             "gpu_launches": int(launches_total),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "implicit_gemm_kernel (tcgen05)", "achieved": achieved,
-                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         # DRAM bytes of the 179 GEMM launches of one UNet step (ncu, cold-cache replays):
-                         # profiles/r1_dram_unet_step.csv; only valid for the default 8-image workload
-                         "traffic": GEMM_DRAM_BYTES_PER_UNET_STEP_B8 if B == 8 else None,
-                         "traffic_unit": "bytes per UNet step (all GEMM launches)",
-                         "peak_source": peaks["source"] + ", sustained bf16",
-                         "launches_per_unet_step": prof["gemm_launches_per_step"],
-                         "kernel_ms_per_unet_step": gemm_ms, "step_ms_graph": t_full, "step_ms_graph_without_gemm": t_rest,
-                         "kernel_share_of_step": gemm_ms / t_full,
-                         "kernel_ms_event_per_launch_sum": prof["gemm_ms_per_step"], "eager_step_ms": prof["step_ms"],
-                         "achieved_event_per_launch": step_gflop / prof["gemm_ms_per_step"],
-                         "algorithmic_gflop_per_unet_step": step_gflop},
-            "roofline_k5": {"bound": "hbm", "kernel": "ddim_update_kernel", "achieved": k5_bytes / (k5_ms * 1e-3) / 1e9,
-                            "peak": peaks["hbm"], "unit": "GB/s", "frac": k5_bytes / (k5_ms * 1e-3) / 1e9 / peaks["hbm"],
-                            "traffic": None, "bytes_per_launch": k5_bytes, "ms_per_launch": k5_ms},
         }
-        line["roofline_k2"] = {
-            "bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel (GroupNorm(32)+SiLU -> 16-bit operand)",
-            "shape": [gn_n, gn_hw, gn_c], "unit": "GB/s", "peak": peaks["hbm"],
-            "stats": {"bytes_per_launch": gn_el * 4, "ms_per_launch": gn_stats_ms,
-                      "achieved": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9,
-                      "frac": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9 / peaks["hbm"]},
-            "apply": {"bytes_per_launch": gn_el * 6, "ms_per_launch": gn_apply_ms,
-                      "achieved": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9,
-                      "frac": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9 / peaks["hbm"]},
-            "traffic": None}
+        line.update(extra)
+        if name == "c5":
+            line["ms_decode_kl"] = acc["decode_ms"] / args.steps
+            line["ms_decode_vq"] = acc["vq_ms"] / args.steps
+            line["images_per_s_kl"] = B / (line["ms_decode_kl"] / 1e3) * world
+            line["images_per_s_vq"] = B / (line["ms_decode_vq"] / 1e3) * world
+            kl_tf = B * GFLOP_KL_DECODE[hw] / line["ms_decode_kl"]
+            line["roofline"] = {"bound": "tensor", "kernel": "implicit_gemm_kernel (tcgen05), KL decoder", "achieved": kl_tf,
+                                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": kl_tf / peaks["tflops"], "traffic": None,
+                                "peak_source": peaks["source"] + ", sustained bf16",
+                                "algorithmic_gflop_per_image": GFLOP_KL_DECODE[hw],
+                                "note": "whole-decode time (conv3x3 = 97.9 % of the decoder FLOPs)"}
+        else:
+            ms_step = acc["loop_ms"] / args.steps / S
+            line["ms_per_unet_step"] = ms_step
+            line["ms_decode"] = acc["decode_ms"] / args.steps
+            step_gflop = B * (GFLOP_UNET_STEP[hw] - GFLOP_CTX_KV)
+            # north_star's number: the whole CFG UNet step (GEMMs, attention, norms, K5) against dense-bf16 peak
+            line["roofline_step"] = {"bound": "tensor", "what": "one CFG UNet step incl. attention, norms and the K5 update",
+                                     "achieved": step_gflop / ms_step, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                                     "frac": step_gflop / ms_step / peaks["tflops"],
+                                     "frac_of_burst": step_gflop / ms_step / peaks["tflops_burst"],
+                                     "algorithmic_gflop_per_step": step_gflop, "peak_source": peaks["source"] + ", sustained bf16"}
+        if not args.no_rooflines:
+            rooflines(line, h, hv, B, hw, name, peaks)
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference(2, 1)
+            r = cpu_reference(name, 2, 1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
+            if name == "c5":
+                got = e2e_out[2]
+                line["index_match"] = float(np.mean(got == r["vq_indices"]))
+                line["index_rows"] = int(got.size)
         else:
             line["cpu_baseline"] = None
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if hv:
+        hv.close()
     sampler.close()
+
+
+def rooflines(line, h, hv, B, hw, name, peaks):
+    """Live microbenchmarks behind the roofline keys (rank 0, after the timed region)."""
+    if name != "c5":
+        # Dominant kernel: implicit_gemm_kernel.  Its time inside the replayed step graph = full step -
+        # the same graph captured without its launches (CUDA events around 20 replays each); numerator =
+        # the GEMM-only algorithmic FLOPs (attention products are executed by flash_attention_kernel).
+        prof = h.profile_unet_step(B, hw, hw, 2)
+        t_full = h.bench_unet_step(B, hw, hw, 20, True)
+        t_rest = h.bench_unet_step(B, hw, hw, 20, True, skip_gemm=True)
+        gemm_ms = t_full - t_rest
+        gemm_gflop = B * GFLOP_GEMM_STEP[hw] if GFLOP_GEMM_STEP.get(hw) else prof["gemm_flops_per_step"] / 1e9
+        achieved = gemm_gflop / gemm_ms
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "implicit_gemm_kernel (tcgen05)", "achieved": achieved, "peak": peaks["tflops"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "frac_of_burst": achieved / peaks["tflops_burst"],
+            "traffic": None, "traffic_unit": "bytes per UNet step (all GEMM launches); see profiles/ for the ncu DRAM list",
+            "peak_source": peaks["source"] + ", sustained bf16",
+            "algorithmic_gflop_per_unet_step": gemm_gflop,
+            "executed_gflop_per_unet_step": prof["gemm_flops_per_step"] / 1e9,
+            "launches_per_unet_step": prof["gemm_launches_per_step"],
+            "kernel_ms_per_unet_step": gemm_ms, "step_ms_graph": t_full, "step_ms_graph_without_gemm": t_rest,
+            "kernel_share_of_step": gemm_ms / t_full,
+            "kernel_ms_event_per_launch_sum": prof["gemm_ms_per_step"], "eager_step_ms": prof["step_ms"]}
+        k5_ms = h.bench_ddim_update(B, hw, hw, False, 200)
+        k5_bytes = 4 * 4 * B * hw * hw * 4  # 3 reads + 1 write of fp32 [B,h,w,4]
+        line["roofline_k5"] = {"bound": "hbm", "kernel": "ddim_update_kernel", "achieved": k5_bytes / (k5_ms * 1e-3) / 1e9,
+                               "peak": peaks["hbm"], "unit": "GB/s", "frac": k5_bytes / (k5_ms * 1e-3) / 1e9 / peaks["hbm"],
+                               "traffic": None, "bytes_per_launch": k5_bytes, "ms_per_launch": k5_ms}
+    # K2 GroupNorm at the decoder's largest activation [8, 256*256, 128] (HBM-resident: 268 MB fp32)
+    gn_n, gn_hw, gn_c = 8, 256 * 256, 128
+    gn_stats_ms, gn_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10)
+    gn_el = gn_n * gn_hw * gn_c
+    line["roofline_k2"] = {
+        "bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel (GroupNorm(32)+SiLU -> 16-bit operand)",
+        "shape": [gn_n, gn_hw, gn_c], "unit": "GB/s", "peak": peaks["hbm"],
+        "stats": {"bytes_per_launch": gn_el * 4, "ms_per_launch": gn_stats_ms,
+                  "achieved": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9,
+                  "frac": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9 / peaks["hbm"]},
+        "apply": {"bytes_per_launch": gn_el * 6, "ms_per_launch": gn_apply_ms,
+                  "achieved": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9,
+                  "frac": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9 / peaks["hbm"]},
+        "traffic": K2_NCU_TRAFFIC}
+    if hv is not None:
+        # K6: rows x 16384 codes, exact fp32 op order without FMA (12 flop per row-code pair); the HBM
+        # bytes are negligible (rows x 40 B + a 256 KB codebook), so the honest bound is the fp32 ALU.
+        rows = 32 * 32 * 32
+        k6_ms = hv.bench_vq_argmin(rows, 20)
+        k6_bytes = rows * (16 + 8 + 16) + 16384 * 16
+        ops = rows * 16384 * 12.0
+        alu_peak = 148 * 128 * 1.965e9   # fp32 lanes x clock: separately rounded mul / add (no FMA contraction)
+        line["roofline_k6"] = {"bound": "hbm", "kernel": "vq_argmin_kernel (+ code norms, z/scale)", "rows": rows, "codes": 16384,
+                               "achieved": k6_bytes / (k6_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                               "frac": k6_bytes / (k6_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                               "bytes_per_launch": k6_bytes, "ms_per_launch": k6_ms,
+                               "alu": {"flop_per_launch": ops, "achieved_tflops": ops / (k6_ms * 1e-3) / 1e12,
+                                       "peak_tflops_fp32_nofma": alu_peak / 1e12,
+                                       "frac": ops / (k6_ms * 1e-3) / alu_peak,
+                                       "note": "the kernel is ALU-bound: HBM frac is small by construction"}}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gn_stats_kernel / gn_apply_kernel at the shape
+# above, from one `ncu --set full` capture (profiles/README.md says which); None until that capture exists
+K2_NCU_TRAFFIC = None
 
 
 if __name__ == "__main__":

@@ -65,6 +65,9 @@ typedef struct ldm_config {
 
 LDM_API const char* ldm_last_error(void);
 LDM_API int ldm_version(void);
+/* cudaDeviceSynchronize on the current device: the shim fences DLPack producers with it (a capsule
+ * carries no stream; TF's eager stream is opaque, SURVEY 8b "Threading / streams"). */
+LDM_API int ldm_device_synchronize(void);
 
 /* Constructors of UNet / TransformerModel / Autoencoder* (run_ldm_sampler.py:56-68). */
 LDM_API int ldm_create(const ldm_config* cfg, int device, ldm_handle** out);
@@ -113,14 +116,17 @@ LDM_API int ldm_ddim_step(ldm_handle* h, const float* xt, const float* eps2, con
  * S steps (or steps_limit > 0 of them) from x_init [b,hh,ww,4] with per-step noise
  * [S,b,hh,ww,4] (NULL when eta = 0).  Context must hold 2b rows (uncond first).
  * eps_trace (optional, HOST) receives the [2b,hh,ww,4] UNet output of every step in
- * execution order.  use_graph: replay the step as a CUDA graph. */
+ * execution order.  use_graph: replay the step as a CUDA graph.  latents_out may be NULL: the final
+ * latents stay on the device and ldm_decode(z = NULL) decodes them (no host round trip between the
+ * loop and decode_first_stage, model_runners.py:503). */
 LDM_API int ldm_sample(ldm_handle* h, const float* x_init, const float* noise, int b, int hh, int ww,
                float guidance_scale, float* latents_out, float* eps_trace, int steps_limit, int use_graph);
 
 /* decode_first_stage (model_runners.py:425-434) when div = scale_factor, or
  * AutoencoderKL.decode / AutoencoderVQ.decode(force_quantize=True) (autoencoder.py:361-364,
  * 430-436) when div = 1: z [b,hh,ww,4] -> images [b,8hh,8ww,3]; VQ also writes the codebook
- * indices int64 [b*hh*ww] (idx_out may be NULL). */
+ * indices int64 [b*hh*ww] (idx_out may be NULL).  z = NULL: the device-resident latents of the last
+ * ldm_sample call (b, hh, ww must be that call's). */
 LDM_API int ldm_decode(ldm_handle* h, const float* z, int b, int hh, int ww, float div, float* images_out,
                int64_t* idx_out);
 
@@ -150,6 +156,9 @@ LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, i
 /* GroupNorm(32)+SiLU microbenchmark over more distinct [n, hw, c] fp32 buffers than fit in L2:
  * average time of the statistics kernel and of the apply kernel (K2's HBM roofline). */
 LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms);
+/* K6 microbenchmark: average time of the codebook argmin (+ gather) over `rows` device-resident latent
+ * rows against the handle's codebook (quantize.py:57-78). */
+LDM_API int ldm_bench_vq_argmin(ldm_handle* h, long long rows, int iters, float* avg_ms);
 /* Fused-attention microbenchmark on zero-filled operands; trace_host (optional) receives
  * [n*heads*ceil(t/128)][32] clock64 stamps of one launch. */
 LDM_API int ldm_bench_attention(ldm_handle* h, int n, int t, int tk, int heads, int d, int iters, float* avg_ms,

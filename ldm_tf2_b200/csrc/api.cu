@@ -12,10 +12,45 @@ struct ldm_handle {
   Model* model = nullptr;
 };
 
+namespace {
+// owners for the microbenchmark / test hooks: nothing leaks when a CUDA_CHECK throws mid-way
+struct Scratch {
+  std::vector<void*> ptrs;
+  template <typename T> T* get(size_t n, bool zero = false) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    ptrs.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+};
+struct EventPair {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventPair() {
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+  }
+  ~EventPair() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+}  // namespace
+
 static thread_local std::string g_err;
 
 const char* ldm_last_error(void) { return g_err.c_str(); }
-int ldm_version(void) { return 100; }
+int ldm_version(void) { return 200; }
+
+int ldm_device_synchronize(void) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    g_err = std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(e);
+    return LDM_ERR_CUDA;
+  }
+  return LDM_OK;
+}
 
 #define API_BEGIN try {
 #define API_END                                \
@@ -61,6 +96,7 @@ int ldm_create(const ldm_config* c, int device, ldm_handle** out) {
   m.precision = c->precision;
   LDM_CHECK(m.model_channels % 32 == 0 && m.ae_channels % 32 == 0, "channels must be multiples of 32 (GroupNorm(32))");
   LDM_CHECK(m.latent_channels == 4, "latent_channels must be 4");
+  LDM_CHECK(m.out_channels == 4, "out_channels must be 4 (the sampler update and the eps buffers assume the latent shape)");
   LDM_CHECK(m.num_heads * m.head_base == m.model_channels, "num_heads*head_base must equal model_channels (unet.py:82)");
   LDM_CHECK(m.context_dim == m.text_hidden, "context_dim must equal the text transformer hidden size");
   ldm_handle* h = new ldm_handle();
@@ -180,7 +216,7 @@ int ldm_sample(ldm_handle* h, const float* x_init, const float* noise, int b, in
                float* latents_out, float* eps_trace, int steps_limit, int use_graph) {
   API_BEGIN
   NEED(h);
-  LDM_CHECK(x_init && latents_out && b > 0 && hh > 0 && ww > 0, "ldm_sample: bad argument");
+  LDM_CHECK(x_init && b > 0 && hh > 0 && ww > 0, "ldm_sample: bad argument");
   const int down = 1 << (h->model->cfg.num_mult - 1);
   LDM_CHECK(hh % down == 0 && ww % down == 0, "latent %dx%d not divisible by %d", hh, ww, down);
   h->model->sample(x_init, noise, b, hh, ww, guidance, latents_out, eps_trace, steps_limit, use_graph);
@@ -190,7 +226,7 @@ int ldm_sample(ldm_handle* h, const float* x_init, const float* noise, int b, in
 int ldm_decode(ldm_handle* h, const float* z, int b, int hh, int ww, float div, float* images_out, int64_t* idx_out) {
   API_BEGIN
   NEED(h);
-  LDM_CHECK(z && images_out && b > 0 && hh > 0 && ww > 0 && div != 0.f, "ldm_decode: bad argument");
+  LDM_CHECK(images_out && b > 0 && hh > 0 && ww > 0 && div != 0.f, "ldm_decode: bad argument");
   h->model->decode(z, b, hh, ww, div, images_out, reinterpret_cast<long long*>(idx_out));
   API_END
 }
@@ -241,11 +277,11 @@ int ldm_bench_ddim_update(ldm_handle* h, int b, int hh, int ww, int with_noise, 
   int nbuf = (int)((192ll << 20) / set_bytes) + 1;
   if (nbuf < 4) nbuf = 4;
   if (nbuf > 4096) nbuf = 4096;
-  float *eps, *xt, *nz = nullptr, *coef;
-  CUDA_CHECK(cudaMalloc(&eps, (size_t)nbuf * 2 * nh * 4));
-  CUDA_CHECK(cudaMalloc(&xt, (size_t)nbuf * nh * 4));
-  if (with_noise) CUDA_CHECK(cudaMalloc(&nz, (size_t)nbuf * nh * 4));
-  CUDA_CHECK(cudaMalloc(&coef, 8 * sizeof(float)));
+  Scratch sc;
+  float* eps = sc.get<float>((size_t)nbuf * 2 * nh);
+  float* xt = sc.get<float>((size_t)nbuf * nh);
+  float* nz = with_noise ? sc.get<float>((size_t)nbuf * nh) : nullptr;
+  float* coef = sc.get<float>(8);
   const float hc[8] = {1.0008531f, 0.04131441f, 0.99957f, 0.0291f, with_noise ? 0.02f : 0.f, 0, 0, 0};
   CUDA_CHECK(cudaMemcpy(coef, hc, sizeof hc, cudaMemcpyHostToDevice));
   launch_fill_f32(eps, (long long)nbuf * 2 * nh, 0.25f, m.eng.stream);
@@ -253,9 +289,8 @@ int ldm_bench_ddim_update(ldm_handle* h, int b, int hh, int ww, int with_noise, 
   if (nz) launch_fill_f32(nz, (long long)nbuf * nh, 0.125f, m.eng.stream);
   for (int i = 0; i < 3; ++i)
     launch_ddim_update(eps, xt, nz, 0, coef, nullptr, 0, 5.0f, 0, xt, nullptr, nh, m.eng.stream);
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0));
-  CUDA_CHECK(cudaEventCreate(&e1));
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
   m.eng.sync();
   CUDA_CHECK(cudaEventRecord(e0, m.eng.stream));
   for (int i = 0; i < iters; ++i) {
@@ -269,9 +304,6 @@ int ldm_bench_ddim_update(ldm_handle* h, int b, int hh, int ww, int with_noise, 
   CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   *avg_ms = ms / iters;
   m.eng.launches += iters + 3;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(eps); cudaFree(xt); cudaFree(coef);
-  if (nz) cudaFree(nz);
   API_END
 }
 
@@ -350,12 +382,10 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   CUDA_CHECK(cudaSetDevice(e.device));
   const int ktot = conv ? 9 * k : k;
   const int wn = act == ACT_GEGLU ? 2 * n : n;
-  bf16 *a, *w, *o;
-  CUDA_CHECK(cudaMalloc(&a, (size_t)rows * k * 2));
-  CUDA_CHECK(cudaMalloc(&w, (size_t)wn * ktot * 2));
-  CUDA_CHECK(cudaMalloc(&o, (size_t)rows * n * 2));
-  CUDA_CHECK(cudaMemset(a, 0, (size_t)rows * k * 2));
-  CUDA_CHECK(cudaMemset(w, 0, (size_t)wn * ktot * 2));
+  Scratch sc;
+  bf16* a = sc.get<bf16>((size_t)rows * k, true);
+  bf16* w = sc.get<bf16>((size_t)wn * ktot, true);
+  bf16* o = sc.get<bf16>((size_t)rows * n);
   GemmOp op;
   op.num_a = 1;
   int bk = 0;
@@ -381,21 +411,15 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual) {
-    CUDA_CHECK(cudaMalloc(&of, (size_t)rows * n * 4));
-    CUDA_CHECK(cudaMemset(of, 0, (size_t)rows * n * 4));
+    of = sc.get<float>((size_t)rows * n, true);
     op.out_f32 = of; op.residual = of;
   }
-  long long* trace_d = nullptr;
-  if (trace_host) {
-    CUDA_CHECK(cudaMalloc(&trace_d, (size_t)148 * 64 * 16 * 8));
-    CUDA_CHECK(cudaMemset(trace_d, 0, (size_t)148 * 64 * 16 * 8));
-  }
+  long long* trace_d = trace_host ? sc.get<long long>((size_t)148 * 64 * 16, true) : nullptr;
   h->model->ensure_arena((size_t)512 << 20);
   e.arena.reset();
   for (int i = 0; i < 3; ++i) e.gemm(op);
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0));
-  CUDA_CHECK(cudaEventCreate(&e1));
+  EventPair ev;
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
   e.sync();
   CUDA_CHECK(cudaEventRecord(e0, e.stream));
   for (int i = 0; i < iters; ++i) { e.arena.reset(); e.gemm(op); }
@@ -410,11 +434,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
     e.gemm(op);
     e.sync();
     CUDA_CHECK(cudaMemcpy(trace_host, trace_d, (size_t)148 * 64 * 16 * 8, cudaMemcpyDeviceToHost));
-    cudaFree(trace_d);
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(a); cudaFree(w); cudaFree(o);
-  if (of) cudaFree(of);
   API_END
 }
 
@@ -444,17 +464,6 @@ static inline float widen16(uint16_t v, int fp16) {
   else f = ldexpf((float)(ma | 1024), (int)ex - 25);
   return s ? -f : f;
 }
-struct Scratch {
-  std::vector<void*> ptrs;
-  template <typename T> T* get(size_t n, bool zero = false) {
-    void* p = nullptr;
-    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
-    ptrs.push_back(p);
-    return reinterpret_cast<T*>(p);
-  }
-  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
-};
 float* up_f32(Scratch& s, Engine& e, const float* host, size_t n) {
   float* d = s.get<float>(n);
   CUDA_CHECK(cudaMemcpyAsync(d, host, n * sizeof(float), cudaMemcpyDefault, e.stream));
@@ -601,9 +610,10 @@ LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, co
   bf16* vtb = up_bf16(s, e, vt.data(), vt.size());
   bf16* ob = s.get<bf16>((size_t)n * t * c);
   float* of = s.get<float>((size_t)n * t * c);
-  e.arena.dry = true; e.dry = true; e.arena.reset();
-  m.attention_core(qb, c, kb, c, (long long)tk * c, tk, vtb, tpad, n, t, heads, d, scale, ob, c);
-  e.arena.dry = false; e.dry = false;
+  {
+    DryPass dry(e);
+    m.attention_core(qb, c, kb, c, (long long)tk * c, tk, vtb, tpad, n, t, heads, d, scale, ob, c);
+  }
   m.ensure_arena(e.arena.peak());
   e.arena.reset();
   m.attention_core(qb, c, kb, c, (long long)tk * c, tk, vtb, tpad, n, t, heads, d, scale, ob, c);
@@ -657,6 +667,37 @@ LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, 
   *apply_ms = ta / iters;
   e.launches += 4 * iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  API_END
+}
+
+// K6 microbenchmark: codebook argmin + gather over `rows` device-resident latent rows against the
+// handle's own codebook (VQ autoencoder weights must be set); average time of the argmin kernel
+// (code norms and the z / div pre-pass included, as on the decode path).
+LDM_API int ldm_bench_vq_argmin(ldm_handle* h, long long rows, int iters, float* avg_ms) {
+  API_BEGIN
+  NEED(h);
+  Model& m = *h->model;
+  LDM_CHECK(m.codebook_ && m.codebook_->set, "ldm_bench_vq_argmin: codebook not set (autoencoder kind must be vq)");
+  LDM_CHECK(rows > 0 && iters > 0 && avg_ms, "ldm_bench_vq_argmin: bad argument");
+  Engine& e = m.eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  Scratch s;
+  std::vector<float> zh((size_t)rows * 4);
+  for (size_t i = 0; i < zh.size(); ++i) zh[i] = 2.5f * sinf(0.7371f * (float)i) + 0.3f * cosf(0.0113f * (float)i);
+  float* z = up_f32(s, e, zh.data(), zh.size());
+  float* zq = s.get<float>((size_t)rows * 4);
+  long long* idx = s.get<long long>((size_t)rows);
+  for (int i = 0; i < 3; ++i) launch_vq_argmin(z, rows, 4, m.codebook_->f32, m.cfg.vq_vocab, 0.18215f, idx, zq, e.stream);
+  EventPair ev;
+  e.sync();
+  CUDA_CHECK(cudaEventRecord(ev.e0, e.stream));
+  for (int i = 0; i < iters; ++i) launch_vq_argmin(z, rows, 4, m.codebook_->f32, m.cfg.vq_vocab, 0.18215f, idx, zq, e.stream);
+  CUDA_CHECK(cudaEventRecord(ev.e1, e.stream));
+  e.sync();
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+  *avg_ms = ms / iters;
+  e.launches += 3ll * (iters + 3);
   API_END
 }
 

@@ -134,6 +134,46 @@ class Engine {
   void* encode_fn_ = nullptr;
 };
 
+// Arena-sizing pass: the same graph code runs with launches suppressed.  The guard restores the
+// engine's flags and launch counters on every exit path (an LDM_CHECK inside the pass throws).
+struct DryPass {
+  Engine& e;
+  long long l0, g0, a0;
+  explicit DryPass(Engine& eng) : e(eng), l0(eng.launches), g0(eng.gemm_launches), a0(eng.attn_launches) {
+    e.arena.dry = true; e.dry = true; e.arena.reset();
+  }
+  long long launches() const { return e.launches - l0; }
+  ~DryPass() {
+    e.launches = l0; e.gemm_launches = g0; e.attn_launches = a0;
+    e.arena.dry = false; e.dry = false;
+    e.arena.reset();
+  }
+};
+
+// Stream capture that is always ended: on unwind the partial graph is discarded and the stream
+// leaves capture mode (otherwise every later call on the handle would fail).
+struct CaptureGuard {
+  cudaStream_t st;
+  bool active = false;
+  explicit CaptureGuard(cudaStream_t s) : st(s) {
+    CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    active = true;
+  }
+  cudaGraph_t end() {
+    cudaGraph_t g = nullptr;
+    active = false;
+    CUDA_CHECK(cudaStreamEndCapture(st, &g));
+    return g;
+  }
+  ~CaptureGuard() {
+    if (!active) return;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+  }
+};
+
 int choose_block_n(int gemm_n, int boundary, int m_tiles, bool geglu, int total_kb, int num_sms, bool pair);
 void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cudaStream_t st);
 

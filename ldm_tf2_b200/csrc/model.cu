@@ -15,10 +15,23 @@ T* Model::dev_alloc(size_t n, bool zero) {
   if (eng.device < 0) return nullptr;   // describe-only model (ldm_create with device -1)
   void* p = nullptr;
   CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  // zero on the engine's own (non-blocking) stream: a legacy-stream memset is unordered against it
+  if (zero) CUDA_CHECK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), eng.stream));
   owned_.push_back(p);
   return reinterpret_cast<T*>(p);
 }
+
+// Frees a dev_alloc'ed buffer that is being replaced (after the stream has drained: kernels in flight
+// may still read it).
+void Model::dev_free(void* p) {
+  if (!p) return;
+  auto it = std::find(owned_.begin(), owned_.end(), p);
+  if (it == owned_.end()) return;
+  eng.sync();
+  owned_.erase(it);
+  cudaFree(p);
+}
+
 
 // =====================================================================================
 // Construction: slots in flat Keras order + packed destinations
@@ -376,9 +389,15 @@ void Model::set_weight(int model, int index, const float* src, const int* shape,
   CUDA_CHECK(cudaMalloc(&dev, n * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(dev, src, n * sizeof(float), cudaMemcpyDefault, eng.stream));
   if (s.kind == Slot::F32) {
-    eng.sync();
-    if (s.f32) cudaFree(s.f32);
-    s.f32 = dev;
+    // keep the address of an already installed tensor (captured graphs and hoisted tables hold it)
+    if (s.f32) {
+      CUDA_CHECK(cudaMemcpyAsync(s.f32, dev, n * sizeof(float), cudaMemcpyDeviceToDevice, eng.stream));
+      eng.sync();
+      cudaFree(dev);
+    } else {
+      eng.sync();
+      s.f32 = dev;
+    }
   } else if (s.kind == Slot::F32MAT) {
     CUDA_CHECK(cudaMemcpy2DAsync(s.f32_dst + s.f32_col0, s.f32_ld * sizeof(float), dev, s.n * sizeof(float),
                                  s.n * sizeof(float), s.k, cudaMemcpyDeviceToDevice, eng.stream));
@@ -391,6 +410,10 @@ void Model::set_weight(int model, int index, const float* src, const int* shape,
   }
   s.set = true;
   finalized = false;
+  // anything derived from the old weights is stale: the captured step, the hoisted time-embedding table
+  // (recomputed by finalize_weights) and the hoisted context K / V^T (set_context must run again)
+  invalidate_graph();
+  if (model == 1) { ctx_rows_ = 0; sampler_stale_ = true; }
 }
 
 void Model::finalize_weights() {
@@ -433,16 +456,20 @@ void Model::finalize_weights() {
   }
   eng.sync();
   finalized = true;
+  if (model_ready_[1] && S_ > 0 && sampler_stale_) {
+    compute_temb_table(ddim_t_.data(), S_, sampler_temb_);   // per-step time projections of the NEW weights
+    sampler_stale_ = false;
+  }
 }
 
 void Model::ensure_arena(size_t bytes) {
   // called right after a dry pass: gn_pool_off_ holds the number of statistic slots it used
   if (gn_pool_off_ > gn_pool_need_) gn_pool_need_ = gn_pool_off_;
   if (gn_pool_need_ > gn_pool_cap_) {
-    eng.sync();
-    const size_t slack = getenv("LDM_B200_GN_SLACK") ? (size_t)atol(getenv("LDM_B200_GN_SLACK")) : 0;
-    gn_pool_ = dev_alloc<double>(gn_pool_need_ + 2 * slack, true) + slack;
+    dev_free(gn_pool_);
+    gn_pool_ = dev_alloc<double>(gn_pool_need_, true);
     gn_pool_cap_ = gn_pool_need_;
+    invalidate_graph();   // a captured step holds the old pool address
   }
   bytes += (64u << 20);
   if (eng.arena.capacity() >= bytes) return;
@@ -817,6 +844,8 @@ void Model::set_context(const float* ctx, int n) {
   for (STW* s : all_st_) {
     const int c = s->c;
     if (n > ctx_cap_rows_ || !s->ctx_k) {   // grow-only: a smaller batch reuses a prefix of the buffers
+      dev_free(s->ctx_k);
+      dev_free(s->ctx_vt);
       s->ctx_k = dev_alloc<bf16>((size_t)n * tk * c);
       s->ctx_vt = dev_alloc<bf16>((size_t)n * c * tpad, true);
       realloc_ctx = true;
@@ -914,6 +943,7 @@ void Model::unet_forward(const float* x, const int* t_host, int n, int h, int w,
   LDM_CHECK(ctx_rows_ == n, "unet_forward: context set for %d rows, input has %d", ctx_rows_, n);
   CUDA_CHECK(cudaSetDevice(eng.device));
   if (fwd_temb_rows_ < n) {
+    dev_free(fwd_temb_);
     fwd_temb_ = dev_alloc<float>((size_t)n * tproj_cols_);
     fwd_temb_rows_ = n;
   }
@@ -925,11 +955,10 @@ void Model::unet_forward(const float* x, const int* t_host, int n, int h, int w,
   float* ed = static_cast<float*>(stage(ST_B, (size_t)n * h * w * cfg.out_channels * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(xd, x, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
   // size the arena with a dry pass, then run
-  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
-  const long long l0 = eng.launches, g0 = eng.gemm_launches;
-  unet_eps(xd, n, n, h, w, ed);
-  eng.launches = l0; eng.gemm_launches = g0;
-  eng.arena.dry = false; eng.dry = false;
+  {
+    DryPass dry(eng);
+    unet_eps(xd, n, n, h, w, ed);
+  }
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
   unet_eps(xd, n, n, h, w, ed);
@@ -946,11 +975,14 @@ void Model::configure_sampler(int S, const int* ddim_t, const float* coeffs) {
   CUDA_CHECK(cudaSetDevice(eng.device));
   S_ = S;
   ddim_t_.assign(ddim_t, ddim_t + S);
+  invalidate_graph();
+  dev_free(coeffs_dev_);
+  dev_free(sampler_temb_);
   coeffs_dev_ = dev_alloc<float>((size_t)S * 8);
-  CUDA_CHECK(cudaMemcpy(coeffs_dev_, coeffs, (size_t)S * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpyAsync(coeffs_dev_, coeffs, (size_t)S * 8 * sizeof(float), cudaMemcpyHostToDevice, eng.stream));
   sampler_temb_ = dev_alloc<float>((size_t)S * tproj_cols_);
   compute_temb_table(ddim_t, S, sampler_temb_);
-  if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
+  sampler_stale_ = false;
 }
 
 void Model::ddim_step(const float* xt, const float* eps2, const float* noise, int index, float guidance, int clip,
@@ -981,12 +1013,15 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
   CUDA_CHECK(cudaSetDevice(eng.device));
   const long long nh = (long long)b * h * w * 4;
   if (xt_cap_ < (size_t)nh) {
+    dev_free(xt_dev_);
+    dev_free(eps_dev_);
     xt_dev_ = dev_alloc<float>(nh);
     eps_dev_ = dev_alloc<float>(2 * nh);
     xt_cap_ = nh;
     if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
   }
   if (noise && noise_cap_ < (size_t)(nh * S_)) {
+    dev_free(noise_dev_);
     noise_dev_ = dev_alloc<float>(nh * S_);
     noise_cap_ = nh * S_;
     if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
@@ -994,12 +1029,12 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
   temb_table_ = sampler_temb_;
   temb_by_img_ = false; temb_use_step_ = true;
   // arena sizing
-  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
-  const long long l0 = eng.launches, g0 = eng.gemm_launches;
-  unet_eps(xt_dev_, b, 2 * b, h, w, eps_dev_);
-  const long long per_step = eng.launches - l0 + 2;
-  eng.launches = l0; eng.gemm_launches = g0;
-  eng.arena.dry = false; eng.dry = false;
+  long long per_step = 0;
+  {
+    DryPass dry(eng);
+    unet_eps(xt_dev_, b, 2 * b, h, w, eps_dev_);
+    per_step = dry.launches() + 2;
+  }
   ensure_arena(eng.arena.peak());
 
   ensure_events();
@@ -1018,23 +1053,31 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
     launch_step_advance(step_dev_, -1, eng.stream);
     eng.launches += 2;
   };
-  const bool graph_ok = use_graph && !eps_trace;
+  const bool graph_ok = use_graph != 0;
   if (graph_ok) {
     if (!step_graph_ || graph_b_ != b || graph_h_ != h || graph_w_ != w || graph_guid_ != guidance ||
         graph_noise_ != (noise != nullptr)) {
       if (step_graph_) { cudaGraphExecDestroy(step_graph_); step_graph_ = nullptr; }
       eng.sync();
-      cudaGraph_t g;
-      const long long l1 = eng.launches, g1 = eng.gemm_launches;
-      CUDA_CHECK(cudaStreamBeginCapture(eng.stream, cudaStreamCaptureModeThreadLocal));
-      one_step();
-      CUDA_CHECK(cudaStreamEndCapture(eng.stream, &g));
-      eng.launches = l1; eng.gemm_launches = g1;
-      CUDA_CHECK(cudaGraphInstantiate(&step_graph_, g, 0));
+      cudaGraph_t g = nullptr;
+      const long long l1 = eng.launches, g1 = eng.gemm_launches, a1 = eng.attn_launches;
+      {
+        CaptureGuard cap(eng.stream);
+        one_step();
+        g = cap.end();
+      }
+      eng.launches = l1; eng.gemm_launches = g1; eng.attn_launches = a1;
+      const cudaError_t ie = cudaGraphInstantiate(&step_graph_, g, 0);
       cudaGraphDestroy(g);
+      if (ie != cudaSuccess) { step_graph_ = nullptr; CUDA_CHECK(ie); }
       graph_b_ = b; graph_h_ = h; graph_w_ = w; graph_guid_ = guidance; graph_noise_ = noise != nullptr;
     }
-    for (int i = 0; i < nsteps; ++i) CUDA_CHECK(cudaGraphLaunch(step_graph_, eng.stream));
+    for (int i = 0; i < nsteps; ++i) {
+      CUDA_CHECK(cudaGraphLaunch(step_graph_, eng.stream));
+      if (eps_trace)   // parity hook: the replayed step's UNet output, copied between two replays
+        CUDA_CHECK(cudaMemcpyAsync(eps_trace + (long long)i * 2 * nh, eps_dev_, 2 * nh * 4, cudaMemcpyDefault,
+                                   eng.stream));
+    }
     eng.launches += per_step * nsteps;
   } else {
     for (int i = 0; i < nsteps; ++i) {
@@ -1044,7 +1087,8 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
                                    eng.stream));
     }
   }
-  CUDA_CHECK(cudaMemcpyAsync(latents_out, xt_dev_, nh * 4, cudaMemcpyDefault, eng.stream));
+  if (latents_out) CUDA_CHECK(cudaMemcpyAsync(latents_out, xt_dev_, nh * 4, cudaMemcpyDefault, eng.stream));
+  last_sample_b_ = b; last_sample_h_ = h; last_sample_w_ = w;
   CUDA_CHECK(cudaEventRecord(e1, eng.stream));
   eng.sync();
   CUDA_CHECK(cudaEventElapsedTime(&last_loop_ms, e0, e1));
@@ -1105,11 +1149,10 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
   float* x = static_cast<float*>(stage(ST_D, (size_t)R * D * sizeof(float)));
   float* y = static_cast<float*>(stage(ST_E, (size_t)R * D * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(ids_dev, uids.data(), uids.size() * sizeof(long long), cudaMemcpyHostToDevice, eng.stream));
-  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
-  const long long l0 = eng.launches, g0 = eng.gemm_launches;
-  body(ids_dev, x);
-  eng.launches = l0; eng.gemm_launches = g0;
-  eng.arena.dry = false; eng.dry = false;
+  {
+    DryPass dry(eng);
+    body(ids_dev, x);
+  }
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
   body(ids_dev, x);
@@ -1201,16 +1244,22 @@ void Model::decode_body(const float* z, int b, int h, int w, float div, float* i
 void Model::decode(const float* z, int b, int h, int w, float div, float* img_out, long long* idx_out) {
   LDM_CHECK(finalized && model_ready_[2], "decode: autoencoder weights not finalized");
   CUDA_CHECK(cudaSetDevice(eng.device));
+  if (!z) {   // the latents the last sample() call left on the device
+    LDM_CHECK(xt_dev_ && last_sample_b_ == b && last_sample_h_ == h && last_sample_w_ == w,
+              "decode(z = NULL): no device-resident latents of shape [%d,%d,%d,4] (last sample: [%d,%d,%d,4])", b, h, w,
+              last_sample_b_, last_sample_h_, last_sample_w_);
+    z = xt_dev_;
+  }
   const long long rows = (long long)b * h * w;
-  const long long img_el = rows * 64 * 3;
+  const long long up = 1ll << (cfg.ae_num_mult - 1);   // the decoder doubles the resolution at every level but the last
+  const long long img_el = rows * up * up * 3;
   float* zd = static_cast<float*>(stage(ST_A, rows * 4 * sizeof(float)));
   float* imgd = static_cast<float*>(stage(ST_B, img_el * sizeof(float)));
   long long* idxd = cfg.ae_kind == 1 ? static_cast<long long*>(stage(ST_C, rows * sizeof(long long))) : nullptr;
-  eng.arena.dry = true; eng.dry = true; eng.arena.reset();
-  const long long l0 = eng.launches, g0 = eng.gemm_launches;
-  decode_body(zd, b, h, w, div, imgd, idxd);
-  eng.launches = l0; eng.gemm_launches = g0;
-  eng.arena.dry = false; eng.dry = false;
+  {
+    DryPass dry(eng);
+    decode_body(zd, b, h, w, div, imgd, idxd);
+  }
   ensure_arena(eng.arena.peak());
   eng.arena.reset();
   ensure_events();

@@ -193,6 +193,9 @@ class Model {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   void ensure_events();
   template <typename T> T* dev_alloc(size_t n, bool zero = false);
+  void dev_free(void* p);
+  int last_sample_b_ = 0, last_sample_h_ = 0, last_sample_w_ = 0;   // shape of the latents sample() left in xt_dev_
+  bool sampler_stale_ = false;   // unet weights changed after configure_sampler: finalize_weights rebuilds the table
 };
 
 }  // namespace ldm

@@ -83,6 +83,13 @@ class Borrowed:
         self.release()
 
 
+def _device_synchronize():
+    """cudaDeviceSynchronize through the library (it links the CUDA runtime statically): a raw
+    DLPack capsule carries no stream, so device producers are fenced on the host."""
+    from . import lib as _lib
+    _lib.check(_lib.load().ldm_device_synchronize())
+
+
 def borrow(obj, dtype=None):
     """numpy array / DLPack capsule / object with __dlpack__ -> (pointer-or-array, shape, keepalive).
     Host tensors come back as C-contiguous numpy arrays of `dtype`; device tensors as a Borrowed
@@ -96,8 +103,18 @@ def borrow(obj, dtype=None):
         if int(dev[0]) == kDLCPU:
             a = np.ascontiguousarray(np.from_dlpack(obj), dtype=dtype)
             return a, a.shape, a
-        cap = obj.__dlpack__()
+        # stream=-1: "producer, do not synchronise for me" is NOT what we want -- the library copies
+        # on its own non-blocking stream, so the producer's pending work must be complete.  Ask the
+        # producer to make the data safe for the legacy default stream (stream=1), then block the
+        # host on the device so that our stream cannot overtake it.
+        try:
+            cap = obj.__dlpack__(stream=1)
+        except TypeError:
+            cap = obj.__dlpack__()
+        _device_synchronize()
     b = Borrowed(cap)
+    if b.on_device and cap is obj:
+        _device_synchronize()
     if dtype is not None and b.dtype != np.dtype(dtype):
         b.release()
         raise ValueError(f"expected dtype {np.dtype(dtype)}, got {b.dtype}")

@@ -33,6 +33,7 @@ _L = C.c_int64
 
 _PROTOS = {
     "ldm_version": ([], _I),
+    "ldm_device_synchronize": ([], _I),
     "ldm_create": ([C.POINTER(LdmConfig), _I, C.POINTER(_P)], _I),
     "ldm_destroy": ([_P], _I),
     "ldm_num_weights": ([_P, _I, C.POINTER(_I)], _I),
@@ -54,6 +55,7 @@ _PROTOS = {
     "ldm_profile_unet_step": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I), C.POINTER(C.c_double)], _I),
     "ldm_profiler": ([_I], _I),
     "ldm_bench_gemm": ([_P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P, _I], _I),
+    "ldm_bench_vq_argmin": ([_P, C.c_longlong, _I, C.POINTER(_F)], _I),
     "ldm_bench_attention": ([_P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P], _I),
     "ldm_crc32c": ([_P, C.c_ulonglong, C.c_uint, C.POINTER(C.c_uint)], _I),
     "ldm_bench_groupnorm": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F)], _I),
@@ -98,17 +100,34 @@ def check(rc: int):
         raise LdmError(f"ldm_b200 error {rc}: {load().ldm_last_error().decode(errors='replace')}")
 
 
+class DevPtr:
+    """A float32 tensor that already lives on the handle's GPU (e.g. unwrapped from a DLPack capsule):
+    raw address + shape.  The C ABI detects the memory space itself, so it goes where a numpy array goes."""
+
+    def __init__(self, address: int, shape, keep=None):
+        self.address, self.shape, self.keep = int(address), tuple(int(s) for s in shape), keep
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if self.shape else 1
+
+
 def ptr(a) -> C.c_void_p:
-    """Raw data pointer of a C-contiguous numpy array, or an int device pointer, or None."""
+    """Raw data pointer of a C-contiguous numpy array, a DevPtr, an int device pointer, or None."""
     if a is None:
         return C.c_void_p(0)
+    if isinstance(a, DevPtr):
+        return C.c_void_p(a.address)
     if isinstance(a, int):
         return C.c_void_p(a)
     assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
     return C.c_void_p(a.ctypes.data)
 
 
-def f32(a) -> np.ndarray:
+def f32(a):
+    """Host input -> C-contiguous float32 numpy array; device tensors (DevPtr) pass through."""
+    if isinstance(a, DevPtr):
+        return a
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
@@ -212,6 +231,8 @@ class Handle:
     # -- model calls --------------------------------------------------------
     def encode_text(self, ids) -> np.ndarray:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
+        if ids.ndim != 2 or ids.shape[1] != self.config.max_seq_len:
+            raise LdmError(f"token ids must be [rows, {self.config.max_seq_len}] (max_seq_len), got {ids.shape}")
         out = np.empty((ids.shape[0], ids.shape[1], self.config.hidden_size), np.float32)
         check(self.lib.ldm_encode_text(self._h, ptr(ids), ids.shape[0], ptr(out)))
         return out
@@ -238,17 +259,19 @@ class Handle:
         xt, eps2 = f32(xt), f32(eps2)
         noise = None if noise is None else f32(noise)
         b, hh, ww, _ = xt.shape
-        out = np.empty_like(xt)
-        x0 = np.empty_like(xt) if return_x0 else None
+        out = np.empty(xt.shape, np.float32)
+        x0 = np.empty(xt.shape, np.float32) if return_x0 else None
         check(self.lib.ldm_ddim_step(self._h, ptr(xt), ptr(eps2), ptr(noise), index, float(guidance),
                                      int(clip), b, hh, ww, ptr(out), ptr(x0)))
         return (out, x0) if return_x0 else out
 
-    def sample(self, x_init, noise, guidance, trace=False, steps_limit=0, use_graph=True, num_steps=None):
+    def sample(self, x_init, noise, guidance, trace=False, steps_limit=0, use_graph=True, num_steps=None,
+               keep_on_device=False):
+        """keep_on_device: do not read the final latents back; decode(None, shape=...) consumes them."""
         x_init = f32(x_init)
         noise = None if noise is None else f32(noise)
         b, hh, ww, _ = x_init.shape
-        out = np.empty_like(x_init)
+        out = None if keep_on_device else np.empty(x_init.shape, np.float32)
         tr = None
         if trace:
             n = steps_limit if steps_limit else num_steps
@@ -257,10 +280,15 @@ class Handle:
                                   ptr(tr), steps_limit, int(use_graph)))
         return (out, tr) if trace else out
 
-    def decode(self, z, div=1.0):
-        z = f32(z)
-        b, hh, ww, _ = z.shape
-        img = np.empty((b, hh * 8, ww * 8, 3), np.float32)
+    def decode(self, z, div=1.0, shape=None):
+        """z = None with shape=(b, hh, ww, 4): the latents the last sample() left on the device."""
+        if z is None:
+            b, hh, ww, _ = shape
+        else:
+            z = f32(z)
+            b, hh, ww, _ = z.shape
+        up = 1 << (self.config.ae_num_multipliers - 1)   # Decoder upsamples at every level but the last
+        img = np.empty((b, hh * up, ww * up, 3), np.float32)
         idx = np.empty((b * hh * ww,), np.int64) if self.config.ae_kind == 1 else None
         check(self.lib.ldm_decode(self._h, ptr(z), b, hh, ww, float(div), ptr(img), ptr(idx)))
         return img, idx
@@ -269,7 +297,7 @@ class Handle:
         z = f32(z)
         rows = z.size // 4
         idx = np.empty((rows,), np.int64)
-        zq = np.empty_like(z)
+        zq = np.empty(z.shape, np.float32)
         check(self.lib.ldm_vq_argmin(self._h, ptr(z), rows, float(div), ptr(idx), ptr(zq)))
         return zq, idx
 
@@ -296,6 +324,11 @@ class Handle:
         a, b = C.c_float(), C.c_float()
         check(self.lib.ldm_bench_groupnorm(self._h, n, hw, c, iters, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def bench_vq_argmin(self, rows, iters=20):
+        ms = C.c_float()
+        check(self.lib.ldm_bench_vq_argmin(self._h, rows, iters, C.byref(ms)))
+        return ms.value
 
     def bench_unet_step(self, b, hh, ww, iters, use_graph=True, skip_gemm=False):
         """ms per sampler step; skip_gemm leaves the implicit-GEMM launches out (measurement only)."""

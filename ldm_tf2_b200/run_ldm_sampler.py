@@ -63,19 +63,17 @@ def main(argv=None):
     h.finalize()
     h.configure_sampler(sampler.schedule.ddim_steps, sampler.schedule.coeff_table())
 
-    try:
-        token_ids = tokens.get_token_ids(s["text_prompt"], s["vocab_dir"], shape[0], config["cond_stage_model"]["max_seq_len"])
-    except Exception:
-        if s["text_prompt"] != tokens.DEFAULT_PROMPT:
-            raise
-        token_ids = tokens.default_token_ids(shape[0])
+    # no fallback: a missing / unreadable vocab.txt is an error here exactly as in the reference
+    token_ids = tokens.get_token_ids(s["text_prompt"], s["vocab_dir"], shape[0], config["cond_stage_model"]["max_seq_len"])
     guidance_scale = s["guidance_scale"]
     if s.get("sample_save_progress"):
         _, sample_prog, pred_x0_prog = sampler.ddim_p_sample_loop_progressive(token_ids, shape, guidance_scale)
         print("[INFO] Save progressive sample images to 'sample_prog.npy'...")
-        np.save("sample_prog.npy", sampler.tensor_to_image(sample_prog.reshape((-1,) + sample_prog.shape[2:])).reshape(sample_prog.shape))
+        # tensor_to_image normalises per leading-axis entry (run_ldm_sampler.py:18-25): for the
+        # [B, records, H, W, 3] stacks that is one min / max per SAMPLE over all of its records
+        np.save("sample_prog.npy", sampler.tensor_to_image(sample_prog))
         print("[INFO] Save progressive estimated `x0` to 'pred_x0_prog.npy'...")
-        np.save("pred_x0_prog.npy", sampler.tensor_to_image(pred_x0_prog.reshape((-1,) + pred_x0_prog.shape[2:])).reshape(pred_x0_prog.shape))
+        np.save("pred_x0_prog.npy", sampler.tensor_to_image(pred_x0_prog))
     else:
         images = sampler.ddim_p_sample_loop(token_ids, shape, guidance_scale)
         print("[INFO] Save generated images to 'images.npy'...")

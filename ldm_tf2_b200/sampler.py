@@ -20,6 +20,14 @@ import numpy as np
 
 from . import lib as _lib
 from .dlpack import borrow
+
+
+def _tensor(obj, dtype=np.float32):
+    """numpy / DLPack capsule / __dlpack__ object -> numpy array (host) or lib.DevPtr (device)."""
+    a, shape, keep = borrow(obj, dtype)
+    if isinstance(a, np.ndarray):
+        return a
+    return _lib.DevPtr(a, shape, keep)
 from .schedule import DDIMSchedule
 
 
@@ -133,17 +141,17 @@ class LatentDiffusionModelSampler:
     def decode_first_stage(self, latents, return_indices=False):
         """model_runners.py:425-434: latents / scale_factor, then AutoencoderKL.decode or
         AutoencoderVQ.decode(force_quantize=True)."""
-        z, _, _ = borrow(latents, np.float32)
-        if not isinstance(z, np.ndarray):
-            raise ValueError("decode_first_stage: pass host latents (device DLPack inputs go through handle.decode)")
-        images, idx = self.handle.decode(z, div=self._scale_factor)
+        images, idx = self.handle.decode(_tensor(latents), div=self._scale_factor)
         return (images, idx) if return_indices else images
 
     def ddim_sample(self, xt, cond, index, guidance_scale=1.0, clip_denoised=True, return_pred_x0=False,
                     noise=None):
         """model_runners.py:438-472.  `noise` replaces tf.random.normal (model_runners.py:466) when
         given; otherwise it is drawn from the sampler's seeded generator (only when sigma != 0)."""
-        xt, _, _ = borrow(xt, np.float32)
+        xt = _tensor(xt)
+        if not isinstance(xt, np.ndarray):
+            raise ValueError("ddim_sample: xt must be host-resident (the CFG concat of model_runners.py:452 is built "
+                             "on the host here); the loop entry points accept device tensors")
         b = xt.shape[0]
         self._set_context(cond)
         t = np.full([2 * b], self._ddim_steps[int(index)], dtype=np.int32)
@@ -163,18 +171,22 @@ class LatentDiffusionModelSampler:
         the sampler's seeded NumPy generator instead of tf.random.normal."""
         context = self.encode_text(cond_model_inputs)
         shape = tuple(int(s) for s in shape)
-        if x_init is None:
-            x_init = self._rng.standard_normal(shape, dtype=np.float32)
+        x_init = self._rng.standard_normal(shape, dtype=np.float32) if x_init is None else _tensor(x_init)
         S = len(self.schedule)
-        if self._eta != 0 and noise is None:
-            noise = self._rng.standard_normal((S,) + shape, dtype=np.float32)
-        if self._eta == 0:
+        if self._eta != 0:
+            noise = self._rng.standard_normal((S,) + shape, dtype=np.float32) if noise is None else _tensor(noise)
+        else:
             noise = None
         self._set_context(context, force=True)
-        x_final = self.handle.sample(x_init, noise, guidance_scale, use_graph=self._use_graph)
+        # the final latents stay on the device between the loop and decode_first_stage unless asked for
+        x_final = self.handle.sample(x_init, noise, guidance_scale, use_graph=self._use_graph,
+                                     keep_on_device=not return_latents)
         print(f"[INFO] Done running denoising for {self._num_ddim_steps} steps with eta {self._eta}")
         sys.stdout.flush()
-        images = self.decode_first_stage(x_final)
+        if return_latents:
+            images = self.decode_first_stage(x_final)
+        else:
+            images, _ = self.handle.decode(None, div=self._scale_factor, shape=x_init.shape)
         print("[INFO] Done decoding images from the final latent variable.")
         sys.stdout.flush()
         return (images, x_final) if return_latents else images
@@ -188,7 +200,13 @@ class LatentDiffusionModelSampler:
         context = self.encode_text(cond_model_inputs)
         shape = tuple(int(s) for s in shape)
         S = len(self.schedule)
-        xt = self._rng.standard_normal(shape, dtype=np.float32) if x_init is None else np.asarray(x_init, np.float32)
+        xt = self._rng.standard_normal(shape, dtype=np.float32) if x_init is None else _tensor(x_init)
+        if not isinstance(xt, np.ndarray):
+            raise ValueError("ddim_p_sample_loop_progressive: x_init must be host-resident")
+        if noise is not None:
+            noise = _tensor(noise)
+            if not isinstance(noise, np.ndarray):
+                raise ValueError("ddim_p_sample_loop_progressive: noise must be host-resident")
         if self._eta != 0 and noise is None:
             noise = self._rng.standard_normal((S,) + shape, dtype=np.float32)
         num_records = S // record_freq

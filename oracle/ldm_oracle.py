@@ -806,6 +806,35 @@ def ddim_sample_loop(Wu, cfg_unet, sched, context, x_init, noise, guidance_scale
     return xt
 
 
+def ddim_sample_loop_progressive(Wu, cfg_unet, sched, context, x_init, noise, guidance_scale, record_freq=5):
+    """ddim_p_sample_loop_progressive (model_runners.py:511-575) by evident intent: the reference body
+    calls a non-existent `self.ddim_p_sample` (:535; the method is ddim_sample, :438) -- with that one
+    name fixed this is what it computes.  Every step's (sample, pred_x0) with clip_denoised=False goes to
+    slot index // record_freq of two [B, S // record_freq, h, w, 4] stacks (the 0/1 `insert_mask` blend
+    of :544-551 is an overwrite; slots >= num_records match no mask entry and are dropped).  Returns the
+    LATENT triple (x_final, sample_progress, pred_x0_progress); the three decode_first_stage calls of
+    :564-574 are applied by the caller."""
+    xt = np.asarray(x_init, dtype=F32)
+    S = len(sched["ddim_steps"])
+    B = xt.shape[0]
+    num_records = S // record_freq
+    sample_prog = np.zeros((B, num_records) + xt.shape[1:], F32)
+    x0_prog = np.zeros_like(sample_prog)
+    for index in range(S - 1, -1, -1):
+        t = np.full([2 * B], sched["ddim_steps"][index], dtype=np.int32)
+        eps2 = unet_forward(Wu, cfg_unet, np.concatenate([xt, xt], axis=0), t, context)
+        coeffs = ddim_coeffs(sched, index)
+        nz = noise[index] if noise is not None else None
+        if nz is None and coeffs[4] != 0:
+            raise ValueError("eta>0 needs injected noise")
+        xt, x0 = ddim_update(xt, eps2[:B], eps2[B:], nz, coeffs, guidance_scale, clip_denoised=False)
+        slot = index // record_freq
+        if slot < num_records:
+            sample_prog[:, slot] = xt
+            x0_prog[:, slot] = x0
+    return xt, sample_prog, x0_prog
+
+
 def decode_first_stage(Wa, cfg_ae, kind, latents, scale_factor=0.18215):
     """model_runners.py:425-434."""
     return ae_decode(Wa, cfg_ae, kind, (np.asarray(latents, F32) / F32(scale_factor)).astype(F32))

@@ -209,19 +209,30 @@ def test_public_sampler_api_loop_and_progressive(tiny):
         sched = O.ddim_schedule(**{k: ldm[k] for k in ("num_steps", "beta_start", "beta_end", "eta", "num_ddim_steps")})
         ref = O.ddim_sample_loop(tiny["Wu"], CFG["unet"], sched, tiny["ctx"], x, nz, 5.0)
         err = rel_l2(x_final, ref)
-        print("public API loop (eta=0.5, 10 steps) latent rel-L2", err)
-        assert err < 3 * EPS_TOL   # ten chained steps of a random-init model
         ref_img, _ = O.decode_first_stage(tiny["Wa"], CFG["autoencoder_kl"], "kl", ref, ldm["scale_factor"])
-        assert psnr(images, ref_img) > PSNR_TOL - 10
+        p_img = psnr(images, ref_img)
+        print(f"public API loop (eta=0.5, 10 steps) latent rel-L2 {err:.3e}, image PSNR {p_img:.1f} dB")
+        assert err < EPS_TOL
+        assert p_img >= PSNR_TOL
+        # progressive sampling against the oracle's restatement of model_runners.py:511-575
         xf, sp, xp = s.ddim_p_sample_loop_progressive(tiny["ids"], shape, 5.0, record_freq=5, x_init=x, noise=nz)
         assert xf.shape == images.shape and sp.shape == (B, S // 5) + images.shape[1:] and xp.shape == sp.shape
-        # per-step API (eager unet_forward + K5) vs the graph-replayed loop: same kernels, but the
-        # timestep bias is added per image (after the layer bias) instead of folded into it, so the
-        # two differ by fp32 rounding amplified over ten steps
-        assert rel_l2(xf, images) < EPS_TOL
+        lat_f, lat_sp, lat_xp = O.ddim_sample_loop_progressive(tiny["Wu"], CFG["unet"], sched, tiny["ctx"], x, nz, 5.0, 5)
+        assert np.array_equal(lat_f, ref)   # the oracle's two loops agree with each other
+        dec = lambda z: O.decode_first_stage(tiny["Wa"], CFG["autoencoder_kl"], "kl", z, ldm["scale_factor"])[0]
+        flat = (B * (S // 5),) + shape[1:]
+        ref_sp = dec(lat_sp.reshape(flat)).reshape(sp.shape)
+        ref_xp = dec(lat_xp.reshape(flat)).reshape(xp.shape)
+        for nm, got, want in (("x_final", xf, ref_img), ("sample_prog", sp, ref_sp), ("pred_x0_prog", xp, ref_xp)):
+            pp = psnr(got, want)
+            print(f"progressive {nm}: PSNR {pp:.1f} dB vs oracle")
+            assert pp >= PSNR_TOL
         # slot 0 holds the last step written into it (index 0 = the final sample)
         assert np.array_equal(sp[:, 0], xf)
-        assert np.isfinite(xp).all()
+        # tensor_to_image of a [B, records, H, W, 3] stack: ONE min / max per sample over all of its records
+        # (run_ldm_sampler.py:18-25 indexes the leading axis only)
+        u8 = s.tensor_to_image(sp)
+        assert u8.shape == sp.shape and np.array_equal(u8, O.tensor_to_image(sp))
     finally:
         s.close()
 

@@ -35,7 +35,7 @@ def main():
     ids = np.array([O.KAT_UNCOND_IDS, O.KAT_COND_IDS], dtype=np.int64)
     ctx = O.text_encode(O.as_dict(ts, wt), CFG["cond_stage_model"], ids)
     del wt
-    out["ctx"] = ctx
+    out["ctx_probe"] = ctx[:, :12, :64].copy()   # consistency check: the tests rebuild ctx with the same weights
     sched = O.ddim_schedule(**CFG["ldm"])
 
     # ---- b8: one CFG step at the benchmarked shape

@@ -171,9 +171,17 @@ LDM_API int ldm_profiler(int on);
 LDM_API int ldm_debug_tap(ldm_handle* h, const char* name, float* host_buf, int64_t numel);
 LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const float* bias, const float* residual,
                             int rows, int k, int n, int act, int block_n, int max_ctas, float* out);
+/* y = a @ w0 + b0 (16 bit, + row statistics), then out = act(LayerNorm(y) @ w1 + b1) [+ y] with the LayerNorm
+ * folded into the second GEMM: the transformer block's fused epilogue terms (unet.py:304-314). */
+LDM_API int ldm_test_ln_linear(ldm_handle* h, const float* a, const float* w0, const float* b0, int rows, int k0, int c,
+                               const float* gamma, const float* beta, const float* w1, const float* b1, int n, int act,
+                               int residual, int dbg, float* y_out, float* stats_out, float* out);
 LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel, const float* bias,
                              const float* sc_x, const float* sc_kernel, int nb, int hh, int ww, int cin,
                              int cout, int sc_cin, float* out);
+/* mode 0: nearest x2 + conv3x3 (phase-collapsed); 1 / 2: pad (1,1) / (0,1) + conv3x3 stride 2 (strided TMA map) */
+LDM_API int ldm_test_resample_conv(ldm_handle* h, const float* x, const float* kernel, const float* bias, int nb, int hh,
+                                   int ww, int cin, int cout, int mode, float* out);
 LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, const float* v, int n, int t,
                                int tk, int heads, int d, float scale, int unfused, float* out);
 LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const float* xb, int cb,

@@ -542,6 +542,94 @@ LDM_API int ldm_test_linear(ldm_handle* h, const float* a, const float* w, const
   API_END
 }
 
+// The transformer block's fused epilogue terms (gemm.cuh): (1) y = a @ w0 + b0 written as 16 bit with its
+// row statistics (rs_out); (2) out = act(LN(y; gamma, beta) @ w1 + b1) [+ y] with the LayerNorm folded
+// into the GEMM (weights carry gamma, epilogue applies the rows' mean / rstd) and the 16-bit residual read in the
+// epilogue.  act 3 = GEGLU (w1 has 2n columns).  dbg 8 forces the row-owner epilogue paths.
+LDM_API int ldm_test_ln_linear(ldm_handle* h, const float* a, const float* w0, const float* b0, int rows, int k0, int c,
+                               const float* gamma, const float* beta, const float* w1, const float* b1, int n, int act,
+                               int residual, int dbg, float* y_out, float* stats_out, float* out) {
+  API_BEGIN
+  NEED(h);
+  Model& m = *h->model;
+  Engine& e = m.eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  LDM_CHECK(!residual || (n == c && act != ACT_GEGLU), "ldm_test_ln_linear: the residual needs n == c");
+  Scratch s;
+  const int wn = act == ACT_GEGLU ? 2 * n : n;
+  bf16* ab = up_bf16(s, e, a, (size_t)rows * k0);
+  bf16* w0t = s.get<bf16>((size_t)c * k0, true);
+  launch_pack_weight(up_f32(s, e, w0, (size_t)k0 * c), k0, c, w0t, k0, 0, 0, e.fp16, e.stream);
+  float* b0d = b0 ? up_f32(s, e, b0, c) : nullptr;
+  bf16* y = s.get<bf16>((size_t)rows * c);
+  float* st = s.get<float>((size_t)rows * 2, true);
+  m.ensure_arena((size_t)256 << 20);
+  e.arena.reset();
+  {
+    GemmOp op;
+    op.num_a = 1;
+    op.a[0] = view_mat(ab, rows, k0, k0);
+    op.b = view_mat(w0t, c, k0, k0);
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, k0, bk);
+    op.W = rows; op.H = 1; op.NB = 1; op.N = c; op.bias = b0d; op.out_bf16 = y; op.rs_out = st; op.os_x = c;
+    op.dbg = dbg;
+    e.gemm(op);
+  }
+  // fold (gamma, beta) into the second linear exactly as Model::apply_folds does
+  float* w1f = up_f32(s, e, w1, (size_t)c * wn);
+  float* gd = up_f32(s, e, gamma, c);
+  float* bd = up_f32(s, e, beta, c);
+  float* b1d = b1 ? up_f32(s, e, b1, wn) : nullptr;
+  int bn = 0;
+  if (act == ACT_GEGLU) { bn = 256; while (wn % bn) bn -= 64; }
+  bf16* w1t = s.get<bf16>((size_t)wn * c, true);
+  launch_pack_weight(w1f, c, wn, w1t, c, 0, act == ACT_GEGLU ? bn / 2 : 0, e.fp16, e.stream, gd);
+  float* cs = s.get<float>(wn);
+  launch_rowsum16(w1t, c, 0, wn, c, cs, e.fp16, e.stream);
+  float* fb = s.get<float>(wn);
+  launch_small_dense_f32(bd, w1f, b1d, 1, c, wn, 0, 0, fb, e.stream);
+  if (act == ACT_GEGLU) {
+    std::vector<float> hb(wn), pb(wn);
+    CUDA_CHECK(cudaMemcpyAsync(hb.data(), fb, wn * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    e.sync();
+    const int half = bn / 2;
+    for (int col = 0; col < wn; ++col) {
+      const int j2 = col < n ? col : col - n;
+      pb[(j2 / half) * bn + (col < n ? 0 : half) + j2 % half] = hb[col];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(fb, pb.data(), wn * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+    e.sync();
+  }
+  bf16* od = residual ? y : s.get<bf16>((size_t)rows * n);
+  {
+    GemmOp op;
+    op.num_a = 1;
+    op.a[0] = view_mat(y, rows, c, c);
+    op.b = view_mat(w1t, wn, c, c);
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, c, bk);
+    op.W = rows; op.H = 1; op.NB = 1; op.N = n; op.gemm_n = wn; op.block_n = bn; op.act = act;
+    op.ln_stats = st; op.ln_cs = cs; op.ln_c = c; op.bias = fb;
+    op.out_bf16 = od; op.os_x = n;
+    op.dbg = dbg;
+    std::vector<uint16_t> raw((size_t)rows * c);
+    if (y_out) {   // y before the (optionally in-place) second GEMM
+      CUDA_CHECK(cudaMemcpyAsync(raw.data(), y, raw.size() * 2, cudaMemcpyDefault, e.stream));
+      e.sync();
+      for (size_t i = 0; i < raw.size(); ++i) y_out[i] = widen16(raw[i], e.fp16);
+    }
+    if (residual) op.res16 = y;
+    e.gemm(op);
+  }
+  std::vector<uint16_t> raw((size_t)rows * n);
+  CUDA_CHECK(cudaMemcpyAsync(raw.data(), od, raw.size() * 2, cudaMemcpyDefault, e.stream));
+  if (stats_out) CUDA_CHECK(cudaMemcpyAsync(stats_out, st, (size_t)rows * 2 * sizeof(float), cudaMemcpyDefault, e.stream));
+  e.sync();
+  for (size_t i = 0; i < raw.size(); ++i) out[i] = widen16(raw[i], e.fp16);
+  API_END
+}
+
 // 3x3 SAME conv (+ optional 1x1 shortcut over a second tensor folded into K)
 LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel, const float* bias, const float* sc_x,
                              const float* sc_kernel, int nb, int hh, int ww, int cin, int cout, int sc_cin,
@@ -585,6 +673,52 @@ LDM_API int ldm_test_conv3x3(ldm_handle* h, const float* x, const float* kernel,
   op.os_x = cout; op.os_y = (long long)ww * cout; op.os_n = (long long)hh * ww * cout;
   e.gemm(op);
   CUDA_CHECK(cudaMemcpyAsync(out, out_d, pix * cout * sizeof(float), cudaMemcpyDefault, e.stream));
+  e.sync();
+  API_END
+}
+
+// Resampling convs of the path through the model's own helpers.  mode 0: nearest x2 + conv3x3 SAME (Upsample,
+// unet.py:44-47 / autoencoder.py:152-155) as four phase-collapsed 2x2 convs; mode 1 / 2: zero pad (1,1) / (0,1) +
+// conv3x3 stride 2 VALID (unet.py:22-27 / autoencoder.py:133-135) through the stride-2 TMA map.
+// x [nb,hh,ww,cin], kernel [3,3,cin,cout] -> out [nb, 2hh | hh/2, 2ww | ww/2, cout]
+LDM_API int ldm_test_resample_conv(ldm_handle* h, const float* x, const float* kernel, const float* bias, int nb, int hh,
+                                   int ww, int cin, int cout, int mode, float* out) {
+  API_BEGIN
+  NEED(h);
+  Model& m = *h->model;
+  Engine& e = m.eng;
+  CUDA_CHECK(cudaSetDevice(e.device));
+  LDM_CHECK(mode >= 0 && mode <= 2 && (mode != 0 || cin == cout), "ldm_test_resample_conv: bad mode");
+  Scratch s;
+  Act a;
+  a.n = nb; a.h = hh; a.w = ww; a.c = cin;
+  a.b = up_bf16(s, e, x, (size_t)nb * hh * ww * cin);
+  float* kf = up_f32(s, e, kernel, (size_t)9 * cin * cout);
+  LinW w9;
+  w9.n = cout; w9.k = 9 * cin; w9.ld = 9 * cin;
+  w9.wt = s.get<bf16>((size_t)cout * 9 * cin, true);
+  launch_pack_weight(kf, 9 * cin, cout, w9.wt, w9.ld, 0, 0, e.fp16, e.stream);
+  float* bias_d = bias ? up_f32(s, e, bias, cout) : nullptr;
+  LinW wp;
+  if (mode == 0) {
+    wp.n = cout; wp.k = 4 * cin; wp.ld = 4 * cin;
+    wp.wt = s.get<bf16>((size_t)16 * cin * cout, true);
+    launch_pack_upconv_phase(kf, cin, cout, wp.wt, e.fp16, e.stream);
+  }
+  size_t out_el = 0;
+  auto run = [&]() {
+    Act o = mode == 0 ? m.upconv(a, w9, wp, bias_d) : m.downconv(a, w9, bias_d, mode == 1 ? 1 : 0);
+    out_el = (size_t)o.numel();
+    return o;
+  };
+  {
+    DryPass dry(e);
+    run();
+  }
+  m.ensure_arena(e.arena.peak());
+  e.arena.reset();
+  Act o = run();
+  CUDA_CHECK(cudaMemcpyAsync(out, o.f, out_el * sizeof(float), cudaMemcpyDefault, e.stream));
   e.sync();
   API_END
 }

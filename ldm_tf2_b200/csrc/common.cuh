@@ -471,6 +471,15 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+// two packed 16-bit operand values -> fp32
+__device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ float load16(const bf16* p, int fp16) {
+  const uint16_t u = *reinterpret_cast<const uint16_t*>(p);
+  return fp16 ? __half2float(__ushort_as_half(u)) : __bfloat162float(__ushort_as_bfloat16(u));
+}
 __device__ __forceinline__ void store16(bf16* p, float v, int fp16) {
   *reinterpret_cast<uint16_t*>(p) = cvt16(v, fp16);
 }

@@ -96,6 +96,13 @@ void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, in
   dims[3] = v.NB;
   strides[2] = (cuuint64_t)v.sn * 2;
   box[3] = box_n;
+  if (v.estride > 1) {
+    // strided traversal (stride-2 convolutions): the box spans estride * N elements and TMA picks every
+    // estride-th one, i.e. ceil(boxDim / elementStride) = N elements land in shared memory
+    estr[1] = estr[2] = (cuuint32_t)v.estride;
+    box[1] *= (cuuint32_t)v.estride;
+    box[2] *= (cuuint32_t)v.estride;
+  }
   LDM_CHECK((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "TMA operand not 16-byte aligned");
   for (int i = 0; i < 3; ++i)
     LDM_CHECK(strides[i] % 16 == 0 && strides[i] > 0, "TMA stride %d = %llu not a positive multiple of 16 B", i,
@@ -200,9 +207,14 @@ void Engine::gemm(const GemmOp& op) {
   int bn = op.block_n;
   int splits = 1;
   // CTA pairs (cta_group::2): plain weights, one phase, at least one full pair of M tiles
-  const bool pair_ok = op.num_phases == 1 && op.b_mode == B_PLAIN && !op.b.swap_xy && m_tiles >= 2;
+  const bool pair_ok = (op.b_mode == B_PLAIN || op.b_mode == B_PHASE) && !op.b.swap_xy && m_tiles >= 2 &&
+                       (op.num_phases == 1 || (p.tiles_x * p.tiles_y * p.tiles_img) % 2 == 0);
   const bool pair = pair_ok && (op.pair > 0 || (op.pair == 0 && pair_default));
-  const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1;
+  const bool fused_rows = op.res16 || op.ln_stats || op.rs_out;   // epilogue terms the split-K finalize kernel does not apply
+  LDM_CHECK(!(op.rs_out && op.residual), "gemm: row statistics are taken before the fp32 residual is added");
+  LDM_CHECK(!op.ln_stats || (op.ln_cs && op.ln_c > 0 && op.alpha == 1.0f), "gemm: folded LayerNorm needs column sums and the row width");
+  LDM_CHECK(!fused_rows || (op.num_phases == 1 && op.b_mode == B_PLAIN), "gemm: row-fused epilogue terms need a plain GEMM");
+  const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1 && !fused_rows;
   if (can_split && bn && op.splits > 1 && total_kb >= 2 * op.splits) splits = op.splits;   // explicit tile + split (tuning hook)
   if (can_split && !bn) {
     // few output tiles and a long K loop (low-resolution convs, text encoder): take the widest
@@ -259,7 +271,7 @@ void Engine::gemm(const GemmOp& op) {
                        (op.out_f32 || op.out_bf16) &&
                        (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
                        (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
-                       (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0) &&
+                       (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0) && !fused_rows &&
                        getenv("LDM_B200_TMA_EPI") != nullptr;   // opt-in: measured on par with the staged path
   // ---- one CTA per SM with 8 epilogue warps, or two per SM with 4 (gemm.cuh): the latter when the
   // main loop is not many times longer than the epilogue (tuned in-graph with profiles/ab_step.py: the
@@ -305,12 +317,21 @@ void Engine::gemm(const GemmOp& op) {
   }
   p.epi_vec = ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 3) == 0 &&
               (!op.residual || (reinterpret_cast<uintptr_t>(op.residual) & 15) == 0) &&
+              (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 7) == 0) &&
               (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
               (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 7) == 0);
   // ---- epilogue
   p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
   p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;
   p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
+  p.res16 = op.res16; p.rs_out = op.rs_out; p.ln_stats = op.ln_stats; p.ln_cs = op.ln_cs;
+  p.ln_inv_c = op.ln_c > 0 ? 1.0f / (float)op.ln_c : 0.f; p.ln_eps = op.ln_eps;
+  {
+    // 16-bit-only outputs: the fragment-layout epilogue (sector-complete 32-byte row pieces, no shared-memory
+    // transposition) beats the staged one; fp32 outputs keep the staged path (gemm.cuh)
+    static const bool no_frag = getenv("LDM_B200_FRAG16") && getenv("LDM_B200_FRAG16")[0] == '0';
+    p.frag_pref = (geglu || (!op.out_f32 && op.out_bf16 && !no_frag)) ? 1 : 0;
+  }
   p.os_n = op.os_n; p.os_y = op.os_y; p.os_x = op.os_x; p.os_phase_y = op.os_phase_y; p.os_phase_x = op.os_phase_x;
   p.out_tr = op.out_tr; p.tr_col0 = op.tr_col0; p.ts_n = op.ts_n; p.ts_y = op.ts_y; p.ts_c = op.ts_c;
   LDM_CHECK(op.out_f32 || op.out_bf16 || op.out_tr, "gemm: no output");
@@ -322,6 +343,7 @@ void Engine::gemm(const GemmOp& op) {
     const AView& v = op.a[i < op.num_a ? i : 0];
     encode_map(&p.amap[i], v, w_b, h_b, n_b);
     p.a_swap[i] = v.swap_xy ? 1 : 0;
+    p.a_stride[i] = v.estride;
   }
   encode_map(&p.bmap, op.b, b_rows, 1, 1);
   p.b_swap = op.b.swap_xy ? 1 : 0;

@@ -14,6 +14,7 @@ struct AView {
   int C = 0, W = 1, H = 1, NB = 1;
   long long sx = 0, sy = 0, sn = 0;
   bool swap_xy = false;  // tensor-map dim order (C, y, x, n) instead of (C, x, y, n)
+  int estride = 1;       // TMA element stride along x and y: tile pixel (x, y) reads element (estride*x + dx, estride*y + dy)
 };
 inline AView view_nhwc(const bf16* p, int nb, int h, int w, int c) {
   AView v; v.ptr = p; v.C = c; v.W = w; v.H = h; v.NB = nb;
@@ -54,6 +55,11 @@ struct GemmOp {
   int act = ACT_NONE;
   float alpha = 1.0f;
   const float* residual = nullptr;
+  const bf16* res16 = nullptr;        // 16-bit residual (same addressing as the outputs; may alias out_bf16)
+  const float* ln_stats = nullptr;    // folded LayerNorm: per-row (sum, sum sq) of the raw A rows, [rows][2]
+  const float* ln_cs = nullptr;       //   column sums of the gamma-scaled weights, [gemm_n] in packed row order
+  int ln_c = 0; float ln_eps = 1e-5f; //   row width of the normalised tensor, epsilon
+  float* rs_out = nullptr;            // per-row (sum, sum sq) of the final output, [rows][2], accumulated atomically
   float* out_f32 = nullptr;
   bf16* out_bf16 = nullptr;
   long long os_n = 0, os_y = 0, os_x = 0, os_phase_y = 0, os_phase_x = 0;

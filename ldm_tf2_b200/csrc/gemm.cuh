@@ -32,7 +32,8 @@ constexpr int GEMM_MAX_SEGS = 12;
 constexpr int GEMM_THREADS = 320;   // producer + MMA + 8 epilogue warps (EW = 8: one CTA per SM)
 constexpr int GEMM_THREADS_EW4 = 192;  // producer + MMA + 4 epilogue warps (EW = 4: two CTAs per SM)
 constexpr int GEMM_EPI_PITCH = 36;    // floats per staged row (32 + 4: 16-byte aligned, conflict-free)
-constexpr int GEMM_CTRL_BYTES = 2048;                                          // barriers, bias
+constexpr int GEMM_CTRL_BYTES = 5120;   // barriers, bias [512,1536), residual-tile barriers [1536,1600), LayerNorm-fold
+                                        // column sums [2048,3072), per-row (scale, shift) [3072,4096), row ids [4096,4608)
 constexpr int GEMM_EPI_LEGACY_BYTES = 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // per-warp staging + row offsets
 constexpr int GEMM_EPI_EW4_BYTES = 4 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);
 constexpr int GEMM_SMEM_BYTES = 227 * 1024;
@@ -83,6 +84,7 @@ struct GemmParams {
   int epi_vec;              // 1: all output offsets are multiples of 4 elements -> coalesced vector epilogue
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
+  int a_stride[3];          // spatial element stride of the map (2: stride-2 conv; box origin = stride * tile origin)
   int b_swap;
   // epilogue
   const float* bias;        // [N] or null
@@ -93,6 +95,15 @@ struct GemmParams {
   int act;
   float alpha;              // scales the accumulator before bias
   const float* residual;    // fp32, same addressing as out
+  const bf16* res16;        // 16-bit residual, same addressing as out (the transformer block's inner stream; may alias out_bf16)
+  // LayerNorm folded into this GEMM (unet.py:304-314): A holds the RAW rows y, the weights carry gamma, and
+  //   out = rstd_r * (acc - mean_r * ln_cs[col]) + bias[col],   bias = beta.W + b precomputed,
+  // with (sum, sum of squares) of every row in ln_stats[row][2] (written by the producer's rs_out)
+  const float* ln_stats;
+  const float* ln_cs;       // [gemm_n] column sums of the gamma-scaled 16-bit weights (packed row order)
+  float ln_inv_c, ln_eps;
+  float* rs_out;            // [rows][2]: atomically accumulated (sum, sum of squares) of the final output rows
+  int frag_pref;            // 16-bit-only outputs: take the fragment-layout epilogue where a tile allows it
   float* out_f32;
   bf16* out_bf16;
   long long os_n, os_y, os_x;  // output element strides for (img, y, x)
@@ -131,7 +142,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
 
 // CTA-pair kernel: pair tile `pt` covers M tiles (2*pm, 2*pm+1) of one N tile; CTA `rank` owns M tile
 // 2*pm + rank.  An odd tile count leaves the last peer with an all-out-of-range box (img0 >= NB: TMA
-// zero-fills, the epilogue's row_ok is false).  num_phases == 1 only.
+// zero-fills, the epilogue's row_ok is false).  With phases (NN-upsample collapsed conv) the M tiles of one
+// phase are an even count, so both CTAs of a pair share the phase (= the B tile they split).
 __device__ __forceinline__ TileCoord decode_pair_tile(const GemmParams& p, int pt, int rank) {
   TileCoord t;
   const int base = p.pm_tiles * p.n_tiles;
@@ -142,8 +154,10 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const GemmParams& p, int p
   const int tx = m % p.tiles_x;
   m /= p.tiles_x;
   const int ty = m % p.tiles_y;
-  const int ti = m / p.tiles_y;
+  m /= p.tiles_y;
+  int ti = m;
   t.phase = 0;
+  if (p.num_phases > 1) { ti = m % p.tiles_img; t.phase = m / p.tiles_img; }
   t.x0 = tx * p.w_b;
   t.y0 = ty * p.h_b;
   t.img0 = ti * p.n_b;
@@ -241,13 +255,16 @@ __device__ __forceinline__ void epi_store_staged32(const float* v, int col0, flo
 
 // Fragment-layout epilogue of one 32-column chunk for a fully valid warp (the common case): the
 // accumulator is read as two 16-lane m16n8 fragments, so thread t holds rows t/4 + 8j (j = 0..3) and
-// the column pairs 8k + 2(t%4) (k = 0..3) of the chunk.  Bias / activation / GEGLU / residual are
-// applied in that layout and every global access of a warp covers 8 rows x 32 contiguous bytes (whole
-// sectors) -- no shared-memory transposition (which cost ~1400 cycles of smem bandwidth per tile).
+// the column pairs 8k + 2(t%4) (k = 0..3) of the chunk.  Bias / folded LayerNorm / activation / GEGLU /
+// residual (fp32 or 16-bit) are applied in that layout and every global access of a warp covers 8 rows x
+// 32 contiguous bytes (whole sectors) -- no shared-memory transposition (which cost ~1400 cycles of
+// smem bandwidth per tile).  ab4 = this thread's four rows' (scale, shift) of the folded LayerNorm (or
+// null); rs (or null) accumulates the four rows' (sum, sum of squares) of the final values.
 template <bool GEGLU>
 __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t t_lane0, int c, int hcols, int col0,
-                                                   const float* bias_s, const int* rowoff4, int lane, int act,
-                                                   float* o32, bf16* o16, const float* resid) {
+                                                   const float* bias_s, const float* cs_s, const float2* ab4,
+                                                   const int* rowoff4, int lane, int act, float* o32, bf16* o16,
+                                                   const float* resid, const bf16* res16, float* rs) {
   uint32_t ra[16], rb[16], ga[16], gb[16];
   tmem_ld_16x256b_x4(t_lane0 + (uint32_t)c, ra);                      // lanes +0..15
   tmem_ld_16x256b_x4(t_lane0 + (16u << 16) + (uint32_t)c, rb);        // lanes +16..31
@@ -264,15 +281,35 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
     float x[8] = {__uint_as_float(ra[4 * k]), __uint_as_float(ra[4 * k + 1]), __uint_as_float(ra[4 * k + 2]),
                   __uint_as_float(ra[4 * k + 3]), __uint_as_float(rb[4 * k]), __uint_as_float(rb[4 * k + 1]),
                   __uint_as_float(rb[4 * k + 2]), __uint_as_float(rb[4 * k + 3])};
+    if (ab4) {
+      const float2 cs = *reinterpret_cast<const float2*>(cs_s + c + 8 * k + cq);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], p.alpha, (i & 1) ? b.y : b.x);
+      for (int i = 0; i < 8; ++i) {
+        const float2 ab = ab4[i >> 1];
+        x[i] = fmaf(x[i], ab.x, fmaf((i & 1) ? cs.y : cs.x, ab.y, (i & 1) ? b.y : b.x));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], p.alpha, (i & 1) ? b.y : b.x);
+    }
     if (GEGLU) {
       const float2 bg = *reinterpret_cast<const float2*>(bias_s + hcols + c + 8 * k + cq);
-      const float g[8] = {__uint_as_float(ga[4 * k]), __uint_as_float(ga[4 * k + 1]), __uint_as_float(ga[4 * k + 2]),
-                          __uint_as_float(ga[4 * k + 3]), __uint_as_float(gb[4 * k]), __uint_as_float(gb[4 * k + 1]),
-                          __uint_as_float(gb[4 * k + 2]), __uint_as_float(gb[4 * k + 3])};
+      float g[8] = {__uint_as_float(ga[4 * k]), __uint_as_float(ga[4 * k + 1]), __uint_as_float(ga[4 * k + 2]),
+                    __uint_as_float(ga[4 * k + 3]), __uint_as_float(gb[4 * k]), __uint_as_float(gb[4 * k + 1]),
+                    __uint_as_float(gb[4 * k + 2]), __uint_as_float(gb[4 * k + 3])};
+      if (ab4) {
+        const float2 cg = *reinterpret_cast<const float2*>(cs_s + hcols + c + 8 * k + cq);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] *= gelu_erf_f(fmaf(g[i], p.alpha, (i & 1) ? bg.y : bg.x));
+        for (int i = 0; i < 8; ++i) {
+          const float2 ab = ab4[i >> 1];
+          g[i] = fmaf(g[i], ab.x, fmaf((i & 1) ? cg.y : cg.x, ab.y, (i & 1) ? bg.y : bg.x));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], p.alpha, (i & 1) ? bg.y : bg.x);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= gelu_erf_f(g[i]);
     } else if (act == ACT_SILU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = silu_f(x[i]);
@@ -315,6 +352,30 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         w[j][h2].x += r[j][h2].x; w[j][h2].y += r[j][h2].y; w[j][h2].z += r[j][h2].z; w[j][h2].w += r[j][h2].w;
+      }
+  }
+  if (res16) {
+    uint2 r[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) r[j][h2] = *reinterpret_cast<const uint2*>(res16 + (rowoff4[j] + wcol[h2]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const float2 lo = unpack16(r[j][h2].x, p.fp16), hi = unpack16(r[j][h2].y, p.fp16);
+        w[j][h2].x += lo.x; w[j][h2].y += lo.y; w[j][h2].z += hi.x; w[j][h2].w += hi.y;
+      }
+  }
+  if (rs) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const float4 q = w[j][h2];
+        rs[j] += (q.x + q.y) + (q.z + q.w);
+        rs[4 + j] = fmaf(q.x, q.x, fmaf(q.y, q.y, fmaf(q.z, q.z, fmaf(q.w, q.w, rs[4 + j]))));
       }
   }
   if (o32) {
@@ -366,7 +427,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
   uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(ctrl + 1536);  // [half][slot] residual tiles landed
-  uint8_t* epi_area = ctrl + 2048;  // legacy: 8 x [32][36] fp32 staging + 8 x [32] offsets; TMA mode: per-half tiles
+  float* cs_s = reinterpret_cast<float*>(ctrl + 2048);        // folded-LayerNorm column sums of this tile's columns
+  float2* ab_s = reinterpret_cast<float2*>(ctrl + 3072);      // per tile row: (rstd, -mean * rstd)
+  int* grow_s = reinterpret_cast<int*>(ctrl + 4096);          // per tile row: global row index (row statistics)
+  uint8_t* epi_area = ctrl + GEMM_CTRL_BYTES;  // legacy: 8 x [32][36] fp32 staging + 8 x [32] offsets; TMA mode: per-half tiles
   // register-staging tiles (and row offsets) of the 8 epilogue warps; the TMA epilogue keeps its own
   // tiles in front of them (boundary / V^T chunks still take the register paths)
   uint8_t* stage_area = epi_area + (p.tma_epi ? 2 * p.epi_half_stride : 0);
@@ -436,8 +500,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       while (kin >= p.segs[s].nkb) { kin -= p.segs[s].nkb; ++s; }
       for (int gk = kb_begin; gk < kb_end; ++s, kin = 0) {
         const GemmSeg sg = p.segs[s];
-        const int ax = t.x0 + sg.dx + (p.num_phases > 1 ? px : 0);
-        const int ay = t.y0 + sg.dy + (p.num_phases > 1 ? py : 0);
+        const int ax = t.x0 * p.a_stride[sg.map] + sg.dx + (p.num_phases > 1 ? px : 0);
+        const int ay = t.y0 * p.a_stride[sg.map] + sg.dy + (p.num_phases > 1 ? py : 0);
         const int a1 = p.a_swap[sg.map] ? ay : ax, a2 = p.a_swap[sg.map] ? ax : ay;
         const void* amap = &p.amap[sg.map];
         int ca = sg.c0 + kin * GEMM_BK, cb = sg.bk0 + kin * GEMM_BK;
@@ -559,6 +623,19 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         row_off = (((long long)img * p.H + yq) * p.W + xq) * p.N;
       }
       const long long tr_row_off = (long long)img * p.ts_n + (long long)yq * p.ts_y;
+      const bf16* res16 = split ? nullptr : p.res16;
+      float* rs_out = split ? nullptr : p.rs_out;
+      const bool ln = p.ln_stats != nullptr && !split;
+      const long long grow = ((long long)img * p.H + yq) * p.W + xq;   // global row id: row statistics in / out
+      float ln_a = p.alpha, ln_b = 0.f;   // value = acc * ln_a + (cs * ln_b + bias)
+      if (ln && row_ok) {
+        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * grow);
+        const float mean = st.x * p.ln_inv_c;
+        const float var = fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_c), 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -mean * ln_a;
+      }
+      float rs_s = 0.f, rs_q = 0.f;       // this row's (sum, sum of squares) over the chunks this thread handles
       const float* bias2_row = nullptr;   // per-thread path only when the row index depends on img
       const float* bias2_tile = nullptr;  // folded into the smem bias vector otherwise
       if (p.bias2 && !split) {
@@ -585,6 +662,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           if (bias2_tile) b += __ldg(bias2_tile + col);
         }
         bias_s[c] = b;
+        if (ln) cs_s[c] = col < lim ? __ldg(p.ln_cs + col) : 0.f;
+      }
+      if (half == 0) {   // one warp per TMEM lane quadrant publishes its rows' LayerNorm terms / global row ids
+        ab_s[r] = make_float2(ln_a, ln_b);
+        grow_s[r] = (int)grow;
       }
       // vector path: aligned 32-bit offsets and every row of this warp inside the tensor
       const bool use_tma = p.tma_epi && !split;
@@ -604,11 +686,18 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       // (measured: 15 % faster for the GEGLU epilogue -- 16-bit output only, two accumulator reads per
       // value -- and 5-10 % slower for fp32 + residual outputs, whose 32-byte row pieces cost more L2
       // transactions than the transposition costs shared-memory bandwidth; dbg bit 3 forces it for A/B runs)
-      const bool frag = (geglu || (p.dbg & 8)) && warp_rows_ok && !p.out_tr && !(p.block_n & 31) && !bias2_row &&
+      // (dbg bit 3 forces the row-owner paths for A/B runs and tests)
+      const bool tile_tr = p.out_tr && t.n0 >= p.tr_col0;
+      const bool frag = (geglu || p.frag_pref) && warp_rows_ok && !tile_tr && !(p.block_n & 31) && !bias2_row &&
                         (geglu ? (t.n_tile + 1) * (p.block_n >> 1) <= p.N : t.n0 + p.block_n <= p.N) && !(p.dbg & 8);
       int rowoff4[4];
+      float2 ab4[4];
+      float rs4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rowoff4[j] = frag ? roff[(lane >> 2) + 8 * j] : 0;
+      for (int j = 0; j < 4; ++j) {
+        rowoff4[j] = frag ? roff[(lane >> 2) + 8 * j] : 0;
+        ab4[j] = frag ? ab_s[quad * 32 + (lane >> 2) + 8 * j] : make_float2(1.f, 0.f);
+      }
       if (tre) tre[8] = clock64();
       const int n32_all = geglu ? (p.block_n >> 6) : (p.block_n >> 5);
       const int kch_total = (n32_all - half + 1) / 2;   // chunks this half handles per tile
@@ -635,8 +724,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int ci = half; ci < n32; ci += NHALF, ++kch) {
         const int c = ci * 32;
         if (frag) {
-          if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, rowoff4, lane, act, o32, o16, resid);
-          else epi_chunk_fragment<false>(p, t_base, c, hcols, t.n0 + c, bias_s, rowoff4, lane, act, o32, o16, resid);
+          if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, cs_s, ln ? ab4 : nullptr, rowoff4, lane, act, o32, o16, resid, res16, rs_out ? rs4 : nullptr);
+          else epi_chunk_fragment<false>(p, t_base, c, hcols, t.n0 + c, bias_s, cs_s, ln ? ab4 : nullptr, rowoff4, lane, act, o32, o16, resid, res16, rs_out ? rs4 : nullptr);
           if (tre && ci < 6) tre[9 + ci] = clock64();
           continue;
         }
@@ -650,24 +739,27 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
-            const float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
-            acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, ba.x) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), p.alpha, bg.x));
-            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, ba.y) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 1]), p.alpha, bg.y));
-            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, ba.z) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 2]), p.alpha, bg.z));
-            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, ba.w) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 3]), p.alpha, bg.w));
+          for (int j = 0; j < 32; ++j) {
+            float ba = bias_s[c + j], bg = bias_s[hcols + c + j];
+            if (ln) { ba = fmaf(cs_s[c + j], ln_b, ba); bg = fmaf(cs_s[hcols + c + j], ln_b, bg); }
+            acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, ba) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), ln_a, bg));
           }
           col0 = t.n_tile * hcols + c;
         } else {
           tmem_ld_wait();
+          if (ln) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
-            acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, b.x);
-            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, b.y);
-            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, b.z);
-            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, b.w);
+            for (int j = 0; j < 32; ++j)
+              acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, fmaf(cs_s[c + j], ln_b, bias_s[c + j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
+              acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, b.x);
+              acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, b.y);
+              acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, b.z);
+              acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, b.w);
+            }
           }
           col0 = t.n0 + c;
           if (bias2_row) {
@@ -684,6 +776,29 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         if (tre && ci < 6) tre[9 + ci] = clock64();
         const bool to_tr = p.out_tr && col0 >= p.tr_col0;
+        // 16-bit residual and row statistics in the row-owner layout (this thread = one row, 32 columns)
+        if (res16 && row_ok && !to_tr) {
+          const bf16* rp = res16 + row_off + col0;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+              const float2 f0 = unpack16(u.x, p.fp16), f1 = unpack16(u.y, p.fp16), f2 = unpack16(u.z, p.fp16),
+                           f3 = unpack16(u.w, p.fp16);
+              acc[j] += f0.x; acc[j + 1] += f0.y; acc[j + 2] += f1.x; acc[j + 3] += f1.y;
+              acc[j + 4] += f2.x; acc[j + 5] += f2.y; acc[j + 6] += f3.x; acc[j + 7] += f3.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) acc[j] += load16(rp + j, p.fp16);
+          }
+        }
+        if (rs_out && !to_tr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) { rs_s += acc[j]; rs_q = fmaf(acc[j], acc[j], rs_q); }
+        }
         if (use_tma && !to_tr) {
           // ---- TMA epilogue: x = acc (+ residual tile from smem) -> swizzled smem tiles -> TMA stores.
           // The 128 threads of this half own one 128-row x 32-column chunk.
@@ -761,10 +876,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         float acc[16];
         const int col0 = t.n0 + c;
         for (int j = 0; j < 16; ++j) {
-          float x = fmaf(__uint_as_float(r16[j]), p.alpha, bias_s[c + j]);
+          float x = fmaf(__uint_as_float(r16[j]), ln_a, ln ? fmaf(cs_s[c + j], ln_b, bias_s[c + j]) : bias_s[c + j]);
           if (bias2_row && col0 + j < p.N) x += __ldg(bias2_row + col0 + j);
           if (act == ACT_SILU) x = silu_f(x);
           else if (act == ACT_GELU) x = gelu_erf_f(x);
+          const bool in_n = col0 + j < p.N && !(p.out_tr && col0 >= p.tr_col0);
+          if (res16 && row_ok && in_n) x += load16(res16 + row_off + col0 + j, p.fp16);
+          if (rs_out && in_n) { rs_s += x; rs_q = fmaf(x, x, rs_q); }
           acc[j] = x;
         }
         float* srow = stage + lane * GEMM_EPI_PITCH;
@@ -774,6 +892,27 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         __syncwarp();
         epi_store_direct<16>(p, srow, col0, row_ok, row_off, xq, tr_row_off, o32, o16, resid);
         __syncwarp();
+      }
+      if (rs_out) {
+        if (frag) {
+          // the four lanes that share a row (lane % 4) combine, then one of them adds to the row's totals
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rs4[i] += __shfl_xor_sync(0xffffffffu, rs4[i], 1);
+            rs4[i] += __shfl_xor_sync(0xffffffffu, rs4[i], 2);
+          }
+          if ((lane & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int g = grow_s[quad * 32 + (lane >> 2) + 8 * j];
+              atomicAdd(rs_out + 2 * (long long)g, rs4[j]);
+              atomicAdd(rs_out + 2 * (long long)g + 1, rs4[4 + j]);
+            }
+          }
+        } else if (row_ok) {
+          atomicAdd(rs_out + 2 * grow, rs_s);
+          atomicAdd(rs_out + 2 * grow + 1, rs_q);
+        }
       }
       tc_fence_before();
       __syncwarp();

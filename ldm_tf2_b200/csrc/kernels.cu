@@ -653,12 +653,15 @@ void launch_fill_f32(float* x, long long n, float v, cudaStream_t st) {
 
 // W[k][n] fp32 -> dst[(row0 + perm(n)) * ld + k] bf16 through a 32x32 smem transpose.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int k, int n, bf16* __restrict__ dst,
-                                   long long ld, int row0, int geglu_half, int fp16) {
+                                   long long ld, int row0, int geglu_half, int fp16,
+                                   const float* __restrict__ k_scale) {
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int kk = k0 + j, nn = n0 + threadIdx.x;
-    tile[j][threadIdx.x] = (kk < k && nn < n) ? w[(long long)kk * n + nn] : 0.f;
+    float v = (kk < k && nn < n) ? w[(long long)kk * n + nn] : 0.f;
+    if (k_scale && kk < k) v *= k_scale[kk];   // LayerNorm gamma folded into the consumer's weights
+    tile[j][threadIdx.x] = v;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -675,9 +678,60 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int k, int n, bf
   }
 }
 void launch_pack_weight(const float* w, int k, int n, bf16* dst, long long dst_ld, int dst_row0,
-                        int geglu_half, int fp16, cudaStream_t st) {
+                        int geglu_half, int fp16, cudaStream_t st, const float* k_scale) {
   dim3 grid(cdiv(n, 32), cdiv(k, 32)), block(32, 8);
-  pack_weight_kernel<<<grid, block, 0, st>>>(w, k, n, dst, dst_ld, dst_row0, geglu_half, fp16);
+  pack_weight_kernel<<<grid, block, 0, st>>>(w, k, n, dst, dst_ld, dst_row0, geglu_half, fp16, k_scale);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Nearest-neighbour x2 followed by a 3x3 SAME conv (unet.py:44-47, autoencoder.py:152-155) collapses, per
+// output parity (py, px), into a 2x2 conv over the SOURCE image: output row 2y+py reads upsampled rows
+// 2y+py+ky-1, i.e. source rows y-1,y,y (py = 0) or y,y,y+1 (py = 1) for ky = 0,1,2.  Weights of taps that hit the
+// same source pixel are summed in fp32:  dst[phase = 2py+px][co][seg = 2dy+dx][ci], dy / dx in {0,1} = source
+// offset (dy + py - 1, dx + px - 1).  4/9 of the multiply-adds, no materialised 4x activation.
+__global__ void pack_upconv_phase_kernel(const float* __restrict__ w, int cin, int cout, bf16* __restrict__ dst, int fp16) {
+  const long long total = 16ll * cin * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    long long r = i / cout;
+    const int ci = (int)(r % cin);
+    r /= cin;
+    const int seg = (int)(r % 4), phase = (int)(r / 4);
+    const int py = phase >> 1, px = phase & 1, dy = seg >> 1, dx = seg & 1;
+    // taps ky with floor((py + ky - 1) / 2) == dy + py - 1  (source row offset)
+    float acc = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = (py + ky + 1) / 2 - 1;           // floor((py + ky - 1) / 2) for py + ky - 1 >= -1
+      if (sy != dy + py - 1) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = (px + kx + 1) / 2 - 1;
+        if (sx != dx + px - 1) continue;
+        acc += w[((long long)(ky * 3 + kx) * cin + ci) * cout + co];
+      }
+    }
+    store16(dst + (((long long)phase * cout + co) * 4 + seg) * cin + ci, acc, fp16);
+  }
+}
+void launch_pack_upconv_phase(const float* w, int cin, int cout, bf16* dst, int fp16, cudaStream_t st) {
+  pack_upconv_phase_kernel<<<grid_for(16ll * cin * cout, 256), 256, 0, st>>>(w, cin, cout, dst, fp16);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// out[r] = sum_k widen(w[(row0 + r) * ld + k]): column sums of a K-major 16-bit weight matrix as the tensor
+// cores will see it (the "mean" term of a LayerNorm folded into the GEMM).  One warp per row.
+__global__ void rowsum16_kernel(const bf16* __restrict__ w, long long ld, int row0, int rows, int k,
+                                float* __restrict__ out, int fp16) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const bf16* p = w + (long long)(row0 + r) * ld;
+  float s = 0.f;
+  for (int i = lane; i < k; i += 32) s += load16(p + i, fp16);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = s;
+}
+void launch_rowsum16(const bf16* w, long long ld, int row0, int rows, int k, float* out, int fp16, cudaStream_t st) {
+  rowsum16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(w, ld, row0, rows, k, out, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -57,8 +57,13 @@ void launch_small_dense_f32(const float* x, const float* w, const float* b, int 
 void launch_fill_f32(float* x, long long n, float v, cudaStream_t st);
 // W fp32 [K,N] (Keras Dense / reshaped conv) -> bf16 [N (dst rows), K] at dst row offset;
 // geglu_half>0 permutes rows so that value/gate columns interleave per block (see gemm.cuh).
+// k_scale (optional, [K]): row scale applied before the conversion (a LayerNorm gamma folded into the weights).
 void launch_pack_weight(const float* w, int k, int n, bf16* dst, long long dst_ld, int dst_row0,
-                        int geglu_half, int fp16, cudaStream_t st);
+                        int geglu_half, int fp16, cudaStream_t st, const float* k_scale = nullptr);
+// conv kernel [3,3,cin,cout] -> the four 2x2 phase kernels of (nearest x2 -> conv3x3): dst [4][cout][4][cin]
+void launch_pack_upconv_phase(const float* w, int cin, int cout, bf16* dst, int fp16, cudaStream_t st);
+// out[r] = sum over K of the packed 16-bit row (row0 + r): folded-LayerNorm column sums
+void launch_rowsum16(const bf16* w, long long ld, int row0, int rows, int k, float* out, int fp16, cudaStream_t st);
 void launch_embed(const long long* ids, const float* tok, const float* pos, int rows, int seq, int d,
                   float* out, cudaStream_t st);
 void launch_time_embed(const int* t, int n, int channels, float* out, cudaStream_t st);

@@ -77,6 +77,14 @@ struct Builder {
     w.wt = m.dev_alloc<bf16>((size_t)n * k, true);
     return w;
   }
+  // up-conv kernel slot `k` [3,3,c,c]: second packing as four phase-collapsed 2x2 kernels
+  LinW up_phase(Slot* k, int c) {
+    LinW w;
+    w.n = c; w.k = 4 * c; w.ld = 4 * c;
+    w.wt = m.dev_alloc<bf16>((size_t)4 * c * 4 * c, true);
+    k->up_dst = w.wt; k->up_cin = c; k->up_cout = c;
+    return w;
+  }
   GNW gnw(const std::string& p, int c, float eps) {
     GNW g; g.c = c; g.eps = eps;
     g.gamma = f32(p + "/gamma", {c});
@@ -136,13 +144,13 @@ struct Builder {
     const int inner = heads * d;
     if (self) {
       a.qkv = lin(3 * inner, cq);
-      pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
-      pack(p + "/_dense_layer_key/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, inner, 0);
-      pack(p + "/_dense_layer_value/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 2 * inner, 0);
+      a.sq = pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
+      a.sk = pack(p + "/_dense_layer_key/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, inner, 0);
+      a.sv = pack(p + "/_dense_layer_value/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 2 * inner, 0);
     } else {
       a.qkv = lin(inner, cq);
       a.kv = lin(2 * inner, ckv);
-      pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
+      a.sq = pack(p + "/_dense_layer_query/kernel", {cq, heads, d}, cq, inner, a.qkv.wt, a.qkv.ld, 0, 0);
       pack(p + "/_dense_layer_key/kernel", {ckv, heads, d}, ckv, inner, a.kv.wt, a.kv.ld, 0, 0);
       pack(p + "/_dense_layer_value/kernel", {ckv, heads, d}, ckv, inner, a.kv.wt, a.kv.ld, inner, 0);
     }
@@ -163,8 +171,8 @@ struct Builder {
     while ((8 * c) % bn) bn -= 64;   // value and gate halves are processed in 32-column chunks
     LDM_CHECK(bn >= 64, "GEGLU width %d has no tile that is a multiple of 64", 8 * c);
     t.geglu_bn = bn;
-    pack(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/kernel", {c, 8 * c}, c, 8 * c, t.geglu.wt, t.geglu.ld, 0,
-         0, bn / 2);
+    t.geglu_k = pack(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/kernel", {c, 8 * c}, c, 8 * c, t.geglu.wt,
+                     t.geglu.ld, 0, 0, bn / 2);
     t.geglu.bias = f32(p + "/_block/_ffn_layer/_geglu_layer/_dense_layer/bias", {8 * c});
     t.ff = dense(p + "/_block/_ffn_layer/_dense_layer", 4 * c, c);
     t.ln1 = lnw(p + "/_block/_layernorm1", c);
@@ -172,6 +180,17 @@ struct Builder {
     t.ln3 = lnw(p + "/_block/_layernorm3", c);
     t.d2 = dense(p + "/_dense2", c, c);
     t.gn = gnw(p + "/_groupnorm", c, 1e-6f);
+    // LayerNorm1 -> q|k|v, LayerNorm2 -> q of the cross attention, LayerNorm3 -> GEGLU (unet.py:309-313) are
+    // folded into those linears: the kernels keep their fp32 copies until finalize_weights has gamma / beta
+    for (Slot* k : {t.a1.sq, t.a1.sk, t.a1.sv}) { k->keep = true; m.folds_.push_back({k, &t.ln1, &t.a1.qkv, nullptr, nullptr}); }
+    t.a2.sq->keep = true;
+    m.folds_.push_back({t.a2.sq, &t.ln2, &t.a2.qkv, nullptr, nullptr});
+    t.geglu_k->keep = true;
+    m.folds_.push_back({t.geglu_k, &t.ln3, &t.geglu, t.geglu.bias, &t});
+    for (LinW* w : {&t.a1.qkv, &t.a2.qkv, &t.geglu}) {
+      w->ln_cs = m.dev_alloc<float>(w->n, true);
+      w->ln_bias = m.dev_alloc<float>(w->n, true);
+    }
   }
   // AE AttentionBlock (autoencoder.py:61-72): GN, then q,k,v,out Dense with bias
   void ae_attn(AEAttnW& a, const std::string& p, int c) {
@@ -297,7 +316,8 @@ void Model::build() {
         ch = mc * m;
         if (blk.has_up) {
           blk.resample = b.lin(ch, 9 * ch);
-          b.pack(p + "/_upsample/_conv/kernel", {3, 3, ch, ch}, 9 * ch, ch, blk.resample.wt, blk.resample.ld, 0, 0);
+          blk.up_phase = b.up_phase(b.pack(p + "/_upsample/_conv/kernel", {3, 3, ch, ch}, 9 * ch, ch, blk.resample.wt,
+                                           blk.resample.ld, 0, 0), ch);
           blk.resample.bias = b.f32(p + "/_upsample/_conv/bias", {ch});
         }
       }
@@ -352,7 +372,7 @@ void Model::build() {
         AEStage& s = ae_up_.back();
         s.kind = 1; s.c = cur; s.hw = hw;
         s.up = b.lin(cur, 9 * cur);
-        b.pack(p + "/_conv/kernel", {3, 3, cur, cur}, 9 * cur, cur, s.up.wt, s.up.ld, 0, 0);
+        s.up_phase = b.up_phase(b.pack(p + "/_conv/kernel", {3, 3, cur, cur}, 9 * cur, cur, s.up.wt, s.up.ld, 0, 0), cur);
         s.up.bias = b.f32(p + "/_conv/bias", {cur});
         hw *= 2;
       }
@@ -405,8 +425,14 @@ void Model::set_weight(int model, int index, const float* src, const int* shape,
     cudaFree(dev);
   } else {
     launch_pack_weight(dev, s.k, s.n, s.dst + s.col0, s.ld, s.row0, s.geglu_half, eng.fp16, eng.stream);
+    if (s.up_dst) launch_pack_upconv_phase(dev, s.up_cin, s.up_cout, s.up_dst, eng.fp16, eng.stream);
     eng.sync();
-    cudaFree(dev);
+    if (s.keep) {   // re-packed with the LayerNorm gamma by finalize_weights (apply_folds)
+      if (s.f32) cudaFree(s.f32);
+      s.f32 = dev;
+    } else {
+      cudaFree(dev);
+    }
   }
   s.set = true;
   finalized = false;
@@ -433,21 +459,7 @@ void Model::finalize_weights() {
     for (auto& pr : tproj_bias_slots_)
       CUDA_CHECK(cudaMemcpyAsync(tproj_bias_ + pr.second, pr.first->f32, pr.first->numel() * sizeof(float),
                                  cudaMemcpyDeviceToDevice, eng.stream));
-    // GEGLU bias permuted like the weight rows
-    for (STW* st : all_st_) {
-      const int n = 8 * st->c, nh = n / 2, half = st->geglu_bn / 2;
-      std::vector<float> hb(n), pb(n);
-      CUDA_CHECK(cudaMemcpyAsync(hb.data(), st->geglu.bias->f32, n * sizeof(float), cudaMemcpyDeviceToHost, eng.stream));
-      eng.sync();
-      for (int c = 0; c < n; ++c) {
-        const int j2 = c < nh ? c : c - nh;
-        const int r = (j2 / half) * (2 * half) + (c < nh ? 0 : half) + j2 % half;
-        pb[r] = hb[c];
-      }
-      if (!st->geglu_bias_perm) st->geglu_bias_perm = dev_alloc<float>(n);
-      CUDA_CHECK(cudaMemcpyAsync(st->geglu_bias_perm, pb.data(), n * sizeof(float), cudaMemcpyHostToDevice, eng.stream));
-      eng.sync();
-    }
+    apply_folds();
   }
   if (model_ready_[2]) {
     for (auto& pr : ae_concat_bias_)
@@ -462,13 +474,53 @@ void Model::finalize_weights() {
   }
 }
 
+// LayerNorm folded into the linear that consumes it (unet.py:309-313):
+//   LN(y) W + b = rstd_r (y (gamma o W) - mean_r 1^T (gamma o W)) + (beta W + b)
+// so the GEMM runs on the RAW 16-bit rows y with weights gamma o W; its epilogue applies the per-row
+// (mean, rstd) -- taken from the producer's epilogue (GemmOp::rs_out) -- with ln_cs = column sums of the
+// packed weights and ln_bias = beta W + b.  Saves the LayerNorm pass and its normalised copy of y.
+void Model::apply_folds() {
+  std::vector<float> tmp_h;
+  for (const Fold& f : folds_) {
+    Slot& k = *f.kernel;
+    LDM_CHECK(k.f32 && f.ln->gamma->f32 && f.ln->beta->f32, "apply_folds: %s not resident", k.name.c_str());
+    launch_pack_weight(k.f32, k.k, k.n, k.dst + k.col0, k.ld, k.row0, k.geglu_half, eng.fp16, eng.stream, f.ln->gamma->f32);
+    // beta W (+ b) in natural column order
+    float* tmp = static_cast<float*>(stage(ST_A, (size_t)k.n * sizeof(float)));
+    launch_small_dense_f32(f.ln->beta->f32, k.f32, f.bias_src ? f.bias_src->f32 : nullptr, 1, k.k, k.n, 0, 0, tmp, eng.stream);
+    if (f.geglu_of) {
+      // permute like the packed weight rows: value / gate columns of a tile side by side
+      STW* st = f.geglu_of;
+      const int n = k.n, nh = n / 2, half = st->geglu_bn / 2;
+      tmp_h.resize(n);
+      std::vector<float> pb(n);
+      CUDA_CHECK(cudaMemcpyAsync(tmp_h.data(), tmp, n * sizeof(float), cudaMemcpyDeviceToHost, eng.stream));
+      eng.sync();
+      for (int c = 0; c < n; ++c) {
+        const int j2 = c < nh ? c : c - nh;
+        pb[(j2 / half) * (2 * half) + (c < nh ? 0 : half) + j2 % half] = tmp_h[c];
+      }
+      CUDA_CHECK(cudaMemcpyAsync(f.lin->ln_bias, pb.data(), n * sizeof(float), cudaMemcpyHostToDevice, eng.stream));
+      eng.sync();
+      st->geglu_bias_perm = f.lin->ln_bias;
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(f.lin->ln_bias + k.row0, tmp, (size_t)k.n * sizeof(float), cudaMemcpyDeviceToDevice, eng.stream));
+    }
+    eng.sync();
+  }
+  // column sums of the packed matrices, as the tensor cores see them (16-bit values, packed row order)
+  for (const Fold& f : folds_)
+    launch_rowsum16(f.lin->wt, f.lin->ld, f.kernel->row0, f.kernel->n, f.lin->k, f.lin->ln_cs + f.kernel->row0, eng.fp16, eng.stream);
+  eng.sync();
+}
+
 void Model::ensure_arena(size_t bytes) {
-  // called right after a dry pass: gn_pool_off_ holds the number of statistic slots it used
-  if (gn_pool_off_ > gn_pool_need_) gn_pool_need_ = gn_pool_off_;
-  if (gn_pool_need_ > gn_pool_cap_) {
-    dev_free(gn_pool_);
-    gn_pool_ = dev_alloc<double>(gn_pool_need_, true);
-    gn_pool_cap_ = gn_pool_need_;
+  // called right after a dry pass: pool_off_ holds the statistic bytes it used
+  if (pool_off_ > pool_need_) pool_need_ = pool_off_;
+  if (pool_need_ > pool_cap_) {
+    dev_free(pool_);
+    pool_ = dev_alloc<uint8_t>(pool_need_, true);
+    pool_cap_ = pool_need_;
     invalidate_graph();   // a captured step holds the old pool address
   }
   bytes += (64u << 20);
@@ -501,9 +553,18 @@ Act Model::alloc_act(int n, int h, int w, int c, bool f, bool b) {
 // Called at the start of every forward graph (UNet step, decode): the dry pass measures how many
 // statistic slots the pass needs, the real pass zeroes exactly those with one memset.
 void Model::begin_pass() {
-  if (!eng.dry && gn_pool_need_)
-    CUDA_CHECK(cudaMemsetAsync(gn_pool_, 0, gn_pool_need_ * sizeof(double), eng.stream));
-  gn_pool_off_ = 0;
+  if (!eng.dry && pool_need_)
+    CUDA_CHECK(cudaMemsetAsync(pool_, 0, pool_need_, eng.stream));
+  pool_off_ = 0;
+}
+
+// zero-initialised statistics slot of the current pass (dry pass: only tallies)
+void* Model::pool_take(size_t bytes) {
+  const size_t off = (pool_off_ + 15) & ~size_t(15);
+  pool_off_ = off + bytes;
+  if (eng.dry) return reinterpret_cast<void*>(uintptr_t(0x100000) + off);   // never dereferenced
+  LDM_CHECK(pool_off_ <= pool_cap_, "statistics pool overflow (%zu of %zu bytes)", pool_off_, pool_cap_);
+  return pool_ + off;
 }
 
 void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out) {
@@ -525,12 +586,10 @@ void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out
     st = eng.alloc<double>((size_t)x.n * 64);
     if (!eng.dry) CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)x.n * 64 * sizeof(double), eng.stream));
   } else {
-    st = gn_pool_ + gn_pool_off_;
-    gn_pool_off_ += (size_t)x.n * 64;
+    st = static_cast<double*>(pool_take((size_t)x.n * 64 * sizeof(double)));
   }
   eng.launches += 2;
   if (eng.dry) return;
-  LDM_CHECK(no_pool || gn_pool_off_ <= gn_pool_cap_, "GroupNorm statistics pool overflow");
   launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, eng.stream);
   launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
                   silu ? 1 : 0, out, eng.fp16, eng.stream);
@@ -570,6 +629,73 @@ Act Model::conv3x3(const Act& x, const LinW& w, const float* bias) {
   op.bias = bias;
   op.out_f32 = out.f; op.out_bf16 = out.b;
   op.os_x = w.n; op.os_y = (long long)x.w * w.n; op.os_n = (long long)x.h * x.w * w.n;
+  eng.gemm(op);
+  return out;
+}
+
+// Upsample.call: nearest x2 (tf.raw_ops.ResizeNearestNeighbor) then a 3x3 SAME conv (unet.py:44-47,
+// autoencoder.py:152-155).  Default: four phase-collapsed 2x2 convs straight over the source image
+// (launch_pack_upconv_phase): 4/9 of the FLOPs and no materialised 4x activation.  LDM_B200_UPCONV=materialize
+// keeps the literal formulation for A/B runs.
+Act Model::upconv(const Act& x, const LinW& w9, const LinW& wp, const float* bias) {
+  static const bool materialize = getenv("LDM_B200_UPCONV") && !strcmp(getenv("LDM_B200_UPCONV"), "materialize");
+  if (materialize) {
+    Act up = alloc_act(x.n, x.h * 2, x.w * 2, x.c, false, true);
+    eng.launches++;
+    if (!eng.dry) launch_upsample2(x.b, x.n, x.h, x.w, x.c, up.b, eng.stream);
+    return conv3x3(up, w9, bias);
+  }
+  const int c = x.c, cout = wp.n;
+  Act out = alloc_act(x.n, 2 * x.h, 2 * x.w, cout);
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(x.b, x.n, x.h, x.w, c);
+  AView b; b.ptr = wp.wt; b.C = 4 * c; b.W = cout; b.H = 4; b.NB = 1;
+  b.sx = 4 * c; b.sy = (long long)cout * 4 * c; b.sn = 4ll * cout * 4 * c;
+  op.b = b; op.b_mode = B_PHASE; op.num_phases = 4;
+  int bk = 0;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) op.add_seg(0, dy - 1, dx - 1, 0, c, bk);   // the kernel adds the phase (py, px)
+  op.W = x.w; op.H = x.h; op.NB = x.n; op.N = cout;
+  op.bias = bias;
+  op.out_f32 = out.f; op.out_bf16 = out.b;
+  // source pixel (y, x), phase (py, px) -> output pixel (2y + py, 2x + px)
+  op.os_x = 2ll * cout; op.os_y = 2ll * (2 * x.w) * cout; op.os_n = 4ll * x.h * x.w * cout;
+  op.os_phase_y = 2ll * x.w * cout; op.os_phase_x = cout;
+  eng.gemm(op);
+  return out;
+}
+
+// Downsample: zero pad + 3x3 stride-2 VALID conv.  UNet pads (1,1) on both axes (unet.py:22,26-27): tap (ky,kx) of
+// output (oy,ox) reads input (2oy + ky - 1, 2ox + kx - 1); the autoencoder's encoder pads (0,1)
+// (autoencoder.py:133): (2oy + ky, 2ox + kx).  No im2col: the A operand is a TMA map with element stride 2, one
+// shifted box per tap, out-of-range elements zero-filled by TMA.  LDM_B200_DOWNCONV=im2col keeps the old path.
+Act Model::downconv(const Act& x, const LinW& w, const float* bias, int pad_lo) {
+  static const bool im2col = getenv("LDM_B200_DOWNCONV") && !strcmp(getenv("LDM_B200_DOWNCONV"), "im2col");
+  const int ho = x.h / 2, wo = x.w / 2;
+  LDM_CHECK(x.h % 2 == 0 && x.w % 2 == 0, "downsample: odd input size %dx%d", x.h, x.w);
+  Act out = alloc_act(x.n, ho, wo, w.n);
+  if (im2col && pad_lo == 1) {
+    const size_t mk = eng.arena.mark();
+    bf16* col = eng.alloc<bf16>((size_t)x.n * ho * wo * 9 * x.c);
+    eng.launches++;
+    if (!eng.dry) launch_im2col_s2(x.b, x.n, x.h, x.w, x.c, col, eng.stream);
+    linear(col, (long long)x.n * ho * wo, w, bias, ACT_NONE, nullptr, out.f, out.b);
+    eng.arena.release(mk);
+    return out;
+  }
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(x.b, x.n, x.h, x.w, x.c);
+  op.a[0].estride = 2;
+  op.b = view_mat(w.wt, w.n, w.k, w.ld);
+  int bk = 0;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) op.add_seg(0, ky - pad_lo, kx - pad_lo, 0, x.c, bk);
+  op.W = wo; op.H = ho; op.NB = x.n; op.N = w.n;
+  op.bias = bias;
+  op.out_f32 = out.f; op.out_bf16 = out.b;
+  op.os_x = w.n; op.os_y = (long long)wo * w.n; op.os_n = (long long)ho * wo * w.n;
   eng.gemm(op);
   return out;
 }
@@ -696,9 +822,10 @@ void Model::attention_core(const bf16* q, long long q_ld, const bf16* k, long lo
 }
 
 // Fused q|k|v projection: q,k row-major into qk [rows, 2*inner]; v transposed into vt
-// [n, heads, d, tpad] so that P.V reads a K-major B operand.
+// [n, heads, d, tpad] so that P.V reads a K-major B operand.  ln_stats != null: z holds RAW rows and the
+// LayerNorm in front of the projection is folded into it (w.ln_cs / w.ln_bias, see apply_folds).
 static void qkv_projection(Engine& eng, const bf16* z, int n, int t, int c, const LinW& w, const float* bias, int inner,
-                           bf16* qk, bf16* vt, int tpad) {
+                           bf16* qk, bf16* vt, int tpad, const float* ln_stats = nullptr) {
   GemmOp op;
   op.num_a = 1;
   AView a; a.ptr = z; a.C = c; a.W = t; a.H = 1; a.NB = n; a.sx = c; a.sy = (long long)t * c; a.sn = (long long)t * c;
@@ -710,6 +837,7 @@ static void qkv_projection(Engine& eng, const bf16* z, int n, int t, int c, cons
   op.N = 3 * inner;
   op.n_boundary = 2 * inner;
   op.bias = bias;
+  if (ln_stats) { op.ln_stats = ln_stats; op.ln_cs = w.ln_cs; op.ln_c = c; op.bias = w.ln_bias; }
   op.out_bf16 = qk;
   op.os_n = (long long)t * 2 * inner; op.os_y = 0; op.os_x = 2 * inner;
   op.out_tr = vt; op.tr_col0 = 2 * inner;
@@ -717,73 +845,103 @@ static void qkv_projection(Engine& eng, const bf16* z, int n, int t, int c, cons
   eng.gemm(op);
 }
 
-// SpatialTransformer.call (unet.py:356-365) + BasicTransformerBlock (unet.py:308-314)
+// SpatialTransformer.call (unet.py:356-365) + BasicTransformerBlock (unet.py:308-314).
+// Inside the block the token stream y is 16-bit and updated in place by the three residual linears
+// (fp32 accumulate, 16-bit residual read in the epilogue); the block's input / output stay fp32.  The
+// three LayerNorms never run as kernels: each producer's epilogue accumulates the rows' (sum, sum sq),
+// and the consumer GEMM (q|k|v, q, GEGLU) applies mean / rstd in its own epilogue (apply_folds).
 Act Model::spatial_transformer(STW& s, const Act& x) {
   const int n = x.n, t = x.h * x.w, c = s.c, heads = cfg.num_heads, d = s.d;
   const long long rows = (long long)n * t;
   LDM_CHECK(x.c == c && heads * d == c, "spatial transformer: channel mismatch");
   LDM_CHECK(s.ctx_k != nullptr && ctx_rows_ == n, "spatial transformer: context not set for %d rows", n);
+  LDM_CHECK(rows < (1ll << 30), "spatial transformer: too many token rows");
   Act out = alloc_act(n, x.h, x.w, c);
   const size_t mk = eng.arena.mark();
   bf16* xn = eng.alloc<bf16>((size_t)rows * c);
   gn(s.gn, x, nullptr, false, xn);
-  float* y = eng.alloc<float>((size_t)rows * c);
-  bf16* z = eng.alloc<bf16>((size_t)rows * c);
+  bf16* y = eng.alloc<bf16>((size_t)rows * c);   // the block's token stream
   bf16* o = eng.alloc<bf16>((size_t)rows * c);
-  linear(xn, rows, s.d1, s.d1.bias->f32, ACT_NONE, nullptr, y, nullptr);
+  float* st1 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
+  float* st2 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
+  float* st3 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
+  // y = dense1(groupnorm(x)) (unet.py:358-361), row statistics for LayerNorm1
+  auto res_linear = [&](const bf16* a, const LinW& w, const bf16* res, bf16* dst, float* stats) {
+    GemmOp op;
+    op.num_a = 1;
+    op.a[0] = view_mat(a, rows, w.k, w.k);
+    op.b = view_mat(w.wt, w.n, w.k, w.ld);
+    int bk = 0;
+    op.add_seg(0, 0, 0, 0, w.k, bk);
+    op.W = (int)rows; op.H = 1; op.NB = 1;
+    op.N = w.n;
+    op.bias = w.bias->f32;
+    op.res16 = res; op.out_bf16 = dst; op.rs_out = stats;
+    op.os_x = w.n;
+    eng.gemm(op);
+  };
+  res_linear(xn, s.d1, nullptr, y, st1);
   const float scale = 1.0f / sqrtf((float)d);
-  // ---- self attention (unet.py:309-310)
+  // ---- self attention: y += attn1(LN1(y)) (unet.py:309-310)
   {
     const size_t mk2 = eng.arena.mark();
-    eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln1.gamma->f32, s.ln1.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     const int tpad = round_up(t, 8);
     bf16* qk = eng.alloc<bf16>((size_t)rows * 2 * c);
     bf16* vt = eng.alloc<bf16>((size_t)n * c * tpad);
     if (tpad != t && !eng.dry) CUDA_CHECK(cudaMemsetAsync(vt, 0, (size_t)n * c * tpad * 2, eng.stream));
-    qkv_projection(eng, z, n, t, c, s.a1.qkv, nullptr, c, qk, vt, tpad);
+    qkv_projection(eng, y, n, t, c, s.a1.qkv, nullptr, c, qk, vt, tpad, st1);
     attention_core(qk, 2 * c, qk + c, 2 * c, (long long)t * 2 * c, t, vt, tpad, n, t, heads, d, scale, o, c);
-    linear(o, rows, s.a1.out, s.a1.out.bias->f32, ACT_NONE, y, y, nullptr);
+    res_linear(o, s.a1.out, y, y, st2);
     eng.arena.release(mk2);
   }
-  // ---- cross attention against the hoisted context K / V^T (unet.py:311-312)
+  // ---- cross attention against the hoisted context K / V^T: y += attn2(LN2(y), ctx) (unet.py:311-312)
   {
     const size_t mk2 = eng.arena.mark();
-    eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln2.gamma->f32, s.ln2.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     bf16* q = eng.alloc<bf16>((size_t)rows * c);
-    linear(z, rows, s.a2.qkv, nullptr, ACT_NONE, nullptr, nullptr, q);
+    {
+      GemmOp op;
+      op.num_a = 1;
+      op.a[0] = view_mat(y, rows, c, c);
+      op.b = view_mat(s.a2.qkv.wt, s.a2.qkv.n, c, s.a2.qkv.ld);
+      int bk = 0;
+      op.add_seg(0, 0, 0, 0, c, bk);
+      op.W = (int)rows; op.H = 1; op.NB = 1;
+      op.N = c;
+      op.ln_stats = st2; op.ln_cs = s.a2.qkv.ln_cs; op.ln_c = c; op.bias = s.a2.qkv.ln_bias;
+      op.out_bf16 = q;
+      op.os_x = c;
+      eng.gemm(op);
+    }
     const int tk = cfg.max_seq_len, tpad = round_up(tk, 8);
     attention_core(q, c, s.ctx_k, c, (long long)tk * c, tk, s.ctx_vt, tpad, n, t, heads, d, scale, o, c);
-    linear(o, rows, s.a2.out, s.a2.out.bias->f32, ACT_NONE, y, y, nullptr);
+    res_linear(o, s.a2.out, y, y, st3);
     eng.arena.release(mk2);
   }
-  // ---- GEGLU feed-forward (unet.py:313, 322-325, 335-338)
+  // ---- GEGLU feed-forward: z = y + ff(geglu(LN3(y))) (unet.py:313, 322-325, 335-338)
+  bf16* z = eng.alloc<bf16>((size_t)rows * c);
   {
     const size_t mk2 = eng.arena.mark();
-    eng.launches++;
-    if (!eng.dry) launch_layernorm(y, s.ln3.gamma->f32, s.ln3.beta->f32, (int)rows, c, 1e-5f, z, nullptr, eng.fp16, eng.stream);
     bf16* g = eng.alloc<bf16>((size_t)rows * 4 * c);
     {
       GemmOp op;
       op.num_a = 1;
-      op.a[0] = view_mat(z, rows, c, c);
+      op.a[0] = view_mat(y, rows, c, c);
       op.b = view_mat(s.geglu.wt, 8 * c, c, s.geglu.ld);
       int bk = 0;
       op.add_seg(0, 0, 0, 0, c, bk);
       op.W = (int)rows; op.H = 1; op.NB = 1;
       op.N = 4 * c; op.gemm_n = 8 * c; op.block_n = s.geglu_bn;
       op.act = ACT_GEGLU;
+      op.ln_stats = st3; op.ln_cs = s.geglu.ln_cs; op.ln_c = c;
       op.bias = s.geglu_bias_perm;
       op.out_bf16 = g;
       op.os_x = 4 * c;
       eng.gemm(op);
     }
-    // y += ff(g); the bf16 copy feeds dense2
-    linear(g, rows, s.ff, s.ff.bias->f32, ACT_NONE, y, y, z);
+    res_linear(g, s.ff, y, z, nullptr);
     eng.arena.release(mk2);
   }
-  // dense2 + input residual (unet.py:363-364)
+  // dense2 + the block's fp32 input residual (unet.py:363-364)
   linear(z, rows, s.d2, s.d2.bias->f32, ACT_NONE, x.f, out.f, out.b);
   eng.arena.release(mk);
   return out;
@@ -886,16 +1044,7 @@ void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_o
   int bi = 0;
   for (auto& blk : in_blocks_) {
     if (blk.kind == 1) {
-      // Downsample: pad(1,1) + 3x3 stride-2 VALID (unet.py:22,26-27) = im2col + GEMM
-      const int ho = cur.h / 2, wo = cur.w / 2;
-      Act out = alloc_act(n, ho, wo, blk.cout);
-      const size_t mk = eng.arena.mark();
-      bf16* col = eng.alloc<bf16>((size_t)n * ho * wo * 9 * cur.c);
-      eng.launches++;
-      if (!eng.dry) launch_im2col_s2(cur.b, n, cur.h, cur.w, cur.c, col, eng.stream);
-      linear(col, (long long)n * ho * wo, blk.resample, blk.resample.bias->f32, ACT_NONE, nullptr, out.f, out.b);
-      eng.arena.release(mk);
-      cur = out;
+      cur = downconv(cur, blk.resample, blk.resample.bias->f32, 1);   // unet.py:22,26-27
     } else {
       cur = resblock(blk.res, cur, nullptr);
       if (bi == 0) tap("in0_res", cur);
@@ -915,11 +1064,7 @@ void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_o
     cur = resblock(blk.res, cur, &skip);
     if (blk.has_st) cur = spatial_transformer(blk.st, cur);
     if (blk.has_up) {
-      // Upsample: nearest x2 (unet.py:44-45) then 3x3 SAME conv
-      Act up = alloc_act(n, cur.h * 2, cur.w * 2, cur.c, false, true);
-      eng.launches++;
-      if (!eng.dry) launch_upsample2(cur.b, n, cur.h, cur.w, cur.c, up.b, eng.stream);
-      cur = conv3x3(up, blk.resample, blk.resample.bias->f32);
+      cur = upconv(cur, blk.resample, blk.up_phase, blk.resample.bias->f32);   // unet.py:44-47
     }
     tap("out" + std::to_string(bi++), cur);
   }
@@ -1221,10 +1366,7 @@ void Model::decode_body(const float* z, int b, int h, int w, float div, float* i
                 cur.h, cfg.ae_build_hw);
       if (want) cur = ae_attention(s.at, cur);
     } else {
-      Act up = alloc_act(b, cur.h * 2, cur.w * 2, cur.c, false, true);
-      eng.launches++;
-      if (!eng.dry) launch_upsample2(cur.b, b, cur.h, cur.w, cur.c, up.b, eng.stream);
-      cur = conv3x3(up, s.up, s.up.bias->f32);
+      cur = upconv(cur, s.up, s.up_phase, s.up.bias->f32);   // autoencoder.py:152-155
     }
   }
   bf16* a = eng.alloc<bf16>((size_t)cur.numel());

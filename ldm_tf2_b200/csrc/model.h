@@ -40,13 +40,18 @@ struct Slot {
   long long ld = 0;
   int row0 = 0, col0 = 0, k = 0, n = 0, geglu_half = 0;
   float* f32_dst = nullptr; long long f32_ld = 0; int f32_col0 = 0;  // F32MAT destination
+  bf16* up_dst = nullptr; int up_cin = 0, up_cout = 0;   // PACK of an up-conv kernel: also packed as four 2x2 phase kernels
+  bool keep = false;        // PACK: the fp32 copy stays on the device (f32) -- finalize_weights re-packs it with a folded LayerNorm gamma
   bool set = false;
   size_t numel() const { size_t s = 1; for (int d : shape) s *= (size_t)d; return s; }
 };
 
 struct GNW { Slot* gamma = nullptr; Slot* beta = nullptr; int c = 0; float eps = 1e-5f; };
 struct LNW { Slot* gamma = nullptr; Slot* beta = nullptr; int c = 0; };
-struct LinW { bf16* wt = nullptr; Slot* bias = nullptr; float* bias_dev = nullptr; int k = 0, n = 0; long long ld = 0; };
+struct LinW { bf16* wt = nullptr; Slot* bias = nullptr; float* bias_dev = nullptr; int k = 0, n = 0; long long ld = 0;
+  // LayerNorm folded into this linear (finalize_weights): weights carry gamma, ln_cs[n] = their column sums as the
+  // tensor cores see them, ln_bias[n] = beta.W + bias; both in packed row order
+  float* ln_cs = nullptr; float* ln_bias = nullptr; };
 
 struct ResW {
   int cin = 0, cout = 0;
@@ -62,6 +67,7 @@ struct AttnW {
   LinW kv;             // cross: [2*inner, ctx]
   LinW out;            // [c_out, inner]
   int heads = 8, d = 0;
+  Slot* sq = nullptr; Slot* sk = nullptr; Slot* sv = nullptr;   // the q / k / v kernel slots (self) / q (cross)
 };
 struct STW {
   int c = 0, d = 0;
@@ -70,7 +76,8 @@ struct STW {
   LNW ln1, ln2, ln3;
   AttnW a1, a2;
   int geglu_bn = 0;
-  float* geglu_bias_perm = nullptr;  // bias permuted like the packed weight rows
+  float* geglu_bias_perm = nullptr;  // (beta.W +) bias permuted like the packed weight rows
+  Slot* geglu_k = nullptr;           // the GEGLU Dense kernel slot
   // hoisted context projections (unet.py:276-277 recomputes them every step)
   bf16* ctx_k = nullptr;   // [N,77,heads,d]
   bf16* ctx_vt = nullptr;  // [N,heads,d,tpad]
@@ -84,6 +91,7 @@ struct UNetBlock {
   int kind = 0;  // 0 = res(+st), 1 = down, 2 = up-stage output block
   ResW res; bool has_st = false; STW st;
   LinW resample;  // down / up conv
+  LinW up_phase;  // up conv as four phase-collapsed 2x2 kernels: [4][cout][4*cin]
   bool has_up = false;
   int cin = 0, cout = 0;
 };
@@ -151,7 +159,7 @@ class Model {
   Slot* codebook_ = nullptr; Slot* pq_k_ = nullptr; Slot* pq_b_ = nullptr;
   Slot* ae_conv_in_k_ = nullptr; Slot* ae_conv_in_b_ = nullptr;
   ResW ae_mid1_, ae_mid2_; AEAttnW ae_mid_attn_;
-  struct AEStage { int kind = 0; ResW res; bool attn = false; AEAttnW at; LinW up; int c = 0; int hw = 0; };
+  struct AEStage { int kind = 0; ResW res; bool attn = false; AEAttnW at; LinW up; LinW up_phase; int c = 0; int hw = 0; };
   std::vector<AEStage> ae_up_; int ae_plan_hw_ = 0;
   GNW ae_out_gn_; LinW ae_conv_out_;
   // sampler state
@@ -175,15 +183,23 @@ class Model {
   void linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
               float* out_f32, bf16* out_bf16);
   Act conv3x3(const Act& x_b16, const LinW& w, const float* bias);
+  Act upconv(const Act& x_b16, const LinW& w9, const LinW& wp, const float* bias);   // nearest x2 + conv3x3
+  Act downconv(const Act& x_b16, const LinW& w, const float* bias, int pad_lo);      // pad + conv3x3 stride 2 VALID
   void gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out);
   Act unet_body(const float* x, int nsrc, int n, int h, int w);
   void unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out);
   void decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   Act ae_attention(AEAttnW& a, const Act& x);
   void build_ae_plan(int hw);
-  // GroupNorm statistics pool: one memset per forward pass instead of one per GroupNorm
-  double* gn_pool_ = nullptr; size_t gn_pool_cap_ = 0, gn_pool_off_ = 0, gn_pool_need_ = 0;
+  // Statistics pool (GroupNorm (sum, sum sq) per (image, group) in double; LayerNorm row sums in float):
+  // the dry pass measures how many bytes a forward pass takes, the real pass zeroes them with ONE memset
+  uint8_t* pool_ = nullptr; size_t pool_cap_ = 0, pool_off_ = 0, pool_need_ = 0;
+  void* pool_take(size_t bytes);
   void begin_pass();
+  // LayerNorm -> linear folds of the SpatialTransformers (unet.py:309-313), applied by finalize_weights
+  struct Fold { Slot* kernel; const LNW* ln; LinW* lin; Slot* bias_src; STW* geglu_of; };
+  std::vector<Fold> folds_;
+  void apply_folds();
   std::vector<void*> owned_;  // cudaMalloc'ed persistent buffers
   // grow-only staging buffers for the API calls' host<->device copies: steady-state calls never
   // touch cudaMalloc / cudaFree (both serialise on the driver and stall behind other processes)

@@ -61,7 +61,9 @@ _PROTOS = {
     "ldm_bench_groupnorm": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F)], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "ldm_test_ln_linear": ([_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     "ldm_test_conv3x3": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "ldm_test_resample_conv": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_attention": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P], _I),
     "ldm_test_groupnorm": ([_P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _P], _I),
     "ldm_test_layernorm": ([_P, _P, _P, _P, _I, _I, _F, _P], _I),
@@ -379,6 +381,21 @@ class Handle:
                                        block_n, max_ctas, ptr(out)))
         return out
 
+    def test_ln_linear(self, a, w0, b0, gamma, beta, w1, b1, act=0, residual=False, dbg=0):
+        a, w0, w1 = f32(a), f32(w0), f32(w1)
+        rows, k0 = a.shape
+        c = w0.shape[1]
+        n = w1.shape[1] // 2 if act == 3 else w1.shape[1]
+        y = np.empty((rows, c), np.float32)
+        st = np.empty((rows, 2), np.float32)
+        out = np.empty((rows, n), np.float32)
+        b0 = None if b0 is None else f32(b0)
+        b1 = None if b1 is None else f32(b1)
+        gamma, beta = f32(gamma), f32(beta)
+        check(self.lib.ldm_test_ln_linear(self._h, ptr(a), ptr(w0), ptr(b0), rows, k0, c, ptr(gamma), ptr(beta), ptr(w1),
+                                          ptr(b1), n, act, int(residual), dbg, ptr(y), ptr(st), ptr(out)))
+        return y, st, out
+
     def test_conv3x3(self, x, kernel, bias=None, sc_x=None, sc_kernel=None):
         x, kernel = f32(x), f32(kernel)
         nb, hh, ww, cin = x.shape
@@ -391,6 +408,17 @@ class Handle:
         out = np.empty((nb, hh, ww, cout), np.float32)
         check(self.lib.ldm_test_conv3x3(self._h, ptr(x), ptr(kernel), ptr(bias), ptr(sc_x), ptr(sc_kernel),
                                         nb, hh, ww, cin, cout, sc_cin, ptr(out)))
+        return out
+
+    def test_resample_conv(self, x, kernel, bias, mode):
+        """mode 0: nearest x2 + conv3x3; 1: pad(1,1) + stride-2 conv (UNet); 2: pad(0,1) + stride-2 conv (AE encoder)."""
+        x, kernel = f32(x), f32(kernel)
+        nb, hh, ww, cin = x.shape
+        cout = kernel.shape[-1]
+        bias = None if bias is None else f32(bias)
+        shape = (nb, 2 * hh, 2 * ww, cout) if mode == 0 else (nb, hh // 2, ww // 2, cout)
+        out = np.empty(shape, np.float32)
+        check(self.lib.ldm_test_resample_conv(self._h, ptr(x), ptr(kernel), ptr(bias), nb, hh, ww, cin, cout, mode, ptr(out)))
         return out
 
     def test_attention(self, q, k, v, scale, unfused=False):

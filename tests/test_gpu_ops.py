@@ -20,7 +20,7 @@ def h(request):
 
 
 def test_library_loads_on_gpu(h):
-    assert h.lib.ldm_version() == 100
+    assert h.lib.ldm_version() == 200
 
 
 # ----------------------------------------------------------------- K5 (bit-exact)
@@ -75,6 +75,44 @@ def test_vq_argmin_bit_exact(vocab, rows):
     assert np.array_equal(idx, idx_ref)
     assert np.array_equal(zq.view(np.uint32), zq_ref.view(np.uint32))
     hd.close()
+
+
+# ----------------------------------------------------------------- transformer-block epilogue terms
+@pytest.mark.parametrize("rows,k0,c,n,act,residual,dbg", [
+    (256, 64, 320, 320, 0, True, 0),      # residual linear, 16-bit stream updated in place, fragment epilogue
+    (256, 64, 320, 320, 0, True, 8),      # same through the row-owner epilogue
+    (384, 128, 320, 960, 0, False, 0),    # q|k|v-like: LayerNorm folded, wider output
+    (200, 64, 64, 64, 0, True, 0),        # ragged rows (partial tile) -> row-owner path
+    (128, 64, 96, 112, 0, False, 0),      # ragged 16-column tail tile
+    (256, 64, 64, 256, 3, False, 0),      # GEGLU with the folded LayerNorm (fragment epilogue)
+    (160, 64, 64, 256, 3, False, 8),      # GEGLU, row-owner epilogue, ragged rows
+])
+def test_layernorm_folded_linear_with_16bit_residual_and_row_stats(h, rows, k0, c, n, act, residual, dbg):
+    """unet.py:304-314: y = dense(a); out = act(dense(LayerNorm(y))) [+ y].  The library keeps y as a 16-bit
+    stream, takes the rows' (sum, sum sq) in the producer's epilogue and folds the LayerNorm into the consumer
+    GEMM; the reference below normalises explicitly in fp32."""
+    rng = np.random.default_rng(rows + n + act)
+    a = round16(rng.standard_normal((rows, k0), dtype=np.float32), h.precision)
+    w0 = rng.standard_normal((k0, c), dtype=np.float32) / np.float32(np.sqrt(k0))
+    b0 = rng.standard_normal(c, dtype=np.float32) * np.float32(0.5) + np.float32(0.3)   # non-zero row mean
+    gamma = (1 + 0.2 * rng.standard_normal(c)).astype(np.float32)
+    beta = (0.3 * rng.standard_normal(c)).astype(np.float32)
+    wn = 2 * n if act == 3 else n
+    w1 = rng.standard_normal((c, wn), dtype=np.float32) / np.float32(np.sqrt(c))
+    b1 = rng.standard_normal(wn, dtype=np.float32) * np.float32(0.1)
+    y, st, out = h.test_ln_linear(a, w0, b0, gamma, beta, w1, b1, act=act, residual=residual, dbg=dbg)
+    y_ref = a @ round16(w0, h.precision) + b0
+    tol = 4e-3 if h.precision == "fp16" else 2.5e-2
+    assert rel_l2(y, y_ref) < (1e-3 if h.precision == "fp16" else 6e-3)
+    assert rel_l2(st[:, 0], y_ref.sum(1)) < 1e-3 + (0 if h.precision == "fp16" else 1e-2)
+    assert rel_l2(st[:, 1], (y_ref * y_ref).sum(1)) < 1e-3
+    z = O.layer_norm(y_ref, gamma, beta, 1e-5) @ w1 + b1
+    if act == 3:
+        z = z[:, :n] * O.gelu_erf(z[:, n:])
+    ref = z + (y_ref if residual else 0)
+    err = rel_l2(out, ref)
+    print(f"rows={rows} c={c} n={n} act={act} res={residual} dbg={dbg}: rel-L2 {err:.2e}")
+    assert err < tol
 
 
 # ----------------------------------------------------------------- K2 / LayerNorm
@@ -189,6 +227,51 @@ def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
         sc_k = rng.standard_normal((sc, cout), dtype=np.float32) / np.float32(np.sqrt(sc))
     got = h.test_conv3x3(x, kern, bias, sc_x, sc_k)
     ref = _conv_ref(x, kern, bias, sc_x, sc_k, h.precision)
+    err = np.abs(got - ref).max()
+    assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("nb,hh,ww,c", [
+    (2, 16, 16, 64),     # one image per tile; two M tiles per phase (CTA pairs inside a phase)
+    (3, 8, 8, 128),      # two images per tile, odd tile count per phase (single-CTA kernel)
+    (16, 4, 4, 64),      # eight images per tile
+    (2, 32, 32, 32),     # Cin < 64: zero-filled k-block per tap
+    (1, 64, 64, 64),     # 2 rows x 64 per tile
+    (5, 1, 1, 64),       # degenerate 1x1 level
+])
+def test_upsample_conv_phase_collapsed(h, nb, hh, ww, c):
+    """Upsample.call (unet.py:44-47, autoencoder.py:152-155): ResizeNearestNeighbor x2 then conv3x3 SAME, computed
+    as four 2x2 phase convs over the source; the reference materialises the upsampled image.  The summed
+    phase weights are rounded to 16 bit once, so the comparison uses unrounded weights with a tolerance of a
+    few 16-bit ulps of the weights."""
+    rng = np.random.default_rng(nb * 100 + hh + c)
+    x = round16(rng.standard_normal((nb, hh, ww, c), dtype=np.float32), h.precision)
+    kern = rng.standard_normal((3, 3, c, c), dtype=np.float32) / np.float32(np.sqrt(9 * c))
+    bias = rng.standard_normal(c, dtype=np.float32)
+    got = h.test_resample_conv(x, kern, bias, 0)
+    ref = O.conv3x3(O.upsample_nn2(x), kern, bias)
+    assert got.shape == ref.shape
+    err = rel_l2(got, ref)
+    print(f"upconv {nb}x{hh}x{ww}x{c}: rel-L2 {err:.2e}")
+    assert err < (1e-3 if h.precision == "fp16" else 6e-3)
+
+
+@pytest.mark.parametrize("nb,hh,ww,cin,cout,mode", [
+    (2, 32, 32, 64, 64, 1), (2, 16, 16, 128, 64, 1), (3, 8, 8, 64, 128, 1), (16, 4, 4, 64, 64, 1), (4, 2, 2, 64, 64, 1),
+    (1, 64, 64, 32, 32, 1),
+    (2, 32, 32, 64, 64, 2), (3, 8, 8, 64, 128, 2), (1, 64, 64, 32, 64, 2), (4, 2, 2, 64, 64, 2),
+])
+def test_stride2_conv_through_strided_tma_map(h, nb, hh, ww, cin, cout, mode):
+    """Downsample: mode 1 = tf.pad (1,1) + conv3x3 stride 2 VALID (unet.py:22-27), mode 2 = tf.pad (0,1) + the same
+    (autoencoder.py:133-135), both without im2col: a TMA map with element stride 2, one shifted box per tap."""
+    rng = np.random.default_rng(nb * 100 + hh + cin + cout + mode)
+    x = rng.standard_normal((nb, hh, ww, cin), dtype=np.float32)
+    kern = rng.standard_normal((3, 3, cin, cout), dtype=np.float32) / np.float32(np.sqrt(9 * cin))
+    bias = rng.standard_normal(cout, dtype=np.float32)
+    got = h.test_resample_conv(x, kern, bias, mode)
+    xr, kr = round16(x, h.precision), round16(kern, h.precision)
+    ref = O.conv3x3(xr, kr, bias, stride=2) if mode == 1 else O.conv3x3_down_ae(xr, kr, bias)
+    assert got.shape == ref.shape
     err = np.abs(got - ref).max()
     assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
 

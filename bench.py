@@ -298,18 +298,21 @@ def main():
         hv.finalize()
 
     extra = {}
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gathered = None
+    gather_buf = None
+    if world > 1:
+        # NCCL communicator owned by the library (comm.cu); the id travels over a TCP rendezvous, not torch
+        parallel.init_comm(h, rank, world)
+        gather_buf = torch.empty((global_b, out_hw, out_hw, 3), dtype=torch.float32, device=dev)
 
     def gather(img_dev):
-        """The one collective of the path: all ranks' decoded images; returns (tensor, ms)."""
+        """The one collective of the path (SURVEY 8e): ldm_allgather_images over NCCL on the library stream;
+        returns (gathered tensor, device ms from CUDA events around the collective)."""
         if world == 1:
             return img_dev, 0.0
-        ev0.record()
-        out = parallel.allgather_images(img_dev, global_b)
-        ev1.record()
-        torch.cuda.synchronize()
-        return out, ev0.elapsed_time(ev1)
+        h.allgather(lib.DevPtr(img_dev.data_ptr(), img_dev.shape), img_dev.numel(),
+                    lib.DevPtr(gather_buf.data_ptr(), gather_buf.shape))
+        return gather_buf, h.timing_ex("gather")
 
     if name == "c5":
         # ------------------------------------------------------------------ decode-only workload
@@ -442,7 +445,7 @@ def main():
                        "parallelism": f"dp{world} (sample-sharded weight replicas, no collective inside the loop)",
                        "l2": "not flushed explicitly: every UNet step streams 1.75 GB of 16-bit weights plus "
                              "activations far larger than the 126 MB L2",
-                       "timing": "CUDA events on the library stream (+ torch events for the all-gather), max over ranks"},
+                       "timing": "CUDA events on the library stream (loop, decode, NCCL all-gather), max over ranks"},
             "wall_ms_per_step": wall_ms / args.steps,
             "model_tflops_per_gpu": value * gflop_per_image / 1e3 / world,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -79,7 +79,8 @@ LDM_API int ldm_destroy(ldm_handle* h);
  * for the checkpoint reader (replaces tf.train.Checkpoint.restore, run_ldm_sampler.py:70-75). */
 LDM_API int ldm_crc32c(const void* data, unsigned long long n, unsigned int crc, unsigned int* out);
 
-/* Weights.  model: 0 = text transformer, 1 = unet, 2 = autoencoder (decode side).
+/* Weights.  model: 0 = text transformer, 1 = unet, 2 = autoencoder (decode side: [codebook,] post_quant_conv, decoder),
+ * 3 = autoencoder (encode side: encoder, quant_conv; the flat order of a model on which only encode() ran).
  * index = position in the flat Keras weight list (layer.weights order; the order
  * convert_ckpt_pytorch_to_tf2.py:395-424 feeds set_weights).  Replaces
  * tf.train.Checkpoint(...).restore (run_ldm_sampler.py:70-75). */
@@ -130,12 +131,37 @@ LDM_API int ldm_sample(ldm_handle* h, const float* x_init, const float* noise, i
 LDM_API int ldm_decode(ldm_handle* h, const float* z, int b, int hh, int ww, float div, float* images_out,
                int64_t* idx_out);
 
+/* AutoencoderKL.encode (autoencoder.py:354-359): images [b,hh,ww,3] -> moments [b,hh/f,ww/f,2*latent_channels]
+ * (mean | logvar of the diagonal Gaussian); AutoencoderVQ.encode(only_encode=True) (autoencoder.py:421-425):
+ * -> [b,hh/f,ww/f,latent_channels].  f = 2^(num_multipliers-1). */
+LDM_API int ldm_encode_images(ldm_handle* h, const float* images, int b, int hh, int ww, float* moments_out);
+/* LatentDiffusionModel.get_latents (model_runners.py:602-625): KL: scale_factor * (mean + exp(logvar / 2) * noise),
+ * noise [b,hh/f,ww/f,latent_channels] replaces the tf.random.normal of DiagonalGaussian.sample (NULL: the mean);
+ * VQ: scale_factor * encode(only_encode=True). */
+LDM_API int ldm_get_latents(ldm_handle* h, const float* images, const float* noise, int b, int hh, int ww, float scale_factor,
+                            float* latents_out);
+
 /* VectorQuantizer.__call__ value path (quantize.py:57-78): rows of 4 floats (divided by div
  * first) -> indices int64 [rows] (first minimum wins, like tf.argmin) and quantized rows. */
 LDM_API int ldm_vq_argmin(ldm_handle* h, const float* z, int64_t rows, float div, int64_t* idx_out, float* zq_out);
 
 /* tensor_to_image (run_ldm_sampler.py:18-25): per-image min-max to uint8. */
 LDM_API int ldm_tensor_to_image(ldm_handle* h, const float* images, int n, int64_t elems_per_image, uint8_t* out);
+
+/* Multi-GPU: one process per GPU, one handle each, samples sharded, no collective inside the loop;
+ * ONE all-gather of the decoded images over NCCL / NVLink on the handle's stream.  NCCL is dlopen'ed at the first
+ * call (nccl_lib: path of libnccl.so.2 or NULL for the default search).  Rank 0 makes the 128-byte id
+ * (ncclGetUniqueId) and hands it to the other ranks by any host channel (ldm_tf2_b200/parallel.py: a TCP
+ * rendezvous on MASTER_ADDR / MASTER_PORT); every rank then calls ldm_comm_init.
+ * ldm_allgather_images: every rank contributes count_per_rank floats (its [b/N,8hh,8ww,3] shard, padded to the
+ * largest shard), and receives world * count_per_rank floats in rank order; host or device pointers. */
+LDM_API int ldm_comm_unique_id(const char* nccl_lib, char id_out[128]);
+LDM_API int ldm_comm_init(ldm_handle* h, const char* nccl_lib, const char id[128], int rank, int world);
+LDM_API int ldm_allgather_images(ldm_handle* h, const float* local, int64_t count_per_rank, float* global);
+LDM_API int ldm_comm_destroy(ldm_handle* h);
+
+/* CUDA-event time (ms) of the last "loop", "step", "decode", "encode" or "gather" interval on the handle's stream. */
+LDM_API int ldm_get_timing_ex(ldm_handle* h, const char* what, float* ms);
 
 /* Timing of the last ldm_sample / ldm_decode call, CUDA events on the handle's stream (ms),
  * and the number of kernels this handle has launched so far. */
@@ -150,7 +176,9 @@ LDM_API int ldm_profile_unet_step(ldm_handle* h, int b, int hh, int ww, int iter
                                   float* step_ms, int* gemm_launches_per_step, double* gemm_flops_per_step);
 
 /* GEMM / conv microbenchmark on zero-filled device buffers (dbg bits: 1 no TMA, 2 no MMA,
- * 4 no stores, 16 single-CTA kernel, 32 CTA-pair kernel, 8..11 activation, 12..15 split-K override). */
+ * 4 no stores, 8 fragment-layout epilogue for 16-bit outputs, 16 single-CTA kernel, 32 CTA-pair kernel, 64 / 128 two / one CTA per SM,
+ * bits 8..11 activation, 12..15 split-K override).  with_residual: 1 fp32 residual + fp32 out, 2 16-bit residual in
+ * place, 3 the same + row statistics. */
 LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, int dbg, int conv, int hw,
                            int iters, float* avg_ms, long long* trace_host, int with_residual);
 /* GroupNorm(32)+SiLU microbenchmark over more distinct [n, hw, c] fp32 buffers than fit in L2:

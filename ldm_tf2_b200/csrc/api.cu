@@ -41,6 +41,8 @@ struct EventPair {
 static thread_local std::string g_err;
 
 const char* ldm_last_error(void) { return g_err.c_str(); }
+ldm::Model* ldm_handle_model(ldm_handle* h) { return h ? h->model : nullptr; }
+void ldm_set_error(const char* msg) { g_err = msg ? msg : ""; }
 int ldm_version(void) { return 200; }
 
 int ldm_device_synchronize(void) {
@@ -136,7 +138,7 @@ int ldm_destroy(ldm_handle* h) {
 int ldm_num_weights(ldm_handle* h, int model, int* count) {
   API_BEGIN
   NEED_ANY(h);
-  LDM_CHECK(model >= 0 && model < 3 && count, "ldm_num_weights: bad argument");
+  LDM_CHECK(model >= 0 && model < Model::NUM_MODELS && count, "ldm_num_weights: bad argument");
   *count = h->model->num_weights(model);
   API_END
 }
@@ -144,7 +146,7 @@ int ldm_num_weights(ldm_handle* h, int model, int* count) {
 int ldm_weight_info(ldm_handle* h, int model, int index, const char** name, int* ndim, int shape[4]) {
   API_BEGIN
   NEED_ANY(h);
-  LDM_CHECK(model >= 0 && model < 3, "ldm_weight_info: model");
+  LDM_CHECK(model >= 0 && model < Model::NUM_MODELS, "ldm_weight_info: model");
   LDM_CHECK(index >= 0 && index < h->model->num_weights(model), "ldm_weight_info: index");
   const Slot& s = h->model->slots[model][index];
   if (name) *name = s.name.c_str();
@@ -231,6 +233,23 @@ int ldm_decode(ldm_handle* h, const float* z, int b, int hh, int ww, float div, 
   API_END
 }
 
+int ldm_encode_images(ldm_handle* h, const float* images, int b, int hh, int ww, float* moments_out) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(images && moments_out && b > 0 && hh > 0 && ww > 0, "ldm_encode_images: bad argument");
+  h->model->encode_images(images, b, hh, ww, nullptr, 1.0f, moments_out, nullptr);
+  API_END
+}
+
+int ldm_get_latents(ldm_handle* h, const float* images, const float* noise, int b, int hh, int ww, float scale_factor,
+                    float* latents_out) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(images && latents_out && b > 0 && hh > 0 && ww > 0, "ldm_get_latents: bad argument");
+  h->model->encode_images(images, b, hh, ww, noise, scale_factor, nullptr, latents_out);
+  API_END
+}
+
 int ldm_vq_argmin(ldm_handle* h, const float* z, int64_t rows, float div, int64_t* idx_out, float* zq_out) {
   API_BEGIN
   NEED(h);
@@ -244,6 +263,21 @@ int ldm_tensor_to_image(ldm_handle* h, const float* images, int n, int64_t per, 
   NEED(h);
   LDM_CHECK(images && out && n > 0 && per > 0, "ldm_tensor_to_image: bad argument");
   h->model->tensor_to_image(images, n, per, out);
+  API_END
+}
+
+int ldm_get_timing_ex(ldm_handle* h, const char* what, float* ms) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(what && ms, "ldm_get_timing_ex: null argument");
+  const std::string w(what);
+  Model& m = *h->model;
+  if (w == "loop") *ms = m.last_loop_ms;
+  else if (w == "step") *ms = m.last_step_ms;
+  else if (w == "decode") *ms = m.last_decode_ms;
+  else if (w == "encode") *ms = m.last_encode_ms;
+  else if (w == "gather") *ms = m.last_gather_ms;
+  else throw Error("ldm_get_timing_ex: unknown interval '" + w + "' (loop, step, decode, encode, gather)");
   API_END
 }
 
@@ -410,9 +444,12 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.dbg = dbg & 15;
   op.out_bf16 = o;
   float* of = nullptr;
-  if (with_residual) {
+  if (with_residual == 1) {          // fp32 residual stream: fp32 + 16-bit outputs
     of = sc.get<float>((size_t)rows * n, true);
     op.out_f32 = of; op.residual = of;
+  } else if (with_residual >= 2) {   // the transformer block's 16-bit stream, updated in place (3: + row statistics)
+    op.res16 = o;
+    if (with_residual == 3) op.rs_out = sc.get<long long>((size_t)rows * 2, true);
   }
   long long* trace_d = trace_host ? sc.get<long long>((size_t)148 * 64 * 16, true) : nullptr;
   h->model->ensure_arena((size_t)512 << 20);
@@ -562,7 +599,7 @@ LDM_API int ldm_test_ln_linear(ldm_handle* h, const float* a, const float* w0, c
   launch_pack_weight(up_f32(s, e, w0, (size_t)k0 * c), k0, c, w0t, k0, 0, 0, e.fp16, e.stream);
   float* b0d = b0 ? up_f32(s, e, b0, c) : nullptr;
   bf16* y = s.get<bf16>((size_t)rows * c);
-  float* st = s.get<float>((size_t)rows * 2, true);
+  long long* st = s.get<long long>((size_t)rows * 2, true);
   m.ensure_arena((size_t)256 << 20);
   e.arena.reset();
   {
@@ -624,8 +661,14 @@ LDM_API int ldm_test_ln_linear(ldm_handle* h, const float* a, const float* w0, c
   }
   std::vector<uint16_t> raw((size_t)rows * n);
   CUDA_CHECK(cudaMemcpyAsync(raw.data(), od, raw.size() * 2, cudaMemcpyDefault, e.stream));
-  if (stats_out) CUDA_CHECK(cudaMemcpyAsync(stats_out, st, (size_t)rows * 2 * sizeof(float), cudaMemcpyDefault, e.stream));
+  std::vector<long long> sth((size_t)rows * 2);
+  CUDA_CHECK(cudaMemcpyAsync(sth.data(), st, sth.size() * sizeof(long long), cudaMemcpyDefault, e.stream));
   e.sync();
+  if (stats_out)   // fixed point -> float: (sum, sum of squares)
+    for (int r = 0; r < rows; ++r) {
+      stats_out[2 * r] = (float)((double)sth[2 * (size_t)r] / 16777216.0);
+      stats_out[2 * r + 1] = (float)((double)sth[2 * (size_t)r + 1] / 65536.0);
+    }
   for (size_t i = 0; i < raw.size(); ++i) out[i] = widen16(raw[i], e.fp16);
   API_END
 }

@@ -462,14 +462,11 @@ __device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
   return __bfloat16_as_ushort(__float2bfloat16(v));
 }
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
-  if (fp16) {
-    // saturate instead of overflowing to inf: clamp the converted pair (inf -> 65504)
-    const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
-    const __half2 h = __hmin2(__hmax2(__floats2half2_rn(a, b), __hneg2(lim)), lim);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&v);
+  uint32_t r;
+  // one F2FP each; fp16 saturates to +-65504 instead of overflowing to inf (a is the low half)
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 // two packed 16-bit operand values -> fp32
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {

@@ -36,6 +36,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// the 12 instantiations of the GEMM kernel: CTA pair or not, 8 / 4 epilogue warps, optional epilogue flavours
+// (0 = default, 1 = + fragment-layout path, 2 = + TMA-store path; the last two are A/B switches)
+typedef void (*GemmKernel)(const GemmParams);
+static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi) {
+#define LDM_K(P, E) (epi == 0 ? (GemmKernel)implicit_gemm_kernel<P, E, 0> : epi == 1 ? (GemmKernel)implicit_gemm_kernel<P, E, 1> \
+                                                                                     : (GemmKernel)implicit_gemm_kernel<P, E, 2>)
+  if (pair) return ew == 4 ? LDM_K(1, 4) : LDM_K(1, 8);
+  return ew == 4 ? LDM_K(0, 4) : LDM_K(0, 8);
+#undef LDM_K
+}
+
 Engine::Engine(int dev) : device(dev) {
   if (dev == -1) return;   // describe-only engine: weight names / shapes without a device
   int count = 0;
@@ -53,14 +64,12 @@ Engine::Engine(int dev) : device(dev) {
   cudaDriverEntryPointQueryResult qres;
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  110 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(implicit_gemm_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  110 * 1024));
+  for (int epi = 0; epi < 3; ++epi) {
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 4, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 4, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  }
   // measured -14 % on the 16384-row projections in isolation, -0.7 % per UNet step (profiles/ab_step.py)
   { const char* e = getenv("LDM_B200_EW4"); ew4_default = !(e && e[0] == '0'); }
   { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
@@ -320,6 +329,9 @@ void Engine::gemm(const GemmOp& op) {
               (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 7) == 0) &&
               (!op.out_f32 || (reinterpret_cast<uintptr_t>(op.out_f32) & 15) == 0) &&
               (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 7) == 0);
+  p.epi_vec16 = ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 7) == 0 &&
+                (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 15) == 0) &&
+                (!op.out_bf16 || (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0);
   // ---- epilogue
   p.bias = op.bias; p.bias2 = op.bias2; p.bias2_stride = op.bias2_stride; p.bias2_by_img = op.bias2_by_img;
   p.step_ptr = op.step_ptr; p.act = op.act; p.alpha = op.alpha; p.residual = op.residual;
@@ -327,10 +339,13 @@ void Engine::gemm(const GemmOp& op) {
   p.res16 = op.res16; p.rs_out = op.rs_out; p.ln_stats = op.ln_stats; p.ln_cs = op.ln_cs;
   p.ln_inv_c = op.ln_c > 0 ? 1.0f / (float)op.ln_c : 0.f; p.ln_eps = op.ln_eps;
   {
-    // 16-bit-only outputs: the fragment-layout epilogue (sector-complete 32-byte row pieces, no shared-memory
-    // transposition) beats the staged one; fp32 outputs keep the staged path (gemm.cuh)
-    static const bool no_frag = getenv("LDM_B200_FRAG16") && getenv("LDM_B200_FRAG16")[0] == '0';
-    p.frag_pref = (geglu || (!op.out_f32 && op.out_bf16 && !no_frag)) ? 1 : 0;
+    // 16-bit-only outputs default to the lean row-owner epilogue (one tcgen05.ld.32x32b.x32 per chunk, four 16-byte
+    // stores of the thread's own row: ~4x fewer instructions than the fragment-layout path, and the epilogue is
+    // issue-bound with 8 warps per SM -- profiles/r2_trace_epilogue.txt).  The fragment layout (sector-complete
+    // 32-byte row pieces) stays selectable for A/B runs: LDM_B200_FRAG16=1 / LDM_B200_FRAG_GEGLU=1.
+    static const bool frag16 = getenv("LDM_B200_FRAG16") && getenv("LDM_B200_FRAG16")[0] == '1';
+    static const bool frag_geglu = getenv("LDM_B200_FRAG_GEGLU") && getenv("LDM_B200_FRAG_GEGLU")[0] == '1';
+    p.frag_pref = ((geglu && frag_geglu) || (!geglu && !op.out_f32 && op.out_bf16 && frag16) || ((op.dbg & 8) && (geglu || (!op.out_f32 && op.out_bf16)))) ? 1 : 0;
   }
   p.os_n = op.os_n; p.os_y = op.os_y; p.os_x = op.os_x; p.os_phase_y = op.os_phase_y; p.os_phase_x = op.os_phase_x;
   p.out_tr = op.out_tr; p.tr_col0 = op.tr_col0; p.ts_n = op.ts_n; p.ts_y = op.ts_y; p.ts_c = op.ts_c;
@@ -377,13 +392,11 @@ void Engine::gemm(const GemmOp& op) {
     if (o == "res" && !is_conv && op.residual) return;
     if (o == "split" && splits > 1) return;
   }
-  if (ew4) {
-    if (pair) launch_pair(implicit_gemm_kernel<1, 4>, dim3(ctas), dim3(GEMM_THREADS_EW4), (size_t)smem, stream, p);
-    else launch_pdl_kind(2, implicit_gemm_kernel<0, 4>, dim3(ctas), dim3(GEMM_THREADS_EW4), (size_t)smem, stream, p);
-  } else {
-    if (pair) launch_pair(implicit_gemm_kernel<1, 8>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
-    else launch_pdl_kind(2, implicit_gemm_kernel<0, 8>, dim3(ctas), dim3(GEMM_THREADS), (size_t)smem, stream, p);
-  }
+  const int epi = p.tma_epi ? 2 : (p.frag_pref ? 1 : 0);
+  const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, ew4 ? 4 : 8, epi);
+  const int threads = ew4 ? GEMM_THREADS_EW4 : GEMM_THREADS;
+  if (pair) launch_pair(kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
+  else launch_pdl_kind(2, kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
   CUDA_CHECK(cudaGetLastError());
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));

@@ -56,10 +56,10 @@ struct GemmOp {
   float alpha = 1.0f;
   const float* residual = nullptr;
   const bf16* res16 = nullptr;        // 16-bit residual (same addressing as the outputs; may alias out_bf16)
-  const float* ln_stats = nullptr;    // folded LayerNorm: per-row (sum, sum sq) of the raw A rows, [rows][2]
+  const long long* ln_stats = nullptr;  // folded LayerNorm: per-row fixed-point (sum, sum sq) of the raw A rows, [rows][2]
   const float* ln_cs = nullptr;       //   column sums of the gamma-scaled weights, [gemm_n] in packed row order
   int ln_c = 0; float ln_eps = 1e-5f; //   row width of the normalised tensor, epsilon
-  float* rs_out = nullptr;            // per-row (sum, sum sq) of the final output, [rows][2], accumulated atomically
+  long long* rs_out = nullptr;        // per-row fixed-point (sum, sum sq) of the final output, [rows][2], integer atomics (deterministic)
   float* out_f32 = nullptr;
   bf16* out_bf16 = nullptr;
   long long os_n = 0, os_y = 0, os_x = 0, os_phase_y = 0, os_phase_x = 0;

@@ -82,6 +82,7 @@ struct GemmParams {
   int epi_half_stride, epi_r_off, epi_o32_off, epi_o16_off;  // layout of one half's area (TMA epilogue)
   int off32;                // 1: every output element offset fits in 31 bits
   int epi_vec;              // 1: all output offsets are multiples of 4 elements -> coalesced vector epilogue
+  int epi_vec16;            // 1: ... multiples of 8 and 16-byte aligned 16-bit pointers -> direct 16-byte row accesses
   int fp16;                 // operand / 16-bit output format: 0 = bf16, 1 = fp16
   int a_swap[3];            // tensor-map dim order (c, y, x, n) instead of (c, x, y, n)
   int a_stride[3];          // spatial element stride of the map (2: stride-2 conv; box origin = stride * tile origin)
@@ -99,10 +100,13 @@ struct GemmParams {
   // LayerNorm folded into this GEMM (unet.py:304-314): A holds the RAW rows y, the weights carry gamma, and
   //   out = rstd_r * (acc - mean_r * ln_cs[col]) + bias[col],   bias = beta.W + b precomputed,
   // with (sum, sum of squares) of every row in ln_stats[row][2] (written by the producer's rs_out)
-  const float* ln_stats;
+  const long long* ln_stats;
   const float* ln_cs;       // [gemm_n] column sums of the gamma-scaled 16-bit weights (packed row order)
   float ln_inv_c, ln_eps;
-  float* rs_out;            // [rows][2]: atomically accumulated (sum, sum of squares) of the final output rows
+  // [rows][2] 64-bit FIXED-POINT (sum * 2^24, sum of squares * 2^16) of the final output rows, accumulated with
+  // integer atomics: integer addition is associative, so the totals -- and everything computed from them -- are
+  // bit-reproducible whatever order the tiles finish in (float atomics are not)
+  long long* rs_out;
   int frag_pref;            // 16-bit-only outputs: take the fragment-layout epilogue where a tile allows it
   float* out_f32;
   bf16* out_bf16;
@@ -115,6 +119,14 @@ struct GemmParams {
 };
 
 #if defined(__CUDACC__) && defined(LDM_GEMM_IMPL)
+
+// fixed-point scales of the row statistics (GemmParams::rs_out): |sum| < 2^39, sum of squares < 2^47
+constexpr float RS_SCALE_SUM = 16777216.f, RS_INV_SUM = 1.f / 16777216.f;
+constexpr float RS_SCALE_SQ = 65536.f, RS_INV_SQ = 1.f / 65536.f;
+__device__ __forceinline__ void rs_add(long long* p, float s, float q) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(s * RS_SCALE_SUM));
+  atomicAdd(reinterpret_cast<unsigned long long*>(p) + 1, (unsigned long long)__float2ll_rn(q * RS_SCALE_SQ));
+}
 
 struct TileCoord {
   int img0, y0, x0, n0, phase, n_tile, split;
@@ -260,11 +272,28 @@ __device__ __forceinline__ void epi_store_staged32(const float* v, int col0, flo
 // 32 contiguous bytes (whole sectors) -- no shared-memory transposition (which cost ~1400 cycles of
 // smem bandwidth per tile).  ab4 = this thread's four rows' (scale, shift) of the folded LayerNorm (or
 // null); rs (or null) accumulates the four rows' (sum, sum of squares) of the final values.
+// The fragment epilogue's 16-bit residual of one chunk: 8 x 8 bytes per lane at the positions
+// epi_chunk_fragment stores to.  Issued one chunk ahead (the first before the accumulator is even ready): the
+// residual does not depend on the MMA, and its L2 latency is what a short-K tile's epilogue otherwise waits for.
+__device__ __forceinline__ void frag_load_res16(const bf16* res16, const int (&rowoff4)[4], int lane, int col0,
+                                                uint2 (&r)[4][2]) {
+  const int cq = 2 * (lane & 3);
+  const bool odd = lane & 1;
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int k = 2 * h2;
+    const int wc = col0 + (odd ? 8 * (k + 1) + cq - 2 : 8 * k + cq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j][h2] = *reinterpret_cast<const uint2*>(res16 + (rowoff4[j] + wc));
+  }
+}
+
 template <bool GEGLU>
 __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t t_lane0, int c, int hcols, int col0,
-                                                   const float* bias_s, const float* cs_s, const float2* ab4,
-                                                   const int* rowoff4, int lane, int act, float* o32, bf16* o16,
-                                                   const float* resid, const bf16* res16, float* rs) {
+                                                   const float* bias_s, const float* cs_s, const float2 (&ab4)[4], bool ln,
+                                                   const int (&rowoff4)[4], int lane, int act, float* o32, bf16* o16,
+                                                   const float* resid, const uint2 (&r16)[4][2], bool use_r16, float (&rs)[8],
+                                                   bool use_rs) {
   uint32_t ra[16], rb[16], ga[16], gb[16];
   tmem_ld_16x256b_x4(t_lane0 + (uint32_t)c, ra);                      // lanes +0..15
   tmem_ld_16x256b_x4(t_lane0 + (16u << 16) + (uint32_t)c, rb);        // lanes +16..31
@@ -281,7 +310,7 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
     float x[8] = {__uint_as_float(ra[4 * k]), __uint_as_float(ra[4 * k + 1]), __uint_as_float(ra[4 * k + 2]),
                   __uint_as_float(ra[4 * k + 3]), __uint_as_float(rb[4 * k]), __uint_as_float(rb[4 * k + 1]),
                   __uint_as_float(rb[4 * k + 2]), __uint_as_float(rb[4 * k + 3])};
-    if (ab4) {
+    if (ln) {
       const float2 cs = *reinterpret_cast<const float2*>(cs_s + c + 8 * k + cq);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -297,7 +326,7 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
       float g[8] = {__uint_as_float(ga[4 * k]), __uint_as_float(ga[4 * k + 1]), __uint_as_float(ga[4 * k + 2]),
                     __uint_as_float(ga[4 * k + 3]), __uint_as_float(gb[4 * k]), __uint_as_float(gb[4 * k + 1]),
                     __uint_as_float(gb[4 * k + 2]), __uint_as_float(gb[4 * k + 3])};
-      if (ab4) {
+      if (ln) {
         const float2 cg = *reinterpret_cast<const float2*>(cs_s + hcols + c + 8 * k + cq);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -354,21 +383,16 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
         w[j][h2].x += r[j][h2].x; w[j][h2].y += r[j][h2].y; w[j][h2].z += r[j][h2].z; w[j][h2].w += r[j][h2].w;
       }
   }
-  if (res16) {
-    uint2 r[4][2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) r[j][h2] = *reinterpret_cast<const uint2*>(res16 + (rowoff4[j] + wcol[h2]));
+  if (use_r16) {   // 16-bit residual, loaded by the caller ahead of the accumulator (frag_load_res16)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const float2 lo = unpack16(r[j][h2].x, p.fp16), hi = unpack16(r[j][h2].y, p.fp16);
+        const float2 lo = unpack16(r16[j][h2].x, p.fp16), hi = unpack16(r16[j][h2].y, p.fp16);
         w[j][h2].x += lo.x; w[j][h2].y += lo.y; w[j][h2].z += hi.x; w[j][h2].w += hi.y;
       }
   }
-  if (rs) {
+  if (use_rs) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -406,9 +430,14 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 // the shared memory, so TWO CTAs (or CTA pairs) share an SM and one's latency-bound epilogue runs
 // under the other's -- the short-K projections of the transformers, whose epilogue (5-8 k cycles
 // per tile) outlasts the 2-3 k-cycle main loop.
-template <int PAIR, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
+// EPI selects which optional epilogue flavours are compiled in (each costs registers in every other path):
+// bit 0 = fragment-layout path (A/B switch), bit 1 = TMA-store path (A/B switch); the default kernels have neither.
+template <int PAIR, int EW, int EPI>
+// register budget: 2 CTAs x 192 threads x 168 (EW = 4) or 1 CTA x 320 threads x 200 (EW = 8) of the SM's 64 K registers
+// (__launch_bounds__(320, 1) makes ptxas stop at 168)
+__global__ void __maxnreg__(EW == 4 ? 168 : 200)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool HAS_FRAG = (EPI & 1) != 0, HAS_TMA = (EPI & 2) != 0;
   constexpr int NHALF = EW / 4;          // column-chunk interleave between the warps of a TMEM lane quadrant
   constexpr int ETHREADS = 32 * EW;      // epilogue threads
   long long* const trace_base = blockIdx.x < 148 ? p.trace : nullptr;   // the trace buffer has 148 CTA slots
@@ -624,14 +653,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       const long long tr_row_off = (long long)img * p.ts_n + (long long)yq * p.ts_y;
       const bf16* res16 = split ? nullptr : p.res16;
-      float* rs_out = split ? nullptr : p.rs_out;
+      long long* rs_out = split ? nullptr : p.rs_out;
       const bool ln = p.ln_stats != nullptr && !split;
       const long long grow = ((long long)img * p.H + yq) * p.W + xq;   // global row id: row statistics in / out
       float ln_a = p.alpha, ln_b = 0.f;   // value = acc * ln_a + (cs * ln_b + bias)
       if (ln && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * grow);
-        const float mean = st.x * p.ln_inv_c;
-        const float var = fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_c), 0.f);
+        const longlong2 st = *reinterpret_cast<const longlong2*>(p.ln_stats + 2 * grow);
+        const float mean = (float)st.x * (RS_INV_SUM * p.ln_inv_c);
+        const float var = fmaxf(fmaf(-mean, mean, (float)st.y * (RS_INV_SQ * p.ln_inv_c)), 0.f);
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -mean * ln_a;
       }
@@ -669,7 +698,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         grow_s[r] = (int)grow;
       }
       // vector path: aligned 32-bit offsets and every row of this warp inside the tensor
-      const bool use_tma = p.tma_epi && !split;
+      const bool use_tma = HAS_TMA && p.tma_epi && !split;
       const bool warp_rows_ok = !use_tma && __all_sync(0xffffffffu, row_ok) && p.epi_vec && p.off32;
       // vectorised V^T stores: the warp's rows are 32 consecutive, valid x of one (img, y), 16-byte aligned
       const bool tr_vec_ok = p.out_tr && !use_tma && (p.w_b & 31) == 0 && __all_sync(0xffffffffu, row_ok) &&
@@ -686,10 +715,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       // (measured: 15 % faster for the GEGLU epilogue -- 16-bit output only, two accumulator reads per
       // value -- and 5-10 % slower for fp32 + residual outputs, whose 32-byte row pieces cost more L2
       // transactions than the transposition costs shared-memory bandwidth; dbg bit 3 forces it for A/B runs)
-      // (dbg bit 3 forces the row-owner paths for A/B runs and tests)
+      // (opt-in: frag_pref comes from LDM_B200_FRAG16 / LDM_B200_FRAG_GEGLU or dbg bit 3; the default for 16-bit
+      // outputs is the lean row-owner path below, which needs a quarter of the instructions)
       const bool tile_tr = p.out_tr && t.n0 >= p.tr_col0;
-      const bool frag = (geglu || p.frag_pref) && warp_rows_ok && !tile_tr && !(p.block_n & 31) && !bias2_row &&
-                        (geglu ? (t.n_tile + 1) * (p.block_n >> 1) <= p.N : t.n0 + p.block_n <= p.N) && !(p.dbg & 8);
+      const bool frag = HAS_FRAG && p.frag_pref && warp_rows_ok && !tile_tr && !(p.block_n & 31) && !bias2_row &&
+                        (geglu ? (t.n_tile + 1) * (p.block_n >> 1) <= p.N : t.n0 + p.block_n <= p.N);
       int rowoff4[4];
       float2 ab4[4];
       float rs4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -714,6 +744,24 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       }
+      uint2 rnext[4][2];
+      const int col_base = geglu ? t.n_tile * (p.block_n >> 1) : t.n0;   // first output column of the tile
+      const bool pre16 = frag && res16 != nullptr;
+      if (pre16 && half < n32_all) frag_load_res16(res16, rowoff4, lane, col_base + half * 32, rnext);
+      // Row-owner epilogue with direct 16-byte accesses: this thread = one row, a chunk = 64 contiguous bytes of
+      // its 16-bit residual / output.  The residual of a chunk is loaded one chunk ahead (the first one before the
+      // accumulator is ready): it does not depend on the MMA, and its L2 latency is otherwise what the tile waits for.
+      const bool d16 = !frag && p.epi_vec16 && !use_tma;
+      const bool r16v = d16 && res16 != nullptr && row_ok;
+      const bf16* r16_row = r16v ? res16 + row_off : nullptr;
+      uint4 rn16[4];
+      {
+        const int c0 = col_base + half * 32;
+        if (r16v && half < n32_all && c0 + 32 <= p.N && !(p.out_tr && c0 >= p.tr_col0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + c0 + 8 * j);
+        }
+      }
       mbar_wait_a(tfull0 + as * 8, aphase);
       tc_fence_after();
       if (tre) tre[5] = clock64();
@@ -724,14 +772,34 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int ci = half; ci < n32; ci += NHALF, ++kch) {
         const int c = ci * 32;
         if (frag) {
-          if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, t.n_tile * hcols + c, bias_s, cs_s, ln ? ab4 : nullptr, rowoff4, lane, act, o32, o16, resid, res16, rs_out ? rs4 : nullptr);
-          else epi_chunk_fragment<false>(p, t_base, c, hcols, t.n0 + c, bias_s, cs_s, ln ? ab4 : nullptr, rowoff4, lane, act, o32, o16, resid, res16, rs_out ? rs4 : nullptr);
+          uint2 rcur[4][2];
+          if (pre16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { rcur[j][0] = rnext[j][0]; rcur[j][1] = rnext[j][1]; }
+            if (ci + NHALF < n32) frag_load_res16(res16, rowoff4, lane, col_base + (ci + NHALF) * 32, rnext);
+          }
+          if (geglu) epi_chunk_fragment<true>(p, t_base, c, hcols, col_base + c, bias_s, cs_s, ab4, ln, rowoff4, lane, act, o32, o16, resid, rcur, pre16, rs4, rs_out != nullptr);
+          else epi_chunk_fragment<false>(p, t_base, c, hcols, col_base + c, bias_s, cs_s, ab4, ln, rowoff4, lane, act, o32, o16, resid, rcur, pre16, rs4, rs_out != nullptr);
           if (tre && ci < 6) tre[9 + ci] = clock64();
           continue;
         }
         uint32_t rr[32];
         float acc[32];
-        int col0;   // first output column of the chunk
+        const int col0 = col_base + c;   // first output column of the chunk
+        const bool to_tr = p.out_tr && col0 >= p.tr_col0;
+        const bool full = col0 + 32 <= p.N;
+        // this chunk's prefetched residual; issue the next chunk's loads before touching the accumulator
+        uint4 rc16[4];
+        const bool have16 = r16v && full && !to_tr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rc16[j] = rn16[j];
+        {
+          const int c1 = col_base + (ci + NHALF) * 32;
+          if (r16v && ci + NHALF < n32 && c1 + 32 <= p.N && !(p.out_tr && c1 >= p.tr_col0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + c1 + 8 * j);
+          }
+        }
         tmem_ld_x32(t_base + (uint32_t)c, rr);
         if (geglu) {
           // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates (unet.py:323-324)
@@ -739,29 +807,34 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float ba = bias_s[c + j], bg = bias_s[hcols + c + j];
-            if (ln) { ba = fmaf(cs_s[c + j], ln_b, ba); bg = fmaf(cs_s[hcols + c + j], ln_b, bg); }
-            acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, ba) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), ln_a, bg));
+          for (int j = 0; j < 32; j += 4) {
+            float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
+            float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
+            if (ln) {
+              const float4 ca = *reinterpret_cast<const float4*>(cs_s + c + j);
+              const float4 cg = *reinterpret_cast<const float4*>(cs_s + hcols + c + j);
+              ba.x = fmaf(ca.x, ln_b, ba.x); ba.y = fmaf(ca.y, ln_b, ba.y); ba.z = fmaf(ca.z, ln_b, ba.z); ba.w = fmaf(ca.w, ln_b, ba.w);
+              bg.x = fmaf(cg.x, ln_b, bg.x); bg.y = fmaf(cg.y, ln_b, bg.y); bg.z = fmaf(cg.z, ln_b, bg.z); bg.w = fmaf(cg.w, ln_b, bg.w);
+            }
+            acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, ba.x) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), ln_a, bg.x));
+            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), ln_a, ba.y) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 1]), ln_a, bg.y));
+            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), ln_a, ba.z) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 2]), ln_a, bg.z));
+            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, ba.w) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 3]), ln_a, bg.w));
           }
-          col0 = t.n_tile * hcols + c;
         } else {
           tmem_ld_wait();
-          if (ln) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, fmaf(cs_s[c + j], ln_b, bias_s[c + j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
-              acc[j] = fmaf(__uint_as_float(rr[j]), p.alpha, b.x);
-              acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), p.alpha, b.y);
-              acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), p.alpha, b.z);
-              acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), p.alpha, b.w);
+          for (int j = 0; j < 32; j += 4) {
+            float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
+            if (ln) {
+              const float4 cs = *reinterpret_cast<const float4*>(cs_s + c + j);
+              b.x = fmaf(cs.x, ln_b, b.x); b.y = fmaf(cs.y, ln_b, b.y); b.z = fmaf(cs.z, ln_b, b.z); b.w = fmaf(cs.w, ln_b, b.w);
             }
+            acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, b.x);
+            acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), ln_a, b.y);
+            acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), ln_a, b.z);
+            acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, b.w);
           }
-          col0 = t.n0 + c;
           if (bias2_row) {
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) acc[j] += __ldg(bias2_row + col0 + j);
@@ -775,29 +848,51 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
         if (tre && ci < 6) tre[9 + ci] = clock64();
-        const bool to_tr = p.out_tr && col0 >= p.tr_col0;
         // 16-bit residual and row statistics in the row-owner layout (this thread = one row, 32 columns)
-        if (res16 && row_ok && !to_tr) {
-          const bf16* rp = res16 + row_off + col0;
-          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+        if (have16) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-              const float2 f0 = unpack16(u.x, p.fp16), f1 = unpack16(u.y, p.fp16), f2 = unpack16(u.z, p.fp16),
-                           f3 = unpack16(u.w, p.fp16);
-              acc[j] += f0.x; acc[j + 1] += f0.y; acc[j + 2] += f1.x; acc[j + 3] += f1.y;
-              acc[j + 4] += f2.x; acc[j + 5] += f2.y; acc[j + 6] += f3.x; acc[j + 7] += f3.y;
+          for (int j = 0; j < 4; ++j) {
+            const float2 f0 = unpack16(rc16[j].x, p.fp16), f1 = unpack16(rc16[j].y, p.fp16),
+                         f2 = unpack16(rc16[j].z, p.fp16), f3 = unpack16(rc16[j].w, p.fp16);
+            acc[8 * j] += f0.x; acc[8 * j + 1] += f0.y; acc[8 * j + 2] += f1.x; acc[8 * j + 3] += f1.y;
+            acc[8 * j + 4] += f2.x; acc[8 * j + 5] += f2.y; acc[8 * j + 6] += f3.x; acc[8 * j + 7] += f3.y;
+          }
+        } else if (res16 && row_ok && !to_tr) {
+          const bf16* rp = res16 + row_off + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) acc[j] += load16(rp + j, p.fp16);
+        }
+        if (rs_out && !to_tr) {
+          if (full) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              s0 += acc[j]; s1 += acc[j + 1];
+              q0 = fmaf(acc[j], acc[j], q0); q1 = fmaf(acc[j + 1], acc[j + 1], q1);
             }
+            rs_s += s0 + s1; rs_q += q0 + q1;
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) acc[j] += load16(rp + j, p.fp16);
+              if (col0 + j < p.N) { rs_s += acc[j]; rs_q = fmaf(acc[j], acc[j], rs_q); }
           }
         }
-        if (rs_out && !to_tr) {
+        if (d16 && !o32 && o16 && !resid && !to_tr && full) {
+          // ---- lean path for 16-bit-only outputs: four 16-byte stores of this thread's own row
+          if (row_ok) {
+            bf16* op16 = o16 + row_off + col0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) { rs_s += acc[j]; rs_q = fmaf(acc[j], acc[j], rs_q); }
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack16(acc[8 * j], acc[8 * j + 1], p.fp16);
+              u.y = pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16);
+              u.z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
+              u.w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
+              *reinterpret_cast<uint4*>(op16 + 8 * j) = u;
+            }
+          }
+          continue;
         }
         if (use_tma && !to_tr) {
           // ---- TMA epilogue: x = acc (+ residual tile from smem) -> swizzled smem tiles -> TMA stores.
@@ -905,13 +1000,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int g = grow_s[quad * 32 + (lane >> 2) + 8 * j];
-              atomicAdd(rs_out + 2 * (long long)g, rs4[j]);
-              atomicAdd(rs_out + 2 * (long long)g + 1, rs4[4 + j]);
+              rs_add(rs_out + 2 * (long long)g, rs4[j], rs4[4 + j]);
             }
           }
         } else if (row_ok) {
-          atomicAdd(rs_out + 2 * grow, rs_s);
-          atomicAdd(rs_out + 2 * grow + 1, rs_q);
+          rs_add(rs_out + 2 * grow, rs_s, rs_q);
         }
       }
       tc_fence_before();
@@ -925,7 +1018,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
   }
 
-  if (p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // drain this half's TMA stores
+  if (HAS_TMA && p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // drain this half's TMA stores
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal / read it
   else __syncthreads();

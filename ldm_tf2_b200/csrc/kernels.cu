@@ -487,6 +487,7 @@ void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, f
 // weights in registers and walked over pixels (186 registers, one CTA per SM) measured 29 us SLOWER
 // inside the step graph and was dropped.
 // =====================================================================================
+template <int CIN>
 __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
                                const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
                                float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
@@ -502,7 +503,7 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int
     pix /= w;
     const int yy = (int)(pix % h);
     const int img = (int)(pix / h);
-    const float* src = x + (long long)(img % nsrc) * h * w * 4;
+    const float* src = x + (long long)(img % nsrc) * h * w * CIN;
     float acc[4] = {__ldg(bias + co), __ldg(bias + co + 1), __ldg(bias + co + 2), __ldg(bias + co + 3)};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -512,11 +513,17 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = xx + kx - 1;
         if (ix < 0 || ix >= w) continue;
-        const float4 v = *reinterpret_cast<const float4*>(src + ((long long)iy * w + ix) * 4);
-        const float in[4] = {v.x, v.y, v.z, v.w};
+        float in[CIN];
+        if (CIN == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((long long)iy * w + ix) * 4);
+          in[0] = v.x; in[1] = v.y; in[2] = v.z; in[CIN - 1] = v.w;
+        } else {
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const float4 kw = __ldg(reinterpret_cast<const float4*>(kernel + ((ky * 3 + kx) * 4 + ci) * cout + co));
+          for (int ci = 0; ci < CIN; ++ci) in[ci] = src[((long long)iy * w + ix) * CIN + ci];
+        }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float4 kw = __ldg(reinterpret_cast<const float4*>(kernel + ((ky * 3 + kx) * CIN + ci) * cout + co));
           acc[0] += in[ci] * kw.x;
           acc[1] += in[ci] * kw.y;
           acc[2] += in[ci] * kw.z;
@@ -536,11 +543,64 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int
 }
 
 void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel, const float* bias,
-                    int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st) {
+                    int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st, int cin) {
   LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
+  LDM_CHECK(cin == 4 || cin == 3, "conv_in: 3 (images) or 4 (latents) input channels");
   const long long total = (long long)n * h * w * (cout / 4);
-  launch_pdl(conv_in_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
-             out_bf16, fp16);
+  if (cin == 4)
+    launch_pdl(conv_in_kernel<4>, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
+               out_bf16, fp16);
+  else
+    launch_pdl(conv_in_kernel<3>, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
+               out_bf16, fp16);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// quant_conv (autoencoder.py:356,423): Dense z -> z over [rows, z] fp32, z = 4 or 8.
+__global__ void dense_small_kernel(const float* __restrict__ x, long long rows, int z, const float* __restrict__ k,
+                                   const float* __restrict__ b, float* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = rows * z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / z;
+    const int j = (int)(i % z);
+    float a = 0.f;
+    for (int c = 0; c < z; ++c) a += x[r * z + c] * __ldg(k + c * z + j);
+    out[i] = a + __ldg(b + j);
+  }
+}
+void launch_dense_small(const float* x, long long rows, int z, const float* kernel, const float* bias, float* out,
+                        cudaStream_t st) {
+  launch_pdl(dense_small_kernel, dim3(grid_for(rows * z, 256)), dim3(256), 0, st, x, rows, z, kernel, bias, out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// get_latents (model_runners.py:602-625).  KL (two_z = 1): moments [rows, 2z] = (mean | logvar);
+// DiagonalGaussian.sample = mean + exp(0.5 * logvar) * noise (noise null: the mean), then * scale_factor.
+// VQ: moments [rows, z] is the encoder output itself.  Separately rounded like the eager TF ops.
+__global__ void posterior_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, long long rows,
+                                        int z, int two_z, float scale, float* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = rows * z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / z;
+    const int j = (int)(i % z);
+    float v;
+    if (two_z) {
+      const float mean = moments[r * 2 * z + j];
+      v = mean;
+      if (noise) v = __fadd_rn(mean, __fmul_rn(expf(__fmul_rn(0.5f, moments[r * 2 * z + z + j])), noise[i]));
+    } else {
+      v = moments[i];
+    }
+    out[i] = __fmul_rn(scale, v);
+  }
+}
+void launch_posterior_sample(const float* moments, const float* noise, long long rows, int z, int two_z, float scale,
+                             float* out, cudaStream_t st) {
+  launch_pdl(posterior_sample_kernel, dim3(grid_for(rows * z, 256)), dim3(256), 0, st, moments, noise, rows, z, two_z, scale, out);
   CUDA_CHECK(cudaGetLastError());
 }
 

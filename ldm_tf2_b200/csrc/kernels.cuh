@@ -40,8 +40,13 @@ void launch_softmax(const float* s, bf16* p, long long rows, int tk, int tpad, f
 // x [nsrc,h,w,4] fp32; output rows n read image (n % nsrc) (virtual concat([xt,xt]),
 // model_runners.py:452).  pre: optional 4x4 Dense applied first (post_quant_conv,
 // autoencoder.py:362) with input scale.
-void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel /*[3,3,4,cout]*/,
-                    const float* bias, int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st);
+void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel /*[3,3,cin,cout]*/,
+                    const float* bias, int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st, int cin = 4);
+// quant_conv: Dense z -> z (autoencoder.py:356,423); posterior sample + scale (model_runners.py:602-625)
+void launch_dense_small(const float* x, long long rows, int z, const float* kernel, const float* bias, float* out,
+                        cudaStream_t st);
+void launch_posterior_sample(const float* moments, const float* noise, long long rows, int z, int two_z, float scale,
+                             float* out, cudaStream_t st);
 void launch_dense4(const float* x, long long rows, float in_scale, const float* kernel, const float* bias,
                    float* out, cudaStream_t st);
 

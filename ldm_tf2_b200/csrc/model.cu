@@ -215,6 +215,7 @@ Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) {
 }
 
 Model::~Model() {
+  if (comm_) comm_destroy();
   if (step_graph_) cudaGraphExecDestroy(step_graph_);
   for (auto& v : slots)
     for (auto& s : v)
@@ -383,6 +384,56 @@ void Model::build() {
     ae_conv_out_.bias = b.f32(d + "/_conv_out/bias", {3});
     ae_concat_bias_.assign(b.concat_bias.begin(), b.concat_bias.end());
   }
+  // ---------------- autoencoder encode side (autoencoder.py:198-249,322-331,395-405): flat Keras order of a
+  // model on which only encode() was called (oracle.ae_encoder_spec)
+  {
+    Builder b(*this, 3);
+    slots[3].reserve(1024);
+    const int z = cfg.latent_channels * (cfg.ae_kind == 0 ? 2 : 1), chn = cfg.ae_channels, L = cfg.ae_num_mult,
+              nb = cfg.ae_num_blocks;
+    enc_z_ = z;
+    const std::string e = "autoencoder/_encoder";
+    enc_conv_in_k_ = b.f32(e + "/_conv_in/kernel", {3, 3, 3, chn});
+    enc_conv_in_b_ = b.f32(e + "/_conv_in/bias", {chn});
+    enc_down_.reserve(64);
+    int hw = cfg.ae_build_hw << (L - 1), cur = chn, idx = 0;   // image side the checkpoint's Encoder was built at
+    for (int i = 0; i < L; ++i) {
+      const int co = chn * cfg.ae_mult[i];
+      for (int j = 0; j < nb; ++j) {
+        const std::string p = e + "/_down/" + std::to_string(idx++);
+        enc_down_.emplace_back();
+        EncStage& s = enc_down_.back();
+        s.kind = 0; s.hw = hw;
+        s.res = b.res(p + "/_residual", cur, co, 0, cur != co, true, nullptr, nullptr, 0);
+        s.attn = false;
+        if (cfg.ae_kind == 1)   // AutoencoderKL builds its Encoder with attention_resolutions=() (autoencoder.py:326)
+          for (int k = 0; k < cfg.ae_num_attn_res; ++k) s.attn |= (cfg.ae_attn_res[k] == hw);
+        if (s.attn) b.ae_attn(s.at, p + "/_attention", co);
+        cur = co;
+      }
+      if (i < L - 1) {
+        const std::string p = e + "/_down/" + std::to_string(idx++);
+        enc_down_.emplace_back();
+        EncStage& s = enc_down_.back();
+        s.kind = 1; s.c = cur; s.hw = hw;
+        s.down = b.lin(cur, 9 * cur);
+        b.pack(p + "/_conv/kernel", {3, 3, cur, cur}, 9 * cur, cur, s.down.wt, s.down.ld, 0, 0);
+        s.down.bias = b.f32(p + "/_conv/bias", {cur});
+        hw /= 2;
+      }
+    }
+    enc_mid1_ = b.res(e + "/_middle/_residual1", cur, cur, 0, false, true, nullptr, nullptr, 0);
+    b.ae_attn(enc_mid_attn_, e + "/_middle/_attention", cur);
+    enc_mid2_ = b.res(e + "/_middle/_residual2", cur, cur, 0, false, true, nullptr, nullptr, 0);
+    enc_out_gn_ = b.gnw(e + "/_group_norm", cur, 1e-6f);
+    enc_conv_out_ = b.lin(z, 9 * cur);
+    b.pack(e + "/_conv_out/kernel", {3, 3, cur, z}, 9 * cur, z, enc_conv_out_.wt, enc_conv_out_.ld, 0, 0);
+    enc_conv_out_.bias = b.f32(e + "/_conv_out/bias", {z});
+    quant_k_ = b.f32("autoencoder/_quant_conv/kernel", {z, z});
+    quant_b_ = b.f32("autoencoder/_quant_conv/bias", {z});
+    for (auto& pr : b.concat_bias) ae_concat_bias_.push_back(pr);   // q|k|v biases of the encoder's attention blocks
+    enc_concat_from_ = ae_concat_bias_.size() - b.concat_bias.size();
+  }
   step_dev_ = dev_alloc<int>(1, true);
 }
 
@@ -390,7 +441,7 @@ void Model::build() {
 // Weights
 // =====================================================================================
 void Model::set_weight(int model, int index, const float* src, const int* shape, int ndim) {
-  LDM_CHECK(model >= 0 && model < 3, "set_weight: model %d", model);
+  LDM_CHECK(model >= 0 && model < NUM_MODELS, "set_weight: model %d", model);
   LDM_CHECK(index >= 0 && index < (int)slots[model].size(), "set_weight: index %d out of range (model %d has %d)",
             index, model, (int)slots[model].size());
   Slot& s = slots[model][index];
@@ -445,7 +496,7 @@ void Model::set_weight(int model, int index, const float* src, const int* shape,
 void Model::finalize_weights() {
   CUDA_CHECK(cudaSetDevice(eng.device));
   // Only models whose weights were all provided are usable; partially set models are an error.
-  for (int mdl = 0; mdl < 3; ++mdl) {
+  for (int mdl = 0; mdl < NUM_MODELS; ++mdl) {
     int nset = 0;
     for (auto& s : slots[mdl]) nset += s.set ? 1 : 0;
     model_ready_[mdl] = nset == (int)slots[mdl].size();
@@ -461,10 +512,11 @@ void Model::finalize_weights() {
                                  cudaMemcpyDeviceToDevice, eng.stream));
     apply_folds();
   }
-  if (model_ready_[2]) {
-    for (auto& pr : ae_concat_bias_)
-      CUDA_CHECK(cudaMemcpyAsync(pr.second, pr.first->f32, pr.first->numel() * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, eng.stream));
+  for (size_t i = 0; i < ae_concat_bias_.size(); ++i) {
+    if (!model_ready_[i < enc_concat_from_ ? 2 : 3]) continue;
+    auto& pr = ae_concat_bias_[i];
+    CUDA_CHECK(cudaMemcpyAsync(pr.second, pr.first->f32, pr.first->numel() * sizeof(float),
+                               cudaMemcpyDeviceToDevice, eng.stream));
   }
   eng.sync();
   finalized = true;
@@ -825,7 +877,7 @@ void Model::attention_core(const bf16* q, long long q_ld, const bf16* k, long lo
 // [n, heads, d, tpad] so that P.V reads a K-major B operand.  ln_stats != null: z holds RAW rows and the
 // LayerNorm in front of the projection is folded into it (w.ln_cs / w.ln_bias, see apply_folds).
 static void qkv_projection(Engine& eng, const bf16* z, int n, int t, int c, const LinW& w, const float* bias, int inner,
-                           bf16* qk, bf16* vt, int tpad, const float* ln_stats = nullptr) {
+                           bf16* qk, bf16* vt, int tpad, const long long* ln_stats = nullptr) {
   GemmOp op;
   op.num_a = 1;
   AView a; a.ptr = z; a.C = c; a.W = t; a.H = 1; a.NB = n; a.sx = c; a.sy = (long long)t * c; a.sn = (long long)t * c;
@@ -862,11 +914,11 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
   gn(s.gn, x, nullptr, false, xn);
   bf16* y = eng.alloc<bf16>((size_t)rows * c);   // the block's token stream
   bf16* o = eng.alloc<bf16>((size_t)rows * c);
-  float* st1 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
-  float* st2 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
-  float* st3 = static_cast<float*>(pool_take((size_t)rows * 2 * sizeof(float)));
+  long long* st1 = static_cast<long long*>(pool_take((size_t)rows * 2 * sizeof(long long)));
+  long long* st2 = static_cast<long long*>(pool_take((size_t)rows * 2 * sizeof(long long)));
+  long long* st3 = static_cast<long long*>(pool_take((size_t)rows * 2 * sizeof(long long)));
   // y = dense1(groupnorm(x)) (unet.py:358-361), row statistics for LayerNorm1
-  auto res_linear = [&](const bf16* a, const LinW& w, const bf16* res, bf16* dst, float* stats) {
+  auto res_linear = [&](const bf16* a, const LinW& w, const bf16* res, bf16* dst, long long* stats) {
     GemmOp op;
     op.num_a = 1;
     op.a[0] = view_mat(a, rows, w.k, w.k);
@@ -1413,6 +1465,84 @@ void Model::decode(const float* z, int b, int h, int w, float div, float* img_ou
   CUDA_CHECK(cudaEventRecord(ev1_, eng.stream));
   eng.sync();
   CUDA_CHECK(cudaEventElapsedTime(&last_decode_ms, ev0_, ev1_));
+}
+
+// =====================================================================================
+// Autoencoder encode side (autoencoder.py:242-249,354-359,421-425) and get_latents (model_runners.py:602-625)
+// =====================================================================================
+void Model::encode_body(const float* img, int b, int h, int w, float* moments_dev) {
+  begin_pass();
+  Act cur = alloc_act(b, h, w, cfg.ae_channels);
+  eng.launches++;
+  if (!eng.dry) launch_conv_in(img, b, b, h, w, enc_conv_in_k_->f32, enc_conv_in_b_->f32, cfg.ae_channels, cur.f, cur.b,
+                               eng.fp16, eng.stream, 3);
+  for (auto& s : enc_down_) {
+    if (s.kind == 0) {
+      cur = resblock(s.res, cur, nullptr);
+      bool want = false;
+      if (cfg.ae_kind == 1)
+        for (int k = 0; k < cfg.ae_num_attn_res; ++k) want |= (cfg.ae_attn_res[k] == cur.h);   // autoencoder.py:116
+      LDM_CHECK(!want || s.attn, "encode: attention needed at resolution %d but the autoencoder was built for %d-pixel images",
+                cur.h, cfg.ae_build_hw << (cfg.ae_num_mult - 1));
+      if (want) cur = ae_attention(s.at, cur);
+    } else {
+      cur = downconv(cur, s.down, s.down.bias->f32, 0);   // tf.pad (0,1) + stride-2 VALID (autoencoder.py:133-135)
+    }
+  }
+  cur = resblock(enc_mid1_, cur, nullptr);
+  cur = ae_attention(enc_mid_attn_, cur);
+  cur = resblock(enc_mid2_, cur, nullptr);
+  bf16* a = eng.alloc<bf16>((size_t)cur.numel());
+  gn(enc_out_gn_, cur, nullptr, true, a);
+  const long long rows = (long long)b * cur.h * cur.w;
+  float* pre = eng.alloc<float>((size_t)rows * enc_z_);
+  GemmOp op;
+  op.num_a = 1;
+  op.a[0] = view_nhwc(a, b, cur.h, cur.w, cur.c);
+  op.b = view_mat(enc_conv_out_.wt, enc_z_, enc_conv_out_.k, enc_conv_out_.ld);
+  conv_segments(op, cur.c);
+  op.W = cur.w; op.H = cur.h; op.NB = b; op.N = enc_z_;
+  op.bias = enc_conv_out_.bias->f32;
+  op.out_f32 = pre;
+  op.os_x = enc_z_; op.os_y = (long long)cur.w * enc_z_; op.os_n = (long long)cur.h * cur.w * enc_z_;
+  eng.gemm(op);
+  eng.launches++;
+  if (!eng.dry) launch_dense_small(pre, rows, enc_z_, quant_k_->f32, quant_b_->f32, moments_dev, eng.stream);
+}
+
+void Model::encode_images(const float* images, int b, int h, int w, const float* noise, float scale, float* moments_out,
+                          float* latents_out) {
+  LDM_CHECK(finalized && model_ready_[3], "encode: autoencoder encoder weights not finalized");
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  const int f = 1 << (cfg.ae_num_mult - 1);
+  LDM_CHECK(h % f == 0 && w % f == 0, "encode: image %dx%d not divisible by %d", h, w, f);
+  const long long rows = (long long)b * (h / f) * (w / f);
+  const int z = cfg.latent_channels;
+  float* imgd = static_cast<float*>(stage(ST_A, (size_t)b * h * w * 3 * sizeof(float)));
+  float* mom = static_cast<float*>(stage(ST_B, (size_t)rows * enc_z_ * sizeof(float)));
+  float* lat = static_cast<float*>(stage(ST_C, (size_t)rows * z * sizeof(float)));
+  float* nz = noise ? static_cast<float*>(stage(ST_D, (size_t)rows * z * sizeof(float))) : nullptr;
+  {
+    DryPass dry(eng);
+    encode_body(imgd, b, h, w, mom);
+  }
+  ensure_arena(eng.arena.peak());
+  eng.arena.reset();
+  ensure_events();
+  CUDA_CHECK(cudaEventRecord(ev0_, eng.stream));
+  CUDA_CHECK(cudaMemcpyAsync(imgd, images, (size_t)b * h * w * 3 * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (nz) CUDA_CHECK(cudaMemcpyAsync(nz, noise, (size_t)rows * z * sizeof(float), cudaMemcpyDefault, eng.stream));
+  encode_body(imgd, b, h, w, mom);
+  if (moments_out)
+    CUDA_CHECK(cudaMemcpyAsync(moments_out, mom, (size_t)rows * enc_z_ * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (latents_out) {
+    launch_posterior_sample(mom, cfg.ae_kind == 0 ? nz : nullptr, rows, z, cfg.ae_kind == 0 ? 1 : 0, scale, lat, eng.stream);
+    eng.launches++;
+    CUDA_CHECK(cudaMemcpyAsync(latents_out, lat, (size_t)rows * z * sizeof(float), cudaMemcpyDefault, eng.stream));
+  }
+  CUDA_CHECK(cudaEventRecord(ev1_, eng.stream));
+  eng.sync();
+  CUDA_CHECK(cudaEventElapsedTime(&last_encode_ms, ev0_, ev1_));
 }
 
 void Model::vq_argmin(const float* z, long long rows, float div, long long* idx_out, float* zq_out) {

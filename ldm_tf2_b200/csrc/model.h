@@ -105,7 +105,8 @@ class Model {
   Engine eng;
 
   // ---- weights (flat Keras order): 0 = text transformer, 1 = unet, 2 = autoencoder
-  std::vector<Slot> slots[3];
+  enum { NUM_MODELS = 4 };   // 0 text, 1 unet, 2 autoencoder decode side, 3 autoencoder encode side
+  std::vector<Slot> slots[NUM_MODELS];
   // debug taps: name -> host buffer receiving the fp32 activation at that point of unet_eps
   std::map<std::string, std::pair<float*, size_t>> taps;
   void tap(const std::string& name, const Act& a);
@@ -130,10 +131,23 @@ class Model {
   // ---- decoder (autoencoder.py:361-364,430-436; model_runners.py:425-434)
   void decode(const float* z, int b, int h, int w, float div, float* img_out, long long* idx_out);
   void vq_argmin(const float* z, long long rows, float div, long long* idx_out, float* zq_out);
+  // ---- encoder (autoencoder.py:354-359,421-425; model_runners.py:602-625)
+  // moments_out [b, H/f, W/f, enc_z] (may be null); latents_out [b, H/f, W/f, 4] = scale * (mean + exp(logvar/2) * noise)
+  // for KL (noise null = the mean), scale * encoder output for VQ (may be null)
+  void encode_images(const float* images, int b, int h, int w, const float* noise, float scale, float* moments_out,
+                     float* latents_out);
+  void encode_body(const float* img, int b, int h, int w, float* moments_dev);
   void tensor_to_image(const float* img, int n, long long per, unsigned char* out);
 
+  // ---- multi-GPU: one NCCL all-gather of the decoded images (comm.cu)
+  void comm_init(const char* lib_hint, const char id_bytes[128], int rank, int world);
+  void comm_destroy();
+  void allgather(const float* local, long long count, float* global);
+  void* comm_ = nullptr; int comm_rank_ = 0, comm_world_ = 1;
+  float last_gather_ms = 0.f;
+
   // timing of the last sample()/decode() call, CUDA events on the engine's stream (ms)
-  float last_loop_ms = 0.f, last_decode_ms = 0.f, last_step_ms = 0.f, last_k5_ms = 0.f;
+  float last_loop_ms = 0.f, last_decode_ms = 0.f, last_step_ms = 0.f, last_k5_ms = 0.f, last_encode_ms = 0.f;
 
   // ---- internals (public so that api.cu's kernel-level test hooks can reach them)
   // text
@@ -151,8 +165,8 @@ class Model {
   GNW out_gn_; LinW conv_out_;
   std::vector<STW*> all_st_;
   std::vector<std::pair<Slot*, int>> tproj_bias_slots_;
-  std::vector<std::pair<Slot*, float*>> ae_concat_bias_;
-  bool model_ready_[3] = {false, false, false};
+  std::vector<std::pair<Slot*, float*>> ae_concat_bias_; size_t enc_concat_from_ = 0;   // [0, from): decode side, rest: encode side
+  bool model_ready_[NUM_MODELS] = {false, false, false, false};
   int ctx_rows_ = 0;
   int ctx_cap_rows_ = 0;   // rows the hoisted context K / V^T buffers were allocated for (grow-only)
   // ae
@@ -162,6 +176,14 @@ class Model {
   struct AEStage { int kind = 0; ResW res; bool attn = false; AEAttnW at; LinW up; LinW up_phase; int c = 0; int hw = 0; };
   std::vector<AEStage> ae_up_; int ae_plan_hw_ = 0;
   GNW ae_out_gn_; LinW ae_conv_out_;
+  // ae encode side (autoencoder.py:198-249,354-359,421-425)
+  Slot* enc_conv_in_k_ = nullptr; Slot* enc_conv_in_b_ = nullptr;
+  struct EncStage { int kind = 0; ResW res; bool attn = false; AEAttnW at; LinW down; int c = 0; int hw = 0; };
+  std::vector<EncStage> enc_down_;
+  ResW enc_mid1_, enc_mid2_; AEAttnW enc_mid_attn_;
+  GNW enc_out_gn_; LinW enc_conv_out_;
+  Slot* quant_k_ = nullptr; Slot* quant_b_ = nullptr;
+  int enc_z_ = 0;   // channels of the encoder output: 2 * latent_channels (KL moments) or latent_channels (VQ)
   // sampler state
   int S_ = 0; std::vector<int> ddim_t_; float* coeffs_dev_ = nullptr; int* step_dev_ = nullptr;
   float* temb_table_ = nullptr;   // table the ResBlocks currently read: [rows, tproj_cols_]
@@ -214,4 +236,11 @@ class Model {
   bool sampler_stale_ = false;   // unet weights changed after configure_sampler: finalize_weights rebuilds the table
 };
 
+void comm_unique_id(const char* lib_hint, char out[128]);
+
 }  // namespace ldm
+
+// glue shared by the translation units that implement the C ABI (api.cu, comm.cu)
+struct ldm_handle;
+ldm::Model* ldm_handle_model(ldm_handle* h);
+void ldm_set_error(const char* msg);

@@ -47,8 +47,15 @@ _PROTOS = {
     "ldm_ddim_step": ([_P, _P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P], _I),
     "ldm_sample": ([_P, _P, _P, _I, _I, _I, _F, _P, _P, _I, _I], _I),
     "ldm_decode": ([_P, _P, _I, _I, _I, _F, _P, _P], _I),
+    "ldm_encode_images": ([_P, _P, _I, _I, _I, _P], _I),
+    "ldm_get_latents": ([_P, _P, _P, _I, _I, _I, _F, _P], _I),
     "ldm_vq_argmin": ([_P, _P, _L, _F, _P, _P], _I),
     "ldm_tensor_to_image": ([_P, _P, _I, _L, _P], _I),
+    "ldm_comm_unique_id": ([C.c_char_p, C.c_char_p], _I),
+    "ldm_comm_init": ([_P, C.c_char_p, C.c_char_p, _I, _I], _I),
+    "ldm_allgather_images": ([_P, _P, _L, _P], _I),
+    "ldm_comm_destroy": ([_P], _I),
+    "ldm_get_timing_ex": ([_P, C.c_char_p, C.POINTER(_F)], _I),
     "ldm_get_timing": ([_P, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), C.POINTER(_L), C.POINTER(_L)], _I),
     "ldm_bench_ddim_update": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
     "ldm_bench_unet_step": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
@@ -91,6 +98,30 @@ def load():
     lib.ldm_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def nccl_library_path():
+    """libnccl.so.2 for ldm_comm_*: LDM_B200_NCCL_LIB, else the wheel torch bundles (nvidia-nccl-cu12), else None
+    (the dynamic loader's default search).  Nothing of PyTorch is imported."""
+    p = os.environ.get("LDM_B200_NCCL_LIB")
+    if p:
+        return p
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
+def comm_unique_id(nccl_lib: str = None) -> bytes:
+    buf = C.create_string_buffer(128)
+    check(load().ldm_comm_unique_id(nccl_lib.encode() if nccl_lib else None, buf))
+    return buf.raw
 
 
 class LdmError(RuntimeError):
@@ -184,7 +215,7 @@ def make_config(cond_stage_model: dict, unet: dict, autoencoder: dict, ae_kind: 
 class Handle:
     """Owns one ldm_handle (one GPU, one stream, one weight replica)."""
 
-    TEXT, UNET, AE = 0, 1, 2
+    TEXT, UNET, AE, ENC = 0, 1, 2, 3   # AE = decode side, ENC = encode side of the autoencoder
 
     def __init__(self, config: LdmConfig, device: int = 0):
         self.lib = load()
@@ -295,6 +326,27 @@ class Handle:
         check(self.lib.ldm_decode(self._h, ptr(z), b, hh, ww, float(div), ptr(img), ptr(idx)))
         return img, idx
 
+    def encode_images(self, images):
+        """AutoencoderKL.encode -> (mean, logvar); AutoencoderVQ.encode(only_encode=True) -> latents."""
+        images = f32(images)
+        b, hh, ww, _ = images.shape
+        f = 1 << (self.config.ae_num_multipliers - 1)
+        z = self.config.latent_channels * (2 if self.config.ae_kind == 0 else 1)
+        out = np.empty((b, hh // f, ww // f, z), np.float32)
+        check(self.lib.ldm_encode_images(self._h, ptr(images), b, hh, ww, ptr(out)))
+        if self.config.ae_kind == 0:
+            return out[..., : z // 2], out[..., z // 2:]
+        return out
+
+    def get_latents(self, images, noise=None, scale_factor=0.18215):
+        images = f32(images)
+        noise = None if noise is None else f32(noise)
+        b, hh, ww, _ = images.shape
+        f = 1 << (self.config.ae_num_multipliers - 1)
+        out = np.empty((b, hh // f, ww // f, self.config.latent_channels), np.float32)
+        check(self.lib.ldm_get_latents(self._h, ptr(images), ptr(noise), b, hh, ww, float(scale_factor), ptr(out)))
+        return out
+
     def vq_argmin(self, z, div=1.0):
         z = f32(z)
         rows = z.size // 4
@@ -309,6 +361,20 @@ class Handle:
         check(self.lib.ldm_tensor_to_image(self._h, ptr(images), images.shape[0],
                                            images.size // images.shape[0], ptr(out)))
         return out
+
+    def timing_ex(self, what: str) -> float:
+        ms = C.c_float()
+        check(self.lib.ldm_get_timing_ex(self._h, what.encode(), C.byref(ms)))
+        return ms.value
+
+    # -- multi-GPU ----------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int, nccl_lib: str = None):
+        check(self.lib.ldm_comm_init(self._h, nccl_lib.encode() if nccl_lib else None, unique_id, rank, world))
+        self._world, self._rank = world, rank
+
+    def allgather(self, local, count_per_rank: int, out):
+        """local / out: numpy arrays or DevPtr; every rank passes count_per_rank floats."""
+        check(self.lib.ldm_allgather_images(self._h, ptr(local), count_per_rank, ptr(out)))
 
     def timing(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
@@ -350,7 +416,7 @@ class Handle:
         ms = C.c_float()
         tr = np.zeros((148, 64, 16), np.int64) if trace else None
         check(self.lib.ldm_bench_gemm(self._h, rows, k, n, block_n, dbg, conv, hw, iters, C.byref(ms), ptr(tr),
-                                      int(residual)))
+                                      int(residual)))   # residual: 0 none, 1 fp32, 2 16-bit in place, 3 + row statistics
         return (ms.value, tr) if trace else ms.value
 
     def bench_attention(self, n, t, tk, heads, d, iters=20, trace=False):

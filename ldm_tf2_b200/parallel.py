@@ -1,9 +1,17 @@
 """Multi-GPU host path: the batch of samples shards across ranks (one process per GPU,
 full weight replica each, both CFG halves of an image on the same rank), there is no collective
-inside the DDIM loop, and ONE all-gather collects the decoded images.  torch.distributed is
-plumbing only (NCCL over NVLink on GPUs, gloo in the CPU tests); the sampling path never imports
-torch."""
+inside the DDIM loop, and ONE all-gather collects the decoded images.
+
+On GPUs the all-gather is `ldm_allgather_images` of the library (NCCL over NVLink on the handle's stream,
+comm.cu); the 128-byte NCCL id travels from rank 0 to the other ranks over a tiny TCP rendezvous on
+MASTER_ADDR / MASTER_PORT+1 (`exchange_unique_id`) -- no PyTorch anywhere on this path.  The torch.distributed
+variant (`allgather_images`) remains for the CPU tests, which run the same shard / pad logic on gloo."""
 from __future__ import annotations
+
+import os
+import socket
+import struct
+import time
 
 import numpy as np
 
@@ -56,3 +64,95 @@ def allgather_images(local, total: int, group=None):
         return out
     parts = [out[r * maxn: r * maxn + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
     return torch.cat(parts, dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# NCCL inside the library: rendezvous + gather (no torch)
+# ------------------------------------------------------------------------------------------------
+def exchange_bytes(payload, rank: int, world: int, addr: str = None, port: int = None, timeout: float = 120.0) -> bytes:
+    """Rank 0 serves `payload` to the world - 1 other ranks over TCP; every rank returns it."""
+    if world == 1:
+        return payload
+    addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    if rank == 0:
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        try:
+            for _ in range(world - 1):
+                c, _ = srv.accept()
+                with c:
+                    c.sendall(struct.pack("<I", len(payload)) + payload)
+        finally:
+            srv.close()
+        return payload
+    deadline = time.time() + timeout
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=5.0) as c:
+                buf = b""
+                while len(buf) < 4:
+                    chunk = c.recv(4 - len(buf))
+                    if not chunk:
+                        raise ConnectionError("rendezvous closed early")
+                    buf += chunk
+                (n,) = struct.unpack("<I", buf)
+                out = b""
+                while len(out) < n:
+                    chunk = c.recv(n - len(out))
+                    if not chunk:
+                        raise ConnectionError("rendezvous closed early")
+                    out += chunk
+                return out
+        except (ConnectionRefusedError, ConnectionError, socket.timeout, OSError):
+            if time.time() > deadline:
+                raise
+            time.sleep(0.05)
+
+
+def init_comm(handle, rank: int, world: int, addr: str = None, port: int = None):
+    """ncclGetUniqueId on rank 0 -> TCP rendezvous -> ncclCommInitRank on every rank's handle."""
+    from . import lib
+    nccl = lib.nccl_library_path()
+    uid = lib.comm_unique_id(nccl) if rank == 0 else None
+    uid = exchange_bytes(uid, rank, world, addr, port)
+    handle.comm_init(uid, rank, world, nccl)
+    return handle
+
+
+def gather_plan(total: int, world: int, per_image: int):
+    """(largest shard in images, per-rank [lo, hi) list): ranks pad their shard to the largest one."""
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    return max(hi - lo for lo, hi in sizes), sizes
+
+
+def allgather_images_nccl(handle, local, total: int, out=None):
+    """local: numpy [b_local, H, W, 3] float32 (host) -> numpy [total, H, W, 3] on every rank, global sample
+    order; or lib.DevPtr in / DevPtr out (device-resident, equal shards only)."""
+    from . import lib
+    world = handle_world(handle)
+    if isinstance(local, lib.DevPtr):
+        b = local.shape[0]
+        if b * world != total:
+            raise ValueError("device-resident gather needs equal shards")
+        handle.allgather(local, local.size, out)
+        return out
+    local = np.ascontiguousarray(local, dtype=np.float32)
+    per = int(np.prod(local.shape[1:]))
+    maxn, sizes = gather_plan(total, world, per)
+    send = local
+    if local.shape[0] < maxn:
+        send = np.zeros((maxn,) + local.shape[1:], np.float32)
+        send[: local.shape[0]] = local
+    buf = np.empty((world * maxn,) + local.shape[1:], np.float32)
+    handle.allgather(send, maxn * per, buf)
+    if all(hi - lo == maxn for lo, hi in sizes):
+        return buf
+    return np.concatenate([buf[r * maxn: r * maxn + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], axis=0)
+
+
+def handle_world(handle) -> int:
+    return getattr(handle, "_world", 1)

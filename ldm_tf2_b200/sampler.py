@@ -105,10 +105,25 @@ class LatentDiffusionModelSampler:
         cfg = _lib.make_config(cond_stage_model.kwargs, unet.kwargs, autoencoder.kwargs, autoencoder.kind,
                                ae_build_latent_hw)
         self.handle = _lib.Handle(cfg, device)
-        for model, holder in ((self.handle.TEXT, cond_stage_model), (self.handle.UNET, unet),
-                              (self.handle.AE, autoencoder)):
+        for model, holder in ((self.handle.TEXT, cond_stage_model), (self.handle.UNET, unet)):
             if holder.get_weights() is not None:
                 self.handle.set_weights(model, holder.get_weights())
+        ae_w = autoencoder.get_weights()
+        if ae_w is not None:
+            # Keras flat order of an autoencoder: [_encoder, _quant_conv,] [_quantize,] _post_quant_conv, _decoder
+            # (attribute order of autoencoder.py:322-347,395-421).  A model built by decode() only has the tail;
+            # one that also ran encode() has the encoder + quant_conv in front.
+            n_dec, n_enc = self.handle.num_weights(self.handle.AE), self.handle.num_weights(self.handle.ENC)
+            if len(ae_w) == n_dec:
+                self.handle.set_weights(self.handle.AE, ae_w)
+            elif len(ae_w) == n_enc + n_dec:
+                self.handle.set_weights(self.handle.ENC, ae_w[:n_enc])
+                self.handle.set_weights(self.handle.AE, ae_w[n_enc:])
+            elif len(ae_w) == n_enc:
+                self.handle.set_weights(self.handle.ENC, ae_w)
+            else:
+                raise _lib.LdmError(f"autoencoder: expected {n_dec} (decode side), {n_enc} (encode side) or "
+                                    f"{n_enc + n_dec} weight tensors, got {len(ae_w)}")
         self.handle.finalize()
         if unet.get_weights() is not None:
             self.handle.configure_sampler(self._ddim_steps, self.schedule.coeff_table())
@@ -143,6 +158,18 @@ class LatentDiffusionModelSampler:
         AutoencoderVQ.decode(force_quantize=True)."""
         images, idx = self.handle.decode(_tensor(latents), div=self._scale_factor)
         return (images, idx) if return_indices else images
+
+    def get_latents(self, inputs, noise=None):
+        """LatentDiffusionModel.get_latents (model_runners.py:602-625): images [B,H,W,3] -> latents
+        [B,H/8,W/8,4] = scale_factor * posterior.sample() (KL) or scale_factor * encode(only_encode=True) (VQ).
+        `noise` replaces the tf.random.normal of DiagonalGaussian.sample (distribution.py:23-25); by default it is
+        drawn from the sampler's seeded generator."""
+        x = _tensor(inputs)
+        if self._autoencoder.kind == "kl" and noise is None:
+            f = 1 << (self.handle.config.ae_num_multipliers - 1)
+            noise = self._rng.standard_normal((x.shape[0], x.shape[1] // f, x.shape[2] // f,
+                                               self.handle.config.latent_channels), dtype=np.float32)
+        return self.handle.get_latents(x, None if noise is None else _tensor(noise), self._scale_factor)
 
     def ddim_sample(self, xt, cond, index, guidance_scale=1.0, clip_denoised=True, return_pred_x0=False,
                     noise=None):

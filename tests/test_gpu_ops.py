@@ -79,13 +79,13 @@ def test_vq_argmin_bit_exact(vocab, rows):
 
 # ----------------------------------------------------------------- transformer-block epilogue terms
 @pytest.mark.parametrize("rows,k0,c,n,act,residual,dbg", [
-    (256, 64, 320, 320, 0, True, 0),      # residual linear, 16-bit stream updated in place, fragment epilogue
-    (256, 64, 320, 320, 0, True, 8),      # same through the row-owner epilogue
+    (256, 64, 320, 320, 0, True, 0),      # residual linear, 16-bit stream updated in place, lean row-owner epilogue
+    (256, 64, 320, 320, 0, True, 8),      # same through the fragment-layout epilogue
     (384, 128, 320, 960, 0, False, 0),    # q|k|v-like: LayerNorm folded, wider output
     (200, 64, 64, 64, 0, True, 0),        # ragged rows (partial tile) -> row-owner path
     (128, 64, 96, 112, 0, False, 0),      # ragged 16-column tail tile
-    (256, 64, 64, 256, 3, False, 0),      # GEGLU with the folded LayerNorm (fragment epilogue)
-    (160, 64, 64, 256, 3, False, 8),      # GEGLU, row-owner epilogue, ragged rows
+    (256, 64, 64, 256, 3, False, 8),      # GEGLU with the folded LayerNorm (fragment epilogue)
+    (160, 64, 64, 256, 3, False, 0),      # GEGLU, row-owner epilogue, ragged rows
 ])
 def test_layernorm_folded_linear_with_16bit_residual_and_row_stats(h, rows, k0, c, n, act, residual, dbg):
     """unet.py:304-314: y = dense(a); out = act(dense(LayerNorm(y))) [+ y].  The library keeps y as a 16-bit
@@ -233,7 +233,8 @@ def test_conv3x3(h, nb, hh, ww, cin, cout, sc):
 
 @pytest.mark.parametrize("nb,hh,ww,c", [
     (2, 16, 16, 64),     # one image per tile; two M tiles per phase (CTA pairs inside a phase)
-    (3, 8, 8, 128),      # two images per tile, odd tile count per phase (single-CTA kernel)
+    (3, 8, 8, 128),      # two images per tile, ragged last tile
+    (1, 8, 8, 64),       # one tile per phase: odd count -> single-CTA kernel
     (16, 4, 4, 64),      # eight images per tile
     (2, 32, 32, 32),     # Cin < 64: zero-filled k-block per tap
     (1, 64, 64, 64),     # 2 rows x 64 per tile

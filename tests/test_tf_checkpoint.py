@@ -93,6 +93,154 @@ def test_hand_assembled_index_is_parsed(tmp_path):
     assert np.array_equal(got["a/kernel2"], payload)
 
 
+class _TfStyleTable:
+    """A second, independent table writer used only by the test below: written from the LevelDB / TensorFlow
+    table format description the way TensorFlow's own BundleWriter drives it (tensorflow/core/lib/io/
+    table_builder.cc, block_builder.cc): prefix compression with a restart point every 16 entries, data blocks cut
+    when they reach `block_size`, index keys shortened to the shortest separator between two blocks
+    (BytewiseComparator::FindShortestSeparator) and the last one to a short successor, a metaindex block, a
+    48-byte footer.  It shares no code with ldm_tf2_b200.tf_checkpoint."""
+
+    def __init__(self, block_size):
+        self.block_size, self.out, self.index = block_size, bytearray(), []
+        self.entries, self.restarts, self.buf, self.last = 0, [0], bytearray(), b""
+        self.pending = None   # (last key of the finished block, handle)
+
+    @staticmethod
+    def _v(n):
+        o = bytearray()
+        while n >= 0x80:
+            o.append((n & 0x7F) | 0x80)
+            n >>= 7
+        o.append(n)
+        return bytes(o)
+
+    @staticmethod
+    def _separator(a, b):
+        n = 0
+        while n < min(len(a), len(b)) and a[n] == b[n]:
+            n += 1
+        if n < min(len(a), len(b)) and a[n] < 0xFF and a[n] + 1 < b[n]:
+            return a[:n] + bytes([a[n] + 1])
+        return a
+
+    def _crc(self, data):
+        c = T._crc32c_py(bytes(data))
+        return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+    def _emit(self, block):
+        off = len(self.out)
+        self.out += block + b"\x00" + struct.pack("<I", self._crc(block + b"\x00"))
+        return self._v(off) + self._v(len(block))
+
+    def _finish_block(self):
+        blk = bytes(self.buf) + b"".join(struct.pack("<I", r) for r in self.restarts) + struct.pack("<I", len(self.restarts))
+        self.pending = (self.last, self._emit(blk))
+        self.entries, self.restarts, self.buf = 0, [0], bytearray()
+
+    def add(self, key, value):
+        if self.pending:
+            self.index.append((self._separator(self.pending[0], key), self.pending[1]))
+            self.pending = None
+        shared = 0
+        if self.entries % 16 == 0 and self.entries:
+            self.restarts.append(len(self.buf))
+        elif self.entries:
+            while shared < min(len(self.last), len(key)) and self.last[shared] == key[shared]:
+                shared += 1
+        self.buf += self._v(shared) + self._v(len(key) - shared) + self._v(len(value)) + key[shared:] + value
+        self.last = key
+        self.entries += 1
+        if len(self.buf) >= self.block_size:
+            self._finish_block()
+
+    def finish(self):
+        if self.entries:
+            self._finish_block()
+        if self.pending:
+            k = self.pending[0]
+            succ = next((k[:i] + bytes([k[i] + 1]) for i in range(len(k)) if k[i] != 0xFF), k)   # FindShortSuccessor
+            self.index.append((succ, self.pending[1]))
+        meta = self._emit(struct.pack("<II", 0, 1))
+        ib = bytearray()
+        restarts = []
+        for k, h in self.index:   # index block: restart interval 1
+            restarts.append(len(ib))
+            ib += self._v(0) + self._v(len(k)) + self._v(len(h)) + k + h
+        idx = self._emit(bytes(ib) + b"".join(struct.pack("<I", r) for r in restarts) + struct.pack("<I", len(restarts)))
+        foot = meta + idx
+        return bytes(self.out) + foot + bytes(40 - len(foot)) + struct.pack("<Q", 0xDB4775248B80FB57)
+
+
+def test_tensorflow_style_object_checkpoint_is_read(tmp_path):
+    """What `tf.train.Checkpoint(unet=unet).save(prefix)` puts on disk (convert_ckpt_pytorch_to_tf2.py:426-431), hand
+    assembled by the independent writer above: the bundle header, the `_CHECKPOINTABLE_OBJECT_GRAPH` string entry, the
+    int64 `save_counter`, and the variables under their attribute paths in bytewise key order -- spread over many
+    small data blocks (restart points inside blocks, shortened index keys).  The reader must find every variable
+    the library asks for, skip the string entry, and verify every checksum."""
+    from ldm_tf2_b200 import lib
+    from oracle import ldm_oracle as O
+    cfg = O.TINY_CONFIG
+    d = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), -1)
+    keys = T.variable_keys(d, d.UNET)
+    shapes = [d.weight_info(d.UNET, i)[1] for i in range(d.num_weights(d.UNET))]
+    d.close()
+    rng = np.random.default_rng(0)
+    tensors = {k: rng.standard_normal(s).astype(np.float32) for k, s in zip(keys, shapes)}
+    graph = b"\x0a\x10fake object graph proto" * 40          # opaque to the reader: a DT_STRING scalar
+    # ---- data file, in key order; a DT_STRING tensor is [varint lengths][masked crc of the lengths][bytes]
+    allkeys = sorted([k.encode() for k in tensors] + [b"_CHECKPOINTABLE_OBJECT_GRAPH", b"save_counter" + T.SUFFIX.encode()])
+    data = bytearray()
+    table = _TfStyleTable(block_size=700)
+    v = _TfStyleTable._v
+    table.add(b"", b"\x08\x01\x1a\x02\x08\x01")   # BundleHeaderProto{num_shards 1, version{producer 1}}
+
+    def crc_of(raw):
+        c = T._crc32c_py(bytes(raw))
+        return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+    def shape_pb(shape):
+        dims = b"".join(b"\x12" + v(len(dpb)) + dpb for dpb in (b"\x08" + v(int(n)) for n in shape))
+        return b"\x12" + v(len(dims)) + dims
+
+    for k in allkeys:
+        off = len(data)
+        if k == b"_CHECKPOINTABLE_OBJECT_GRAPH":
+            lens = v(len(graph))
+            raw = lens + struct.pack("<I", crc_of(lens)) + graph
+            dtype, shp = 7, ()
+        elif k.startswith(b"save_counter"):
+            raw = np.int64(1).tobytes()
+            dtype, shp = 9, ()
+        else:
+            a = tensors[k.decode()]
+            raw = a.tobytes()
+            dtype, shp = 1, a.shape
+        data += raw
+        entry = b"\x08" + v(dtype) + shape_pb(shp) + (b"\x20" + v(off) if off else b"") + b"\x28" + v(len(raw)) + \
+            b"\x35" + struct.pack("<I", crc_of(raw))
+        table.add(k, entry)
+    prefix = str(tmp_path / "unet-1")
+    open(prefix + ".index", "wb").write(table.finish())
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    assert len(table.index) > 20                     # many data blocks, shortened separator keys in the index
+    header, entries = T.read_index(prefix)
+    assert header["num_shards"] == 1 and len(entries) == len(allkeys) - 0
+    assert entries["_CHECKPOINTABLE_OBJECT_GRAPH"]["dtype"] == T.DT_STRING
+    got = T.load_checkpoint(prefix, keys)           # exactly what restore() asks for
+    for k in keys:
+        assert np.array_equal(got[k], tensors[k]), k
+    everything = T.load_checkpoint(prefix)          # the string entry is skipped, save_counter is read
+    assert "_CHECKPOINTABLE_OBJECT_GRAPH" not in everything
+    assert everything["save_counter" + T.SUFFIX] == 1 and everything["save_counter" + T.SUFFIX].dtype == np.int64
+    # a flipped payload byte in the middle of the data file is caught by the entry checksum
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(bad))
+    with pytest.raises(T.CheckpointError, match="checksum"):
+        T.load_checkpoint(prefix, keys)
+
+
 def test_corruption_is_detected(tmp_path):
     prefix = str(tmp_path / "c")
     T.write_checkpoint(prefix, {"w" + T.SUFFIX: np.ones((64, 64), np.float32)})

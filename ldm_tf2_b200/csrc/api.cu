@@ -442,6 +442,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.pair = (dbg & 16) ? -1 : ((dbg & 32) ? 1 : 0);   // bit 4: single-CTA kernel, bit 5: CTA-pair kernel
   op.ew = (dbg & 64) ? 4 : ((dbg & 128) ? 8 : 0);   // bit 6: two CTAs per SM (4 epilogue warps), bit 7: one (8)
   op.dbg = dbg & 15;
+  if (getenv("LDM_B200_TRACE_FINE")) op.dbg |= 0x100;   // fine-grained stamps of one chunk (profiles/trace_epilogue.py)
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual == 1) {          // fp32 residual stream: fp32 + 16-bit outputs
@@ -761,7 +762,13 @@ LDM_API int ldm_test_resample_conv(ldm_handle* h, const float* x, const float* k
   m.ensure_arena(e.arena.peak());
   e.arena.reset();
   Act o = run();
-  CUDA_CHECK(cudaMemcpyAsync(out, o.f, out_el * sizeof(float), cudaMemcpyDefault, e.stream));
+  if (o.f) {
+    CUDA_CHECK(cudaMemcpyAsync(out, o.f, out_el * sizeof(float), cudaMemcpyDefault, e.stream));
+  } else {   // 16-bit residual stream: widen the 16-bit output
+    float* wide = s.get<float>(out_el);
+    launch_widen16(o.b, wide, (long long)out_el, e.fp16, e.stream);
+    CUDA_CHECK(cudaMemcpyAsync(out, wide, out_el * sizeof(float), cudaMemcpyDefault, e.stream));
+  }
   e.sync();
   API_END
 }

@@ -132,6 +132,7 @@ void Engine::encode_map(CUtensorMap* m, const AView& v, int box_x, int box_y, in
 // (32 cols, w_b, h_b, n_b), 128-byte swizzle for fp32 rows (128 B), 64-byte swizzle for 16-bit rows.
 void Engine::encode_out_map(CUtensorMap* m, const void* ptr, int elem_bytes, bool is_float32, int N, int W, int H,
                             int NB, long long sx, long long sy, long long sn, int w_b, int h_b, int n_b) {
+  LDM_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA epilogue tensor not 16-byte aligned");
   cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   // size-1 dims get packed strides (any positive multiple of 16 B is legal)
   if (W == 1 || sx == 0) sx = N;
@@ -292,9 +293,31 @@ void Engine::gemm(const GemmOp& op) {
   const long long work_tiles = (long long)(pair ? (m_tiles + 1) / 2 : m_tiles) * ((gemm_n + bn - 1) / bn) * splits;
   const bool many_tiles = work_tiles * 20 >= LDM_TUNE("LDM_B200_T_EW4_TILES", 30) * (pair ? num_sms / 2 : num_sms);
   const bool fits_half = 3 * slot + GEMM_CTRL_BYTES + GEMM_EPI_EW4_BYTES + 1024 <= 110 * 1024;   // >= 3 stages in half an SM
-  const bool ew4 = !tma_epi && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
+  // 16-bit-only outputs go through per-warp TMA tiles (gemm.cuh, GemmParams::w16) when a warp's 32 rows are 32
+  // consecutive x of one image row; that flavour runs one CTA per SM (8 epilogue warps x 8 KB of tiles)
+  static const bool w16_off = getenv("LDM_B200_W16") && getenv("LDM_B200_W16")[0] == '0';
+  // a warp's 32 tile rows (x fastest, then y, then image) must form one TMA box: (bx x, by y, bi images)
+  const int w16_bx = std::min(w_b, 32), w16_by = std::min(h_b, 32 / std::max(w16_bx, 1)),
+            w16_bi = 32 / std::max(w16_bx * w16_by, 1);
+  const bool w16_box_ok = box_rows % 32 == 0 && 32 % w16_bx == 0 && w_b % w16_bx == 0 && h_b % w16_by == 0 &&
+                          w16_bx * w16_by * w16_bi == 32 && n_b % w16_bi == 0 &&
+                          (w16_bx == w_b || w16_by == 1) && (w16_by == h_b || w16_bi == 1);
+  static const bool frag16 = getenv("LDM_B200_FRAG16") && getenv("LDM_B200_FRAG16")[0] == '1';
+  static const bool frag_geglu = getenv("LDM_B200_FRAG_GEGLU") && getenv("LDM_B200_FRAG_GEGLU")[0] == '1';
+  const bool frag_want = (geglu && frag_geglu) || (!geglu && !op.out_f32 && op.out_bf16 && frag16) ||
+                         ((op.dbg & 8) && (geglu || (!op.out_f32 && op.out_bf16)));
+  const bool w16 = !w16_off && !tma_epi && !frag_want && op.out_bf16 && !op.out_f32 && !op.residual && op.num_phases == 1 &&
+                   op.b_mode == B_PLAIN && splits == 1 && w16_box_ok && op.ew != 4 &&
+                   ((op.N | op.os_n | op.os_y | op.os_x) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0 &&
+                   (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 15) == 0) &&
+                   (!op.out_tr || (op.tr_col0 & 31) == 0);
+  const bool ew4 = !tma_epi && !w16 && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
   p.tma_epi = tma_epi ? 1 : 0;
-  if (ew4) {
+  p.w16 = w16 ? 1 : 0;
+  if (w16) {
+    p.epi_bytes = GEMM_EPI_LEGACY_BYTES + 8 * GEMM_W16_WARP_BYTES;
+  } else if (ew4) {
     p.epi_bytes = GEMM_EPI_EW4_BYTES;
   } else if (tma_epi) {
     p.epi_r_off = 0;
@@ -338,15 +361,11 @@ void Engine::gemm(const GemmOp& op) {
   p.out_f32 = op.out_f32; p.out_bf16 = op.out_bf16;
   p.res16 = op.res16; p.rs_out = op.rs_out; p.ln_stats = op.ln_stats; p.ln_cs = op.ln_cs;
   p.ln_inv_c = op.ln_c > 0 ? 1.0f / (float)op.ln_c : 0.f; p.ln_eps = op.ln_eps;
-  {
-    // 16-bit-only outputs default to the lean row-owner epilogue (one tcgen05.ld.32x32b.x32 per chunk, four 16-byte
-    // stores of the thread's own row: ~4x fewer instructions than the fragment-layout path, and the epilogue is
-    // issue-bound with 8 warps per SM -- profiles/r2_trace_epilogue.txt).  The fragment layout (sector-complete
-    // 32-byte row pieces) stays selectable for A/B runs: LDM_B200_FRAG16=1 / LDM_B200_FRAG_GEGLU=1.
-    static const bool frag16 = getenv("LDM_B200_FRAG16") && getenv("LDM_B200_FRAG16")[0] == '1';
-    static const bool frag_geglu = getenv("LDM_B200_FRAG_GEGLU") && getenv("LDM_B200_FRAG_GEGLU")[0] == '1';
-    p.frag_pref = ((geglu && frag_geglu) || (!geglu && !op.out_f32 && op.out_bf16 && frag16) || ((op.dbg & 8) && (geglu || (!op.out_f32 && op.out_bf16)))) ? 1 : 0;
-  }
+  // 16-bit-only outputs default to per-warp TMA tiles (w16), else the lean row-owner epilogue (one
+  // tcgen05.ld.32x32b.x32 per chunk, four 16-byte stores of the thread's own row).  The fragment layout
+  // (sector-complete 32-byte row pieces, ~4x the instructions) stays selectable for A/B runs:
+  // LDM_B200_FRAG16=1 / LDM_B200_FRAG_GEGLU=1 (profiles/r2_trace_epilogue.txt).
+  p.frag_pref = frag_want ? 1 : 0;
   p.os_n = op.os_n; p.os_y = op.os_y; p.os_x = op.os_x; p.os_phase_y = op.os_phase_y; p.os_phase_x = op.os_phase_x;
   p.out_tr = op.out_tr; p.tr_col0 = op.tr_col0; p.ts_n = op.ts_n; p.ts_y = op.ts_y; p.ts_c = op.ts_c;
   LDM_CHECK(op.out_f32 || op.out_bf16 || op.out_tr, "gemm: no output");
@@ -362,6 +381,11 @@ void Engine::gemm(const GemmOp& op) {
   }
   encode_map(&p.bmap, op.b, b_rows, 1, 1);
   p.b_swap = op.b.swap_xy ? 1 : 0;
+  if (p.w16) {
+    const int ncols = op.out_tr ? op.tr_col0 : op.N;   // columns beyond tr_col0 are the transposed V^T output
+    encode_out_map(&p.wmap16, op.out_bf16, 2, false, ncols, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w16_bx, w16_by, w16_bi);
+    if (op.res16) encode_out_map(&p.wrmap16, op.res16, 2, false, ncols, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w16_bx, w16_by, w16_bi);
+  }
   if (p.tma_epi) {
     if (op.out_f32) encode_out_map(&p.omap32, op.out_f32, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
     if (op.out_bf16) encode_out_map(&p.omap16, op.out_bf16, 2, false, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);

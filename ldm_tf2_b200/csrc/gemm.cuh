@@ -36,6 +36,7 @@ constexpr int GEMM_CTRL_BYTES = 5120;   // barriers, bias [512,1536), residual-t
                                         // column sums [2048,3072), per-row (scale, shift) [3072,4096), row ids [4096,4608)
 constexpr int GEMM_EPI_LEGACY_BYTES = 8 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);  // per-warp staging + row offsets
 constexpr int GEMM_EPI_EW4_BYTES = 4 * (32 * GEMM_EPI_PITCH * 4 + 32 * 8);
+constexpr int GEMM_W16_WARP_BYTES = 4 * 2048;   // per epilogue warp: 2 store tiles + 2 residual tiles of 32 rows x 64 B
 constexpr int GEMM_SMEM_BYTES = 227 * 1024;
 
 enum ActKind : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };
@@ -107,6 +108,12 @@ struct GemmParams {
   // integer atomics: integer addition is associative, so the totals -- and everything computed from them -- are
   // bit-reproducible whatever order the tiles finish in (float atomics are not)
   long long* rs_out;
+  // 16-bit-only outputs through per-warp TMA tiles (w16 = 1): every epilogue warp stages its 32 rows x 32 columns
+  // in shared memory (64-byte rows, 64 B swizzle) and one lane issues a TMA store; the 16-bit residual arrives the
+  // same way one chunk ahead.  Global memory is touched in whole lines by the TMA unit instead of 32 partial lines
+  // per warp instruction (the LSU processes one line per clock: the row-owner stores were bound by it).
+  int w16;
+  CUtensorMap wmap16, wrmap16;   // (32 cols, 32 x, 1, 1) boxes over out_bf16 / res16
   int frag_pref;            // 16-bit-only outputs: take the fragment-layout epilogue where a tile allows it
   float* out_f32;
   bf16* out_bf16;
@@ -433,9 +440,10 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 // EPI selects which optional epilogue flavours are compiled in (each costs registers in every other path):
 // bit 0 = fragment-layout path (A/B switch), bit 1 = TMA-store path (A/B switch); the default kernels have neither.
 template <int PAIR, int EW, int EPI>
-// register budget: 2 CTAs x 192 threads x 168 (EW = 4) or 1 CTA x 320 threads x 200 (EW = 8) of the SM's 64 K registers
-// (__launch_bounds__(320, 1) makes ptxas stop at 168)
-__global__ void __maxnreg__(EW == 4 ? 168 : 200)
+// register budget: 168 per thread either way.  The register file is 4 x 16 K (one per scheduler partition): the
+// 10 warps of the EW = 8 flavour put three warps on two of the partitions (16384 / 3 / 32 = 170), and two EW = 4
+// CTAs put three warps on every partition -- a launch with more registers fails with cudaErrorLaunchOutOfResources.
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   constexpr bool HAS_FRAG = (EPI & 1) != 0, HAS_TMA = (EPI & 2) != 0;
   constexpr int NHALF = EW / 4;          // column-chunk interleave between the warps of a TMEM lane quadrant
@@ -456,6 +464,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(ctrl + 512);  // block_n floats, <= 1 KB
   uint64_t* rfull_bar = reinterpret_cast<uint64_t*>(ctrl + 1536);  // [half][slot] residual tiles landed
+  uint64_t* w16_bar = reinterpret_cast<uint64_t*>(ctrl + 1664);    // [epilogue warp][slot] per-warp residual tiles landed
   float* cs_s = reinterpret_cast<float*>(ctrl + 2048);        // folded-LayerNorm column sums of this tile's columns
   float2* ab_s = reinterpret_cast<float2*>(ctrl + 3072);      // per tile row: (rstd, -mean * rstd)
   int* grow_s = reinterpret_cast<int*>(ctrl + 4096);          // per tile row: global row index (row statistics)
@@ -488,6 +497,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(&tempty_bar[i], PAIR ? 2 * EW : EW);   // one arrival per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
+    for (int i = 0; i < 2 * EW; ++i) mbar_init(&w16_bar[i], 1);
+    if (p.w16) { tma_prefetch_desc(&p.wmap16); tma_prefetch_desc(&p.wrmap16); }
     if (p.tma_epi) {
       tma_prefetch_desc(&p.omap32);
       tma_prefetch_desc(&p.omap16);
@@ -619,6 +630,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
     float* stage = stage_all + ew * 32 * GEMM_EPI_PITCH;
     int* roff = reinterpret_cast<int*>(roff_all) + ew * 32;
+    // per-warp TMA tiles of the 16-bit epilogue: [store 0 | store 1 | residual 0 | residual 1], 2 KB each
+    uint8_t* const w16_tiles = stage_area + EW * (32 * GEMM_EPI_PITCH * 4 + 32 * 8) + ew * GEMM_W16_WARP_BYTES;
+    const uint32_t w16_tiles_a = smem_u32(w16_tiles);
+    const uint32_t w16_bar0 = smem_u32(w16_bar) + (uint32_t)(ew * 16);
+    int w16_rseq = 0;    // residual tiles consumed so far by this warp (slot = & 1, parity = (>> 1) & 1)
+    int w16_sseq = 0;    // store tiles issued so far by this warp
     int as = 0;
     uint32_t aphase = 0;
     const int hw_b = p.h_b * p.w_b;
@@ -751,8 +768,25 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       // Row-owner epilogue with direct 16-byte accesses: this thread = one row, a chunk = 64 contiguous bytes of
       // its 16-bit residual / output.  The residual of a chunk is loaded one chunk ahead (the first one before the
       // accumulator is ready): it does not depend on the MMA, and its L2 latency is otherwise what the tile waits for.
+      // per-warp TMA tiles (see GemmParams::w16): this warp's 32 rows are 32 consecutive x of one (img, y)
+      const bool w16 = p.w16 && !frag && !use_tma && !split && quad * 32 < p.box_rows;
+      const int w16_x = t.x0 + (quad * 32) % p.w_b, w16_y = t.y0 + ((quad * 32) % hw_b) / p.w_b,
+                w16_n = t.img0 + (quad * 32) / hw_b;
+      const bool w16_res = w16 && res16 != nullptr;
+      if (w16_res && lane == 0) {
+        // this warp's first two residual chunks: in flight while the MMA still runs
+        for (int k = 0; k < 2; ++k) {
+          const int ci0 = half + k * NHALF;
+          const int c0 = col_base + ci0 * 32;
+          if (ci0 < n32_all && c0 + 32 <= p.N && !(p.out_tr && c0 >= p.tr_col0)) {
+            const int slot = (w16_rseq + k) & 1;
+            mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
+            tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, c0, w16_x, w16_y, w16_n);
+          }
+        }
+      }
       const bool d16 = !frag && p.epi_vec16 && !use_tma;
-      const bool r16v = d16 && res16 != nullptr && row_ok;
+      const bool r16v = d16 && !w16 && res16 != nullptr && row_ok;
       const bf16* r16_row = r16v ? res16 + row_off : nullptr;
       uint4 rn16[4];
       {
@@ -800,7 +834,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + c1 + 8 * j);
           }
         }
+        const bool fine = tre && (p.dbg & 0x100) && kch == 1;   // fine-grained stamps of this warp's SECOND chunk
         tmem_ld_x32(t_base + (uint32_t)c, rr);
+        if (fine) tre[9] = clock64();
         if (geglu) {
           // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates (unet.py:323-324)
           uint32_t rg[32];
@@ -823,6 +859,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         } else {
           tmem_ld_wait();
+          if (fine) tre[10] = clock64();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
@@ -847,9 +884,24 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 32; ++j) acc[j] = gelu_erf_f(acc[j]);
           }
         }
-        if (tre && ci < 6) tre[9 + ci] = clock64();
+        if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
+        if (fine) tre[11] = clock64();
         // 16-bit residual and row statistics in the row-owner layout (this thread = one row, 32 columns)
-        if (have16) {
+        const bool w16c = w16 && full && !to_tr;   // this chunk goes through the per-warp TMA tiles
+        if (w16c && w16_res) {
+          const int slot = w16_rseq & 1;
+          mbar_wait_a(w16_bar0 + slot * 8, (uint32_t)((w16_rseq >> 1) & 1));
+          const uint8_t* rrow = w16_tiles + 4096 + slot * 2048 + lane * 64;
+          const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((j ^ sw) << 4));
+            const float2 f0 = unpack16(u.x, p.fp16), f1 = unpack16(u.y, p.fp16), f2 = unpack16(u.z, p.fp16),
+                         f3 = unpack16(u.w, p.fp16);
+            acc[8 * j] += f0.x; acc[8 * j + 1] += f0.y; acc[8 * j + 2] += f1.x; acc[8 * j + 3] += f1.y;
+            acc[8 * j + 4] += f2.x; acc[8 * j + 5] += f2.y; acc[8 * j + 6] += f3.x; acc[8 * j + 7] += f3.y;
+          }
+        } else if (have16) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f0 = unpack16(rc16[j].x, p.fp16), f1 = unpack16(rc16[j].y, p.fp16),
@@ -877,6 +929,48 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) { rs_s += acc[j]; rs_q = fmaf(acc[j], acc[j], rs_q); }
           }
+        }
+        if (fine) tre[12] = clock64();
+        if (w16c) {
+          // ---- 16-bit-only outputs: pack this row into the warp's swizzled tile, one lane issues the TMA store
+          const int sslot = w16_sseq & 1;
+          if (lane == 0) tma_store_wait_read1();   // the store issued two chunks ago has drained this tile
+          __syncwarp();
+          if (fine) tre[13] = clock64();
+          uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
+          const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack16(acc[8 * j], acc[8 * j + 1], p.fp16);
+            u.y = pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16);
+            u.z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
+            u.w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
+            *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_cta();
+          if (fine) tre[14] = clock64();
+          __syncwarp();   // all rows written (and the residual tile read) before lane 0 hands them to the TMA unit
+          if (lane == 0) {
+            if (!(p.dbg & 4)) {
+              tma_store_4d_a(&p.wmap16, w16_tiles_a + sslot * 2048u, col0, w16_x, w16_y, w16_n);
+              tma_store_commit();
+            }
+            if (w16_res) {
+              // the residual slot just consumed is free: fetch this warp's chunk after next
+              const int ci2 = ci + 2 * NHALF;
+              const int c2 = col_base + ci2 * 32;
+              if (ci2 < n32 && c2 + 32 <= p.N && !(p.out_tr && c2 >= p.tr_col0)) {
+                const int slot = w16_rseq & 1;
+                mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
+                tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, c2, w16_x, w16_y, w16_n);
+              }
+            }
+          }
+          ++w16_sseq;
+          if (w16_res) ++w16_rseq;
+          if (fine) tre[15] = clock64();
+          continue;
         }
         if (d16 && !o32 && o16 && !resid && !to_tr && full) {
           // ---- lean path for 16-bit-only outputs: four 16-byte stores of this thread's own row
@@ -1018,7 +1112,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
   }
 
-  if (HAS_TMA && p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // drain this half's TMA stores
+  if (HAS_TMA && p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();
+  if (p.w16 && warp >= 2 && lane == 0) tma_store_wait_all();   // this warp's TMA stores have left shared memory and landed   // drain this half's TMA stores
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal / read it
   else __syncthreads();

@@ -87,8 +87,20 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st) {
 // Apply: same mapping; mean/rstd per group derived once per CTA, gamma/beta live in registers.
 // Handles the virtual concat [a | b] along C (unet.py:135).  HBM/L2-bound: 1 read (+1 write).
 // =====================================================================================
-__global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
-                                int strip, double* __restrict__ stats) {
+// four consecutive channels of an activation stored as fp32 or as 16-bit operands (IN16)
+template <bool IN16>
+__device__ __forceinline__ float4 load4(const void* base, long long idx, int fp16) {
+  if (IN16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + idx);
+    const float2 lo = unpack16(u.x, fp16), hi = unpack16(u.y, fp16);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+}
+
+template <bool IN16>
+__global__ void gn_stats_kernel(const void* __restrict__ a, int ca, const void* __restrict__ b, int cb, int hw,
+                                int strip, double* __restrict__ stats, int fp16) {
   pdl_launch();
   pdl_wait();
   __shared__ double s_acc[64];
@@ -102,14 +114,15 @@ __global__ void gn_stats_kernel(const float* __restrict__ a, int ca, const float
   __syncthreads();
   if (pl < lanes) {
     const int ch = q * 4;
-    const float* src;
+    const void* src;
+    long long img_off;
     int cs, co;
-    if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
-    else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
+    if (ch < ca) { src = a; img_off = (long long)n * hw * ca; cs = ca; co = ch; }
+    else { src = b; img_off = (long long)n * hw * cb; cs = cb; co = ch - ca; }
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
     for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
-      const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+      const float4 v = load4<IN16>(src, img_off + (long long)pix * cs + co, fp16);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
       ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
@@ -148,18 +161,20 @@ static void gn_launch_shape(int c, int hw, int n, int* threads, int* strip, int*
   *strips = (hw + st - 1) / st;
 }
 
-void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, double* stats,
-                     cudaStream_t st) {
+void launch_gn_stats(const void* a, int ca, const void* b, int cb, int n, int hw, double* stats,
+                     cudaStream_t st, int in16, int fp16) {
   const int c = ca + cb;
   LDM_CHECK(c % 32 == 0 && ca % 4 == 0 && cb % 4 == 0, "GroupNorm(32): bad channel counts %d+%d", ca, cb);
   LDM_CHECK(c / 4 <= 1024, "GroupNorm: too many channels");
   int threads, strip, strips;
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
-  launch_pdl(gn_stats_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats);
+  if (in16) launch_pdl(gn_stats_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16);
+  else launch_pdl(gn_stats_kernel<false>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
-__global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int hw,
+template <bool IN16>
+__global__ void gn_apply_kernel(const void* __restrict__ a, int ca, const void* __restrict__ b, int cb, int hw,
                                 int strip, const double* __restrict__ stats, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
                                 bf16* __restrict__ out, int fp16) {
@@ -183,10 +198,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
   __syncthreads();
   if (pl >= lanes) return;
   const int ch = q * 4;
-  const float* src;
+  const void* src;
+  long long img_off;
   int cs, co;
-  if (ch < ca) { src = a + (long long)n * hw * ca; cs = ca; co = ch; }
-  else { src = b + (long long)n * hw * cb; cs = cb; co = ch - ca; }
+  if (ch < ca) { src = a; img_off = (long long)n * hw * ca; cs = ca; co = ch; }
+  else { src = b; img_off = (long long)n * hw * cb; cs = cb; co = ch - ca; }
   float sc[4], sh[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -198,7 +214,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
   bf16* dst = out + (long long)n * hw * c + ch;
 #pragma unroll 8
   for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
-    const float4 v = *reinterpret_cast<const float4*>(src + (long long)pix * cs + co);
+    const float4 v = load4<IN16>(src, img_off + (long long)pix * cs + co, fp16);
     float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
     if (do_silu) {
 #pragma unroll
@@ -211,13 +227,17 @@ __global__ void gn_apply_kernel(const float* __restrict__ a, int ca, const float
   }
 }
 
-void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const double* stats, float eps,
-                     const float* gamma, const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st) {
+void launch_gn_apply(const void* a, int ca, const void* b, int cb, int n, int hw, const double* stats, float eps,
+                     const float* gamma, const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st, int in16) {
   const int c = ca + cb;
   int threads, strip, strips;
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
-  launch_pdl(gn_apply_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, eps, gamma, beta, do_silu, out,
-                                                      fp16);
+  if (in16)
+    launch_pdl(gn_apply_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, eps, gamma, beta,
+               do_silu, out, fp16);
+  else
+    launch_pdl(gn_apply_kernel<false>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, eps, gamma, beta,
+               do_silu, out, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -700,6 +720,14 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict
 }
 void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, int fp16, cudaStream_t st) {
   f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, do_silu, fp16);
+  CUDA_CHECK(cudaGetLastError());
+}
+__global__ void widen16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n, int fp16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = load16(x + i, fp16);
+}
+void launch_widen16(const bf16* x, float* y, long long n, int fp16, cudaStream_t st) {
+  widen16_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, y, n, fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 __global__ void fill_f32_kernel(float* x, long long n, float v) {

@@ -18,11 +18,12 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st);
 // ---- K2: GroupNorm(32) statistics + apply (unet.py:374,377,354; autoencoder.py:31,33,68) --
 // Input is fp32 NHWC, optionally the virtual concat of two tensors along C (unet.py:135).
 // stats[n][32][2] = per (sample, group) {sum, sum of squares} in double; zero on entry.
-void launch_gn_stats(const float* a, int ca, const float* b, int cb, int n, int hw, double* stats,
-                     cudaStream_t st);
-void launch_gn_apply(const float* a, int ca, const float* b, int cb, int n, int hw, const double* stats,
+// in16: the inputs are 16-bit operand tensors (the 16-bit residual stream) instead of fp32
+void launch_gn_stats(const void* a, int ca, const void* b, int cb, int n, int hw, double* stats,
+                     cudaStream_t st, int in16 = 0, int fp16 = 0);
+void launch_gn_apply(const void* a, int ca, const void* b, int cb, int n, int hw, const double* stats,
                      float eps, const float* gamma, const float* beta, int do_silu, bf16* out, int fp16,
-                     cudaStream_t st);
+                     cudaStream_t st, int in16 = 0);
 // one-launch GroupNorm (cluster + distributed shared memory); gn_fused_supported says when it applies
 bool gn_fused_supported(int c, int hw, int n);
 void launch_gn_fused(const float* a, int ca, const float* b, int cb, int n, int hw, float eps, const float* gamma,
@@ -56,6 +57,7 @@ void launch_im2col_s2(const bf16* x, int n, int h, int w, int c, bf16* out /*[n*
 void launch_upsample2(const bf16* x, int n, int h, int w, int c, bf16* out, cudaStream_t st);
 
 // ---- misc ---------------------------------------------------------------------------------
+void launch_widen16(const bf16* x, float* y, long long n, int fp16, cudaStream_t st);
 void launch_f32_to_bf16(const float* x, bf16* y, long long n, int do_silu, int fp16, cudaStream_t st);
 void launch_small_dense_f32(const float* x, const float* w, const float* b, int rows, int k, int n, int act_in_silu,
                             int act_out_silu, float* y, cudaStream_t st);

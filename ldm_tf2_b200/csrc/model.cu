@@ -211,6 +211,13 @@ struct Builder {
 
 Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) {
   eng.fp16 = c.precision == 1 ? 1 : 0;
+  // Residual stream format at block boundaries.  Default: 16 bit (fp32 only inside accumulators and statistics),
+  // i.e. every GEMM epilogue writes one 16-bit tensor and GroupNorm reads 2 bytes per element; LDM_B200_STREAM=fp32
+  // keeps an fp32 stream with a 16-bit shadow (round 1's layout) for accuracy comparisons.
+  {
+    const char* e = getenv("LDM_B200_STREAM");
+    stream16_ = !(e && !strcmp(e, "fp32"));
+  }
   build();
 }
 
@@ -592,11 +599,20 @@ void Model::tap(const std::string& name, const Act& a) {
   if (it == taps.end()) return;
   LDM_CHECK(it->second.second == (size_t)a.numel(), "tap %s: buffer has %zu elements, activation %lld",
             name.c_str(), it->second.second, a.numel());
-  CUDA_CHECK(cudaMemcpyAsync(it->second.first, a.f, (size_t)a.numel() * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (a.f) {
+    CUDA_CHECK(cudaMemcpyAsync(it->second.first, a.f, (size_t)a.numel() * sizeof(float), cudaMemcpyDefault, eng.stream));
+  } else {   // 16-bit residual stream: widen into a scratch buffer first
+    float* tmp = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&tmp, (size_t)a.numel() * sizeof(float), eng.stream));
+    launch_widen16(a.b, tmp, a.numel(), eng.fp16, eng.stream);
+    CUDA_CHECK(cudaMemcpyAsync(it->second.first, tmp, (size_t)a.numel() * sizeof(float), cudaMemcpyDefault, eng.stream));
+    CUDA_CHECK(cudaFreeAsync(tmp, eng.stream));
+  }
 }
 
 Act Model::alloc_act(int n, int h, int w, int c, bool f, bool b) {
   Act a; a.n = n; a.h = h; a.w = w; a.c = c;
+  if (f && b && stream16_) f = false;   // block-boundary tensors: the 16-bit copy IS the residual stream
   if (f) a.f = eng.alloc<float>((size_t)a.numel());
   if (b) a.b = eng.alloc<bf16>((size_t)a.numel());
   return a;
@@ -625,7 +641,11 @@ void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out
   // one-launch cluster kernel: correct but measured ~2 % slower per UNet step than statistics + apply
   // (two cluster barriers and a serial second pass per CTA outweigh the saved launch): opt-in
   static const bool fused = getenv("LDM_B200_GN_FUSED") && getenv("LDM_B200_GN_FUSED")[0] == '1';
-  if (fused && gn_fused_supported(g.c, x.h * x.w, x.n)) {
+  const bool in16 = x.f == nullptr;
+  LDM_CHECK(!skip || ((skip->f == nullptr) == in16), "GroupNorm over a concat needs both halves in the same format");
+  const void* xa = in16 ? static_cast<const void*>(x.b) : static_cast<const void*>(x.f);
+  const void* xb = !skip ? nullptr : (in16 ? static_cast<const void*>(skip->b) : static_cast<const void*>(skip->f));
+  if (fused && !in16 && gn_fused_supported(g.c, x.h * x.w, x.n)) {
     eng.launches += 1;
     if (eng.dry) return;
     launch_gn_fused(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, g.eps, g.gamma->f32, g.beta->f32,
@@ -642,13 +662,13 @@ void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out
   }
   eng.launches += 2;
   if (eng.dry) return;
-  launch_gn_stats(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, eng.stream);
-  launch_gn_apply(x.f, x.c, skip ? skip->f : nullptr, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
-                  silu ? 1 : 0, out, eng.fp16, eng.stream);
+  launch_gn_stats(xa, x.c, xb, cb, x.n, x.h * x.w, st, eng.stream, in16 ? 1 : 0, eng.fp16);
+  launch_gn_apply(xa, x.c, xb, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
+                  silu ? 1 : 0, out, eng.fp16, eng.stream, in16 ? 1 : 0);
 }
 
 void Model::linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
-                   float* out_f32, bf16* out_bf16) {
+                   float* out_f32, bf16* out_bf16, const bf16* res16) {
   GemmOp op;
   op.num_a = 1;
   op.a[0] = view_mat(a, rows, w.k, w.k);
@@ -657,7 +677,7 @@ void Model::linear(const bf16* a, long long rows, const LinW& w, const float* bi
   op.add_seg(0, 0, 0, 0, w.k, bk);
   op.W = (int)rows; op.H = 1; op.NB = 1;
   op.N = w.n;
-  op.bias = bias; op.act = act; op.residual = residual; op.out_f32 = out_f32; op.out_bf16 = out_bf16;
+  op.bias = bias; op.act = act; op.residual = residual; op.res16 = res16; op.out_f32 = out_f32; op.out_bf16 = out_bf16;
   op.os_x = w.n; op.os_y = 0; op.os_n = 0;
   eng.gemm(op);
 }
@@ -763,7 +783,7 @@ Act Model::resblock(const ResW& r, const Act& x, const Act* skip) {
   Act a1 = alloc_act(x.n, x.h, x.w, cin, false, true);
   gn(r.gn1, x, skip, true, a1.b);
   // conv1 + bias + time projection (unet.py:384-388)
-  Act h1 = alloc_act(x.n, x.h, x.w, r.cout, true, false);
+  Act h1 = alloc_act(x.n, x.h, x.w, r.cout, !stream16_, stream16_);   // feeds GroupNorm 2 only
   {
     GemmOp op;
     op.num_a = 1;
@@ -779,7 +799,7 @@ Act Model::resblock(const ResW& r, const Act& x, const Act* skip) {
       op.bias2_by_img = temb_by_img_ ? 1 : 0;
       op.step_ptr = temb_use_step_ ? step_dev_ : nullptr;
     }
-    op.out_f32 = h1.f;
+    op.out_f32 = h1.f; op.out_bf16 = h1.b;
     op.os_x = r.cout; op.os_y = (long long)x.w * r.cout; op.os_n = (long long)x.h * x.w * r.cout;
     eng.gemm(op);
   }
@@ -805,8 +825,10 @@ Act Model::resblock(const ResW& r, const Act& x, const Act* skip) {
       }
       op.bias2 = r.sc_bias->f32;
       op.bias2_stride = 0;
-    } else {
+    } else if (x.f) {
       op.residual = x.f;
+    } else {
+      op.res16 = x.b;   // 16-bit residual stream
     }
     op.W = x.w; op.H = x.h; op.NB = x.n; op.N = r.cout;
     op.bias = r.conv2.bias->f32;
@@ -994,7 +1016,7 @@ Act Model::spatial_transformer(STW& s, const Act& x) {
     eng.arena.release(mk2);
   }
   // dense2 + the block's fp32 input residual (unet.py:363-364)
-  linear(z, rows, s.d2, s.d2.bias->f32, ACT_NONE, x.f, out.f, out.b);
+  linear(z, rows, s.d2, s.d2.bias->f32, ACT_NONE, x.f, out.f, out.b, x.f ? nullptr : x.b);
   eng.arena.release(mk);
   return out;
 }
@@ -1378,7 +1400,7 @@ Act Model::ae_attention(AEAttnW& a, const Act& x) {
   if (tpad != t && !eng.dry) CUDA_CHECK(cudaMemsetAsync(vt, 0, (size_t)n * c * tpad * 2, eng.stream));
   qkv_projection(eng, xn, n, t, c, a.qkv, a.qkv_bias, c, qk, vt, tpad);
   attention_core(qk, 2 * c, qk + c, 2 * c, (long long)t * 2 * c, t, vt, tpad, n, t, 1, c, 1.0f / sqrtf((float)c), o, c);
-  linear(o, rows, a.out, a.out.bias->f32, ACT_NONE, x.f, out.f, out.b);
+  linear(o, rows, a.out, a.out.bias->f32, ACT_NONE, x.f, out.f, out.b, x.f ? nullptr : x.b);
   eng.arena.release(mk);
   return out;
 }

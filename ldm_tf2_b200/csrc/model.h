@@ -203,7 +203,8 @@ class Model {
   void attention_core(const bf16* q, long long q_ld, const bf16* k, long long k_ld, long long k_sn, int tk,
                       const bf16* vt, int tpad, int n, int t, int heads, int d, float scale, bf16* o, long long o_ld);
   void linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
-              float* out_f32, bf16* out_bf16);
+              float* out_f32, bf16* out_bf16, const bf16* res16 = nullptr);
+  bool stream16_ = true;   // block-boundary residual stream in 16 bit (LDM_B200_STREAM=fp32: fp32 + 16-bit shadow)
   Act conv3x3(const Act& x_b16, const LinW& w, const float* bias);
   Act upconv(const Act& x_b16, const LinW& w9, const LinW& wp, const float* bias);   // nearest x2 + conv3x3
   Act downconv(const Act& x_b16, const LinW& w, const float* bias, int pad_lo);      // pad + conv3x3 stride 2 VALID

@@ -1,4 +1,6 @@
-"""clock64 trace of the GEMM epilogue for the transformer-block linears: where a tile's cycles go.
+"""LDM_B200_TRACE_FINE=1: the chunk@ list becomes the stamps of warp 2's SECOND chunk, relative to accumulator-ready:
+   [tmem ld issued, ld done, math done, residual+stats done, store tile free, STS+fence done, TMA store issued].
+clock64 trace of the GEMM epilogue for the transformer-block linears: where a tile's cycles go.
    stamps (gemm.cuh `tre`): tile start -> bar1 -> bias staged + bar2 -> accumulator ready -> per-chunk math done -> tile end"""
 import os, sys
 import numpy as np
@@ -31,7 +33,7 @@ for rows, k, n, res, dbg, label in cases:
         for s in range(3):
             a = t[s]
             if a[0] == 0: break
-            ch = [int(a[9 + i] - a[5]) for i in range(6) if a[9 + i]]
+            ch = [int(a[9 + i] - a[5]) for i in range(7) if a[9 + i]]
             line += f" | tile{s}: mainloop {a[3]-a[2]} epi(bar1 {a[7]-a[4]}, stage {a[8]-a[7]}, wait_acc {a[5]-a[8]}, body {a[6]-a[5]}, chunk@ {ch})"
         print(line, flush=True)
 h.close()

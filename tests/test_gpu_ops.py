@@ -254,7 +254,8 @@ def test_upsample_conv_phase_collapsed(h, nb, hh, ww, c):
     assert got.shape == ref.shape
     err = rel_l2(got, ref)
     print(f"upconv {nb}x{hh}x{ww}x{c}: rel-L2 {err:.2e}")
-    assert err < (1e-3 if h.precision == "fp16" else 6e-3)
+    # weights rounded once after the phase sum + the output rounded to the 16-bit residual stream
+    assert err < (2e-3 if h.precision == "fp16" else 8e-3)
 
 
 @pytest.mark.parametrize("nb,hh,ww,cin,cout,mode", [
@@ -274,7 +275,8 @@ def test_stride2_conv_through_strided_tma_map(h, nb, hh, ww, cin, cout, mode):
     ref = O.conv3x3(xr, kr, bias, stride=2) if mode == 1 else O.conv3x3_down_ae(xr, kr, bias)
     assert got.shape == ref.shape
     err = np.abs(got - ref).max()
-    assert err <= 2e-3 * max(1.0, np.abs(ref).max()), f"max abs err {err}"
+    ulp16 = 2.0 ** -10 if h.precision == "fp16" else 2.0 ** -7   # the output is rounded to the 16-bit residual stream
+    assert err <= (2e-3 + ulp16) * max(1.0, np.abs(ref).max()), f"max abs err {err}"
 
 
 @pytest.mark.parametrize("n,t,tk,heads,d", [(1, 512, 1024, 4, 40), (2, 200, 333, 2, 80), (1, 128, 77, 8, 40)])

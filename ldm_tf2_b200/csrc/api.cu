@@ -443,6 +443,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.ew = (dbg & 64) ? 4 : ((dbg & 128) ? 8 : 0);   // bit 6: two CTAs per SM (4 epilogue warps), bit 7: one (8)
   op.dbg = dbg & 15;
   if (getenv("LDM_B200_TRACE_FINE")) op.dbg |= 0x100;   // fine-grained stamps of one chunk (profiles/trace_epilogue.py)
+  if (getenv("LDM_B200_TRACE_GENERAL")) op.dbg |= 0x200;   // keep this launch on the general kernel
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual == 1) {          // fp32 residual stream: fp32 + 16-bit outputs

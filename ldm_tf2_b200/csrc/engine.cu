@@ -42,6 +42,8 @@ typedef void (*GemmKernel)(const GemmParams);
 static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi) {
 #define LDM_K(P, E) (epi == 0 ? (GemmKernel)implicit_gemm_kernel<P, E, 0> : epi == 1 ? (GemmKernel)implicit_gemm_kernel<P, E, 1> \
                                                                                      : (GemmKernel)implicit_gemm_kernel<P, E, 2>)
+  if (epi == 3) return pair ? (GemmKernel)implicit_gemm_kernel<1, 8, 3> : (GemmKernel)implicit_gemm_kernel<0, 8, 3>;   // lean 16-bit
+  if (epi == 4) return pair ? (GemmKernel)implicit_gemm_kernel<1, 8, 4> : (GemmKernel)implicit_gemm_kernel<0, 8, 4>;   // lean GEGLU
   if (pair) return ew == 4 ? LDM_K(1, 4) : LDM_K(1, 8);
   return ew == 4 ? LDM_K(0, 4) : LDM_K(0, 8);
 #undef LDM_K
@@ -64,6 +66,10 @@ Engine::Engine(int dev) : device(dev) {
   cudaDriverEntryPointQueryResult qres;
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  for (int epi = 3; epi < 5; ++epi) {
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  }
   for (int epi = 0; epi < 3; ++epi) {
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -312,10 +318,21 @@ void Engine::gemm(const GemmOp& op) {
                    (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0 &&
                    (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 15) == 0) &&
                    (!op.out_tr || (op.tr_col0 & 31) == 0);
-  const bool ew4 = !tma_epi && !w16 && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
+  // The lean kernels (gemm.cuh, EPI = 3 / 4) carry ONLY the 16-bit epilogue: the hot launches of the 16-bit residual
+  // stream.  LDM_B200_LEAN=0 sends everything through the general kernel (A/B).
+  static const bool lean_off = getenv("LDM_B200_LEAN") && getenv("LDM_B200_LEAN")[0] == '0';
+  const bool lean = !lean_off && !tma_epi && !frag_want && op.out_bf16 && !op.out_f32 && !op.residual && !op.out_tr &&
+                    !(op.bias2 && op.bias2_by_img) && splits == 1 && (op.act == ACT_NONE || geglu) && op.ew != 4 &&
+                    op.N % 32 == 0 && bn % (geglu ? 64 : 32) == 0 && gemm_n % bn == 0 && op.alpha == 1.0f &&
+                    ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(op.out_bf16) & 15) == 0 &&
+                    (!op.res16 || (reinterpret_cast<uintptr_t>(op.res16) & 15) == 0) && !(op.dbg & 0x200);
+  const bool ew4 = !tma_epi && !w16 && !lean && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
   p.tma_epi = tma_epi ? 1 : 0;
   p.w16 = w16 ? 1 : 0;
-  if (w16) {
+  if (lean) {
+    p.epi_bytes = w16 ? 8 * GEMM_W16_WARP_BYTES : 0;
+  } else if (w16) {
     p.epi_bytes = GEMM_EPI_LEGACY_BYTES + 8 * GEMM_W16_WARP_BYTES;
   } else if (ew4) {
     p.epi_bytes = GEMM_EPI_EW4_BYTES;
@@ -416,7 +433,7 @@ void Engine::gemm(const GemmOp& op) {
     if (o == "res" && !is_conv && op.residual) return;
     if (o == "split" && splits > 1) return;
   }
-  const int epi = p.tma_epi ? 2 : (p.frag_pref ? 1 : 0);
+  const int epi = lean ? (geglu ? 4 : 3) : (p.tma_epi ? 2 : (p.frag_pref ? 1 : 0));
   const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, ew4 ? 4 : 8, epi);
   const int threads = ew4 ? GEMM_THREADS_EW4 : GEMM_THREADS;
   if (pair) launch_pair(kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
@@ -425,8 +442,8 @@ void Engine::gemm(const GemmOp& op) {
   if (profile) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
     prof_events.push_back({e0, e1});
-    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d ew=%d", rows_total * op.num_phases, gemm_n,
-                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0, ew4 ? 4 : 8));
+    prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d ew=%d epi=%d%s", rows_total * op.num_phases, gemm_n,
+                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0, ew4 ? 4 : 8, epi, p.w16 ? "t" : ""));
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);

@@ -438,14 +438,16 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 // under the other's -- the short-K projections of the transformers, whose epilogue (5-8 k cycles
 // per tile) outlasts the 2-3 k-cycle main loop.
 // EPI selects which optional epilogue flavours are compiled in (each costs registers in every other path):
-// bit 0 = fragment-layout path (A/B switch), bit 1 = TMA-store path (A/B switch); the default kernels have neither.
+// 0 = the general epilogue; 1 = + fragment-layout path (A/B switch); 2 = + block-wide TMA-store path (A/B switch);
+// 3 / 4 = ONLY the lean 16-bit epilogue (4: with GEGLU gating) -- the hot launches of the 16-bit residual stream.
 template <int PAIR, int EW, int EPI>
 // register budget: 168 per thread either way.  The register file is 4 x 16 K (one per scheduler partition): the
 // 10 warps of the EW = 8 flavour put three warps on two of the partitions (16384 / 3 / 32 = 170), and two EW = 4
 // CTAs put three warps on every partition -- a launch with more registers fails with cudaErrorLaunchOutOfResources.
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr bool HAS_FRAG = (EPI & 1) != 0, HAS_TMA = (EPI & 2) != 0;
+  constexpr int LEAN = EPI == 3 ? 1 : (EPI == 4 ? 2 : 0);   // 16-bit-only outputs (2: GEGLU); see the lean epilogue
+  constexpr bool HAS_FRAG = EPI == 1, HAS_TMA = EPI == 2;
   constexpr int NHALF = EW / 4;          // column-chunk interleave between the warps of a TMEM lane quadrant
   constexpr int ETHREADS = 32 * EW;      // epilogue threads
   long long* const trace_base = blockIdx.x < 148 ? p.trace : nullptr;   // the trace buffer has 148 CTA slots
@@ -622,6 +624,228 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 2) {
+    if constexpr (LEAN != 0) {
+      // ------------------------------------------------ LEAN epilogue (EPI = 3 / 4): 16-bit-only outputs.
+      // The general epilogue below serves every output flavour of the path and is ~50 KB of straight-line code per
+      // chunk iteration; its warps then run at ~0.1 instructions per clock, whatever they execute
+      // (profiles/r2_trace_epilogue.txt: 300-500 cycles for 40 instructions) -- instruction fetch, not the memory
+      // system, bounds it.  This path is what the transformer-block linears, GEGLU (LEAN = 2) and the convolutions
+      // of the 16-bit residual stream need, and nothing else: row-owner layout (thread = row, chunk = 32 columns),
+      // bias / folded LayerNorm / GEGLU, 16-bit residual, row statistics, and 16-bit stores either through
+      // per-warp TMA tiles (w16) or as four 16-byte stores of the thread's own row.  The engine selects it only when
+      // N % 32 == 0, offsets are 16-byte aligned, and there is no fp32 output / fp32 residual / transposed output /
+      // per-image bias / split-K (Engine::gemm).
+      constexpr bool GEGLU = LEAN == 2;
+      const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
+      const int r = quad * 32 + lane;
+      const int et = threadIdx.x - 64;
+      uint8_t* const w16_tiles = epi_area + ew * GEMM_W16_WARP_BYTES;   // [store 0 | store 1 | residual 0 | residual 1]
+      const uint32_t w16_tiles_a = smem_u32(w16_tiles);
+      const uint32_t w16_bar0 = smem_u32(w16_bar) + (uint32_t)(ew * 16);
+      int w16_rseq = 0, w16_sseq = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const int hw_b = p.h_b * p.w_b;
+      const bool ln = p.ln_stats != nullptr;
+      const int n32 = GEGLU ? (p.block_n >> 6) : (p.block_n >> 5);
+      const int hcols = p.block_n >> 1;
+      const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+      for (int tile = cta_id; tile < total_tiles; tile += n_workers) {
+        const TileCoord t = PAIR ? decode_pair_tile(p, tile, rank) : decode_tile(p, tile);
+        const int img = t.img0 + r / hw_b;
+        const int yq = t.y0 + (r % hw_b) / p.w_b;
+        const int xq = t.x0 + r % p.w_b;
+        const bool row_ok = (r < p.box_rows) && (img < p.NB) && (yq < p.H) && (xq < p.W) && !(p.dbg & 4);
+        const long long row_off = (long long)img * p.os_n + (long long)yq * p.os_y + (long long)xq * p.os_x +
+                                  (long long)(t.phase >> 1) * p.os_phase_y + (long long)(t.phase & 1) * p.os_phase_x;
+        const long long grow = ((long long)img * p.H + yq) * p.W + xq;
+        float ln_a = p.alpha, ln_b = 0.f;
+        if (ln && row_ok) {
+          const longlong2 st = *reinterpret_cast<const longlong2*>(p.ln_stats + 2 * grow);
+          const float mean = (float)st.x * (RS_INV_SUM * p.ln_inv_c);
+          const float var = fmaxf(fmaf(-mean, mean, (float)st.y * (RS_INV_SQ * p.ln_inv_c)), 0.f);
+          ln_a = rsqrtf(var + p.ln_eps);
+          ln_b = -mean * ln_a;
+        }
+        float rs_s = 0.f, rs_q = 0.f;
+        long long* tre = nullptr;
+        if (trace_base && warp == 2 && lane == 0) {
+          const int tslot = (tile - cta_id) / n_workers;
+          if (tslot < 63) tre = trace_base + ((long long)blockIdx.x * 64 + tslot) * 16;
+        }
+        if (tre) tre[4] = clock64();
+        named_bar_sync(1, ETHREADS);   // the previous tile's readers of bias_s / cs_s are done
+        if (tre) tre[7] = clock64();
+        {
+          const float* bias2_tile = p.bias2 ? p.bias2 + (p.step_ptr ? (long long)__ldg(p.step_ptr) : 0ll) * p.bias2_stride : nullptr;
+          const int lim = GEGLU ? 2 * p.N : p.N;
+          for (int c = et; c < p.block_n; c += ETHREADS) {
+            const int col = t.n0 + c;
+            float b = 0.f;
+            if (col < lim) {
+              if (p.bias) b += __ldg(p.bias + col);
+              if (bias2_tile) b += __ldg(bias2_tile + col);
+            }
+            bias_s[c] = b;
+            if (ln) cs_s[c] = col < lim ? __ldg(p.ln_cs + col) : 0.f;
+          }
+        }
+        named_bar_sync(1, ETHREADS);
+        if (tre) tre[8] = clock64();
+        const int col_base = GEGLU ? t.n_tile * hcols : t.n0;
+        const bool w16 = p.w16 && quad * 32 < p.box_rows;
+        const int w16_x = t.x0 + (quad * 32) % p.w_b, w16_y = t.y0 + ((quad * 32) % hw_b) / p.w_b,
+                  w16_n = t.img0 + (quad * 32) / hw_b;
+        const bool res = p.res16 != nullptr;
+        const bf16* r16_row = p.res16 + row_off;
+        uint4 rn16[4];
+        if (res) {
+          if (w16) {
+            if (lane == 0) {   // this warp's first two residual chunks: in flight while the MMA still runs
+              for (int k = 0; k < 2; ++k) {
+                const int ci0 = half + k * NHALF;
+                if (ci0 < n32) {
+                  const int slot = (w16_rseq + k) & 1;
+                  mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
+                  tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col_base + ci0 * 32,
+                                w16_x, w16_y, w16_n);
+                }
+              }
+            }
+          } else if (row_ok && half < n32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + col_base + half * 32 + 8 * j);
+          }
+        }
+        mbar_wait_a(tfull0 + as * 8, aphase);
+        tc_fence_after();
+        if (tre) tre[5] = clock64();
+        const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
+        for (int ci = half; ci < n32; ci += NHALF) {
+          const int c = ci * 32;
+          const int col0 = col_base + c;
+          uint32_t rr[32];
+          float acc[32];
+          uint4 rc16[4];
+          if (res && !w16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rc16[j] = rn16[j];
+            if (row_ok && ci + NHALF < n32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + col0 + NHALF * 32 + 8 * j);
+            }
+          }
+          tmem_ld_x32(t_base + (uint32_t)c, rr);
+          if (GEGLU) {
+            uint32_t rg[32];
+            tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
+              float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
+              if (ln) {
+                const float4 ca = *reinterpret_cast<const float4*>(cs_s + c + j);
+                const float4 cg = *reinterpret_cast<const float4*>(cs_s + hcols + c + j);
+                ba.x = fmaf(ca.x, ln_b, ba.x); ba.y = fmaf(ca.y, ln_b, ba.y); ba.z = fmaf(ca.z, ln_b, ba.z); ba.w = fmaf(ca.w, ln_b, ba.w);
+                bg.x = fmaf(cg.x, ln_b, bg.x); bg.y = fmaf(cg.y, ln_b, bg.y); bg.z = fmaf(cg.z, ln_b, bg.z); bg.w = fmaf(cg.w, ln_b, bg.w);
+              }
+              acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, ba.x) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), ln_a, bg.x));
+              acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), ln_a, ba.y) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 1]), ln_a, bg.y));
+              acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), ln_a, ba.z) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 2]), ln_a, bg.z));
+              acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, ba.w) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 3]), ln_a, bg.w));
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
+              if (ln) {
+                const float4 cs = *reinterpret_cast<const float4*>(cs_s + c + j);
+                b.x = fmaf(cs.x, ln_b, b.x); b.y = fmaf(cs.y, ln_b, b.y); b.z = fmaf(cs.z, ln_b, b.z); b.w = fmaf(cs.w, ln_b, b.w);
+              }
+              acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, b.x);
+              acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), ln_a, b.y);
+              acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), ln_a, b.z);
+              acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, b.w);
+            }
+          }
+          if (tre && ci < 6) tre[9 + ci] = clock64();
+          if (res) {
+            if (w16) {
+              const int slot = w16_rseq & 1;
+              mbar_wait_a(w16_bar0 + slot * 8, (uint32_t)((w16_rseq >> 1) & 1));
+              const uint8_t* rrow = w16_tiles + 4096 + slot * 2048 + lane * 64;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rc16[j] = *reinterpret_cast<const uint4*>(rrow + ((j ^ sw) << 4));
+            }
+            if (w16 || row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f0 = unpack16(rc16[j].x, p.fp16), f1 = unpack16(rc16[j].y, p.fp16),
+                             f2 = unpack16(rc16[j].z, p.fp16), f3 = unpack16(rc16[j].w, p.fp16);
+                acc[8 * j] += f0.x; acc[8 * j + 1] += f0.y; acc[8 * j + 2] += f1.x; acc[8 * j + 3] += f1.y;
+                acc[8 * j + 4] += f2.x; acc[8 * j + 5] += f2.y; acc[8 * j + 6] += f3.x; acc[8 * j + 7] += f3.y;
+              }
+            }
+          }
+          if (p.rs_out) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              s0 += acc[j]; s1 += acc[j + 1];
+              q0 = fmaf(acc[j], acc[j], q0); q1 = fmaf(acc[j + 1], acc[j + 1], q1);
+            }
+            rs_s += s0 + s1; rs_q += q0 + q1;
+          }
+          uint4 u[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            u[j].x = pack16(acc[8 * j], acc[8 * j + 1], p.fp16);
+            u[j].y = pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16);
+            u[j].z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
+            u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
+          }
+          if (w16) {
+            const int sslot = w16_sseq & 1;
+            if (lane == 0) tma_store_wait_read1();   // the store issued two chunks ago has drained this tile
+            __syncwarp();
+            uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u[j];
+            fence_proxy_async_cta();
+            __syncwarp();
+            if (lane == 0) {
+              if (!(p.dbg & 4)) {
+                tma_store_4d_a(&p.wmap16, w16_tiles_a + sslot * 2048u, col0, w16_x, w16_y, w16_n);
+                tma_store_commit();
+              }
+              if (res && ci + 2 * NHALF < n32) {   // the residual slot just consumed is free: fetch the chunk after next
+                const int slot = w16_rseq & 1;
+                mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
+                tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col0 + 2 * NHALF * 32,
+                              w16_x, w16_y, w16_n);
+              }
+            }
+            ++w16_sseq;
+            if (res) ++w16_rseq;
+          } else if (row_ok) {
+            bf16* op16 = p.out_bf16 + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(op16 + 8 * j) = u[j];
+          }
+        }
+        if (p.rs_out && row_ok) rs_add(p.rs_out + 2 * grow, rs_s, rs_q);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && rank) mbar_arrive_cluster(tempty0 + as * 8, 0);
+          else mbar_arrive_a(tempty0 + as * 8);
+        }
+        if (tre) tre[6] = clock64();
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+      }
+    } else {
     // ------------------------------------------------ epilogue warps 2..9
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // takes column chunks with (chunk index % NHALF) == half (EW = 4: always 0)
@@ -1110,6 +1334,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (tre) tre[6] = clock64();
       if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
+    }   // general epilogue
   }
 
   if (HAS_TMA && p.tma_epi && warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();

@@ -25,7 +25,7 @@ cases = [  # rows, k, n, residual mode, dbg, label
     (ROWS // 16, 1280, 1280, 3, 0, "level 2 C x C residual + stats"),
 ]
 for rows, k, n, res, dbg, label in cases:
-    for flavour, fl in ((0, "auto"), (64, "2 CTA/SM"), (128, "1 CTA/SM")):
+    for flavour, fl in ((0, "auto"),) if os.environ.get("ONLY_AUTO") else ((0, "auto"), (64, "2 CTA/SM"), (128, "1 CTA/SM")):
         ms, tr = h.bench_gemm(rows, k, n, 256 if dbg >> 8 == 3 else 0, dbg | flavour, 0, 32, 30, trace=True, residual=res)
         t = tr[0]
         entry, body, end = t[63, 2], t[63, 0], t[63, 1]

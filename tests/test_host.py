@@ -5,6 +5,7 @@ import ast
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -193,24 +194,31 @@ def test_wordpiece_matches_hf_golden(tmp_path):
     assert (ids[:3] == np.array(tokens.UNCOND_IDS)).all() and (ids[3:] == np.array(tokens.COND_IDS)).all()
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    """profiles/r1_bench_n1.json is a bench.py line as the driver reads it: the base contract's keys plus
-    roofline / cpu_baseline / e2e / gpu_launches / clocks, with consistent arithmetic."""
-    import json
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")))
-    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
-        assert k in d, k
-    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert "workload" in d["config"] and "model" not in d["config"]
-    r = d["roofline"]
-    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert abs(r["achieved"] - r["algorithmic_gflop_per_unet_step"] / r["kernel_ms_per_unet_step"]) < 1e-6
-    assert r["traffic"] > 0
-    c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
-    e = d["e2e"]
-    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
-    assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == []
-    images = d["config"]["global_batch"] * d["steps"]
-    assert abs(d["value"] - images / (d["ms_per_step"] * d["steps"] / 1e3)) / d["value"] < 1e-6
+def test_bench_configs_and_reference_arm_plumbing(monkeypatch, capsys):
+    """bench.py host logic without a GPU: the BASELINE.json configs shard over 1 / 2 / 4 / 8 ranks as strong
+    scaling, the workload text names the BASELINE config, non-zero ranks of the reference arm exit without work, the
+    BLAS pool is pinned to the cores the process may use (torchrun exports OMP_NUM_THREADS=1), and the checksum helper
+    is the leading 16 hex digits of SHA-256."""
+    import hashlib
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    assert set(bench.CONFIGS) == {"c2", "c3", "c4", "c5"} and bench.CONFIGS["c3"]["B"] == 64
+    for world in (1, 2, 4, 8):
+        assert bench.CONFIGS["c3"]["B"] % world == 0
+        txt = bench.workload_text("c3", bench.CONFIGS["c3"], world, 64 // world, False)
+        assert "configs[2]" in txt and "[64,32,32,4]" in txt and f"({64 // world}/GPU, strong scaling)" in txt
+    assert "configs[1]" in bench.workload_text("c2", bench.CONFIGS["c2"], 1, 4, False)
+    assert "eta=1" in bench.workload_text("c2", bench.CONFIGS["c2"], 1, 4, False)
+    assert "512x512" in bench.workload_text("c4", bench.CONFIGS["c4"], 8, 1, False)
+    assert "16384 codes" in bench.workload_text("c5", bench.CONFIGS["c5"], 1, 32, False)
+    n = bench.cpu_threads()
+    assert 1 <= n <= (os.cpu_count() or 1)
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    assert bench.sha16(a) == hashlib.sha256(a.tobytes()).hexdigest()[:16]
+    # under torchrun only rank 0 runs the CPU arm: the other ranks return before touching the oracle
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2"])
+    bench.main()
+    assert capsys.readouterr().out == ""

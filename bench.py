@@ -440,7 +440,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": precision, "data": "synthetic",
             "config": {"workload": workload, "baseline_config_index": c["index"],
-                       "operands": f"{precision} tensor-core operands, fp32 accumulate, fp32 residual stream at block boundaries",
+                       "operands": f"{precision} tensor-core operands, fp32 accumulate and statistics, "
+                                   + ("fp32" if os.environ.get("LDM_B200_STREAM") == "fp32" else "16-bit") + " residual stream between blocks",
                        "global_batch": global_b, "per_gpu_batch": B,
                        "parallelism": f"dp{world} (sample-sharded weight replicas, no collective inside the loop)",
                        "l2": "not flushed explicitly: every UNet step streams 1.75 GB of 16-bit weights plus "

@@ -38,15 +38,19 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    stamp = os.path.join(HERE, "build", "stamp")
+    # LDM_B200_BUILD_DIR: build objects + library somewhere else (e.g. while a gpurun snapshot of the tree is pending)
+    out_dir = os.environ.get("LDM_B200_BUILD_DIR")
+    lib = os.path.join(out_dir, "libldm_b200.so") if out_dir else LIB
+    obj_dir = os.path.join(out_dir, "build") if out_dir else os.path.join(HERE, "build")
+    stamp = os.path.join(obj_dir, "stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return lib
+    os.makedirs(obj_dir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def cc(src):
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -57,13 +61,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    cmd = [NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -214,6 +214,7 @@ __device__ __forceinline__ void tma_store_4d_a(const void* map, uint32_t smem_sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // at most one bulk group of this thread still reading shared memory (double-buffered staging tiles)
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

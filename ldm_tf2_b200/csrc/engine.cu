@@ -42,8 +42,11 @@ typedef void (*GemmKernel)(const GemmParams);
 static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi) {
 #define LDM_K(P, E) (epi == 0 ? (GemmKernel)implicit_gemm_kernel<P, E, 0> : epi == 1 ? (GemmKernel)implicit_gemm_kernel<P, E, 1> \
                                                                                      : (GemmKernel)implicit_gemm_kernel<P, E, 2>)
-  if (epi == 3) return pair ? (GemmKernel)implicit_gemm_kernel<1, 8, 3> : (GemmKernel)implicit_gemm_kernel<0, 8, 3>;   // lean 16-bit
-  if (epi == 4) return pair ? (GemmKernel)implicit_gemm_kernel<1, 8, 4> : (GemmKernel)implicit_gemm_kernel<0, 8, 4>;   // lean GEGLU
+#define LDM_L(P, X) (ew == 16 ? (GemmKernel)implicit_gemm_kernel<P, 16, X> : ew == 12 ? (GemmKernel)implicit_gemm_kernel<P, 12, X> \
+                                                                                          : (GemmKernel)implicit_gemm_kernel<P, 8, X>)
+  if (epi == 3) return pair ? LDM_L(1, 3) : LDM_L(0, 3);   // lean 16-bit, 8 / 12 / 16 epilogue warps
+  if (epi == 4) return pair ? LDM_L(1, 4) : LDM_L(0, 4);   // lean GEGLU
+#undef LDM_L
   if (pair) return ew == 4 ? LDM_K(1, 4) : LDM_K(1, 8);
   return ew == 4 ? LDM_K(0, 4) : LDM_K(0, 8);
 #undef LDM_K
@@ -66,10 +69,11 @@ Engine::Engine(int dev) : device(dev) {
   cudaDriverEntryPointQueryResult qres;
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-  for (int epi = 3; epi < 5; ++epi) {
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  }
+  for (int epi = 3; epi < 5; ++epi)
+    for (int ew : {8, 12, 16}) {
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, ew, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, ew, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    }
   for (int epi = 0; epi < 3; ++epi) {
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -230,7 +234,9 @@ void Engine::gemm(const GemmOp& op) {
   LDM_CHECK(!(op.rs_out && op.residual), "gemm: row statistics are taken before the fp32 residual is added");
   LDM_CHECK(!op.ln_stats || (op.ln_cs && op.ln_c > 0 && op.alpha == 1.0f), "gemm: folded LayerNorm needs column sums and the row width");
   LDM_CHECK(!fused_rows || (op.num_phases == 1 && op.b_mode == B_PLAIN), "gemm: row-fused epilogue terms need a plain GEMM");
-  const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1 && !fused_rows;
+  // (the finalize kernel adds a 16-bit residual; the folded LayerNorm / row statistics are not split-K material)
+  const bool can_split = !geglu && !op.out_tr && op.num_phases == 1 && op.b_mode == B_PLAIN && op.splits != 1 &&
+                         !op.ln_stats && !op.rs_out;
   if (can_split && bn && op.splits > 1 && total_kb >= 2 * op.splits) splits = op.splits;   // explicit tile + split (tuning hook)
   if (can_split && !bn) {
     // few output tiles and a long K loop (low-resolution convs, text encoder): take the widest
@@ -321,7 +327,11 @@ void Engine::gemm(const GemmOp& op) {
   // The lean kernels (gemm.cuh, EPI = 3 / 4) carry ONLY the 16-bit epilogue: the hot launches of the 16-bit residual
   // stream.  LDM_B200_LEAN=0 sends everything through the general kernel (A/B).
   static const bool lean_off = getenv("LDM_B200_LEAN") && getenv("LDM_B200_LEAN")[0] == '0';
-  const bool lean = !lean_off && !tma_epi && !frag_want && op.out_bf16 && !op.out_f32 && !op.residual && !op.out_tr &&
+  // transposed V^T columns in the lean kernel: a warp's 32 rows must be 32 consecutive x of one image row
+  const bool lean_tr_ok = !op.out_tr || ((w_b % 32) == 0 && ((op.ts_c | op.ts_n | op.ts_y) & 7) == 0 && (op.W & 7) == 0 &&
+                                         (op.tr_col0 % bn) == 0 && (reinterpret_cast<uintptr_t>(op.out_tr) & 15) == 0 &&
+                                         !op.res16 && !op.rs_out);
+  const bool lean = !lean_off && !tma_epi && !frag_want && op.out_bf16 && !op.out_f32 && !op.residual && lean_tr_ok &&
                     !(op.bias2 && op.bias2_by_img) && splits == 1 && (op.act == ACT_NONE || geglu) && op.ew != 4 &&
                     op.N % 32 == 0 && bn % (geglu ? 64 : 32) == 0 && gemm_n % bn == 0 && op.alpha == 1.0f &&
                     ((op.N | op.os_n | op.os_y | op.os_x | op.os_phase_y | op.os_phase_x) & 7) == 0 &&
@@ -330,8 +340,19 @@ void Engine::gemm(const GemmOp& op) {
   const bool ew4 = !tma_epi && !w16 && !lean && op.ew != 8 && fits_half && (op.ew == 4 || (ew4_default && short_k && many_tiles));
   p.tma_epi = tma_epi ? 1 : 0;
   p.w16 = w16 ? 1 : 0;
+  p.w16_nbuf = w16 ? 2 : 1;   // (also the per-warp stride of the lean kernel's tile area: nbuf * 4 KB)
+  // epilogue warps of the lean kernels (LDM_B200_LEAN_EW = 8 / 12 / 16).  Measured in-graph (profiles/r2_ab_switches.txt):
+  // 8 warps 5.36 ms per UNet step at 8 images, 12 warps 5.52, 16 warps 5.75 -- more warps make every chunk slower
+  // (the 64 B/clk TMEM read port and the shrinking operand pipeline), so 8 it is.
+  const int lean_ew = lean ? LDM_TUNE("LDM_B200_LEAN_EW", 8) : 8;
   if (lean) {
-    p.epi_bytes = w16 ? 8 * GEMM_W16_WARP_BYTES : 0;
+    p.epi_bytes = op.out_tr ? lean_ew * 4096 : 0;   // the V^T transposition tile of every warp
+    if (w16) {
+      // double-buffered tiles unless they would squeeze the operand pipeline below 5 stages
+      const int stages2 = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - lean_ew * 8192 - 1024) / slot;
+      p.w16_nbuf = (stages2 >= LDM_TUNE("LDM_B200_W16_MINSTAGES", 5) || total_kb / splits <= stages2) ? 2 : 1;
+      p.epi_bytes = lean_ew * p.w16_nbuf * 4096;
+    }
   } else if (w16) {
     p.epi_bytes = GEMM_EPI_LEGACY_BYTES + 8 * GEMM_W16_WARP_BYTES;
   } else if (ew4) {
@@ -434,8 +455,8 @@ void Engine::gemm(const GemmOp& op) {
     if (o == "split" && splits > 1) return;
   }
   const int epi = lean ? (geglu ? 4 : 3) : (p.tma_epi ? 2 : (p.frag_pref ? 1 : 0));
-  const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, ew4 ? 4 : 8, epi);
-  const int threads = ew4 ? GEMM_THREADS_EW4 : GEMM_THREADS;
+  const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, lean ? lean_ew : (ew4 ? 4 : 8), epi);
+  const int threads = lean ? 64 + 32 * lean_ew : (ew4 ? GEMM_THREADS_EW4 : GEMM_THREADS);
   if (pair) launch_pair(kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
   else launch_pdl_kind(2, kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
   CUDA_CHECK(cudaGetLastError());
@@ -443,7 +464,7 @@ void Engine::gemm(const GemmOp& op) {
     CUDA_CHECK(cudaEventRecord(e1, stream));
     prof_events.push_back({e0, e1});
     prof_labels.push_back(fmt("M=%lld N=%d K=%d bn=%d splits=%d segs=%d act=%d pair=%d ew=%d epi=%d%s", rows_total * op.num_phases, gemm_n,
-                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0, ew4 ? 4 : 8, epi, p.w16 ? "t" : ""));
+                              total_kb * GEMM_BK, bn, splits, op.num_segs, op.act, pair ? 1 : 0, lean ? lean_ew : (ew4 ? 4 : 8), epi, p.w16 ? (p.w16_nbuf == 2 ? "t2" : "t1") : ""));
     prof_flops += 2.0 * (double)op.NB * op.H * op.W * op.num_phases * (double)gemm_n * (double)total_kb * GEMM_BK;
   }
   if (splits > 1) launch_splitk_finalize(p, splits, rows_total, stream);
@@ -461,6 +482,7 @@ void Engine::attention(const AttnOp& op) {
   p.kv_tiles = (op.tk + ATT_BN - 1) / ATT_BN;
   p.scale_log2 = op.scale * 1.4426950408889634f;
   p.o = op.o; p.o_ld = op.o_ld; p.fp16 = fp16;
+  { static const bool off = getenv("LDM_B200_POLY_EXP") && getenv("LDM_B200_POLY_EXP")[0] == '0'; p.poly_exp = off ? 0 : 1; }
   p.trace = op.trace;
   const int q_bytes = p.dp_atoms * ATT_BM * 128;
   const int kv_bytes = p.dp_atoms * ATT_BN * 128 + ((p.dv * 128 + 1023) & ~1023);
@@ -502,8 +524,8 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, long long s
                                        int N, int W, int H, const float* __restrict__ bias,
                                        const float* __restrict__ bias2, int bias2_stride, int bias2_by_img,
                                        const int* __restrict__ step_ptr, int act, const float* residual,
-                                       float* out_f32, bf16* out_bf16, long long os_n, long long os_y, long long os_x,
-                                       int fp16) {
+                                       const bf16* res16, float* out_f32, bf16* out_bf16, long long os_n, long long os_y,
+                                       long long os_x, int fp16) {
   pdl_launch();
   pdl_wait();
   const int n4 = (N + 3) >> 2;
@@ -539,6 +561,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, long long s
       if (act == ACT_SILU) t = silu_f(t);
       else if (act == ACT_GELU) t = gelu_erf_f(t);
       if (residual) t += residual[off + j];
+      if (res16) t += load16(res16 + off + j, fp16);
       if (out_f32) out_f32[off + j] = t;
       if (out_bf16) store16(out_bf16 + off + j, t, fp16);
     }
@@ -551,7 +574,7 @@ void launch_splitk_finalize(const GemmParams& p, int splits, long long rows, cud
   if (blocks > 148 * 8) blocks = 148 * 8;
   launch_pdl(splitk_finalize_kernel, dim3((int)blocks), dim3(256), 0, st, (const float*)p.ws, p.ws_split_stride, splits,
              rows, p.N, p.W, p.H, p.bias, p.bias2, p.bias2_stride, p.bias2_by_img, p.step_ptr, p.act,
-             (const float*)p.residual, p.out_f32, p.out_bf16, p.os_n, p.os_y, p.os_x, p.fp16);
+             (const float*)p.residual, (const bf16*)p.res16, p.out_f32, p.out_bf16, p.os_n, p.os_y, p.os_x, p.fp16);
   CUDA_CHECK(cudaGetLastError());
 }
 

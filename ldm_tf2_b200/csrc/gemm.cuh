@@ -113,6 +113,7 @@ struct GemmParams {
   // same way one chunk ahead.  Global memory is touched in whole lines by the TMA unit instead of 32 partial lines
   // per warp instruction (the LSU processes one line per clock: the row-owner stores were bound by it).
   int w16;
+  int w16_nbuf;                  // store / residual tiles per warp: 2 (double-buffered) or 1 (leaves shared memory to the pipeline)
   CUtensorMap wmap16, wrmap16;   // (32 cols, 32 x, 1, 1) boxes over out_bf16 / res16
   int frag_pref;            // 16-bit-only outputs: take the fragment-layout epilogue where a tile allows it
   float* out_f32;
@@ -639,7 +640,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
       const int r = quad * 32 + lane;
       const int et = threadIdx.x - 64;
-      uint8_t* const w16_tiles = epi_area + ew * GEMM_W16_WARP_BYTES;   // [store 0 | store 1 | residual 0 | residual 1]
+      const int nbuf = p.w16_nbuf;                                        // 1 or 2 tiles of each kind
+      uint8_t* const w16_tiles = epi_area + ew * (nbuf * 4096);         // [store tiles | residual tiles], 2 KB each
+      const uint32_t w16_res_off = (uint32_t)(nbuf * 2048);
       const uint32_t w16_tiles_a = smem_u32(w16_tiles);
       const uint32_t w16_bar0 = smem_u32(w16_bar) + (uint32_t)(ew * 16);
       int w16_rseq = 0, w16_sseq = 0;
@@ -702,12 +705,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (res) {
           if (w16) {
             if (lane == 0) {   // this warp's first two residual chunks: in flight while the MMA still runs
-              for (int k = 0; k < 2; ++k) {
+              for (int k = 0; k < nbuf; ++k) {
                 const int ci0 = half + k * NHALF;
                 if (ci0 < n32) {
-                  const int slot = (w16_rseq + k) & 1;
+                  const int slot = (w16_rseq + k) & (nbuf - 1);
                   mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
-                  tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col_base + ci0 * 32,
+                  tma_load_4d_a(w16_tiles_a + w16_res_off + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col_base + ci0 * 32,
                                 w16_x, w16_y, w16_n);
                 }
               }
@@ -773,9 +776,9 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           if (tre && ci < 6) tre[9 + ci] = clock64();
           if (res) {
             if (w16) {
-              const int slot = w16_rseq & 1;
-              mbar_wait_a(w16_bar0 + slot * 8, (uint32_t)((w16_rseq >> 1) & 1));
-              const uint8_t* rrow = w16_tiles + 4096 + slot * 2048 + lane * 64;
+              const int slot = w16_rseq & (nbuf - 1);
+              mbar_wait_a(w16_bar0 + slot * 8, (uint32_t)((nbuf == 2 ? (w16_rseq >> 1) : w16_rseq) & 1));
+              const uint8_t* rrow = w16_tiles + w16_res_off + slot * 2048 + lane * 64;
 #pragma unroll
               for (int j = 0; j < 4; ++j) rc16[j] = *reinterpret_cast<const uint4*>(rrow + ((j ^ sw) << 4));
             }
@@ -798,6 +801,38 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             }
             rs_s += s0 + s1; rs_q += q0 + q1;
           }
+          if (p.out_tr && col0 >= p.tr_col0) {
+            // ---- V^T for attention (q|k|v projection): out_tr[(col - tr_col0) * ts_c + x].  The warp's 32 rows x 32
+            // columns go through a 4 KB fp32 tile (float4 chunks XOR-swizzled by the row: conflict-free both ways), after
+            // which lane = column holds 32 consecutive x and writes them as four 16-byte stores.
+            float* tt = reinterpret_cast<float*>(w16_tiles);
+            if (p.w16 && lane == 0) tma_store_wait_all_read();   // TMA stores that still read this warp's tiles
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(tt + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                  make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            __syncwarp();
+            float x[32];
+#pragma unroll
+            for (int tq = 0; tq < 32; ++tq) x[tq] = tt[tq * 32 + ((((lane >> 2) ^ (tq & 7))) << 2) + (lane & 3)];
+            __syncwarp();
+            if (!(p.dbg & 4)) {
+              // this warp's rows: x = w16_x .. w16_x + 31 of image w16_n (host guarantees the geometry)
+              bf16* dst = p.out_tr + (long long)w16_n * p.ts_n + (long long)w16_y * p.ts_y +
+                          (long long)(col0 + lane - p.tr_col0) * p.ts_c + w16_x;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                uint4 q;
+                q.x = pack16(x[8 * g8], x[8 * g8 + 1], p.fp16);
+                q.y = pack16(x[8 * g8 + 2], x[8 * g8 + 3], p.fp16);
+                q.z = pack16(x[8 * g8 + 4], x[8 * g8 + 5], p.fp16);
+                q.w = pack16(x[8 * g8 + 6], x[8 * g8 + 7], p.fp16);
+                if (quad * 32 < p.box_rows && w16_n < p.NB && w16_x + 8 * g8 < p.W) *reinterpret_cast<uint4*>(dst + 8 * g8) = q;
+              }
+            }
+            continue;
+          }
           uint4 u[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -807,8 +842,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
           }
           if (w16) {
-            const int sslot = w16_sseq & 1;
-            if (lane == 0) tma_store_wait_read1();   // the store issued two chunks ago has drained this tile
+            const int sslot = w16_sseq & (nbuf - 1);
+            if (lane == 0) {   // the store that last used this tile has drained it
+              if (nbuf == 2) tma_store_wait_read1();
+              else tma_store_wait_read();
+            }
             __syncwarp();
             uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
 #pragma unroll
@@ -820,10 +858,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
                 tma_store_4d_a(&p.wmap16, w16_tiles_a + sslot * 2048u, col0, w16_x, w16_y, w16_n);
                 tma_store_commit();
               }
-              if (res && ci + 2 * NHALF < n32) {   // the residual slot just consumed is free: fetch the chunk after next
-                const int slot = w16_rseq & 1;
+              if (res && ci + nbuf * NHALF < n32) {   // the residual slot just consumed is free: fetch nbuf chunks ahead
+                const int slot = w16_rseq & (nbuf - 1);
                 mbar_expect_tx_a(w16_bar0 + slot * 8, 2048u);
-                tma_load_4d_a(w16_tiles_a + 4096u + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col0 + 2 * NHALF * 32,
+                tma_load_4d_a(w16_tiles_a + w16_res_off + slot * 2048u, &p.wrmap16, w16_bar0 + slot * 8, col0 + nbuf * NHALF * 32,
                               w16_x, w16_y, w16_n);
               }
             }

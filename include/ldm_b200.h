@@ -160,6 +160,10 @@ LDM_API int ldm_comm_init(ldm_handle* h, const char* nccl_lib, const char id[128
 LDM_API int ldm_allgather_images(ldm_handle* h, const float* local, int64_t count_per_rank, float* global);
 LDM_API int ldm_comm_destroy(ldm_handle* h);
 
+/* fp16 operands saturate at +-65504 instead of overflowing to inf.  count = residual-stream values found clamped at that
+ * limit by the GroupNorm statistics passes since ldm_create (0 for a checkpoint whose activations fit fp16). */
+LDM_API int ldm_get_saturation_count(ldm_handle* h, int64_t* count);
+
 /* CUDA-event time (ms) of the last "loop", "step", "decode", "encode" or "gather" interval on the handle's stream. */
 LDM_API int ldm_get_timing_ex(ldm_handle* h, const char* what, float* ms);
 

@@ -266,6 +266,14 @@ int ldm_tensor_to_image(ldm_handle* h, const float* images, int n, int64_t per, 
   API_END
 }
 
+int ldm_get_saturation_count(ldm_handle* h, int64_t* count) {
+  API_BEGIN
+  NEED(h);
+  LDM_CHECK(count, "ldm_get_saturation_count: null argument");
+  *count = h->model->saturated();
+  API_END
+}
+
 int ldm_get_timing_ex(ldm_handle* h, const char* what, float* ms) {
   API_BEGIN
   NEED(h);

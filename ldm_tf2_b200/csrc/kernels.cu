@@ -100,7 +100,7 @@ __device__ __forceinline__ float4 load4(const void* base, long long idx, int fp1
 
 template <bool IN16>
 __global__ void gn_stats_kernel(const void* __restrict__ a, int ca, const void* __restrict__ b, int cb, int hw,
-                                int strip, double* __restrict__ stats, int fp16) {
+                                int strip, double* __restrict__ stats, int fp16, unsigned long long* __restrict__ sat) {
   pdl_launch();
   pdl_wait();
   __shared__ double s_acc[64];
@@ -120,13 +120,17 @@ __global__ void gn_stats_kernel(const void* __restrict__ a, int ca, const void* 
     if (ch < ca) { src = a; img_off = (long long)n * hw * ca; cs = ca; co = ch; }
     else { src = b; img_off = (long long)n * hw * cb; cs = cb; co = ch - ca; }
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    int nsat = 0;
 #pragma unroll 8
     for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
       const float4 v = load4<IN16>(src, img_off + (long long)pix * cs + co, fp16);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
       ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+      // fp16 stream: a value AT the format's limit was clamped by the saturating conversion that wrote it
+      if (IN16 && fp16) nsat += (fabsf(v.x) >= 65504.f) + (fabsf(v.y) >= 65504.f) + (fabsf(v.z) >= 65504.f) + (fabsf(v.w) >= 65504.f);
     }
+    if (nsat && sat) atomicAdd(sat, (unsigned long long)nsat);
     // the 4 channels of a quad fall in at most 2 groups
     const int g0 = ch / cg, g3 = (ch + 3) / cg;
     if (g0 == g3) {
@@ -162,14 +166,14 @@ static void gn_launch_shape(int c, int hw, int n, int* threads, int* strip, int*
 }
 
 void launch_gn_stats(const void* a, int ca, const void* b, int cb, int n, int hw, double* stats,
-                     cudaStream_t st, int in16, int fp16) {
+                     cudaStream_t st, int in16, int fp16, unsigned long long* sat) {
   const int c = ca + cb;
   LDM_CHECK(c % 32 == 0 && ca % 4 == 0 && cb % 4 == 0, "GroupNorm(32): bad channel counts %d+%d", ca, cb);
   LDM_CHECK(c / 4 <= 1024, "GroupNorm: too many channels");
   int threads, strip, strips;
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
-  if (in16) launch_pdl(gn_stats_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16);
-  else launch_pdl(gn_stats_kernel<false>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16);
+  if (in16) launch_pdl(gn_stats_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16, sat);
+  else launch_pdl(gn_stats_kernel<false>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16, sat);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -19,8 +19,9 @@ void launch_step_advance(int* step_ptr, int delta, cudaStream_t st);
 // Input is fp32 NHWC, optionally the virtual concat of two tensors along C (unet.py:135).
 // stats[n][32][2] = per (sample, group) {sum, sum of squares} in double; zero on entry.
 // in16: the inputs are 16-bit operand tensors (the 16-bit residual stream) instead of fp32
+// sat (optional): device counter of fp16 stream values found AT +-65504, i.e. clamped by the saturating conversion
 void launch_gn_stats(const void* a, int ca, const void* b, int cb, int n, int hw, double* stats,
-                     cudaStream_t st, int in16 = 0, int fp16 = 0);
+                     cudaStream_t st, int in16 = 0, int fp16 = 0, unsigned long long* sat = nullptr);
 void launch_gn_apply(const void* a, int ca, const void* b, int cb, int n, int hw, const double* stats,
                      float eps, const float* gamma, const float* beta, int do_silu, bf16* out, int fp16,
                      cudaStream_t st, int in16 = 0);

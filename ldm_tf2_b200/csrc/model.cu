@@ -442,6 +442,7 @@ void Model::build() {
     enc_concat_from_ = ae_concat_bias_.size() - b.concat_bias.size();
   }
   step_dev_ = dev_alloc<int>(1, true);
+  sat_dev_ = dev_alloc<unsigned long long>(1, true);
 }
 
 // =====================================================================================
@@ -662,7 +663,7 @@ void Model::gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out
   }
   eng.launches += 2;
   if (eng.dry) return;
-  launch_gn_stats(xa, x.c, xb, cb, x.n, x.h * x.w, st, eng.stream, in16 ? 1 : 0, eng.fp16);
+  launch_gn_stats(xa, x.c, xb, cb, x.n, x.h * x.w, st, eng.stream, in16 ? 1 : 0, eng.fp16, sat_dev_);
   launch_gn_apply(xa, x.c, xb, cb, x.n, x.h * x.w, st, g.eps, g.gamma->f32, g.beta->f32,
                   silu ? 1 : 0, out, eng.fp16, eng.stream, in16 ? 1 : 0);
 }
@@ -1042,6 +1043,14 @@ void Model::compute_temb_table(const int* t_host, int rows, float* table) {
   eng.launches += 4;
   eng.sync();
   cudaFree(t_dev); cudaFree(emb); cudaFree(h1); cudaFree(temb);
+}
+
+long long Model::saturated() {
+  unsigned long long v = 0;
+  CUDA_CHECK(cudaSetDevice(eng.device));
+  eng.sync();
+  CUDA_CHECK(cudaMemcpy(&v, sat_dev_, sizeof v, cudaMemcpyDeviceToHost));
+  return (long long)v;
 }
 
 void* Model::stage(int slot, size_t bytes) {

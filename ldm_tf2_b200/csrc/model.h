@@ -204,6 +204,10 @@ class Model {
                       const bf16* vt, int tpad, int n, int t, int heads, int d, float scale, bf16* o, long long o_ld);
   void linear(const bf16* a, long long rows, const LinW& w, const float* bias, int act, const float* residual,
               float* out_f32, bf16* out_bf16, const bf16* res16 = nullptr);
+  // fp16 residual stream: number of values every GroupNorm statistics pass found clamped at +-65504 since ldm_create
+  // (the conversion saturates silently; a non-zero count says the checkpoint's activations do not fit fp16)
+  unsigned long long* sat_dev_ = nullptr;
+  long long saturated();
   bool stream16_ = true;   // block-boundary residual stream in 16 bit (LDM_B200_STREAM=fp32: fp32 + 16-bit shadow)
   Act conv3x3(const Act& x_b16, const LinW& w, const float* bias);
   Act upconv(const Act& x_b16, const LinW& w9, const LinW& wp, const float* bias);   // nearest x2 + conv3x3

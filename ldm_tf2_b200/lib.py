@@ -55,6 +55,7 @@ _PROTOS = {
     "ldm_comm_init": ([_P, C.c_char_p, C.c_char_p, _I, _I], _I),
     "ldm_allgather_images": ([_P, _P, _L, _P], _I),
     "ldm_comm_destroy": ([_P], _I),
+    "ldm_get_saturation_count": ([_P, C.POINTER(_L)], _I),
     "ldm_get_timing_ex": ([_P, C.c_char_p, C.POINTER(_F)], _I),
     "ldm_get_timing": ([_P, C.POINTER(_F), C.POINTER(_F), C.POINTER(_F), C.POINTER(_L), C.POINTER(_L)], _I),
     "ldm_bench_ddim_update": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F)], _I),
@@ -361,6 +362,12 @@ class Handle:
         check(self.lib.ldm_tensor_to_image(self._h, ptr(images), images.shape[0],
                                            images.size // images.shape[0], ptr(out)))
         return out
+
+    def saturation_count(self) -> int:
+        """fp16 residual-stream values found clamped at +-65504 so far (0 = the activations fit fp16)."""
+        n = C.c_int64()
+        check(self.lib.ldm_get_saturation_count(self._h, C.byref(n)))
+        return n.value
 
     def timing_ex(self, what: str) -> float:
         ms = C.c_float()

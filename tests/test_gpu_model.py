@@ -98,6 +98,22 @@ def test_ddim_loop_eps_trace(tiny, eta, S, graph):
         assert np.array_equal(got_g, got)
 
 
+def test_fp16_saturation_is_counted_not_silent(tiny):
+    """The fp16 operand conversion clamps at +-65504 instead of producing inf.  The GroupNorm statistics passes count
+    the residual-stream values they find AT the limit (ldm_get_saturation_count): 0 for ordinary inputs, > 0 as
+    soon as activations leave the fp16 range -- so a checkpoint that does not fit fp16 is reported, not hidden."""
+    h = tiny["h"]
+    h.set_context(tiny["ctx"])
+    x = np.random.default_rng(5).standard_normal((4, 8, 8, 4), dtype=np.float32)
+    t = np.array([981] * 4, np.int32)
+    before = h.saturation_count()
+    h.unet_forward(x, t)
+    assert h.saturation_count() == before
+    out = h.unet_forward(x * np.float32(3e6), t)   # conv_in output far outside the fp16 range
+    assert np.isfinite(out).all()                  # clamped, never inf / nan
+    assert h.saturation_count() > before
+
+
 def test_unet_forward_bf16_mode(tiny):
     """bf16 operand mode (ldm_config.precision = 0).  NOT held to north_star's 1e-2: with
     random-init weights every residual branch is as large as the stream, and the two operand

@@ -516,7 +516,9 @@ def rooflines(line, h, hv, B, hw, name, peaks):
         line["roofline"] = {
             "bound": "tensor", "kernel": "implicit_gemm_kernel (tcgen05)", "achieved": achieved, "peak": peaks["tflops"],
             "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "frac_of_burst": achieved / peaks["tflops_burst"],
-            "traffic": None, "traffic_unit": "bytes per UNet step (all GEMM launches); see profiles/ for the ncu DRAM list",
+            "traffic": GEMM_DRAM_BYTES_PER_UNET_STEP.get((hw, B)),
+            "traffic_unit": "DRAM bytes per UNet step summed over all GEMM launches (profiles/r2_launches_unet_step_b64_summary.txt); "
+                            "null for shapes without an ncu capture",
             "peak_source": peaks["source"] + ", sustained bf16",
             "algorithmic_gflop_per_unet_step": gemm_gflop,
             "executed_gflop_per_unet_step": prof["gemm_flops_per_step"] / 1e9,
@@ -561,9 +563,13 @@ def rooflines(line, h, hv, B, hw, name, peaks):
                                        "note": "the kernel is ALU-bound: HBM frac is small by construction"}}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of gn_stats_kernel / gn_apply_kernel at the shape
-# above, from one `ncu --set full` capture (profiles/README.md says which); None until that capture exists
-K2_NCU_TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gn_stats_kernel / gn_apply_kernel at the shape above,
+# from one `ncu --set full` capture (profiles/r2_ncu_gn_kernels.csv): 268.45 + 4.49 MB and 268.47 + 103.6 MB (the
+# rest of the 134 MB the apply pass writes is still in L2 when the kernel ends)
+K2_NCU_TRAFFIC = {"stats": 272.9e6, "apply": 372.1e6, "source": "profiles/r2_ncu_gn_kernels.csv"}
+# DRAM bytes of all implicit-GEMM launches of ONE CFG UNet step at 64 images (177 + 2 launches), ncu cold-cache replays:
+# profiles/r2_launches_unet_step_b64_summary.txt (16039 + 4047 + 957 + 2203 + 99 MB)
+GEMM_DRAM_BYTES_PER_UNET_STEP = {(32, 64): 23.35e9}
 
 
 if __name__ == "__main__":

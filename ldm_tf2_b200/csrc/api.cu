@@ -452,6 +452,7 @@ extern "C" LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int
   op.dbg = dbg & 15;
   if (getenv("LDM_B200_TRACE_FINE")) op.dbg |= 0x100;   // fine-grained stamps of one chunk (profiles/trace_epilogue.py)
   if (getenv("LDM_B200_TRACE_GENERAL")) op.dbg |= 0x200;   // keep this launch on the general kernel
+  if (getenv("LDM_B200_TRACE_TMEM_ONLY")) op.dbg |= 0x400; // lean epilogue: drain the accumulator and nothing else
   op.out_bf16 = o;
   float* of = nullptr;
   if (with_residual == 1) {          // fp32 residual stream: fp32 + 16-bit outputs
@@ -949,10 +950,22 @@ LDM_API int ldm_test_groupnorm(ldm_handle* h, const float* xa, int ca, const flo
   float* bt = up_f32(s, e, beta, c);
   double* mr = s.get<double>((size_t)n * 64, true);
   bf16* ob = s.get<bf16>((size_t)n * hw * c);
-  // silu bit 1 (value 2) forces the two-kernel path so both flavours are testable on any shape
+  // silu bit 1 (value 2) forces the two-kernel path so both flavours are testable on any shape;
+  // bit 2 (value 4): the inputs are first rounded to the 16-bit stream format and the 16-bit-input kernels run
   const bool two_kernels = (silu & 2) || !gn_fused_supported(c, hw, n);
+  const bool in16 = (silu & 4) != 0;
   silu &= 1;
-  if (two_kernels) {
+  if (in16) {
+    bf16* a16 = s.get<bf16>((size_t)n * hw * ca);
+    launch_f32_to_bf16(a, a16, (long long)n * hw * ca, 0, e.fp16, e.stream);
+    bf16* b16 = nullptr;
+    if (b) {
+      b16 = s.get<bf16>((size_t)n * hw * cb);
+      launch_f32_to_bf16(b, b16, (long long)n * hw * cb, 0, e.fp16, e.stream);
+    }
+    launch_gn_stats(a16, ca, b16, cb, n, hw, mr, e.stream, 1, e.fp16, nullptr);
+    launch_gn_apply(a16, ca, b16, cb, n, hw, mr, eps, g, bt, silu, ob, e.fp16, e.stream, 1);
+  } else if (two_kernels) {
     launch_gn_stats(a, ca, b, cb, n, hw, mr, e.stream);
     launch_gn_apply(a, ca, b, cb, n, hw, mr, eps, g, bt, silu, ob, e.fp16, e.stream);
   } else {

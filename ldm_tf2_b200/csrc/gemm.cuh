@@ -738,6 +738,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + col0 + NHALF * 32 + 8 * j);
             }
           }
+          const bool fine = tre && (p.dbg & 0x100) && ci == half + NHALF;   // stamps of this warp's SECOND chunk
+          if (fine) tre[9] = clock64();
           tmem_ld_x32(t_base + (uint32_t)c, rr);
           if (GEGLU) {
             uint32_t rg[32];
@@ -760,6 +762,15 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             }
           } else {
             tmem_ld_wait();
+            if (fine) tre[10] = clock64();
+            if (p.dbg & 0x400) {   // microbenchmark: accumulator drain only (TMEM -> registers), nothing else
+              uint32_t x = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x ^= rr[j];
+              if (x == 0x7fc01234u) reinterpret_cast<uint32_t*>(p.out_bf16)[0] = x;   // never true: keeps the load alive
+              if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
@@ -773,7 +784,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, b.w);
             }
           }
-          if (tre && ci < 6) tre[9 + ci] = clock64();
+          if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
+          if (fine) tre[11] = clock64();
           if (res) {
             if (w16) {
               const int slot = w16_rseq & (nbuf - 1);
@@ -841,6 +853,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             u[j].z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
             u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
           }
+          if (fine) tre[12] = clock64();
           if (w16) {
             const int sslot = w16_sseq & (nbuf - 1);
             if (lane == 0) {   // the store that last used this tile has drained it
@@ -848,11 +861,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               else tma_store_wait_read();
             }
             __syncwarp();
+            if (fine) tre[13] = clock64();
             uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u[j];
+            if (fine) tre[14] = clock64();
             fence_proxy_async_cta();
             __syncwarp();
+            if (fine) tre[15] = clock64();
             if (lane == 0) {
               if (!(p.dbg & 4)) {
                 tma_store_4d_a(&p.wmap16, w16_tiles_a + sslot * 2048u, col0, w16_x, w16_y, w16_n);

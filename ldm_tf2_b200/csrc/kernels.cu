@@ -149,6 +149,144 @@ __global__ void gn_stats_kernel(const void* __restrict__ a, int ca, const void* 
   if (threadIdx.x < 64) atomicAdd(&stats[(long long)n * 64 + threadIdx.x], s_acc[threadIdx.x]);
 }
 
+
+// ---- 16-bit stream, 8 channels (one 16-byte load) per thread.  With 8-byte loads the 16-bit variants above issue as
+// many instructions as the fp32 ones for half the bytes and stop at ~1.5 TB/s (profiles/r2_launches_unet_step_b64_summary.txt);
+// these move 16 bytes per load like the fp32 kernels do.
+__device__ __forceinline__ void unpack8(const uint4 u, int fp16, float* v) {
+  const float2 a = unpack16(u.x, fp16), b = unpack16(u.y, fp16), c = unpack16(u.z, fp16), d = unpack16(u.w, fp16);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+__global__ void gn_stats16x8_kernel(const bf16* __restrict__ a, int ca, const bf16* __restrict__ b, int cb, int hw,
+                                    int strip, double* __restrict__ stats, int fp16, unsigned long long* __restrict__ sat) {
+  pdl_launch();
+  pdl_wait();
+  __shared__ double s_acc[64];
+  const int c = ca + cb, c8 = c >> 3, cg = c / 32;
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * strip;
+  const int pix1 = min(hw, pix0 + strip);
+  const int lanes = blockDim.x / c8;
+  const int q = threadIdx.x % c8, pl = threadIdx.x / c8;
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  if (pl < lanes) {
+    const int ch = q * 8;
+    const bf16* src;
+    int cs;
+    if (ch < ca) { src = a + (long long)n * hw * ca + ch; cs = ca; }
+    else { src = b + (long long)n * hw * cb + (ch - ca); cs = cb; }
+    float s[8], ss[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
+    int nsat = 0;
+#pragma unroll 4
+    for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(src + (long long)pix * cs), fp16, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] += v[k];
+        ss[k] = fmaf(v[k], v[k], ss[k]);
+        if (fp16) nsat += fabsf(v[k]) >= 65504.f;
+      }
+    }
+    if (nsat && sat) atomicAdd(sat, (unsigned long long)nsat);
+    const int g0 = ch / cg, g7 = (ch + 7) / cg;
+    if (g0 == g7) {
+      double ds = 0.0, dq = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { ds += (double)s[k]; dq += (double)ss[k]; }
+      atomicAdd(&s_acc[g0 * 2], ds);
+      atomicAdd(&s_acc[g0 * 2 + 1], dq);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int g = (ch + k) / cg;
+        atomicAdd(&s_acc[g * 2], (double)s[k]);
+        atomicAdd(&s_acc[g * 2 + 1], (double)ss[k]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&stats[(long long)n * 64 + threadIdx.x], s_acc[threadIdx.x]);
+}
+
+__global__ void gn_apply16x8_kernel(const bf16* __restrict__ a, int ca, const bf16* __restrict__ b, int cb, int hw,
+                                    int strip, const double* __restrict__ stats, float eps,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                                    bf16* __restrict__ out, int fp16) {
+  pdl_launch();
+  pdl_wait();
+  __shared__ float s_mr[64];
+  const int c = ca + cb, c8 = c >> 3, cg = c / 32;
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * strip;
+  const int pix1 = min(hw, pix0 + strip);
+  const int lanes = blockDim.x / c8;
+  const int q = threadIdx.x % c8, pl = threadIdx.x / c8;
+  if (threadIdx.x < 32) {
+    const double cnt = (double)hw * cg;
+    const double mean = stats[(long long)n * 64 + threadIdx.x * 2] / cnt;
+    double var = stats[(long long)n * 64 + threadIdx.x * 2 + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mr[threadIdx.x * 2] = (float)mean;
+    s_mr[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (pl >= lanes) return;
+  const int ch = q * 8;
+  const bf16* src;
+  int cs;
+  if (ch < ca) { src = a + (long long)n * hw * ca + ch; cs = ca; }
+  else { src = b + (long long)n * hw * cb + (ch - ca); cs = cb; }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (ch + k) / cg;
+    const float mean = s_mr[g * 2], rstd = s_mr[g * 2 + 1];
+    sc[k] = rstd * __ldg(gamma + ch + k);
+    sh[k] = __ldg(beta + ch + k) - mean * sc[k];
+  }
+  bf16* dst = out + (long long)n * hw * c + ch;
+#pragma unroll 4
+  for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(src + (long long)pix * cs), fp16, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = fmaf(v[k], sc[k], sh[k]);
+      if (do_silu) v[k] = silu_f(v[k]);
+    }
+    uint4 u;
+    u.x = pack16(v[0], v[1], fp16);
+    u.y = pack16(v[2], v[3], fp16);
+    u.z = pack16(v[4], v[5], fp16);
+    u.w = pack16(v[6], v[7], fp16);
+    *reinterpret_cast<uint4*>(dst + (long long)pix * c) = u;
+  }
+}
+
+static void gn_launch_shape8(int c, int hw, int n, int* threads, int* strip, int* strips) {
+  const int c8 = c / 8;
+  int lanes = 256 / c8;
+  if (lanes < 1) lanes = 1;
+  *threads = (c8 * lanes + 31) / 32 * 32;
+  int want = (148 * LDM_TUNE("LDM_B200_T_GN_WANT", 4) + n - 1) / n;
+  int st = (hw + want - 1) / want;
+  const int min_strip = lanes * 8;
+  if (st < min_strip) st = min_strip;
+  if (st > hw) st = hw;
+  *strip = st;
+  *strips = (hw + st - 1) / st;
+}
+static bool gn_vec8_ok(const void* a, int ca, const void* b, int cb) {
+  static const bool off = getenv("LDM_B200_GN_VEC8") && getenv("LDM_B200_GN_VEC8")[0] == '0';
+  return !off && ca % 8 == 0 && cb % 8 == 0 && (ca + cb) / 8 <= 1024 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+         (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0);
+}
+
 static void gn_launch_shape(int c, int hw, int n, int* threads, int* strip, int* strips) {
   const int c4 = c / 4;
   int lanes = 256 / c4;
@@ -171,6 +309,13 @@ void launch_gn_stats(const void* a, int ca, const void* b, int cb, int n, int hw
   LDM_CHECK(c % 32 == 0 && ca % 4 == 0 && cb % 4 == 0, "GroupNorm(32): bad channel counts %d+%d", ca, cb);
   LDM_CHECK(c / 4 <= 1024, "GroupNorm: too many channels");
   int threads, strip, strips;
+  if (in16 && gn_vec8_ok(a, ca, b, cb)) {
+    gn_launch_shape8(c, hw, n, &threads, &strip, &strips);
+    launch_pdl(gn_stats16x8_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, static_cast<const bf16*>(a), ca,
+               static_cast<const bf16*>(b), cb, hw, strip, stats, fp16, sat);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
   if (in16) launch_pdl(gn_stats_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16, sat);
   else launch_pdl(gn_stats_kernel<false>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, fp16, sat);
@@ -235,6 +380,13 @@ void launch_gn_apply(const void* a, int ca, const void* b, int cb, int n, int hw
                      const float* gamma, const float* beta, int do_silu, bf16* out, int fp16, cudaStream_t st, int in16) {
   const int c = ca + cb;
   int threads, strip, strips;
+  if (in16 && gn_vec8_ok(a, ca, b, cb) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    gn_launch_shape8(c, hw, n, &threads, &strip, &strips);
+    launch_pdl(gn_apply16x8_kernel, dim3(dim3(strips, n)), dim3(threads), 0, st, static_cast<const bf16*>(a), ca,
+               static_cast<const bf16*>(b), cb, hw, strip, stats, eps, gamma, beta, do_silu, out, fp16);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   gn_launch_shape(c, hw, n, &threads, &strip, &strips);
   if (in16)
     launch_pdl(gn_apply_kernel<true>, dim3(dim3(strips, n)), dim3(threads), 0, st, a, ca, b, cb, hw, strip, stats, eps, gamma, beta,

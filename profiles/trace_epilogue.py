@@ -1,5 +1,6 @@
-"""LDM_B200_TRACE_FINE=1: the chunk@ list becomes the stamps of warp 2's SECOND chunk, relative to accumulator-ready:
-   [tmem ld issued, ld done, math done, residual+stats done, store tile free, STS+fence done, TMA store issued].
+"""LDM_B200_TRACE_FINE=1: the chunk@ list becomes the stamps of warp 2's SECOND chunk, relative to accumulator-ready.
+   lean kernels:   [before tmem ld, ld done, math done, residual+stats done, store tile free, packed + STS done, fence + syncwarp done]
+   general kernel: [tmem ld issued, ld done, math done, residual+stats done, store tile free, STS+fence done, TMA store issued].
 clock64 trace of the GEMM epilogue for the transformer-block linears: where a tile's cycles go.
    stamps (gemm.cuh `tre`): tile start -> bar1 -> bias staged + bar2 -> accumulator ready -> per-chunk math done -> tile end"""
 import os, sys

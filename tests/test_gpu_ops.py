@@ -136,6 +136,28 @@ def test_groupnorm(h, n, hw, ca, cb, silu, eps, two_kernels):
     assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-3  # 16-bit output rounding
 
 
+@pytest.mark.parametrize("n,hw,ca,cb,silu,eps", [(2, 64, 64, 0, True, 1e-5), (3, 256, 320, 0, False, 1e-6),
+                                                 (2, 16, 1280, 640, True, 1e-5), (1, 1024, 640, 320, True, 1e-5),
+                                                 (16, 1024, 320, 0, True, 1e-5), (2, 4, 2560, 0, True, 1e-5),
+                                                 (1, 16384, 128, 0, True, 1e-6), (2, 64, 36, 28, True, 1e-6)])
+def test_groupnorm_on_the_16bit_stream(h, n, hw, ca, cb, silu, eps):
+    """GroupNorm(32) reading the 16-bit residual stream (8 channels = one 16-byte load per thread; the last case has
+    channel counts that are not multiples of 8 and takes the 4-channel kernels): the reference normalises the same
+    16-bit-rounded input in fp32."""
+    rng = np.random.default_rng(hw + ca + 1)
+    xa = round16(rng.standard_normal((n, hw, ca), dtype=np.float32) * 2 + 0.5, h.precision)
+    xb = round16(rng.standard_normal((n, hw, cb), dtype=np.float32), h.precision) if cb else None
+    c = ca + cb
+    gamma = 1 + 0.1 * rng.standard_normal(c, dtype=np.float32)
+    beta = 0.1 * rng.standard_normal(c, dtype=np.float32)
+    got = h.test_groupnorm(xa, gamma, beta, eps, int(silu) | 4, xb)
+    x = xa if xb is None else np.concatenate([xa, xb], -1)
+    ref = O.group_norm(x.reshape(n, hw, 1, c), gamma, beta, eps).reshape(n, hw, c)
+    if silu:
+        ref = O.silu(ref)
+    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-3  # 16-bit output rounding
+
+
 @pytest.mark.parametrize("rows,c", [(77, 128), (1024, 320), (300, 1280)])
 def test_layernorm(h, rows, c):
     rng = np.random.default_rng(rows)

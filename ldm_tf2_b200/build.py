@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libldm_b200.so")
-SOURCES = ["kernels.cu", "engine.cu", "model.cu", "api.cu", "comm.cu"]
+SOURCES = ["kernels.cu", "engine.cu", "model.cu", "api.cu", "comm.cu", "validate.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-msse4.2", "--expt-relaxed-constexpr",

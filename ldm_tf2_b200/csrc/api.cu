@@ -94,7 +94,7 @@ int ldm_create(const ldm_config* c, int device, ldm_handle** out) {
   for (int i = 0; i < 8; ++i) { m.ae_mult[i] = c->ae_multipliers[i]; m.ae_attn_res[i] = c->ae_attention_resolutions[i]; }
   m.ae_num_attn_res = c->ae_num_attention_resolutions; m.vq_vocab = c->vq_vocab_size;
   m.ae_build_hw = c->ae_build_latent_hw > 0 ? c->ae_build_latent_hw : 32;
-  LDM_CHECK(c->precision == 0 || c->precision == 1, "precision must be 0 (bf16) or 1 (fp16)");
+  LDM_CHECK(c->precision >= 0 && c->precision <= 2, "precision must be 0 (bf16), 1 (fp16) or 2 (fp32 validation mode)");
   m.precision = c->precision;
   LDM_CHECK(m.model_channels % 32 == 0 && m.ae_channels % 32 == 0, "channels must be multiples of 32 (GroupNorm(32))");
   LDM_CHECK(m.latent_channels == 4, "latent_channels must be 4");

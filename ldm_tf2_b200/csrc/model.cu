@@ -210,7 +210,7 @@ struct Builder {
 };
 
 Model::Model(const ModelConfig& c, int device) : cfg(c), eng(device) {
-  eng.fp16 = c.precision == 1 ? 1 : 0;
+  eng.fp16 = c.precision >= 1 ? 1 : 0;   // validation mode (2): the parts that stay 16-bit use fp16
   // Residual stream format at block boundaries.  Default: 16 bit (fp32 only inside accumulators and statistics),
   // i.e. every GEMM epilogue writes one 16-bit tensor and GroupNorm reads 2 bytes per element; LDM_B200_STREAM=fp32
   // keeps an fp32 stream with a 16-bit shadow (round 1's layout) for accuracy comparisons.
@@ -441,6 +441,10 @@ void Model::build() {
     for (auto& pr : b.concat_bias) ae_concat_bias_.push_back(pr);   // q|k|v biases of the encoder's attention blocks
     enc_concat_from_ = ae_concat_bias_.size() - b.concat_bias.size();
   }
+  // validation mode walks the raw fp32 kernels of the unet (validate.cu)
+  if (cfg.precision == 2)
+    for (auto& s : slots[1])
+      if (s.kind == Slot::PACK) s.keep = true;
   step_dev_ = dev_alloc<int>(1, true);
   sat_dev_ = dev_alloc<unsigned long long>(1, true);
 }
@@ -1081,6 +1085,10 @@ void Model::set_context(const float* ctx, int n) {
   bf16* cb = static_cast<bf16*>(stage(ST_B, nel * sizeof(bf16)));
   bool realloc_ctx = false;
   CUDA_CHECK(cudaMemcpyAsync(cf, ctx, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
+  if (cfg.precision == 2) {
+    if (ctx_f32_cap_ < nel) { dev_free(ctx_f32_); ctx_f32_ = dev_alloc<float>(nel); ctx_f32_cap_ = nel; }
+    CUDA_CHECK(cudaMemcpyAsync(ctx_f32_, cf, nel * sizeof(float), cudaMemcpyDeviceToDevice, eng.stream));
+  }
   launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.fp16, eng.stream);
   for (STW* s : all_st_) {
     const int c = s->c;
@@ -1118,6 +1126,10 @@ void Model::set_context(const float* ctx, int n) {
 // =====================================================================================
 void Model::unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out) {
   const int mc = cfg.model_channels;
+  if (cfg.precision == 2) {   // fp32 validation mode: nothing of the 16-bit engine runs
+    if (!eng.dry) unet_eps_f32(x, nsrc, n, h, w, eps_out);
+    return;
+  }
   begin_pass();
   Act cur = alloc_act(n, h, w, mc);
   eng.launches++;
@@ -1281,7 +1293,7 @@ void Model::sample(const float* x_init, const float* noise, int b, int h, int w,
     launch_step_advance(step_dev_, -1, eng.stream);
     eng.launches += 2;
   };
-  const bool graph_ok = use_graph != 0;
+  const bool graph_ok = use_graph != 0 && cfg.precision != 2;   // the validation path allocates as it goes
   if (graph_ok) {
     if (!step_graph_ || graph_b_ != b || graph_h_ != h || graph_w_ != w || graph_guid_ != guidance ||
         graph_noise_ != (noise != nullptr)) {

@@ -26,7 +26,8 @@ struct ModelConfig {
   int latent_channels = 4, ae_channels = 128, ae_num_blocks = 2, ae_num_mult = 4, ae_mult[8] = {1, 2, 4, 4},
       ae_num_attn_res = 0, ae_attn_res[8] = {0}, vq_vocab = 16384,
       ae_build_hw = 32;  // latent size the checkpoint's Decoder was built at (autoencoder.py:176)
-  int precision = 1;       // 16-bit tensor-core operand format: 0 = bf16, 1 = fp16
+  int precision = 1;       // 16-bit tensor-core operand format: 0 = bf16, 1 = fp16; 2 = fp32 validation mode: the UNet
+                           // runs in fp32 on the CUDA cores (validate.cu), everything else as with fp16
 };
 
 // One tensor of a model in flat Keras order, with how it is consumed.
@@ -215,6 +216,9 @@ class Model {
   void gn(const GNW& g, const Act& x, const Act* skip, bool silu, bf16* out);
   Act unet_body(const float* x, int nsrc, int n, int h, int w);
   void unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out);
+  // precision = 2 (validate.cu): the same function in fp32 from the raw checkpoint tensors
+  void unet_eps_f32(const float* x, int nsrc, int n, int h, int w, float* eps_out);
+  float* ctx_f32_ = nullptr; size_t ctx_f32_cap_ = 0;   // fp32 copy of the context (validation mode only)
   void decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   Act ae_attention(AEAttnW& a, const Act& x);
   void build_ae_plan(int hw);

@@ -165,7 +165,7 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-PRECISIONS = {"bf16": 0, "fp16": 1}
+PRECISIONS = {"bf16": 0, "fp16": 1, "fp32": 2}   # fp32 = validation mode (UNet on the CUDA cores in fp32)
 DEFAULT_PRECISION = "fp16"
 
 

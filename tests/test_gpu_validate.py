@@ -1,0 +1,94 @@
+"""fp32 validation mode (ldm_config.precision = 2, csrc/validate.cu): the UNet denoiser evaluated in fp32 on
+the CUDA cores from the raw checkpoint tensors.  north_star's bound for this mode: per-step eps relative
+L2 <= 1e-4 against the reference (here: the fp32 oracle, oracle/ldm_oracle.py, and the committed full-size
+golden trajectory tests/golden/full_oracle.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ldm_oracle as O
+from tests.util import make_handle, rel_l2, sampler_tables
+
+pytestmark = pytest.mark.gpu
+
+VALIDATION_TOL = 1e-4   # north_star: per-step eps relative L2 in the fp32 validation mode
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_oracle.npz")
+
+
+def _unet_handle(cfg, wu, ae_hw):
+    h = make_handle(cfg, "kl", ae_hw=ae_hw, precision="fp32")
+    h.set_weights(h.UNET, wu)
+    h.finalize()
+    return h
+
+
+def test_validation_mode_tiny_unet_taps_and_loop():
+    cfg = O.TINY_CONFIG
+    us, ts = O.unet_spec(cfg["unet"]), O.text_spec(cfg["cond_stage_model"])
+    wu, wt = O.init_weights(us, 0), O.init_weights(ts, 1)
+    Wu = O.as_dict(us, wu)
+    ids = np.array([O.KAT_UNCOND_IDS, O.KAT_COND_IDS], dtype=np.int64)
+    ctx = O.text_encode(O.as_dict(ts, wt), cfg["cond_stage_model"], ids)[[0, 0, 1, 1]]
+    h = _unet_handle(cfg, wu, 8)
+    try:
+        x = np.random.default_rng(1234).standard_normal((2, 8, 8, 4), dtype=np.float32)
+        x2 = np.concatenate([x, x], 0)
+        h.set_context(ctx)
+        for t in (np.array([981] * 4, np.int32), np.array([1, 21, 501, 981], np.int32)):
+            taps_ref = {}
+            ref = O.unet_forward(Wu, cfg["unet"], x2, t, ctx, taps=taps_ref)
+            bufs = {k: h.tap(k, v.shape) for k, v in taps_ref.items() if k != "temb"}
+            got = h.unet_forward(x2, t)
+            h.clear_taps()
+            worst = max(rel_l2(bufs[k], taps_ref[k]) for k in bufs)
+            err = rel_l2(got, ref)
+            print(f"validation mode (tiny) t={t.tolist()}: worst tap rel-L2 {worst:.3e}, eps rel-L2 {err:.3e}")
+            assert worst < VALIDATION_TOL and err < VALIDATION_TOL
+        # the whole DDIM loop (eta = 1: per-step noise) through ldm_sample in this mode
+        sched = O.ddim_schedule(**dict(cfg["ldm"], eta=1.0, num_ddim_steps=20))
+        h.configure_sampler(*sampler_tables(sched))
+        noise = np.random.default_rng(7).standard_normal((20, 2, 8, 8, 4), dtype=np.float32)
+        trace_ref = []
+        ref = O.ddim_sample_loop(Wu, cfg["unet"], sched, ctx, x, noise, 5.0, eps_trace=trace_ref)
+        got, trace = h.sample(x, noise, 5.0, trace=True, num_steps=20)
+        errs = [rel_l2(trace[i], trace_ref[i]) for i in range(20)]
+        print(f"validation mode (tiny) 20-step loop: max eps rel-L2 {max(errs):.3e}, latent rel-L2 {rel_l2(got, ref):.3e}")
+        assert max(errs) < VALIDATION_TOL and rel_l2(got, ref) < VALIDATION_TOL
+    finally:
+        h.close()
+
+
+def test_validation_mode_full_size_eps_and_trajectory():
+    """txt2img-f8-large, BASELINE.json configs[0] shapes: one CFG evaluation at t = 981 and t = 1 against the
+    oracle, then the 50-step trajectory against the golden eps trace (11 of the 50 steps) and final latents."""
+    cfg = O.FULL_CONFIG
+    us, ts = O.unet_spec(cfg["unet"]), O.text_spec(cfg["cond_stage_model"])
+    wu, wt = O.init_weights(us, 0), O.init_weights(ts, 1)
+    ids = np.array([O.KAT_UNCOND_IDS, O.KAT_COND_IDS], dtype=np.int64)
+    ctx = O.text_encode(O.as_dict(ts, wt), cfg["cond_stage_model"], ids)
+    del wt
+    g = np.load(GOLD)
+    assert np.array_equal(g["ctx_probe"], ctx[:, :12, :64])   # the golden was made with these weights / prompts
+    h = _unet_handle(cfg, wu, 32)
+    try:
+        Wu = O.as_dict(us, wu)
+        x = np.random.default_rng(1234).standard_normal((1, 32, 32, 4), dtype=np.float32)
+        x2 = np.concatenate([x, x], 0)
+        h.set_context(ctx)
+        for tval in (981, 1):
+            t = np.array([tval, tval], np.int32)
+            err = rel_l2(h.unet_forward(x2, t), O.unet_forward(Wu, cfg["unet"], x2, t, ctx))
+            print(f"validation mode (full size) t={tval}: eps rel-L2 {err:.3e}")
+            assert err < VALIDATION_TOL
+        sched = O.ddim_schedule(**cfg["ldm"])
+        h.configure_sampler(*sampler_tables(sched))
+        got, trace = h.sample(x, None, 5.0, trace=True, num_steps=50)
+        steps = g["c1_trace_steps"].tolist()
+        errs = [rel_l2(trace[s], g["c1_eps"][i]) for i, s in enumerate(steps)]
+        lat = rel_l2(got, g["c1_latents"])
+        print("validation mode (full size) 50-step eps rel-L2 at steps", steps, [f"{e:.2e}" for e in errs])
+        print(f"validation mode (full size) final latent rel-L2 {lat:.3e}")
+        assert max(errs) < VALIDATION_TOL and lat < VALIDATION_TOL
+    finally:
+        h.close()

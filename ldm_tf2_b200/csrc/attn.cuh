@@ -23,6 +23,7 @@
 // quadrant w%4, i.e. thread (w%4)*32+lane owns one query row and sees all of its logits -- row max
 // and row sum need no exchange between threads.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace ldm {
@@ -44,7 +45,7 @@ struct AttnParams {
   bf16* o;
   long long o_ld;
   int fp16;
-  int poly_exp;       // 1: every second exponential on the FMA pipe (ex2_poly) instead of MUFU
+  int poly_exp;       // share of the exponentials on the FMA pipe (ex2_poly2) instead of MUFU: 0 none, 1 = 1/2, 2 = 1/4 (kernel flavour POLY)
   long long* trace;   // optional [cta][32] clock64 stamps (microbenchmark only)
 };
 
@@ -55,19 +56,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // not volatile: let the scheduler batch MUFU ops
   return y;
 }
-// 2^x on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic constant,
-// degree-4 polynomial for 2^f on [-0.5, 0.5] (relative error ~4e-6, far below the 16-bit P it feeds), exponent
-// n added to the result's bits.  The softmax loop is bound by the 16 ex2/clk/SM MUFU pipe; computing every second
-// exponential this way moves half of that load to the 128 lanes/clk FMA pipe.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;             // low mantissa bits = round(x)
-  const float f = x - (t - 12582912.0f);       // in [-0.5, 0.5]
-  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+// 2^x for a PAIR on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic
+// constant, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (relative error 7.5e-5, well below the 2^-11 of the
+// 16-bit P it feeds), exponent n added to the result's bits.  MUFU does 16 ex2/clk/SM; computing every second pair
+// this way moves half of that load to the FMA pipe at 6 issued instructions per exponential.
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2 magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const f32x2 t = f2_add(x, magic);                                   // low mantissa bits = round(x)
+  const f32x2 f = f2_fma(f2_add(t, nmagic), f2_pack(-1.0f, -1.0f), x);  // x - round(x), in [-0.5, 0.5]
+  f32x2 q = f2_fma(f, f2_pack(0.05517032743f, 0.05517032743f), f2_pack(0.2426078171f, 0.2426078171f));
+  q = f2_fma(q, f, f2_pack(0.6932609081f, 0.6932609081f));
+  q = f2_fma(q, f, f2_pack(0.9999282956f, 0.9999282956f));
+  float q0, q1, t0, t1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(t, t0, t1);
+  return f2_pack(__uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23)),
+                 __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23)));
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -83,7 +90,7 @@ __device__ __forceinline__ uint32_t pack_prob(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <bool FP16>
+template <bool FP16, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared-space pointer
@@ -238,35 +245,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
     uint32_t sph = 0;
     uint32_t ra[32], rb[32];
     float ms = -INFINITY;           // running (lazy) row max, already multiplied by scale*log2e
-    float l0 = 0.f, l1 = 0.f;
+    f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);   // four partial row sums
     int prev_sb = 0;
     uint32_t prev_sph = 0;
     bool have_o = false;            // O holds at least one tile's P V
     const uint32_t o_lane = lane_base + o_col;
-    // scaled max of one 32-key half; `v` = valid keys in it (may be <= 0 on the last tile)
-    auto half_max = [&](const uint32_t* rr, int v) {
+    // scaled max of one 32-key half (keys beyond the sequence were set to -inf by the caller)
+    auto half_max = [&](const uint32_t* rr) {
       float m0 = -INFINITY, m1 = -INFINITY;
-      if (v >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = fmaxf(m0, __uint_as_float(rr[i]));
-          m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < v) m0 = fmaxf(m0, __uint_as_float(rr[i]));
+      for (int i = 0; i < 32; i += 2) {
+        m0 = fmaxf(m0, __uint_as_float(rr[i]));
+        m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
       }
       return fmaxf(m0, m1) * p.scale_log2;   // scale > 0
     };
     // Lazy max update: raise the running max only when this half would push P above 2^8 (always on
     // the very first half); rescales l and, through a TMEM load/store, this row of O.  Returns
     // whether any row of the warp raised its max.
-    auto raise_to = [&](float mt) {
+    auto raise_to = [&](float mt, float& f) {
       const bool raise = mt > ms + 8.0f;
       if (!__any_sync(0xffffffffu, raise)) return false;
       const float new_ms = raise ? mt : ms;
-      const float f = ex2_approx(ms - new_ms);   // 1 for rows that keep their max, 0 on the first half
+      f = ex2_approx(ms - new_ms);   // 1 for rows that keep their max, 0 on the first half
       if (have_o) {
         // O holds P V of the previous tiles: wait for the last of those MMAs, then rescale
         mbar_wait_a(bar(S_EMPTY + prev_sb), prev_sph);
@@ -276,46 +277,43 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
           tmem_ld_x16(o_lane + (uint32_t)c, ro);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * f);
+          for (int i = 0; i < 16; i += 2) {
+            float a, b;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(ro[i]), __uint_as_float(ro[i + 1])), f2_pack(f, f)), a, b);
+            ro[i] = __float_as_uint(a);
+            ro[i + 1] = __float_as_uint(b);
+          }
           tmem_st_x16(o_lane + (uint32_t)c, ro);
         }
         tmem_st_wait();
         tc_fence_before();
       }
-      l0 *= f;
-      l1 *= f;
+      l01 = f2_mul(l01, f2_pack(f, f));
+      l23 = f2_mul(l23, f2_pack(f, f));
       ms = new_ms;
       return true;
     };
     // P = exp2(S*scale*log2e - ms) of one 32-key half as 16 packed 16-bit pairs, stored to TMEM
     // columns [taddr, taddr + 16) of this thread's lane; row sum in fp32
-    auto emit = [&](const uint32_t* rr, int v, uint32_t taddr) {
-      float e[32];
-      if (p.poly_exp) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          e[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms));
-          e[i + 1] = ex2_poly(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -ms));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(rr[i]), p.scale_log2, -ms));
-      }
-      if (v < 32) {   // last, partial tile only (warp-uniform branch)
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i >= v) e[i] = 0.f;
-      }
+    auto emit = [&](const uint32_t* rr, uint32_t taddr) {
+      const f32x2 sc2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(-ms, -ms);
       uint32_t pk[16];
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
-        pk[i >> 1] = pack_prob<FP16>(e[i], e[i + 1]);
-        pk[(i >> 1) + 1] = pack_prob<FP16>(e[i + 2], e[i + 3]);
+      for (int i = 0; i < 32; i += 2) {
+        const f32x2 x = f2_fma(f2_pack(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), sc2, nm2);
+        float a, b;
+        // POLY = 1: every second pair on the FMA pipe, 2: every fourth pair, 0: all on MUFU
+        if ((POLY == 1 && (i & 2)) || (POLY == 2 && (i & 6) == 6)) {
+          f2_unpack(ex2_poly2(x), a, b);
+        } else {
+          f2_unpack(x, a, b);
+          a = ex2_approx(a);
+          b = ex2_approx(b);
+        }
+        if (i & 2) l23 = f2_add(l23, f2_pack(a, b));
+        else l01 = f2_add(l01, f2_pack(a, b));
+        pk[i >> 1] = pack_prob<FP16>(a, b);
       }
-      l0 += s0 + s1;
-      l1 += s2 + s3;
       tmem_st_x16(taddr, pk);
     };
     if (p.q_tmem) {
@@ -333,8 +331,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar(QT_FULL));
     }
-    for (int j = 0; j < p.kv_tiles; ++j) {
-      const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence (>= 1)
+    // One 64-key tile.  MASKED (a separate instantiation, so that the full tiles carry none of its instructions --
+    // the compiler if-converts a runtime `valid < 64` test into ~250 predicated-off issue slots per tile): the
+    // last tile of a sequence that is not a multiple of 64 keys (cross attention, 77 = 64 + 13); keys beyond the
+    // sequence get a logit of -inf, i.e. probability 0 (2^-125 on the polynomial path).
+    auto tile = [&](int j, auto masked) {
+      constexpr bool MASKED = decltype(masked)::value;
       // both 32-column halves of S buffer sb -> registers
       mbar_wait_a(bar(S_FULL + sb), sph);
       tc_fence_after();
@@ -344,10 +346,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       tmem_ld_wait();
       if (tr && j == 0) tr[2] = clock64();
       if (tr && j < 8) tr[8 + 2 * j] = clock64();
-      raise_to(fmaxf(half_max(ra, valid), half_max(rb, valid - 32)));
+      if (MASKED) {
+        const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence, in [1, 63]
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) ra[i] = 0xff800000u;
+          if (i + 32 >= valid) rb[i] = 0xff800000u;
+        }
+      }
+      float f;
+      raise_to(fmaxf(half_max(ra), half_max(rb)), f);
       // P overwrites the first 32 columns of this thread's own S lane (already in registers)
-      emit(ra, valid, s_lane);
-      emit(rb, valid - 32, s_lane + 16);
+      emit(ra, s_lane);
+      emit(rb, s_lane + 16);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -357,9 +368,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       have_o = true;
       if (++sb == 2) { sb = 0; sph ^= 1; }
       if (tr && j < 8) tr[9 + 2 * j] = clock64();
-    }
+    };
+    const int full_tiles = p.tk / ATT_BN;
+    for (int j = 0; j < full_tiles; ++j) tile(j, std::false_type{});
+    if (full_tiles < p.kv_tiles) tile(full_tiles, std::true_type{});
     if (tr) tr[5] = clock64();
-    const float inv = 1.0f / (l0 + l1);
+    float inv;
+    {
+      float s0, s1, s2, s3;
+      f2_unpack(l01, s0, s1);
+      f2_unpack(l23, s2, s3);
+      inv = 1.0f / ((s0 + s1) + (s2 + s3));
+    }
     // ---- epilogue: O / l -> 16-bit [n, t, heads*d]
     mbar_wait_a(bar(O_FULL), 0);
     tc_fence_after();

@@ -39,13 +39,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // the 12 instantiations of the GEMM kernel: CTA pair or not, 8 / 4 epilogue warps, optional epilogue flavours
 // (0 = default, 1 = + fragment-layout path, 2 = + TMA-store path; the last two are A/B switches)
 typedef void (*GemmKernel)(const GemmParams);
-static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi) {
+static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi, int fp16 = 0) {
 #define LDM_K(P, E) (epi == 0 ? (GemmKernel)implicit_gemm_kernel<P, E, 0> : epi == 1 ? (GemmKernel)implicit_gemm_kernel<P, E, 1> \
                                                                                      : (GemmKernel)implicit_gemm_kernel<P, E, 2>)
-#define LDM_L(P, X) (ew == 16 ? (GemmKernel)implicit_gemm_kernel<P, 16, X> : ew == 12 ? (GemmKernel)implicit_gemm_kernel<P, 12, X> \
-                                                                                          : (GemmKernel)implicit_gemm_kernel<P, 8, X>)
-  if (epi == 3) return pair ? LDM_L(1, 3) : LDM_L(0, 3);   // lean 16-bit, 8 / 12 / 16 epilogue warps
-  if (epi == 4) return pair ? LDM_L(1, 4) : LDM_L(0, 4);   // lean GEGLU
+  // lean 16-bit (3) / lean GEGLU (4): 8 epilogue warps (12 and 16 measured slower per chunk, profiles/r2_trace_epilogue_ew12.txt);
+  // the fp16 flavours know the operand format at compile time
+#define LDM_L(P, X) (fp16 ? (GemmKernel)implicit_gemm_kernel<P, 8, X, 1> : (GemmKernel)implicit_gemm_kernel<P, 8, X, -1>)
+  if (epi == 3) return pair ? LDM_L(1, 3) : LDM_L(0, 3);
+  if (epi == 4) return pair ? LDM_L(1, 4) : LDM_L(0, 4);
 #undef LDM_L
   if (pair) return ew == 4 ? LDM_K(1, 4) : LDM_K(1, 8);
   return ew == 4 ? LDM_K(0, 4) : LDM_K(0, 8);
@@ -70,9 +71,9 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_fn_, cudaEnableDefault, &qres));
   LDM_CHECK(encode_fn_ && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
   for (int epi = 3; epi < 5; ++epi)
-    for (int ew : {8, 12, 16}) {
-      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, ew, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, ew, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    for (int f16 = 0; f16 < 2; ++f16) {
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     }
   for (int epi = 0; epi < 3; ++epi) {
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -83,10 +84,12 @@ Engine::Engine(int dev) : device(dev) {
   // measured -14 % on the 16384-row projections in isolation, -0.7 % per UNet step (profiles/ab_step.py)
   { const char* e = getenv("LDM_B200_EW4"); ew4_default = !(e && e[0] == '0'); }
   { const char* e = getenv("LDM_B200_PAIR"); pair_default = !(e && e[0] == '0'); }
-  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
 }
 
 Engine::~Engine() {
@@ -344,7 +347,7 @@ void Engine::gemm(const GemmOp& op) {
   // epilogue warps of the lean kernels (LDM_B200_LEAN_EW = 8 / 12 / 16).  Measured in-graph (profiles/r2_ab_switches.txt):
   // 8 warps 5.36 ms per UNet step at 8 images, 12 warps 5.52, 16 warps 5.75 -- more warps make every chunk slower
   // (the 64 B/clk TMEM read port and the shrinking operand pipeline), so 8 it is.
-  const int lean_ew = lean ? LDM_TUNE("LDM_B200_LEAN_EW", 8) : 8;
+  const int lean_ew = 8;   // 12 / 16 epilogue warps measured slower per chunk (profiles/r2_trace_epilogue_ew12.txt); flavours removed
   if (lean) {
     p.epi_bytes = op.out_tr ? lean_ew * 4096 : 0;   // the V^T transposition tile of every warp
     if (w16) {
@@ -455,7 +458,7 @@ void Engine::gemm(const GemmOp& op) {
     if (o == "split" && splits > 1) return;
   }
   const int epi = lean ? (geglu ? 4 : 3) : (p.tma_epi ? 2 : (p.frag_pref ? 1 : 0));
-  const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, lean ? lean_ew : (ew4 ? 4 : 8), epi);
+  const GemmKernel kern = gemm_kernel_ptr(pair ? 1 : 0, lean ? lean_ew : (ew4 ? 4 : 8), epi, fp16);
   const int threads = lean ? 64 + 32 * lean_ew : (ew4 ? GEMM_THREADS_EW4 : GEMM_THREADS);
   if (pair) launch_pair(kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
   else launch_pdl_kind(2, kern, dim3(ctas), dim3(threads), (size_t)smem, stream, p);
@@ -482,7 +485,10 @@ void Engine::attention(const AttnOp& op) {
   p.kv_tiles = (op.tk + ATT_BN - 1) / ATT_BN;
   p.scale_log2 = op.scale * 1.4426950408889634f;
   p.o = op.o; p.o_ld = op.o_ld; p.fp16 = fp16;
-  { static const bool off = getenv("LDM_B200_POLY_EXP") && getenv("LDM_B200_POLY_EXP")[0] == '0'; p.poly_exp = off ? 0 : 1; }
+  // share of the exponentials computed on the FMA pipe instead of MUFU (0 none, 1 = 1/2, 2 = 1/4).  Measured equal within
+  // 0.5 % per step once the loop ran on packed f32x2 instructions (profiles/r2_ab_attention.txt): at head dim 40 the tile
+  // is paced by reading its 128 x 64 fp32 logits out of TMEM (32 KB at 64 B/clk per SM), not by MUFU or issue slots
+  p.poly_exp = LDM_TUNE("LDM_B200_POLY_EXP", 0);
   p.trace = op.trace;
   const int q_bytes = p.dp_atoms * ATT_BM * 128;
   const int kv_bytes = p.dp_atoms * ATT_BN * 128 + ((p.dv * 128 + 1023) & ~1023);
@@ -513,8 +519,9 @@ void Engine::attention(const AttnOp& op) {
   encode_map(&p.kmap, k, ATT_BN, 1, 1);
   encode_map(&p.vmap, v, p.dv, 1, 1);
   const int grid = op.n * op.heads * p.q_tiles;
-  if (fp16) launch_pdl_kind(4, flash_attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
-  else launch_pdl_kind(4, flash_attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
+  auto kern = fp16 ? (p.poly_exp == 1 ? flash_attention_kernel<true, 1> : p.poly_exp == 2 ? flash_attention_kernel<true, 2> : flash_attention_kernel<true, 0>)
+                   : (p.poly_exp == 1 ? flash_attention_kernel<false, 1> : p.poly_exp == 2 ? flash_attention_kernel<false, 2> : flash_attention_kernel<false, 0>);
+  launch_pdl_kind(4, kern, dim3(grid), dim3(ATT_THREADS), (size_t)need(), stream, p);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -441,7 +441,9 @@ __device__ __forceinline__ void epi_chunk_fragment(const GemmParams& p, uint32_t
 // EPI selects which optional epilogue flavours are compiled in (each costs registers in every other path):
 // 0 = the general epilogue; 1 = + fragment-layout path (A/B switch); 2 = + block-wide TMA-store path (A/B switch);
 // 3 / 4 = ONLY the lean 16-bit epilogue (4: with GEGLU gating) -- the hot launches of the 16-bit residual stream.
-template <int PAIR, int EW, int EPI>
+// F16 (lean flavours): 1 = fp16 operands / outputs known at compile time, -1 = read p.fp16.  With a runtime format
+// every 16-bit pack / unpack is issued twice (predicated fp16 and bf16 variants): ~80 dead issue slots per chunk.
+template <int PAIR, int EW, int EPI, int F16 = -1>
 // register budget: 168 per thread either way.  The register file is 4 x 16 K (one per scheduler partition): the
 // 10 warps of the EW = 8 flavour put three warps on two of the partitions (16384 / 3 / 32 = 170), and two EW = 4
 // CTAs put three warps on every partition -- a launch with more registers fails with cudaErrorLaunchOutOfResources.
@@ -637,6 +639,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
       // N % 32 == 0, offsets are 16-byte aligned, and there is no fp32 output / fp32 residual / transposed output /
       // per-image bias / split-K (Engine::gemm).
       constexpr bool GEGLU = LEAN == 2;
+      const int fp16 = F16 >= 0 ? F16 : p.fp16;   // compile-time in the fp16 flavours
       const int quad = warp & 3, half = (warp - 2) >> 2, ew = warp - 2;
       const int r = quad * 32 + lane;
       const int et = threadIdx.x - 64;
@@ -797,8 +800,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             if (w16 || row_ok) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f0 = unpack16(rc16[j].x, p.fp16), f1 = unpack16(rc16[j].y, p.fp16),
-                             f2 = unpack16(rc16[j].z, p.fp16), f3 = unpack16(rc16[j].w, p.fp16);
+                const float2 f0 = unpack16(rc16[j].x, fp16), f1 = unpack16(rc16[j].y, fp16),
+                             f2 = unpack16(rc16[j].z, fp16), f3 = unpack16(rc16[j].w, fp16);
                 acc[8 * j] += f0.x; acc[8 * j + 1] += f0.y; acc[8 * j + 2] += f1.x; acc[8 * j + 3] += f1.y;
                 acc[8 * j + 4] += f2.x; acc[8 * j + 5] += f2.y; acc[8 * j + 6] += f3.x; acc[8 * j + 7] += f3.y;
               }
@@ -836,10 +839,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) {
                 uint4 q;
-                q.x = pack16(x[8 * g8], x[8 * g8 + 1], p.fp16);
-                q.y = pack16(x[8 * g8 + 2], x[8 * g8 + 3], p.fp16);
-                q.z = pack16(x[8 * g8 + 4], x[8 * g8 + 5], p.fp16);
-                q.w = pack16(x[8 * g8 + 6], x[8 * g8 + 7], p.fp16);
+                q.x = pack16(x[8 * g8], x[8 * g8 + 1], fp16);
+                q.y = pack16(x[8 * g8 + 2], x[8 * g8 + 3], fp16);
+                q.z = pack16(x[8 * g8 + 4], x[8 * g8 + 5], fp16);
+                q.w = pack16(x[8 * g8 + 6], x[8 * g8 + 7], fp16);
                 if (quad * 32 < p.box_rows && w16_n < p.NB && w16_x + 8 * g8 < p.W) *reinterpret_cast<uint4*>(dst + 8 * g8) = q;
               }
             }
@@ -848,10 +851,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           uint4 u[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            u[j].x = pack16(acc[8 * j], acc[8 * j + 1], p.fp16);
-            u[j].y = pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16);
-            u[j].z = pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16);
-            u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16);
+            u[j].x = pack16(acc[8 * j], acc[8 * j + 1], fp16);
+            u[j].y = pack16(acc[8 * j + 2], acc[8 * j + 3], fp16);
+            u[j].z = pack16(acc[8 * j + 4], acc[8 * j + 5], fp16);
+            u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], fp16);
           }
           if (fine) tre[12] = clock64();
           if (w16) {

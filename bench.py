@@ -531,19 +531,24 @@ def rooflines(line, h, hv, B, hw, name, peaks):
         line["roofline_k5"] = {"bound": "hbm", "kernel": "ddim_update_kernel", "achieved": k5_bytes / (k5_ms * 1e-3) / 1e9,
                                "peak": peaks["hbm"], "unit": "GB/s", "frac": k5_bytes / (k5_ms * 1e-3) / 1e9 / peaks["hbm"],
                                "traffic": None, "bytes_per_launch": k5_bytes, "ms_per_launch": k5_ms}
-    # K2 GroupNorm at the decoder's largest activation [8, 256*256, 128] (HBM-resident: 268 MB fp32)
+    # K2 GroupNorm at the decoder's largest activation [8, 256*256, 128], the kernels the sampling path runs: 16-bit
+    # residual stream in (134 MB, several buffers so that it is HBM-resident), 16-bit MMA operand out
     gn_n, gn_hw, gn_c = 8, 256 * 256, 128
-    gn_stats_ms, gn_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10)
+    gn_stats_ms, gn_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10, in16=True)
+    f32_stats_ms, f32_apply_ms = h.bench_groupnorm(gn_n, gn_hw, gn_c, 10, in16=False)
     gn_el = gn_n * gn_hw * gn_c
+
+    def _gb(nbytes, ms):
+        return nbytes / (ms * 1e-3) / 1e9
     line["roofline_k2"] = {
-        "bound": "hbm", "kernel": "gn_stats_kernel + gn_apply_kernel (GroupNorm(32)+SiLU -> 16-bit operand)",
+        "bound": "hbm", "kernel": "gn_stats16x8_kernel + gn_apply16x8_kernel (GroupNorm(32)+SiLU, 16-bit stream -> 16-bit operand)",
         "shape": [gn_n, gn_hw, gn_c], "unit": "GB/s", "peak": peaks["hbm"],
-        "stats": {"bytes_per_launch": gn_el * 4, "ms_per_launch": gn_stats_ms,
-                  "achieved": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9,
-                  "frac": gn_el * 4 / (gn_stats_ms * 1e-3) / 1e9 / peaks["hbm"]},
-        "apply": {"bytes_per_launch": gn_el * 6, "ms_per_launch": gn_apply_ms,
-                  "achieved": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9,
-                  "frac": gn_el * 6 / (gn_apply_ms * 1e-3) / 1e9 / peaks["hbm"]},
+        "stats": {"bytes_per_launch": gn_el * 2, "ms_per_launch": gn_stats_ms, "achieved": _gb(gn_el * 2, gn_stats_ms),
+                  "frac": _gb(gn_el * 2, gn_stats_ms) / peaks["hbm"]},
+        "apply": {"bytes_per_launch": gn_el * 4, "ms_per_launch": gn_apply_ms, "achieved": _gb(gn_el * 4, gn_apply_ms),
+                  "frac": _gb(gn_el * 4, gn_apply_ms) / peaks["hbm"]},
+        "fp32_input_flavour": {"stats_gbs": _gb(gn_el * 4, f32_stats_ms), "apply_gbs": _gb(gn_el * 6, f32_apply_ms),
+                               "note": "LDM_B200_STREAM=fp32 / text-free paths: 4 B read (stats), 4 B read + 2 B write (apply)"},
         "traffic": K2_NCU_TRAFFIC}
     if hv is not None:
         # K6: rows x 16384 codes, exact fp32 op order without FMA (12 flop per row-code pair); the HBM
@@ -563,13 +568,13 @@ def rooflines(line, h, hv, B, hw, name, peaks):
                                        "note": "the kernel is ALU-bound: HBM frac is small by construction"}}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of gn_stats_kernel / gn_apply_kernel at the shape above,
-# from one `ncu --set full` capture (profiles/r2_ncu_gn_kernels.csv): 268.45 + 4.49 MB and 268.47 + 103.6 MB (the
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of gn_stats16x8_kernel / gn_apply16x8_kernel at the shape above,
+# from one `ncu --set full` capture (profiles/r2_ncu_gn_kernels.csv): 134.24 + 5.71 MB and 134.26 + 92.1 MB (the
 # rest of the 134 MB the apply pass writes is still in L2 when the kernel ends)
-K2_NCU_TRAFFIC = {"stats": 272.9e6, "apply": 372.1e6, "source": "profiles/r2_ncu_gn_kernels.csv"}
+K2_NCU_TRAFFIC = {"stats": 139.95e6, "apply": 226.4e6, "source": "profiles/r2_ncu_gn_kernels.csv"}
 # DRAM bytes of all implicit-GEMM launches of ONE CFG UNet step at 64 images (177 + 2 launches), ncu cold-cache replays:
-# profiles/r2_launches_unet_step_b64_summary.txt (16039 + 4047 + 957 + 2203 + 99 MB)
-GEMM_DRAM_BYTES_PER_UNET_STEP = {(32, 64): 23.35e9}
+# profiles/r2_launches_unet_step_b64_summary.txt (16009 + 3973 + 957 + 2203 + 99 MB)
+GEMM_DRAM_BYTES_PER_UNET_STEP = {(32, 64): 23.24e9}
 
 
 if __name__ == "__main__":

@@ -188,6 +188,9 @@ LDM_API int ldm_bench_gemm(ldm_handle* h, int rows, int k, int n, int block_n, i
 /* GroupNorm(32)+SiLU microbenchmark over more distinct [n, hw, c] fp32 buffers than fit in L2:
  * average time of the statistics kernel and of the apply kernel (K2's HBM roofline). */
 LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms);
+/* the same with in16 = 1: 16-bit input, the kernels the sampling path runs on its 16-bit residual stream */
+LDM_API int ldm_bench_groupnorm_ex(ldm_handle* h, int n, int hw, int c, int iters, int in16, float* stats_ms,
+                                   float* apply_ms);
 /* K6 microbenchmark: average time of the codebook argmin (+ gather) over `rows` device-resident latent
  * rows against the handle's codebook (quantize.py:57-78). */
 LDM_API int ldm_bench_vq_argmin(ldm_handle* h, long long rows, int iters, float* avg_ms);

@@ -24,6 +24,11 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I", os.path.join(ROOT, "include")]
 
 
+def _extra_flags():
+    # e.g. LDM_B200_NVCC_FLAGS=-DLDM_GEMM_TRACE_FINE for the instrumented epilogue (profiles/trace_epilogue.py)
+    return os.environ.get("LDM_B200_NVCC_FLAGS", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     names = sorted(os.listdir(CSRC)) + ["../../include/ldm_b200.h"]
@@ -33,7 +38,7 @@ def _digest() -> str:
             h.update(n.encode())
             with open(p, "rb") as f:
                 h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    h.update(" ".join(FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -47,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
         return lib
     os.makedirs(obj_dir, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + _extra_flags()
 
     def cc(src):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))

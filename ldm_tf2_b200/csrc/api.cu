@@ -822,23 +822,28 @@ LDM_API int ldm_test_attention(ldm_handle* h, const float* q, const float* k, co
 
 // GroupNorm(32)+SiLU microbenchmark: statistics and apply kernels timed separately over enough
 // distinct [n, hw, c] buffers to exceed the L2, so the numbers are HBM numbers (K2 roofline).
-LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms) {
+// in16 = 1: the input is the 16-bit residual stream (what the sampling path runs since round 2); 0: fp32 input
+LDM_API int ldm_bench_groupnorm_ex(ldm_handle* h, int n, int hw, int c, int iters, int in16, float* stats_ms, float* apply_ms) {
   API_BEGIN
   NEED(h);
   LDM_CHECK(n > 0 && hw > 0 && c > 0 && c % 32 == 0 && iters > 0 && stats_ms && apply_ms, "ldm_bench_groupnorm: bad argument");
   Engine& e = h->model->eng;
   CUDA_CHECK(cudaSetDevice(e.device));
   const size_t el = (size_t)n * hw * c;
-  int nbuf = (int)(((size_t)256 << 20) / (el * 4)) + 1;
+  const size_t esz = in16 ? 2 : 4;
+  int nbuf = (int)(((size_t)256 << 20) / (el * esz)) + 1;   // more distinct buffers than fit in L2
   if (nbuf < 2) nbuf = 2;
   Scratch s;
-  float* x = s.get<float>(el * nbuf);
+  float* xf = s.get<float>(el * nbuf);
+  bf16* x16 = in16 ? s.get<bf16>(el * nbuf) : nullptr;
   bf16* out = s.get<bf16>(el * nbuf);
   float* gamma = s.get<float>(c);
   float* beta = s.get<float>(c, true);
   double* st = s.get<double>((size_t)n * 64 * nbuf, true);
-  launch_fill_f32(x, (long long)(el * nbuf), 0.5f, e.stream);
+  launch_fill_f32(xf, (long long)(el * nbuf), 0.5f, e.stream);
+  if (in16) launch_f32_to_bf16(xf, x16, (long long)(el * nbuf), 0, e.fp16, e.stream);
   launch_fill_f32(gamma, c, 1.0f, e.stream);
+  const char* x = in16 ? reinterpret_cast<const char*>(x16) : reinterpret_cast<const char*>(xf);
   cudaEvent_t e0, e1, e2;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -847,11 +852,12 @@ LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, 
   for (int pass = 0; pass < 2; ++pass) {   // pass 0 = warm-up
     e.sync();
     CUDA_CHECK(cudaEventRecord(e0, e.stream));
-    for (int i = 0; i < iters; ++i) launch_gn_stats(x + el * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), e.stream);
+    for (int i = 0; i < iters; ++i)
+      launch_gn_stats(x + el * esz * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), e.stream, in16, e.fp16);
     CUDA_CHECK(cudaEventRecord(e1, e.stream));
     for (int i = 0; i < iters; ++i)
-      launch_gn_apply(x + el * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), 1e-5f, gamma, beta, 1,
-                      out + el * (i % nbuf), e.fp16, e.stream);
+      launch_gn_apply(x + el * esz * (i % nbuf), c, nullptr, 0, n, hw, st + (size_t)n * 64 * (i % nbuf), 1e-5f, gamma, beta, 1,
+                      out + el * (i % nbuf), e.fp16, e.stream, in16);
     CUDA_CHECK(cudaEventRecord(e2, e.stream));
     e.sync();
     CUDA_CHECK(cudaEventElapsedTime(&ts, e0, e1));
@@ -862,6 +868,9 @@ LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, 
   e.launches += 4 * iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   API_END
+}
+LDM_API int ldm_bench_groupnorm(ldm_handle* h, int n, int hw, int c, int iters, float* stats_ms, float* apply_ms) {
+  return ldm_bench_groupnorm_ex(h, n, hw, c, iters, 0, stats_ms, apply_ms);
 }
 
 // K6 microbenchmark: codebook argmin + gather over `rows` device-resident latent rows against the

@@ -128,6 +128,16 @@ struct GemmParams {
 
 #if defined(__CUDACC__) && defined(LDM_GEMM_IMPL)
 
+// Fine-grained clock64 stamps inside one epilogue chunk and the accumulator-drain-only microbenchmark
+// (profiles/trace_epilogue.py with LDM_B200_TRACE_FINE / LDM_B200_TRACE_TMEM_ONLY) exist only in builds made with
+// LDM_B200_NVCC_FLAGS=-DLDM_GEMM_TRACE_FINE: each stamp is a volatile asm with a memory clobber, i.e. a scheduling
+// barrier for the compiler in the middle of the chunk, and even predicated off they cost the lean chunk ~25 %.
+#ifdef LDM_GEMM_TRACE_FINE
+#define LDM_FINE_STAMP(k) do { if (fine) tre[k] = clock64(); } while (0)
+#else
+#define LDM_FINE_STAMP(k) do { } while (0)
+#endif
+
 // fixed-point scales of the row statistics (GemmParams::rs_out): |sum| < 2^39, sum of squares < 2^47
 constexpr float RS_SCALE_SUM = 16777216.f, RS_INV_SUM = 1.f / 16777216.f;
 constexpr float RS_SCALE_SQ = 65536.f, RS_INV_SQ = 1.f / 65536.f;
@@ -741,8 +751,10 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + col0 + NHALF * 32 + 8 * j);
             }
           }
+#ifdef LDM_GEMM_TRACE_FINE
           const bool fine = tre && (p.dbg & 0x100) && ci == half + NHALF;   // stamps of this warp's SECOND chunk
-          if (fine) tre[9] = clock64();
+#endif
+          LDM_FINE_STAMP(9);
           tmem_ld_x32(t_base + (uint32_t)c, rr);
           if (GEGLU) {
             uint32_t rg[32];
@@ -765,7 +777,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             }
           } else {
             tmem_ld_wait();
-            if (fine) tre[10] = clock64();
+            LDM_FINE_STAMP(10);
+#ifdef LDM_GEMM_TRACE_FINE
             if (p.dbg & 0x400) {   // microbenchmark: accumulator drain only (TMEM -> registers), nothing else
               uint32_t x = 0;
 #pragma unroll
@@ -774,6 +787,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
               continue;
             }
+#endif
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
@@ -787,8 +801,12 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, b.w);
             }
           }
+#ifdef LDM_GEMM_TRACE_FINE
           if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
-          if (fine) tre[11] = clock64();
+#else
+          if (tre && ci < 6) tre[9 + ci] = clock64();
+#endif
+          LDM_FINE_STAMP(11);
           if (res) {
             if (w16) {
               const int slot = w16_rseq & (nbuf - 1);
@@ -856,7 +874,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             u[j].z = pack16(acc[8 * j + 4], acc[8 * j + 5], fp16);
             u[j].w = pack16(acc[8 * j + 6], acc[8 * j + 7], fp16);
           }
-          if (fine) tre[12] = clock64();
+          LDM_FINE_STAMP(12);
           if (w16) {
             const int sslot = w16_sseq & (nbuf - 1);
             if (lane == 0) {   // the store that last used this tile has drained it
@@ -864,14 +882,14 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               else tma_store_wait_read();
             }
             __syncwarp();
-            if (fine) tre[13] = clock64();
+            LDM_FINE_STAMP(13);
             uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u[j];
-            if (fine) tre[14] = clock64();
+            LDM_FINE_STAMP(14);
             fence_proxy_async_cta();
             __syncwarp();
-            if (fine) tre[15] = clock64();
+            LDM_FINE_STAMP(15);
             if (lane == 0) {
               if (!(p.dbg & 4)) {
                 tma_store_4d_a(&p.wmap16, w16_tiles_a + sslot * 2048u, col0, w16_x, w16_y, w16_n);
@@ -1115,9 +1133,11 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 4; ++j) rn16[j] = *reinterpret_cast<const uint4*>(r16_row + c1 + 8 * j);
           }
         }
+#ifdef LDM_GEMM_TRACE_FINE
         const bool fine = tre && (p.dbg & 0x100) && kch == 1;   // fine-grained stamps of this warp's SECOND chunk
+#endif
         tmem_ld_x32(t_base + (uint32_t)c, rr);
-        if (fine) tre[9] = clock64();
+        LDM_FINE_STAMP(9);
         if (geglu) {
           // columns [0,bn/2) of the tile are values, [bn/2,bn) the matching gates (unet.py:323-324)
           uint32_t rg[32];
@@ -1140,7 +1160,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         } else {
           tmem_ld_wait();
-          if (fine) tre[10] = clock64();
+          LDM_FINE_STAMP(10);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b = *reinterpret_cast<const float4*>(bias_s + c + j);
@@ -1166,7 +1186,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
         if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
-        if (fine) tre[11] = clock64();
+        LDM_FINE_STAMP(11);
         // 16-bit residual and row statistics in the row-owner layout (this thread = one row, 32 columns)
         const bool w16c = w16 && full && !to_tr;   // this chunk goes through the per-warp TMA tiles
         if (w16c && w16_res) {
@@ -1211,13 +1231,13 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               if (col0 + j < p.N) { rs_s += acc[j]; rs_q = fmaf(acc[j], acc[j], rs_q); }
           }
         }
-        if (fine) tre[12] = clock64();
+        LDM_FINE_STAMP(12);
         if (w16c) {
           // ---- 16-bit-only outputs: pack this row into the warp's swizzled tile, one lane issues the TMA store
           const int sslot = w16_sseq & 1;
           if (lane == 0) tma_store_wait_read1();   // the store issued two chunks ago has drained this tile
           __syncwarp();
-          if (fine) tre[13] = clock64();
+          LDM_FINE_STAMP(13);
           uint8_t* srow = w16_tiles + sslot * 2048 + lane * 64;
           const uint32_t sw = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
@@ -1230,7 +1250,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = u;
           }
           fence_proxy_async_cta();
-          if (fine) tre[14] = clock64();
+          LDM_FINE_STAMP(14);
           __syncwarp();   // all rows written (and the residual tile read) before lane 0 hands them to the TMA unit
           if (lane == 0) {
             if (!(p.dbg & 4)) {
@@ -1250,7 +1270,7 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
           ++w16_sseq;
           if (w16_res) ++w16_rseq;
-          if (fine) tre[15] = clock64();
+          LDM_FINE_STAMP(15);
           continue;
         }
         if (d16 && !o32 && o16 && !resid && !to_tr && full) {

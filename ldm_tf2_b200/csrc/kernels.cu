@@ -162,14 +162,14 @@ __global__ void gn_stats16x8_kernel(const bf16* __restrict__ a, int ca, const bf
                                     int strip, double* __restrict__ stats, int fp16, unsigned long long* __restrict__ sat) {
   pdl_launch();
   pdl_wait();
-  __shared__ double s_acc[64];
+  __shared__ double s_acc[32 * 64];   // [warp][group][sum, sum of squares]
   const int c = ca + cb, c8 = c >> 3, cg = c / 32;
   const int n = blockIdx.y;
   const int pix0 = blockIdx.x * strip;
   const int pix1 = min(hw, pix0 + strip);
   const int lanes = blockDim.x / c8;
   const int q = threadIdx.x % c8, pl = threadIdx.x / c8;
-  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.0;
+  for (int i = threadIdx.x; i < (int)(blockDim.x >> 5) * 64; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   if (pl < lanes) {
     const int ch = q * 8;
@@ -181,36 +181,53 @@ __global__ void gn_stats16x8_kernel(const bf16* __restrict__ a, int ca, const bf
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
     int nsat = 0;
-#pragma unroll 4
-    for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+    auto take = [&](const uint4& u) {
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(src + (long long)pix * cs), fp16, v);
+      unpack8(u, fp16, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s[k] += v[k];
         ss[k] = fmaf(v[k], v[k], ss[k]);
         if (fp16) nsat += fabsf(v[k]) >= 65504.f;
       }
+    };
+    // four independent 16-byte loads in flight per thread before the first is consumed
+    int pix = pix0 + pl;
+    for (; pix + 3 * lanes < pix1; pix += 4 * lanes) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(src + (long long)pix * cs);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(src + (long long)(pix + lanes) * cs);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(src + (long long)(pix + 2 * lanes) * cs);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(src + (long long)(pix + 3 * lanes) * cs);
+      take(u0); take(u1); take(u2); take(u3);
     }
+    for (; pix < pix1; pix += lanes) take(*reinterpret_cast<const uint4*>(src + (long long)pix * cs));
     if (nsat && sat) atomicAdd(sat, (unsigned long long)nsat);
-    const int g0 = ch / cg, g7 = (ch + 7) / cg;
-    if (g0 == g7) {
-      double ds = 0.0, dq = 0.0;
+    // one pair of shared atomics per GROUP this thread's 8 channels touch (1 or 2 for 8 or more channels per group),
+    // into the warp's own copy of the 64 sums: shared double atomics are CAS loops, and 256 threads x 16 of them on
+    // one array were a serial tail as long as the streaming part
+    double* const w_acc = s_acc + (threadIdx.x >> 5) * 64;
+    int g_cur = ch / cg;
+    double ds = 0.0, dq = 0.0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { ds += (double)s[k]; dq += (double)ss[k]; }
-      atomicAdd(&s_acc[g0 * 2], ds);
-      atomicAdd(&s_acc[g0 * 2 + 1], dq);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int g = (ch + k) / cg;
-        atomicAdd(&s_acc[g * 2], (double)s[k]);
-        atomicAdd(&s_acc[g * 2 + 1], (double)ss[k]);
+    for (int k = 0; k < 8; ++k) {
+      const int g = (ch + k) / cg;
+      if (g != g_cur) {
+        atomicAdd(&w_acc[g_cur * 2], ds);
+        atomicAdd(&w_acc[g_cur * 2 + 1], dq);
+        g_cur = g; ds = 0.0; dq = 0.0;
       }
+      ds += (double)s[k];
+      dq += (double)ss[k];
     }
+    atomicAdd(&w_acc[g_cur * 2], ds);
+    atomicAdd(&w_acc[g_cur * 2 + 1], dq);
   }
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&stats[(long long)n * 64 + threadIdx.x], s_acc[threadIdx.x]);
+  if (threadIdx.x < 64) {
+    double t = 0.0;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += s_acc[wi * 64 + threadIdx.x];
+    atomicAdd(&stats[(long long)n * 64 + threadIdx.x], t);
+  }
 }
 
 __global__ void gn_apply16x8_kernel(const bf16* __restrict__ a, int ca, const bf16* __restrict__ b, int cb, int hw,
@@ -250,10 +267,9 @@ __global__ void gn_apply16x8_kernel(const bf16* __restrict__ a, int ca, const bf
     sh[k] = __ldg(beta + ch + k) - mean * sc[k];
   }
   bf16* dst = out + (long long)n * hw * c + ch;
-#pragma unroll 4
-  for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+  auto put = [&](const uint4& in, int pix) {
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(src + (long long)pix * cs), fp16, v);
+    unpack8(in, fp16, v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       v[k] = fmaf(v[k], sc[k], sh[k]);
@@ -265,7 +281,17 @@ __global__ void gn_apply16x8_kernel(const bf16* __restrict__ a, int ca, const bf
     u.z = pack16(v[4], v[5], fp16);
     u.w = pack16(v[6], v[7], fp16);
     *reinterpret_cast<uint4*>(dst + (long long)pix * c) = u;
+  };
+  // four independent 16-byte loads in flight per thread before the first is consumed
+  int pix = pix0 + pl;
+  for (; pix + 3 * lanes < pix1; pix += 4 * lanes) {
+    const uint4 u0 = *reinterpret_cast<const uint4*>(src + (long long)pix * cs);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(src + (long long)(pix + lanes) * cs);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(src + (long long)(pix + 2 * lanes) * cs);
+    const uint4 u3 = *reinterpret_cast<const uint4*>(src + (long long)(pix + 3 * lanes) * cs);
+    put(u0, pix); put(u1, pix + lanes); put(u2, pix + 2 * lanes); put(u3, pix + 3 * lanes);
   }
+  for (; pix < pix1; pix += lanes) put(*reinterpret_cast<const uint4*>(src + (long long)pix * cs), pix);
 }
 
 static void gn_launch_shape8(int c, int hw, int n, int* threads, int* strip, int* strips) {

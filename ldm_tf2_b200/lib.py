@@ -67,6 +67,7 @@ _PROTOS = {
     "ldm_bench_attention": ([_P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), _P], _I),
     "ldm_crc32c": ([_P, C.c_ulonglong, C.c_uint, C.POINTER(C.c_uint)], _I),
     "ldm_bench_groupnorm": ([_P, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F)], _I),
+    "ldm_bench_groupnorm_ex": ([_P, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F)], _I),
     "ldm_debug_tap": ([_P, C.c_char_p, _P, _L], _I),
     "ldm_test_linear": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ldm_test_ln_linear": ([_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
@@ -395,9 +396,10 @@ class Handle:
         check(self.lib.ldm_bench_ddim_update(self._h, b, hh, ww, int(with_noise), iters, C.byref(ms)))
         return ms.value
 
-    def bench_groupnorm(self, n, hw, c, iters=20):
+    def bench_groupnorm(self, n, hw, c, iters=20, in16=False):
+        """(stats ms, apply ms) per launch; in16: 16-bit input (the sampling path's residual stream)."""
         a, b = C.c_float(), C.c_float()
-        check(self.lib.ldm_bench_groupnorm(self._h, n, hw, c, iters, C.byref(a), C.byref(b)))
+        check(self.lib.ldm_bench_groupnorm_ex(self._h, n, hw, c, iters, int(in16), C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def bench_vq_argmin(self, rows, iters=20):

@@ -19,7 +19,12 @@ struct Scratch {
   template <typename T> T* get(size_t n, bool zero = false) {
     void* p = nullptr;
     CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    if (zero) {
+      // the memset runs on the legacy stream, which is unordered against the engine's non-blocking stream: finish it
+      // before any kernel can touch the buffer (an intermittent zero-init race in the test hooks otherwise)
+      CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+      CUDA_CHECK(cudaDeviceSynchronize());
+    }
     ptrs.push_back(p);
     return reinterpret_cast<T*>(p);
   }

@@ -344,8 +344,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       tmem_ld_x32(s_lane, ra);
       tmem_ld_x32(s_lane + 32, rb);
       tmem_ld_wait();
+#ifdef LDM_GEMM_TRACE_FINE   // per-tile stamps (profiles/trace_attn.py) only in instrumented builds: LDM_B200_NVCC_FLAGS=-DLDM_GEMM_TRACE_FINE
       if (tr && j == 0) tr[2] = clock64();
       if (tr && j < 8) tr[8 + 2 * j] = clock64();
+#endif
       if (MASKED) {
         const int valid = p.tk - j * ATT_BN;   // keys of this tile inside the sequence, in [1, 63]
 #pragma unroll
@@ -367,7 +369,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attention_kernel(const _
       prev_sph = sph;
       have_o = true;
       if (++sb == 2) { sb = 0; sph ^= 1; }
+#ifdef LDM_GEMM_TRACE_FINE
       if (tr && j < 8) tr[9 + 2 * j] = clock64();
+#endif
     };
     const int full_tiles = p.tk / ATT_BN;
     for (int j = 0; j < full_tiles; ++j) tile(j, std::false_type{});

@@ -803,8 +803,6 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
 #ifdef LDM_GEMM_TRACE_FINE
           if (tre && ci < 6 && !(p.dbg & 0x100)) tre[9 + ci] = clock64();
-#else
-          if (tre && ci < 6) tre[9 + ci] = clock64();
 #endif
           LDM_FINE_STAMP(11);
           if (res) {

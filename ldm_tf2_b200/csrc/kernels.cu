@@ -744,10 +744,92 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int nsrc, int n, int
   }
 }
 
+// The same with four horizontally adjacent pixels per thread: every weight float4 fetched from L1 feeds 16 FMAs instead
+// of 4 (the one-pixel kernel issues one load per four FMAs and ran at a sixth of the FMA rate: 0.26 ms per UNet step at
+// 64 images for 1.5 GFLOP).  w % 4 == 0.
+template <int CIN>
+__global__ void conv_in_x4_kernel(const float* __restrict__ x, int nsrc, int n, int h, int w,
+                                  const float* __restrict__ kernel, const float* __restrict__ bias, int cout,
+                                  float* __restrict__ of, bf16* __restrict__ ob, int fp16) {
+  pdl_launch();
+  pdl_wait();
+  const int c4 = cout / 4, wq = w / 4;
+  const long long total = (long long)n * h * wq * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c4) * 4;
+    long long t = i / c4;
+    const int x0 = (int)(t % wq) * 4;
+    t /= wq;
+    const int yy = (int)(t % h);
+    const int img = (int)(t / h);
+    const float* src = x + (long long)(img % nsrc) * h * w * CIN;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co));
+    float acc[4][4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) { acc[px][0] = b4.x; acc[px][1] = b4.y; acc[px][2] = b4.z; acc[px][3] = b4.w; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+      float in[6][CIN];   // input pixels x0 - 1 .. x0 + 4 of this row, zero outside the image (SAME padding)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int ix = x0 + j - 1;
+        const bool ok = ix >= 0 && ix < w;
+        if (CIN == 4) {
+          const float4 v = ok ? *reinterpret_cast<const float4*>(src + ((long long)iy * w + ix) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][CIN - 1] = v.w;
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) in[j][ci] = ok ? src[((long long)iy * w + ix) * CIN + ci] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float4 kw = __ldg(reinterpret_cast<const float4*>(kernel + ((ky * 3 + kx) * CIN + ci) * cout + co));
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = in[px + kx][ci];
+            acc[px][0] += v * kw.x;
+            acc[px][1] += v * kw.y;
+            acc[px][2] += v * kw.z;
+            acc[px][3] += v * kw.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const long long o = (((long long)img * h + yy) * w + x0 + px) * cout + co;
+      if (of) *reinterpret_cast<float4*>(of + o) = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+      if (ob) {
+        uint2 u;
+        u.x = pack16(acc[px][0], acc[px][1], fp16);
+        u.y = pack16(acc[px][2], acc[px][3], fp16);
+        *reinterpret_cast<uint2*>(ob + o) = u;
+      }
+    }
+  }
+}
+
 void launch_conv_in(const float* x, int nsrc, int n, int h, int w, const float* kernel, const float* bias,
                     int cout, float* out_f32, bf16* out_bf16, int fp16, cudaStream_t st, int cin) {
   LDM_CHECK(cout % 4 == 0, "conv_in: cout must be a multiple of 4");
   LDM_CHECK(cin == 4 || cin == 3, "conv_in: 3 (images) or 4 (latents) input channels");
+  if (w % 4 == 0) {
+    const long long total4 = (long long)n * h * (w / 4) * (cout / 4);
+    if (cin == 4)
+      launch_pdl(conv_in_x4_kernel<4>, dim3(grid_for(total4, 128)), dim3(128), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
+                 out_bf16, fp16);
+    else
+      launch_pdl(conv_in_x4_kernel<3>, dim3(grid_for(total4, 128)), dim3(128), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,
+                 out_bf16, fp16);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   const long long total = (long long)n * h * w * (cout / 4);
   if (cin == 4)
     launch_pdl(conv_in_kernel<4>, dim3(grid_for(total, 256)), dim3(256), 0, st, x, nsrc, n, h, w, kernel, bias, cout, out_f32,

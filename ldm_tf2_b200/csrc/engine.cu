@@ -44,7 +44,8 @@ static GemmKernel gemm_kernel_ptr(int pair, int ew, int epi, int fp16 = 0) {
                                                                                      : (GemmKernel)implicit_gemm_kernel<P, E, 2>)
   // lean 16-bit (3) / lean GEGLU (4): 8 epilogue warps (12 and 16 measured slower per chunk, profiles/r2_trace_epilogue_ew12.txt);
   // the fp16 flavours know the operand format at compile time
-#define LDM_L(P, X) (fp16 ? (GemmKernel)implicit_gemm_kernel<P, 8, X, 1> : (GemmKernel)implicit_gemm_kernel<P, 8, X, -1>)
+#define LDM_L(P, X) (ew == 4 ? (fp16 ? (GemmKernel)implicit_gemm_kernel<P, 4, X, 1> : (GemmKernel)implicit_gemm_kernel<P, 4, X, -1>) \
+                             : (fp16 ? (GemmKernel)implicit_gemm_kernel<P, 8, X, 1> : (GemmKernel)implicit_gemm_kernel<P, 8, X, -1>))
   if (epi == 3) return pair ? LDM_L(1, 3) : LDM_L(0, 3);
   if (epi == 4) return pair ? LDM_L(1, 4) : LDM_L(0, 4);
 #undef LDM_L
@@ -74,6 +75,8 @@ Engine::Engine(int dev) : device(dev) {
     for (int f16 = 0; f16 < 2; ++f16) {
       CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
       CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 8, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 4, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(1, 4, epi, f16), cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     }
   for (int epi = 0; epi < 3; ++epi) {
     CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel_ptr(0, 8, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -347,12 +350,28 @@ void Engine::gemm(const GemmOp& op) {
   // epilogue warps of the lean kernels (LDM_B200_LEAN_EW = 8 / 12 / 16).  Measured in-graph (profiles/r2_ab_switches.txt):
   // 8 warps 5.36 ms per UNet step at 8 images, 12 warps 5.52, 16 warps 5.75 -- more warps make every chunk slower
   // (the 64 B/clk TMEM read port and the shrinking operand pipeline), so 8 it is.
-  const int lean_ew = 8;   // 12 / 16 epilogue warps measured slower per chunk (profiles/r2_trace_epilogue_ew12.txt); flavours removed
+  // Lean flavours: 8 epilogue warps and one CTA per SM, or 4 epilogue warps, 256 TMEM columns and TWO CTAs per SM, so
+  // that one tile's epilogue runs under the other's main loop and a launch has 296 tile slots instead of 148.  Measured
+  // per shape (profiles/r2_lean_ew4_shapes.txt): the two-CTA flavour wins for K = 320 (5 k-blocks: -5 % on the C x C
+  // linears, -16 % on q|k|v at 64 images) and whenever the launch has at most two waves of tiles (8 images per GPU: the
+  // last wave is half empty with 148 slots); with more waves and K >= 640 it loses 3 - 20 % (3 operand stages per CTA).
+  // Inside the replayed step graph, where programmatic dependent launch already hides the tails, the net effect is
+  // within noise at 8 / 16 / 64 images and -1 % at 32, so the flavour is OFF by default (LDM_B200_LEAN_EW4=1 enables it).
+  // 12 / 16 warps per CTA measured slower (profiles/r2_trace_epilogue_ew12.txt).
+  int lean_ew = 8;
+  const bool few_waves = work_tiles <= (long long)LDM_TUNE("LDM_B200_T_LEAN4_WAVES", 2) * (pair ? num_sms / 2 : num_sms);
+  if (lean && op.ew != 8 && LDM_TUNE("LDM_B200_LEAN_EW4", 0) && short_k && many_tiles &&
+      (total_kb / splits <= LDM_TUNE("LDM_B200_T_LEAN4_MAXKB", 5) || few_waves)) {
+    const int epi4 = w16 ? 4 * 4096 : (op.out_tr ? 4 * 4096 : 0);   // single-buffered tiles
+    if (3 * slot + GEMM_CTRL_BYTES + epi4 + 1024 <= 110 * 1024) lean_ew = 4;
+  }
+  const bool lean4 = lean && lean_ew == 4;
   if (lean) {
     p.epi_bytes = op.out_tr ? lean_ew * 4096 : 0;   // the V^T transposition tile of every warp
     if (w16) {
       // double-buffered tiles unless they would squeeze the operand pipeline below 5 stages
-      const int stages2 = (GEMM_SMEM_BYTES - GEMM_CTRL_BYTES - lean_ew * 8192 - 1024) / slot;
+      const int budget = lean4 ? 110 * 1024 : GEMM_SMEM_BYTES;
+      const int stages2 = (budget - GEMM_CTRL_BYTES - lean_ew * 8192 - 1024) / slot;
       p.w16_nbuf = (stages2 >= LDM_TUNE("LDM_B200_W16_MINSTAGES", 5) || total_kb / splits <= stages2) ? 2 : 1;
       p.epi_bytes = lean_ew * p.w16_nbuf * 4096;
     }
@@ -369,14 +388,15 @@ void Engine::gemm(const GemmOp& op) {
   } else {
     p.epi_bytes = GEMM_EPI_LEGACY_BYTES;
   }
-  const int smem_budget = ew4 ? 110 * 1024 : GEMM_SMEM_BYTES;   // two CTAs per SM: (228 KB - 2 x (1 KB reserved + 1 KB static)) / 2
+  const bool half_sm = ew4 || lean4;   // two CTAs per SM
+  const int smem_budget = half_sm ? 110 * 1024 : GEMM_SMEM_BYTES;   // two CTAs per SM: (228 KB - 2 x (1 KB reserved + 1 KB static)) / 2
   int stages = (smem_budget - GEMM_CTRL_BYTES - p.epi_bytes - 1024) / slot;  // + 1 KB alignment slack
   if (stages > 8) stages = 8;
   // accumulator ring in TMEM: 2 x 256 columns normally; with 256 columns per CTA two stages only
   // for tiles up to 128 wide, else a single stage (the co-resident CTA fills the gap)
-  p.tmem_cols = ew4 ? 256 : 512;
-  p.acc_stages = (!ew4 || bn <= 128) ? 2 : 1;
-  p.acc_stride = ew4 ? 128 : 256;
+  p.tmem_cols = half_sm ? 256 : 512;
+  p.acc_stages = (!half_sm || bn <= 128) ? 2 : 1;
+  p.acc_stride = half_sm ? 128 : 256;
   LDM_CHECK(stages >= 2, "gemm: tile does not fit shared memory");
   p.stages = stages;
   p.tx_bytes = stage_bytes;
@@ -433,7 +453,7 @@ void Engine::gemm(const GemmOp& op) {
     if (op.residual) encode_out_map(&p.rmap, op.residual, 4, true, op.N, op.W, op.H, op.NB, op.os_x, op.os_y, op.os_n, w_b, h_b, n_b);
   }
   const int total_tiles = (pair ? p.pm_tiles : m_tiles) * p.n_tiles * splits;
-  int ctas = max_ctas > 0 ? max_ctas : (ew4 ? 2 * num_sms : num_sms);
+  int ctas = max_ctas > 0 ? max_ctas : (half_sm ? 2 * num_sms : num_sms);
   if (pair) ctas /= 2;
   if (ctas < 1) ctas = 1;
   if (ctas > total_tiles) ctas = total_tiles;

@@ -27,5 +27,6 @@ h.set_weights(h.UNET, synth.random_weights(h, h.UNET, 0))
 h.finalize()
 sch = DDIMSchedule(1000, 0.00085, 0.012, 0.0, 0.0, 50)
 h.configure_sampler(sch.ddim_steps, sch.coeff_table())
-h.set_context(np.random.default_rng(3).standard_normal((16, 77, 1280), dtype=np.float32))
-print(h.profile_unet_step(8, 32, 32, 1))
+B = int(os.environ.get("SHAPES_B", "8"))   # images per GPU
+h.set_context(np.random.default_rng(3).standard_normal((2 * B, 77, 1280), dtype=np.float32))
+print(h.profile_unet_step(B, 32, 32, 1))

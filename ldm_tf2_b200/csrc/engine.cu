@@ -360,8 +360,10 @@ void Engine::gemm(const GemmOp& op) {
   // 12 / 16 warps per CTA measured slower (profiles/r2_trace_epilogue_ew12.txt).
   int lean_ew = 8;
   const bool few_waves = work_tiles <= (long long)LDM_TUNE("LDM_B200_T_LEAN4_WAVES", 2) * (pair ? num_sms / 2 : num_sms);
-  if (lean && op.ew != 8 && LDM_TUNE("LDM_B200_LEAN_EW4", 0) && short_k && many_tiles &&
-      (total_kb / splits <= LDM_TUNE("LDM_B200_T_LEAN4_MAXKB", 5) || few_waves)) {
+  const bool lean4_forced = (op.dbg & 0x800) != 0;   // test hook: take the flavour whenever it fits
+  if (lean && op.ew != 8 &&
+      (lean4_forced || (LDM_TUNE("LDM_B200_LEAN_EW4", 0) && short_k && many_tiles &&
+                        (total_kb / splits <= LDM_TUNE("LDM_B200_T_LEAN4_MAXKB", 5) || few_waves)))) {
     const int epi4 = w16 ? 4 * 4096 : (op.out_tr ? 4 * 4096 : 0);   // single-buffered tiles
     if (3 * slot + GEMM_CTRL_BYTES + epi4 + 1024 <= 110 * 1024) lean_ew = 4;
   }

@@ -86,6 +86,9 @@ def test_vq_argmin_bit_exact(vocab, rows):
     (128, 64, 96, 112, 0, False, 0),      # ragged 16-column tail tile
     (256, 64, 64, 256, 3, False, 8),      # GEGLU with the folded LayerNorm (fragment epilogue)
     (160, 64, 64, 256, 3, False, 0),      # GEGLU, row-owner epilogue, ragged rows
+    (512, 64, 320, 320, 0, True, 0x800),  # lean flavour with two CTAs per SM (4 epilogue warps, 256 TMEM columns)
+    (384, 128, 320, 960, 0, False, 0x800),
+    (256, 64, 64, 128, 3, False, 0x800),  # ... GEGLU: one accumulator stage of 2 x 64 columns
 ])
 def test_layernorm_folded_linear_with_16bit_residual_and_row_stats(h, rows, k0, c, n, act, residual, dbg):
     """unet.py:304-314: y = dense(a); out = act(dense(LayerNorm(y))) [+ y].  The library keeps y as a 16-bit

@@ -443,8 +443,9 @@ void Model::build() {
   }
   // validation mode walks the raw fp32 kernels of the unet (validate.cu)
   if (cfg.precision == 2)
-    for (auto& s : slots[1])
-      if (s.kind == Slot::PACK) s.keep = true;
+    for (int mdl = 1; mdl <= 2; ++mdl)
+      for (auto& s : slots[mdl])
+        if (s.kind == Slot::PACK) s.keep = true;
   step_dev_ = dev_alloc<int>(1, true);
   sat_dev_ = dev_alloc<unsigned long long>(1, true);
 }
@@ -1429,6 +1430,10 @@ Act Model::ae_attention(AEAttnW& a, const Act& x) {
 void Model::decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev) {
   const int zc = cfg.latent_channels;
   LDM_CHECK(zc == 4, "decode: latent_channels must be 4");
+  if (cfg.precision == 2) {   // fp32 validation mode (validate.cu)
+    if (!eng.dry) decode_body_f32(z, b, h, w, div, img_dev, idx_dev);
+    return;
+  }
   begin_pass();
   const long long rows = (long long)b * h * w;
   const float* zin = z;

@@ -27,7 +27,7 @@ struct ModelConfig {
       ae_num_attn_res = 0, ae_attn_res[8] = {0}, vq_vocab = 16384,
       ae_build_hw = 32;  // latent size the checkpoint's Decoder was built at (autoencoder.py:176)
   int precision = 1;       // 16-bit tensor-core operand format: 0 = bf16, 1 = fp16; 2 = fp32 validation mode: the UNet
-                           // runs in fp32 on the CUDA cores (validate.cu), everything else as with fp16
+                           // and the autoencoder's decoder run in fp32 on the CUDA cores (validate.cu), the rest as with fp16
 };
 
 // One tensor of a model in flat Keras order, with how it is consumed.
@@ -218,6 +218,7 @@ class Model {
   void unet_eps(const float* x, int nsrc, int n, int h, int w, float* eps_out);
   // precision = 2 (validate.cu): the same function in fp32 from the raw checkpoint tensors
   void unet_eps_f32(const float* x, int nsrc, int n, int h, int w, float* eps_out);
+  void decode_body_f32(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   float* ctx_f32_ = nullptr; size_t ctx_f32_cap_ = 0;   // fp32 copy of the context (validation mode only)
   void decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   Act ae_attention(AEAttnW& a, const Act& x);

@@ -1,16 +1,20 @@
-// fp32 validation mode (ldm_config.precision = 2): the UNet denoiser of the sampling path evaluated
-// end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no folded LayerNorm, no
-// hoisting -- from the RAW checkpoint tensors (Keras layouts, kept on the device in this mode).
+// fp32 validation mode (ldm_config.precision = 2): the UNet denoiser and the autoencoder's decoder of the
+// sampling path evaluated end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no
+// folded LayerNorm, no hoisting -- from the RAW checkpoint tensors (Keras layouts, kept on the device in
+// this mode).
 //
 // It exists to answer one question the 16-bit product path cannot: "is the remaining 1.6e-3 of eps
 // error operand rounding, or a semantic difference?"  north_star's bound for this mode is per-step eps
 // rel-L2 <= 1e-4 against the reference; tests/test_gpu_validate.py holds it to that at full size.
-// It is a checker-grade path (tens of ms per UNet evaluation), never the benchmarked one.
+// The decoder (KL / VQ) is held to the same bound on the images.  It is a checker-grade path (the full-size
+// 50-step trajectory + decode at B = 1 takes a few seconds), never the benchmarked one.
 //
 // Layer semantics restated from the reference:
 //   UNet.call unet.py:118-138, ResidualBlock unet.py:382-398, SpatialTransformer unet.py:356-365,
 //   BasicTransformerBlock unet.py:308-314, CrossAttention unet.py:269-292, GEGLU / FeedForward
-//   unet.py:322-325,335-338, Downsample unet.py:22-27, Upsample unet.py:44-47.
+//   unet.py:322-325,335-338, Downsample unet.py:22-27, Upsample unet.py:44-47; autoencoder ResidualBlock
+//   autoencoder.py:43-58, AttentionBlock autoencoder.py:74-97, Decoder autoencoder.py:252-298, decode
+//   autoencoder.py:361-364,430-436.
 // Summation order: every GEMM accumulates 16 products in one fp32 register and adds that partial sum
 // to the running total (two-level summation; error ~ sqrt(K/16) ulp instead of sqrt(K)); GroupNorm /
 // LayerNorm statistics are two-pass in double like the oracle's.
@@ -270,7 +274,8 @@ struct Validator {
   std::vector<void*> live;
   std::unordered_map<std::string, Slot*> by_name;
   explicit Validator(Model& mm) : m(mm), st(mm.eng.stream) {
-    for (auto& s : m.slots[1]) by_name[s.name] = &s;
+    for (int mdl = 1; mdl <= 2; ++mdl)
+      for (auto& s : m.slots[mdl]) by_name[s.name] = &s;
   }
   ~Validator() { release(0); }
   float* alloc(long long n) {
@@ -286,7 +291,7 @@ struct Validator {
   }
   const float* W(const std::string& name) {
     auto it = by_name.find(name);
-    LDM_CHECK(it != by_name.end(), "validation mode: no unet tensor named %s", name.c_str());
+    LDM_CHECK(it != by_name.end(), "validation mode: no tensor named %s", name.c_str());
     LDM_CHECK(it->second->f32 != nullptr, "validation mode: %s has no resident fp32 copy", name.c_str());
     return it->second->f32;
   }
@@ -343,27 +348,32 @@ struct Validator {
     m.eng.launches++;
   }
 
-  // ResidualBlock.call (unet.py:382-398)
-  T32 resblock(const ResW& r, const std::string& p, const T32& x) {
+  // ResidualBlock.call (unet.py:382-398); ae: the autoencoder's (autoencoder.py:43-58: eps 1e-6, no time input)
+  T32 resblock(const ResW& r, const std::string& p, const T32& x, bool ae = false) {
     LDM_CHECK(x.c == r.cin, "validation resblock %s: %d input channels, expected %d", p.c_str(), x.c, r.cin);
+    const std::string gn1 = p + (ae ? "/_group_norm1" : "/_group_norm_1"), c1 = p + (ae ? "/_conv1" : "/_conv2d_1"),
+                      gn2 = p + (ae ? "/_group_norm2" : "/_group_norm_2"), c2 = p + (ae ? "/_conv2" : "/_conv2d_2");
+    const float eps = ae ? 1e-6f : 1e-5f;
     T32 out = tensor(x.n, x.h, x.w, r.cout);
     const size_t mk = mark();
     T32 a1 = tensor(x.n, x.h, x.w, x.c);
-    group_norm(x, p + "/_group_norm_1", 1e-5f, true, a1.p);
+    group_norm(x, gn1, eps, true, a1.p);
     T32 h1 = tensor(x.n, x.h, x.w, r.cout);
     {
       ConvP c{};
       c.x = a1.p; c.n = x.n; c.h = x.h; c.w = x.w; c.cin = x.c; c.nsrc = x.n;
-      c.wgt = W(p + "/_conv2d_1/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
-      c.oh = x.h; c.ow = x.w; c.cout = r.cout; c.bias = W(p + "/_conv2d_1/bias");
-      LDM_CHECK(m.temb_table_ != nullptr && r.temb_off >= 0, "validation resblock: no time projection");
-      c.bias2 = m.temb_table_ + r.temb_off; c.bias2_stride = m.tproj_cols_;
-      c.bias2_by_img = m.temb_by_img_ ? 1 : 0; c.step_ptr = m.temb_use_step_ ? m.step_dev_ : nullptr;
+      c.wgt = W(c1 + "/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
+      c.oh = x.h; c.ow = x.w; c.cout = r.cout; c.bias = W(c1 + "/bias");
+      if (!ae) {
+        LDM_CHECK(m.temb_table_ != nullptr && r.temb_off >= 0, "validation resblock: no time projection");
+        c.bias2 = m.temb_table_ + r.temb_off; c.bias2_stride = m.tproj_cols_;
+        c.bias2_by_img = m.temb_by_img_ ? 1 : 0; c.step_ptr = m.temb_use_step_ ? m.step_dev_ : nullptr;
+      }
       c.out = h1.p;
       conv(c);
     }
     T32 a2 = tensor(x.n, x.h, x.w, r.cout);
-    group_norm(h1, p + "/_group_norm_2", 1e-5f, true, a2.p);
+    group_norm(h1, gn2, eps, true, a2.p);
     const float* res = x.p;
     if (r.shortcut) {
       float* sc = alloc(out.numel());
@@ -373,10 +383,31 @@ struct Validator {
     {
       ConvP c{};
       c.x = a2.p; c.n = x.n; c.h = x.h; c.w = x.w; c.cin = r.cout; c.nsrc = x.n;
-      c.wgt = W(p + "/_conv2d_2/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
-      c.oh = x.h; c.ow = x.w; c.cout = r.cout; c.bias = W(p + "/_conv2d_2/bias"); c.res = res; c.out = out.p;
+      c.wgt = W(c2 + "/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
+      c.oh = x.h; c.ow = x.w; c.cout = r.cout; c.bias = W(c2 + "/bias"); c.res = res; c.out = out.p;
       conv(c);
     }
+    release(mk);
+    return out;
+  }
+
+  // AE AttentionBlock.call (autoencoder.py:74-97): single head, d = C, scale C^-0.5 after the dot product
+  T32 ae_attention(const std::string& p, const T32& x) {
+    const int n = x.n, t = x.h * x.w, c = x.c;
+    const long long rows = (long long)n * t;
+    T32 out = tensor(n, x.h, x.w, c);
+    const size_t mk = mark();
+    float* y = alloc(rows * c);
+    group_norm(x, p + "/_group_norm", 1e-6f, false, y);
+    float* q = alloc(rows * c);
+    float* k = alloc(rows * c);
+    float* v = alloc(rows * c);
+    dense(y, rows, c, p + "/_dense_query/kernel", W(p + "/_dense_query/bias"), c, nullptr, q);
+    dense(y, rows, c, p + "/_dense_key/kernel", W(p + "/_dense_key/bias"), c, nullptr, k);
+    dense(y, rows, c, p + "/_dense_value/kernel", W(p + "/_dense_value/bias"), c, nullptr, v);
+    float* o = alloc(rows * c);
+    attention(q, c, k, v, c, n, t, t, 1, c, o, c);
+    dense(o, rows, c, p + "/_dense_output/kernel", W(p + "/_dense_output/bias"), c, x.p, out.p);
     release(mk);
     return out;
   }
@@ -489,6 +520,54 @@ void Model::unet_eps_f32(const float* x, int nsrc, int n, int h, int w, float* e
   c.x = a.p; c.n = n; c.h = h; c.w = w; c.cin = mc; c.nsrc = n;
   c.wgt = v.W("unet/_conv_out/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
   c.oh = h; c.ow = w; c.cout = cfg.out_channels; c.bias = v.W("unet/_conv_out/bias"); c.out = eps_out;
+  v.conv(c);
+}
+
+// AutoencoderKL.decode / AutoencoderVQ.decode(force_quantize = True) (autoencoder.py:361-364, 430-436) in fp32.
+// z [b, h, w, 4] device latents, img_dev [b, 8h, 8w, 3]; the VQ lookup (bit-exact fp32 already) and the 4 x 4
+// post_quant_conv are the product path's own kernels.
+void Model::decode_body_f32(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev) {
+  Validator v(*this);
+  const long long rows = (long long)b * h * w;
+  const float* zin = z;
+  float pq_div = div;
+  if (cfg.ae_kind == 1) {
+    float* zq = v.alloc(rows * 4);
+    eng.launches += 3;
+    launch_vq_argmin(z, rows, 4, codebook_->f32, cfg.vq_vocab, div, idx_dev, zq, eng.stream);
+    zin = zq;
+    pq_div = 1.0f;
+  }
+  T32 pq = v.tensor(b, h, w, 4);
+  eng.launches++;
+  launch_dense4(zin, rows, pq_div, pq_k_->f32, pq_b_->f32, pq.p, eng.stream);
+  const std::string d = "autoencoder/_decoder";
+  const int top = cfg.ae_channels * cfg.ae_mult[cfg.ae_num_mult - 1];
+  T32 cur = v.conv3x3(pq, b, d + "/_conv_in", top, 1, false);
+  cur = v.resblock(ae_mid1_, d + "/_middle/_residual1", cur, true);
+  cur = v.ae_attention(d + "/_middle/_attention", cur);
+  cur = v.resblock(ae_mid2_, d + "/_middle/_residual2", cur, true);
+  int idx = 0;
+  for (auto& s : ae_up_) {
+    const std::string p = d + "/_up/" + std::to_string(idx++);
+    if (s.kind == 0) {
+      cur = v.resblock(s.res, p + "/_residual", cur, true);
+      bool want = false;
+      if (cfg.ae_kind == 1)
+        for (int k = 0; k < cfg.ae_num_attn_res; ++k) want |= (cfg.ae_attn_res[k] == cur.h);
+      LDM_CHECK(!want || s.attn, "decode: attention needed at resolution %d but the autoencoder was built for latent %d",
+                cur.h, cfg.ae_build_hw);
+      if (want) cur = v.ae_attention(p + "/_attention", cur);
+    } else {
+      cur = v.conv3x3(cur, cur.n, p + "/_conv", cur.c, 1, true);   // nearest x2 + conv3x3 (autoencoder.py:152-155)
+    }
+  }
+  T32 a = v.tensor(b, cur.h, cur.w, cur.c);
+  v.group_norm(cur, d + "/_group_norm", 1e-6f, true, a.p);
+  ConvP c{};
+  c.x = a.p; c.n = b; c.h = cur.h; c.w = cur.w; c.cin = cur.c; c.nsrc = b;
+  c.wgt = v.W(d + "/_conv_out/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
+  c.oh = cur.h; c.ow = cur.w; c.cout = 3; c.bias = v.W(d + "/_conv_out/bias"); c.out = img_dev;
   v.conv(c);
 }
 

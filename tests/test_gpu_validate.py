@@ -1,5 +1,5 @@
-"""fp32 validation mode (ldm_config.precision = 2, csrc/validate.cu): the UNet denoiser evaluated in fp32 on
-the CUDA cores from the raw checkpoint tensors.  north_star's bound for this mode: per-step eps relative
+"""fp32 validation mode (ldm_config.precision = 2, csrc/validate.cu): the UNet denoiser and the autoencoder's
+decoder evaluated in fp32 on the CUDA cores from the raw checkpoint tensors.  north_star's bound for this mode: per-step eps relative
 L2 <= 1e-4 against the reference (here: the fp32 oracle, oracle/ldm_oracle.py, and the committed full-size
 golden trajectory tests/golden/full_oracle.npz)."""
 import os
@@ -16,9 +16,11 @@ VALIDATION_TOL = 1e-4   # north_star: per-step eps relative L2 in the fp32 valid
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_oracle.npz")
 
 
-def _unet_handle(cfg, wu, ae_hw):
-    h = make_handle(cfg, "kl", ae_hw=ae_hw, precision="fp32")
+def _unet_handle(cfg, wu, ae_hw, wa=None, ae_kind="kl"):
+    h = make_handle(cfg, ae_kind, ae_hw=ae_hw, precision="fp32")
     h.set_weights(h.UNET, wu)
+    if wa is not None:
+        h.set_weights(h.AE, wa)
     h.finalize()
     return h
 
@@ -30,7 +32,9 @@ def test_validation_mode_tiny_unet_taps_and_loop():
     Wu = O.as_dict(us, wu)
     ids = np.array([O.KAT_UNCOND_IDS, O.KAT_COND_IDS], dtype=np.int64)
     ctx = O.text_encode(O.as_dict(ts, wt), cfg["cond_stage_model"], ids)[[0, 0, 1, 1]]
-    h = _unet_handle(cfg, wu, 8)
+    as_ = O.ae_spec(cfg["autoencoder_kl"], "kl", 8)
+    wa = O.init_weights(as_, 2)
+    h = _unet_handle(cfg, wu, 8, wa)
     try:
         x = np.random.default_rng(1234).standard_normal((2, 8, 8, 4), dtype=np.float32)
         x2 = np.concatenate([x, x], 0)
@@ -55,6 +59,29 @@ def test_validation_mode_tiny_unet_taps_and_loop():
         errs = [rel_l2(trace[i], trace_ref[i]) for i in range(20)]
         print(f"validation mode (tiny) 20-step loop: max eps rel-L2 {max(errs):.3e}, latent rel-L2 {rel_l2(got, ref):.3e}")
         assert max(errs) < VALIDATION_TOL and rel_l2(got, ref) < VALIDATION_TOL
+        # ... and the KL decoder in this mode
+        img, _ = h.decode(ref, div=0.18215)
+        img_ref, _ = O.decode_first_stage(O.as_dict(as_, wa), cfg["autoencoder_kl"], "kl", ref)
+        print(f"validation mode (tiny) KL decode rel-L2 {rel_l2(img, img_ref):.3e}")
+        assert rel_l2(img, img_ref) < VALIDATION_TOL
+    finally:
+        h.close()
+
+
+def test_validation_mode_tiny_vq_decode():
+    """VQ autoencoder (attention blocks inside the decoder) in the validation mode: indices exact, image <= 1e-4."""
+    cfg = O.TINY_CONFIG
+    us = O.unet_spec(cfg["unet"])
+    vs = O.ae_spec(cfg["autoencoder_vq"], "vq", 8)
+    wv = O.init_weights(vs, 3)
+    h = _unet_handle(cfg, O.init_weights(us, 0), 8, wv, ae_kind="vq")
+    try:
+        z = np.random.default_rng(11).standard_normal((2, 8, 8, 4), dtype=np.float32)
+        img, idx = h.decode(z, div=0.18215)
+        img_ref, idx_ref = O.decode_first_stage(O.as_dict(vs, wv), cfg["autoencoder_vq"], "vq", z)
+        print(f"validation mode (tiny) VQ decode rel-L2 {rel_l2(img, img_ref):.3e}")
+        assert np.array_equal(idx.reshape(-1), np.asarray(idx_ref).reshape(-1))
+        assert rel_l2(img, img_ref) < VALIDATION_TOL
     finally:
         h.close()
 
@@ -70,7 +97,9 @@ def test_validation_mode_full_size_eps_and_trajectory():
     del wt
     g = np.load(GOLD)
     assert np.array_equal(g["ctx_probe"], ctx[:, :12, :64])   # the golden was made with these weights / prompts
-    h = _unet_handle(cfg, wu, 32)
+    wa = O.init_weights(O.ae_spec(cfg["autoencoder_kl"], "kl"), 2)
+    h = _unet_handle(cfg, wu, 32, wa)
+    del wa
     try:
         Wu = O.as_dict(us, wu)
         x = np.random.default_rng(1234).standard_normal((1, 32, 32, 4), dtype=np.float32)
@@ -90,5 +119,10 @@ def test_validation_mode_full_size_eps_and_trajectory():
         print("validation mode (full size) 50-step eps rel-L2 at steps", steps, [f"{e:.2e}" for e in errs])
         print(f"validation mode (full size) final latent rel-L2 {lat:.3e}")
         assert max(errs) < VALIDATION_TOL and lat < VALIDATION_TOL
+        # the KL decoder in this mode: the golden latents, and the whole job end to end (own latents)
+        e_dec = rel_l2(h.decode(g["c1_latents"], div=0.18215)[0], g["c1_image"])
+        e_job = rel_l2(h.decode(got, div=0.18215)[0], g["c1_image"])
+        print(f"validation mode (full size) KL decode rel-L2 {e_dec:.3e}; 50 steps + decode vs the oracle's image {e_job:.3e}")
+        assert e_dec < VALIDATION_TOL and e_job < VALIDATION_TOL
     finally:
         h.close()

@@ -443,7 +443,7 @@ void Model::build() {
   }
   // validation mode walks the raw fp32 kernels of the unet (validate.cu)
   if (cfg.precision == 2)
-    for (int mdl = 1; mdl <= 2; ++mdl)
+    for (int mdl = 0; mdl <= 2; ++mdl)
       for (auto& s : slots[mdl])
         if (s.kind == Slot::PACK) s.keep = true;
   step_dev_ = dev_alloc<int>(1, true);
@@ -1390,15 +1390,21 @@ void Model::encode_text(const long long* ids, int rows, float* ctx_out) {
   float* x = static_cast<float*>(stage(ST_D, (size_t)R * D * sizeof(float)));
   float* y = static_cast<float*>(stage(ST_E, (size_t)R * D * sizeof(float)));
   CUDA_CHECK(cudaMemcpyAsync(ids_dev, uids.data(), uids.size() * sizeof(long long), cudaMemcpyHostToDevice, eng.stream));
-  {
-    DryPass dry(eng);
+  if (cfg.precision == 2) {   // fp32 validation mode (validate.cu)
+    launch_embed(ids_dev, tok_emb_->f32, pos_emb_->f32, (int)R, T, D, x, eng.stream);
+    eng.launches++;
+    encode_text_f32(x, n, y);
+  } else {
+    {
+      DryPass dry(eng);
+      body(ids_dev, x);
+    }
+    ensure_arena(eng.arena.peak());
+    eng.arena.reset();
     body(ids_dev, x);
+    launch_layernorm(x, text_ln_.gamma->f32, text_ln_.beta->f32, (int)R, D, 1e-5f, nullptr, y, eng.fp16, eng.stream);
+    eng.launches++;
   }
-  ensure_arena(eng.arena.peak());
-  eng.arena.reset();
-  body(ids_dev, x);
-  launch_layernorm(x, text_ln_.gamma->f32, text_ln_.beta->f32, (int)R, D, 1e-5f, nullptr, y, eng.fp16, eng.stream);
-  eng.launches++;
   for (int r = 0; r < rows; ++r)
     CUDA_CHECK(cudaMemcpyAsync(ctx_out + (long long)r * T * D, y + (long long)uniq_of[r] * T * D,
                                (size_t)T * D * sizeof(float), cudaMemcpyDefault, eng.stream));

@@ -1,5 +1,5 @@
-// fp32 validation mode (ldm_config.precision = 2): the UNet denoiser and the autoencoder's decoder of the
-// sampling path evaluated end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no
+// fp32 validation mode (ldm_config.precision = 2): the text transformer, the UNet denoiser and the autoencoder's
+// decoder of the sampling path evaluated end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no
 // folded LayerNorm, no hoisting -- from the RAW checkpoint tensors (Keras layouts, kept on the device in
 // this mode).
 //
@@ -34,6 +34,7 @@ struct ConvP {
   const float* bias;                        // [cout] or null
   const float* bias2; long long bias2_stride; int bias2_by_img; const int* step_ptr;   // time projection rows
   const float* res;                         // [M, cout] or null
+  int act;                                  // 1: exact-erf GELU on (acc + bias) (transformer.py:169)
   float* out;                               // [M, cout]
 };
 
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) f32_conv_gemm_kernel(const ConvP p) {
       float v = acc[i][j];
       if (p.bias) v += p.bias[nn];
       if (b2) v += b2[nn];          // h + time projection (unet.py:386-387)
+      if (p.act == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
       if (p.res) v += p.res[m * p.cout + nn];
       p.out[m * p.cout + nn] = v;
     }
@@ -274,7 +276,7 @@ struct Validator {
   std::vector<void*> live;
   std::unordered_map<std::string, Slot*> by_name;
   explicit Validator(Model& mm) : m(mm), st(mm.eng.stream) {
-    for (int mdl = 1; mdl <= 2; ++mdl)
+    for (int mdl = 0; mdl <= 2; ++mdl)
       for (auto& s : m.slots[mdl]) by_name[s.name] = &s;
   }
   ~Validator() { release(0); }
@@ -305,12 +307,12 @@ struct Validator {
   }
   // Dense over the last axis: out [rows, nout] = x [rows, k] W[k, nout] + bias (+ res)
   void dense(const float* x, long long rows, int k, const std::string& kernel, const float* bias, int nout,
-             const float* res, float* out) {
+             const float* res, float* out, int act = 0) {
     LDM_CHECK(rows < (1ll << 31), "validation mode: too many rows");
     ConvP p{};
     p.x = x; p.n = 1; p.h = 1; p.w = (int)rows; p.cin = k; p.nsrc = 1;
     p.wgt = W(kernel); p.taps = 1; p.stride = 1; p.pad = 0; p.ups = 0;
-    p.oh = 1; p.ow = (int)rows; p.cout = nout; p.bias = bias; p.res = res; p.out = out;
+    p.oh = 1; p.ow = (int)rows; p.cout = nout; p.bias = bias; p.res = res; p.act = act; p.out = out;
     conv(p);
   }
   // conv3x3: SAME (stride 1), pad-1 + VALID stride 2 (unet.py:22-27), or nearest x2 + SAME (unet.py:44-47)
@@ -569,6 +571,34 @@ void Model::decode_body_f32(const float* z, int b, int h, int w, float div, floa
   c.wgt = v.W(d + "/_conv_out/kernel"); c.taps = 9; c.stride = 1; c.pad = 1;
   c.oh = cur.h; c.ow = cur.w; c.cout = 3; c.bias = v.W(d + "/_conv_out/bias"); c.out = img_dev;
   v.conv(c);
+}
+
+// TransformerModel.call (transformer.py:254-272, oracle text_encode): x [n * T, D] holds tok-emb + pos-emb on entry
+// (launch_embed, fp32 in both modes); pre-LN encoder stack, final LayerNorm into y.
+void Model::encode_text_f32(float* x, int n, float* y) {
+  Validator v(*this);
+  const int T = cfg.max_seq_len, D = cfg.text_hidden, H = cfg.text_heads, S = cfg.text_head_dim, inner = H * S;
+  const long long R = (long long)n * T;
+  float* z = v.alloc(R * D);
+  float* q = v.alloc(R * inner);
+  float* k = v.alloc(R * inner);
+  float* vv = v.alloc(R * inner);
+  float* o = v.alloc(R * inner);
+  float* hb = v.alloc(R * cfg.text_filter);
+  float* x2 = v.alloc(R * D);
+  for (int i = 0; i < cfg.text_layers; ++i) {
+    const std::string p = "transformer/_encoder/_stack/" + std::to_string(i);
+    v.layer_norm(x, R, D, p + "/_layernorm_mha", z);
+    v.dense(z, R, D, p + "/_mha/_dense_layer_query/kernel", nullptr, inner, nullptr, q);
+    v.dense(z, R, D, p + "/_mha/_dense_layer_key/kernel", nullptr, inner, nullptr, k);
+    v.dense(z, R, D, p + "/_mha/_dense_layer_value/kernel", nullptr, inner, nullptr, vv);
+    v.attention(q, inner, k, vv, inner, n, T, T, H, S, o, inner);
+    v.dense(o, R, inner, p + "/_mha/_dense_layer_output/kernel", v.W(p + "/_mha/_dense_layer_output/bias"), D, x, x2);
+    v.layer_norm(x2, R, D, p + "/_layernorm_ffn", z);
+    v.dense(z, R, D, p + "/_ffn/_dense_layer_filter/kernel", v.W(p + "/_ffn/_dense_layer_filter/bias"), cfg.text_filter, nullptr, hb, 1);
+    v.dense(hb, R, cfg.text_filter, p + "/_ffn/_dense_layer_output/kernel", v.W(p + "/_ffn/_dense_layer_output/bias"), D, x2, x);
+  }
+  v.layer_norm(x, R, D, "transformer/_encoder/_layernorm", y);
 }
 
 }  // namespace ldm

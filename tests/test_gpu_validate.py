@@ -16,11 +16,13 @@ VALIDATION_TOL = 1e-4   # north_star: per-step eps relative L2 in the fp32 valid
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_oracle.npz")
 
 
-def _unet_handle(cfg, wu, ae_hw, wa=None, ae_kind="kl"):
+def _unet_handle(cfg, wu, ae_hw, wa=None, ae_kind="kl", wt=None):
     h = make_handle(cfg, ae_kind, ae_hw=ae_hw, precision="fp32")
     h.set_weights(h.UNET, wu)
     if wa is not None:
         h.set_weights(h.AE, wa)
+    if wt is not None:
+        h.set_weights(h.TEXT, wt)
     h.finalize()
     return h
 
@@ -34,8 +36,11 @@ def test_validation_mode_tiny_unet_taps_and_loop():
     ctx = O.text_encode(O.as_dict(ts, wt), cfg["cond_stage_model"], ids)[[0, 0, 1, 1]]
     as_ = O.ae_spec(cfg["autoencoder_kl"], "kl", 8)
     wa = O.init_weights(as_, 2)
-    h = _unet_handle(cfg, wu, 8, wa)
+    h = _unet_handle(cfg, wu, 8, wa, wt=wt)
     try:
+        e_txt = rel_l2(h.encode_text(ids), ctx[[0, 2]])
+        print(f"validation mode (tiny) text encoder rel-L2 {e_txt:.3e}")
+        assert e_txt < VALIDATION_TOL
         x = np.random.default_rng(1234).standard_normal((2, 8, 8, 4), dtype=np.float32)
         x2 = np.concatenate([x, x], 0)
         h.set_context(ctx)
@@ -94,13 +99,15 @@ def test_validation_mode_full_size_eps_and_trajectory():
     wu, wt = O.init_weights(us, 0), O.init_weights(ts, 1)
     ids = np.array([O.KAT_UNCOND_IDS, O.KAT_COND_IDS], dtype=np.int64)
     ctx = O.text_encode(O.as_dict(ts, wt), cfg["cond_stage_model"], ids)
-    del wt
     g = np.load(GOLD)
     assert np.array_equal(g["ctx_probe"], ctx[:, :12, :64])   # the golden was made with these weights / prompts
     wa = O.init_weights(O.ae_spec(cfg["autoencoder_kl"], "kl"), 2)
-    h = _unet_handle(cfg, wu, 32, wa)
-    del wa
+    h = _unet_handle(cfg, wu, 32, wa, wt=wt)
+    del wa, wt
     try:
+        e_txt = rel_l2(h.encode_text(ids), ctx)
+        print(f"validation mode (full size) text encoder rel-L2 {e_txt:.3e}")
+        assert e_txt < VALIDATION_TOL
         Wu = O.as_dict(us, wu)
         x = np.random.default_rng(1234).standard_normal((1, 32, 32, 4), dtype=np.float32)
         x2 = np.concatenate([x, x], 0)

@@ -59,9 +59,9 @@ typedef struct ldm_config {
   int32_t latent_channels, ae_channels, ae_num_blocks, ae_num_multipliers, ae_multipliers[8],
       ae_num_attention_resolutions, ae_attention_resolutions[8], vq_vocab_size, ae_build_latent_hw;
   /* 0 = bf16, 1 = fp16: the 16-bit tensor-core operand format (fp32 accumulate; same tcgen05 rate, fp16 has 3 more
-   * mantissa bits).  2 = fp32 validation mode: text transformer, UNet and decoder run in fp32 on the CUDA
+   * mantissa bits).  2 = fp32 validation mode: text transformer, UNet and autoencoder run in fp32 on the CUDA
    * cores from the raw checkpoint tensors (csrc/validate.cu; per-step eps and image rel-L2 ~3e-6 vs the reference
-   * semantics), everything else as with fp16.  A checker, not a production mode: eager launches, a few seconds per 50-step trajectory. */
+   * semantics); nothing of the 16-bit engine runs.  A checker, not a production mode: eager launches, a few seconds per 50-step trajectory. */
   int32_t precision;
 } ldm_config;
 

@@ -443,7 +443,7 @@ void Model::build() {
   }
   // validation mode walks the raw fp32 kernels of the unet (validate.cu)
   if (cfg.precision == 2)
-    for (int mdl = 0; mdl <= 2; ++mdl)
+    for (int mdl = 0; mdl < NUM_MODELS; ++mdl)
       for (auto& s : slots[mdl])
         if (s.kind == Slot::PACK) s.keep = true;
   step_dev_ = dev_alloc<int>(1, true);
@@ -1525,6 +1525,10 @@ void Model::decode(const float* z, int b, int h, int w, float div, float* img_ou
 // Autoencoder encode side (autoencoder.py:242-249,354-359,421-425) and get_latents (model_runners.py:602-625)
 // =====================================================================================
 void Model::encode_body(const float* img, int b, int h, int w, float* moments_dev) {
+  if (cfg.precision == 2) {   // fp32 validation mode (validate.cu)
+    if (!eng.dry) encode_body_f32(img, b, h, w, moments_dev);
+    return;
+  }
   begin_pass();
   Act cur = alloc_act(b, h, w, cfg.ae_channels);
   eng.launches++;

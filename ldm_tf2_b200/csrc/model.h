@@ -27,7 +27,7 @@ struct ModelConfig {
       ae_num_attn_res = 0, ae_attn_res[8] = {0}, vq_vocab = 16384,
       ae_build_hw = 32;  // latent size the checkpoint's Decoder was built at (autoencoder.py:176)
   int precision = 1;       // 16-bit tensor-core operand format: 0 = bf16, 1 = fp16; 2 = fp32 validation mode: the UNet
-                           // the text transformer and the autoencoder's decoder run in fp32 on the CUDA cores (validate.cu)
+                           // the text transformer and the autoencoder run in fp32 on the CUDA cores (validate.cu)
 };
 
 // One tensor of a model in flat Keras order, with how it is consumed.
@@ -220,6 +220,7 @@ class Model {
   void unet_eps_f32(const float* x, int nsrc, int n, int h, int w, float* eps_out);
   void decode_body_f32(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   void encode_text_f32(float* x /*[n*T, D] embeddings, overwritten*/, int n, float* y);
+  void encode_body_f32(const float* img, int b, int h, int w, float* moments_dev);
   float* ctx_f32_ = nullptr; size_t ctx_f32_cap_ = 0;   // fp32 copy of the context (validation mode only)
   void decode_body(const float* z, int b, int h, int w, float div, float* img_dev, long long* idx_dev);
   Act ae_attention(AEAttnW& a, const Act& x);

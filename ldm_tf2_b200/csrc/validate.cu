@@ -1,5 +1,5 @@
-// fp32 validation mode (ldm_config.precision = 2): the text transformer, the UNet denoiser and the autoencoder's
-// decoder of the sampling path evaluated end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no
+// fp32 validation mode (ldm_config.precision = 2): the text transformer, the UNet denoiser and the autoencoder
+// (decoder and encoder) of the sampling path evaluated end to end in fp32 on the CUDA cores -- no 16-bit operand, no tensor core, no
 // folded LayerNorm, no hoisting -- from the RAW checkpoint tensors (Keras layouts, kept on the device in
 // this mode).
 //
@@ -276,7 +276,7 @@ struct Validator {
   std::vector<void*> live;
   std::unordered_map<std::string, Slot*> by_name;
   explicit Validator(Model& mm) : m(mm), st(mm.eng.stream) {
-    for (int mdl = 0; mdl <= 2; ++mdl)
+    for (int mdl = 0; mdl <= 3; ++mdl)   // (decoder and encoder share no tensor name)
       for (auto& s : m.slots[mdl]) by_name[s.name] = &s;
   }
   ~Validator() { release(0); }
@@ -316,13 +316,14 @@ struct Validator {
     conv(p);
   }
   // conv3x3: SAME (stride 1), pad-1 + VALID stride 2 (unet.py:22-27), or nearest x2 + SAME (unet.py:44-47)
-  T32 conv3x3(const T32& x, int nsrc, const std::string& pfx, int cout, int stride, bool ups, const float* res = nullptr) {
+  T32 conv3x3(const T32& x, int nsrc, const std::string& pfx, int cout, int stride, bool ups, const float* res = nullptr,
+              int pad = 1) {   // pad 0 + stride 2: the autoencoder's tf.pad (0,1),(0,1) + VALID (autoencoder.py:133-135)
     const int oh = ups ? 2 * x.h : (stride == 2 ? (x.h + 2 - 3) / 2 + 1 : x.h);
     const int ow = ups ? 2 * x.w : (stride == 2 ? (x.w + 2 - 3) / 2 + 1 : x.w);
     T32 out = tensor(x.n, oh, ow, cout);
     ConvP p{};
     p.x = x.p; p.n = x.n; p.h = x.h; p.w = x.w; p.cin = x.c; p.nsrc = nsrc;
-    p.wgt = W(pfx + "/kernel"); p.taps = 9; p.stride = stride; p.pad = 1; p.ups = ups ? 1 : 0;
+    p.wgt = W(pfx + "/kernel"); p.taps = 9; p.stride = stride; p.pad = pad; p.ups = ups ? 1 : 0;
     p.oh = oh; p.ow = ow; p.cout = cout; p.bias = W(pfx + "/bias"); p.res = res; p.out = out.p;
     conv(p);
     return out;
@@ -599,6 +600,39 @@ void Model::encode_text_f32(float* x, int n, float* y) {
     v.dense(hb, R, cfg.text_filter, p + "/_ffn/_dense_layer_output/kernel", v.W(p + "/_ffn/_dense_layer_output/bias"), D, x2, x);
   }
   v.layer_norm(x, R, D, "transformer/_encoder/_layernorm", y);
+}
+
+// AutoencoderKL.encode / AutoencoderVQ.encode up to quant_conv (autoencoder.py:198-249,354-359,421-425) in fp32:
+// img [b, h, w, 3] device images -> moments_dev [b, h/8, w/8, enc_z_]; the posterior sample stays the product's
+// (fp32) kernel.
+void Model::encode_body_f32(const float* img, int b, int h, int w, float* moments_dev) {
+  Validator v(*this);
+  const std::string e = "autoencoder/_encoder";
+  T32 x; x.p = const_cast<float*>(img); x.n = b; x.h = h; x.w = w; x.c = 3;
+  T32 cur = v.conv3x3(x, b, e + "/_conv_in", cfg.ae_channels, 1, false);
+  int idx = 0;
+  for (auto& s : enc_down_) {
+    const std::string p = e + "/_down/" + std::to_string(idx++);
+    if (s.kind == 0) {
+      cur = v.resblock(s.res, p + "/_residual", cur, true);
+      bool want = false;
+      if (cfg.ae_kind == 1)
+        for (int k = 0; k < cfg.ae_num_attn_res; ++k) want |= (cfg.ae_attn_res[k] == cur.h);
+      LDM_CHECK(!want || s.attn, "encode: attention needed at resolution %d but the autoencoder was built for %d-pixel images",
+                cur.h, cfg.ae_build_hw << (cfg.ae_num_mult - 1));
+      if (want) cur = v.ae_attention(p + "/_attention", cur);
+    } else {
+      cur = v.conv3x3(cur, cur.n, p + "/_conv", cur.c, 2, false, nullptr, 0);
+    }
+  }
+  cur = v.resblock(enc_mid1_, e + "/_middle/_residual1", cur, true);
+  cur = v.ae_attention(e + "/_middle/_attention", cur);
+  cur = v.resblock(enc_mid2_, e + "/_middle/_residual2", cur, true);
+  T32 a = v.tensor(b, cur.h, cur.w, cur.c);
+  v.group_norm(cur, e + "/_group_norm", 1e-6f, true, a.p);
+  T32 pre = v.conv3x3(a, b, e + "/_conv_out", enc_z_, 1, false);
+  eng.launches++;
+  launch_dense_small(pre.p, pre.rows(), enc_z_, quant_k_->f32, quant_b_->f32, moments_dev, eng.stream);
 }
 
 }  // namespace ldm

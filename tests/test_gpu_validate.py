@@ -133,3 +133,33 @@ def test_validation_mode_full_size_eps_and_trajectory():
         assert e_dec < VALIDATION_TOL and e_job < VALIDATION_TOL
     finally:
         h.close()
+
+
+def test_validation_mode_encoders_match_the_reference_codes_own_output():
+    """The autoencoder's encode side in the validation mode against the golden vectors made by the
+    reference's OWN encode() on the TensorFlow stand-in (tests/golden/reference_encoder_small.npz)."""
+    from ldm_tf2_b200 import lib
+    from tests.test_gpu_encoder import SMALL_KL, SMALL_VQ
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_encoder_small.npz"))
+    x = g["images"]
+    tiny = O.TINY_CONFIG
+    h = lib.Handle(lib.make_config(tiny["cond_stage_model"], tiny["unet"], SMALL_KL, "kl", 4, "fp32"), 0)
+    try:
+        h.set_weights(h.ENC, O.init_weights(O.ae_encoder_spec(SMALL_KL, "kl", 32), 31))
+        h.finalize()
+        mean, logvar = h.encode_images(x)
+        e1, e2 = rel_l2(mean, g["kl_mean"]), rel_l2(logvar, g["kl_logvar"])
+        print(f"validation mode KL encode vs reference code: mean {e1:.2e} logvar {e2:.2e}")
+        assert e1 < VALIDATION_TOL and e2 < VALIDATION_TOL
+    finally:
+        h.close()
+    hv = lib.Handle(lib.make_config(tiny["cond_stage_model"], tiny["unet"], SMALL_VQ, "vq", 4, "fp32"), 0)
+    try:
+        hv.set_weights(hv.ENC, O.init_weights(O.ae_encoder_spec(SMALL_VQ, "vq", 32), 32))
+        hv.finalize()
+        lat = hv.encode_images(x)
+        e3 = rel_l2(lat, g["vq_latents"])
+        print(f"validation mode VQ encode vs reference code: {e3:.2e}")
+        assert e3 < VALIDATION_TOL
+    finally:
+        hv.close()

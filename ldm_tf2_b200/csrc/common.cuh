@@ -483,6 +483,28 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// exact-erf GELU of a PAIR (same Abramowitz-Stegun form as gelu_erf_f; ~11 issued instructions per element instead
+// of 19: the polynomial, the products and the final combination run on packed pairs, |z|, rcp, ex2 and copysign per half)
+__device__ __forceinline__ f32x2 gelu_erf_f2(f32x2 x) {
+  const f32x2 z = f2_mul(x, f2_pack(0.70710678118654752f, 0.70710678118654752f));
+  float z0, z1;
+  f2_unpack(z, z0, z1);
+  const f32x2 az = f2_pack(fabsf(z0), fabsf(z1));
+  float d0, d1;
+  f2_unpack(f2_fma(az, f2_pack(0.3275911f, 0.3275911f), f2_pack(1.0f, 1.0f)), d0, d1);
+  const f32x2 t = f2_pack(mufu_rcp(d0), mufu_rcp(d1));
+  f32x2 y = f2_fma(t, f2_pack(1.061405429f, 1.061405429f), f2_pack(-1.453152027f, -1.453152027f));
+  y = f2_fma(y, t, f2_pack(1.421413741f, 1.421413741f));
+  y = f2_fma(y, t, f2_pack(-0.284496736f, -0.284496736f));
+  y = f2_fma(y, t, f2_pack(0.254829592f, 0.254829592f));
+  float e0, e1;
+  f2_unpack(f2_mul(f2_mul(az, az), f2_pack(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+  y = f2_mul(f2_mul(y, t), f2_pack(mufu_ex2(e0), mufu_ex2(e1)));
+  float y0, y1;
+  f2_unpack(f2_fma(y, f2_pack(-1.0f, -1.0f), f2_pack(1.0f, 1.0f)), y0, y1);   // 1 - y = erf(|z|)
+  const f32x2 erf2 = f2_pack(copysignf(y0, z0), copysignf(y1, z1));
+  return f2_mul(f2_mul(x, f2_pack(0.5f, 0.5f)), f2_add(erf2, f2_pack(1.0f, 1.0f)));
+}
 // fp32 -> 16-bit operand bits; fp16 saturates instead of overflowing to inf
 __device__ __forceinline__ uint16_t cvt16(float v, int fp16) {
   if (fp16) {

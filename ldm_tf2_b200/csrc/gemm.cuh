@@ -703,7 +703,8 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
               if (bias2_tile) b += __ldg(bias2_tile + col);
             }
             bias_s[c] = b;
-            if (ln) cs_s[c] = col < lim ? __ldg(p.ln_cs + col) : 0.f;
+            if (GEGLU) cs_s[c] = (ln && col < lim) ? __ldg(p.ln_cs + col) : 0.f;   // always the folded form (ln_b = 0 without LayerNorm)
+            else if (ln) cs_s[c] = col < lim ? __ldg(p.ln_cs + col) : 0.f;
           }
         }
         named_bar_sync(1, ETHREADS);
@@ -760,20 +761,25 @@ implicit_gemm_kernel(const __grid_constant__ GemmParams p) {
             uint32_t rg[32];
             tmem_ld_x32(t_base + (uint32_t)(hcols + c), rg);
             tmem_ld_wait();
+            // packed pairs (FFMA2 / FMUL2): the GELU is ~600 of this chunk's ~800 issued instructions in scalar form.
+            // No runtime-conditional assignments here -- they turn the 64-bit pairs into register moves.
+            const f32x2 lna2 = f2_pack(ln_a, ln_a), lnb2 = f2_pack(ln_b, ln_b);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
-              float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
-              if (ln) {
-                const float4 ca = *reinterpret_cast<const float4*>(cs_s + c + j);
-                const float4 cg = *reinterpret_cast<const float4*>(cs_s + hcols + c + j);
-                ba.x = fmaf(ca.x, ln_b, ba.x); ba.y = fmaf(ca.y, ln_b, ba.y); ba.z = fmaf(ca.z, ln_b, ba.z); ba.w = fmaf(ca.w, ln_b, ba.w);
-                bg.x = fmaf(cg.x, ln_b, bg.x); bg.y = fmaf(cg.y, ln_b, bg.y); bg.z = fmaf(cg.z, ln_b, bg.z); bg.w = fmaf(cg.w, ln_b, bg.w);
-              }
-              acc[j] = fmaf(__uint_as_float(rr[j]), ln_a, ba.x) * gelu_erf_f(fmaf(__uint_as_float(rg[j]), ln_a, bg.x));
-              acc[j + 1] = fmaf(__uint_as_float(rr[j + 1]), ln_a, ba.y) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 1]), ln_a, bg.y));
-              acc[j + 2] = fmaf(__uint_as_float(rr[j + 2]), ln_a, ba.z) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 2]), ln_a, bg.z));
-              acc[j + 3] = fmaf(__uint_as_float(rr[j + 3]), ln_a, ba.w) * gelu_erf_f(fmaf(__uint_as_float(rg[j + 3]), ln_a, bg.w));
+              const float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
+              const float4 bg = *reinterpret_cast<const float4*>(bias_s + hcols + c + j);
+              const float4 ca = *reinterpret_cast<const float4*>(cs_s + c + j);
+              const float4 cg = *reinterpret_cast<const float4*>(cs_s + hcols + c + j);
+              const f32x2 v01 = f2_fma(f2_pack(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), lna2,
+                                       f2_fma(f2_pack(ca.x, ca.y), lnb2, f2_pack(ba.x, ba.y)));
+              const f32x2 v23 = f2_fma(f2_pack(__uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3])), lna2,
+                                       f2_fma(f2_pack(ca.z, ca.w), lnb2, f2_pack(ba.z, ba.w)));
+              const f32x2 g01 = f2_fma(f2_pack(__uint_as_float(rg[j]), __uint_as_float(rg[j + 1])), lna2,
+                                       f2_fma(f2_pack(cg.x, cg.y), lnb2, f2_pack(bg.x, bg.y)));
+              const f32x2 g23 = f2_fma(f2_pack(__uint_as_float(rg[j + 2]), __uint_as_float(rg[j + 3])), lna2,
+                                       f2_fma(f2_pack(cg.z, cg.w), lnb2, f2_pack(bg.z, bg.w)));
+              f2_unpack(f2_mul(v01, gelu_erf_f2(g01)), acc[j], acc[j + 1]);
+              f2_unpack(f2_mul(v23, gelu_erf_f2(g23)), acc[j + 2], acc[j + 3]);
             }
           } else {
             tmem_ld_wait();

@@ -1086,9 +1086,12 @@ void Model::set_context(const float* ctx, int n) {
   bf16* cb = static_cast<bf16*>(stage(ST_B, nel * sizeof(bf16)));
   bool realloc_ctx = false;
   CUDA_CHECK(cudaMemcpyAsync(cf, ctx, nel * sizeof(float), cudaMemcpyDefault, eng.stream));
-  if (cfg.precision == 2) {
+  if (cfg.precision == 2) {   // fp32 validation mode: the context stays fp32, K / V are projected per evaluation (validate.cu)
     if (ctx_f32_cap_ < nel) { dev_free(ctx_f32_); ctx_f32_ = dev_alloc<float>(nel); ctx_f32_cap_ = nel; }
     CUDA_CHECK(cudaMemcpyAsync(ctx_f32_, cf, nel * sizeof(float), cudaMemcpyDeviceToDevice, eng.stream));
+    ctx_rows_ = n;
+    eng.sync();
+    return;
   }
   launch_f32_to_bf16(cf, cb, (long long)nel, 0, eng.fp16, eng.stream);
   for (STW* s : all_st_) {

@@ -41,7 +41,8 @@ NcclApi& nccl(const char* hint) {
   for (const std::string& c : cands) {
     void* l = dlopen(c.c_str(), RTLD_NOW | RTLD_GLOBAL);
     if (l) { g_nccl.lib = l; g_nccl.path = c; break; }
-    tried += c + " (" + (dlerror() ? dlerror() : "?") + "); ";
+    const char* why = dlerror();   // one call: dlerror() clears the message it returns
+    tried += c + " (" + (why ? why : "?") + "); ";
   }
   LDM_CHECK(g_nccl.lib, "NCCL not found: tried %s", tried.c_str());
   auto sym = [&](const char* name) {
@@ -125,7 +126,6 @@ void Model::allgather(const float* local, long long count, float* global) {
 }  // namespace ldm
 
 using namespace ldm;
-extern thread_local std::string g_ldm_err;
 
 #define COMM_API_BEGIN try {
 #define COMM_API_END                                     \

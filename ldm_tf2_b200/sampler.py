@@ -20,6 +20,7 @@ import numpy as np
 
 from . import lib as _lib
 from .dlpack import borrow
+from .schedule import DDIMSchedule
 
 
 def _tensor(obj, dtype=np.float32):
@@ -28,7 +29,6 @@ def _tensor(obj, dtype=np.float32):
     if isinstance(a, np.ndarray):
         return a
     return _lib.DevPtr(a, shape, keep)
-from .schedule import DDIMSchedule
 
 
 class _WeightHolder:

@@ -4,7 +4,7 @@ inside the DDIM loop, and ONE all-gather collects the decoded images.
 
 On GPUs the all-gather is `ldm_allgather_images` of the library (NCCL over NVLink on the handle's stream,
 comm.cu); the 128-byte NCCL id travels from rank 0 to the other ranks over a tiny TCP rendezvous on
-MASTER_ADDR / MASTER_PORT+1 (`exchange_unique_id`) -- no PyTorch anywhere on this path.  The torch.distributed
+MASTER_ADDR / MASTER_PORT+1.. (`exchange_bytes`) -- no PyTorch anywhere on this path.  The torch.distributed
 variant (`allgather_images`) remains for the CPU tests, which run the same shard / pad logic on gloo."""
 from __future__ import annotations
 
@@ -69,48 +69,94 @@ def allgather_images(local, total: int, group=None):
 # ------------------------------------------------------------------------------------------------
 # NCCL inside the library: rendezvous + gather (no torch)
 # ------------------------------------------------------------------------------------------------
+_MAGIC = b"LDMB200\x01"
+_PORT_TRIES = 8   # rank 0 binds the first free port of MASTER_PORT+1 .. +8; the other ranks probe the same list
+
+
+def _job_token(addr: str, base_port: int, world: int) -> bytes:
+    import hashlib
+    return hashlib.sha256(f"{addr}:{base_port}:{world}".encode()).digest()[:8]
+
+
+def _recv_exact(c, n: int) -> bytes:
+    buf = b""
+    while len(buf) < n:
+        chunk = c.recv(n - len(buf))
+        if not chunk:
+            raise ConnectionError("rendezvous closed early")
+        buf += chunk
+    return buf
+
+
 def exchange_bytes(payload, rank: int, world: int, addr: str = None, port: int = None, timeout: float = 120.0) -> bytes:
-    """Rank 0 serves `payload` to the world - 1 other ranks over TCP; every rank returns it."""
+    """Rank 0 serves `payload` to the world - 1 other ranks over TCP; every rank returns it.
+
+    The first port is MASTER_PORT + 1 (or `port`).  When something else already listens there, rank 0 moves on to
+    the next of `_PORT_TRIES` consecutive ports and the other ranks probe the same list: a connection counts only
+    after a hello that carries the magic and this job's token (address, base port, world size), so a foreign service
+    or another job's rendezvous on a neighbouring port is skipped instead of believed."""
     if world == 1:
         return payload
     addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
-    port = int(port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    base = int(port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    ports = [base + i for i in range(_PORT_TRIES)]
+    hello = _MAGIC + _job_token(addr, base, world)
+    deadline = time.time() + timeout
     if rank == 0:
-        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
-        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        srv.bind((addr, port))
-        srv.listen(world)
-        srv.settimeout(timeout)
+        srv, err = None, None
+        for p in ports:
+            s = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            try:
+                s.bind((addr, p))
+                s.listen(world)
+                srv = s
+                break
+            except OSError as e:
+                err = e
+                s.close()
+        if srv is None:
+            raise OSError(f"rendezvous: no free port in {ports[0]}..{ports[-1]} on {addr}: {err}")
         try:
-            for _ in range(world - 1):
-                c, _ = srv.accept()
+            served = 0
+            while served < world - 1:
+                left = deadline - time.time()
+                if left <= 0:
+                    raise TimeoutError(f"rendezvous: {served} of {world - 1} ranks arrived within {timeout:.0f} s")
+                srv.settimeout(left)
+                try:
+                    c, _ = srv.accept()
+                except socket.timeout:
+                    continue
                 with c:
-                    c.sendall(struct.pack("<I", len(payload)) + payload)
+                    c.settimeout(5.0)
+                    try:
+                        if _recv_exact(c, len(hello)) != hello:
+                            continue   # not one of ours
+                        c.sendall(_MAGIC + struct.pack("<I", len(payload)) + payload)
+                        served += 1
+                    except (ConnectionError, socket.timeout, OSError):
+                        continue
         finally:
             srv.close()
         return payload
-    deadline = time.time() + timeout
+    i = 0
     while True:
+        p = ports[i % len(ports)]
+        i += 1
         try:
-            with socket.create_connection((addr, port), timeout=5.0) as c:
-                buf = b""
-                while len(buf) < 4:
-                    chunk = c.recv(4 - len(buf))
-                    if not chunk:
-                        raise ConnectionError("rendezvous closed early")
-                    buf += chunk
-                (n,) = struct.unpack("<I", buf)
-                out = b""
-                while len(out) < n:
-                    chunk = c.recv(n - len(out))
-                    if not chunk:
-                        raise ConnectionError("rendezvous closed early")
-                    out += chunk
-                return out
+            with socket.create_connection((addr, p), timeout=5.0) as c:
+                c.settimeout(5.0)
+                c.sendall(hello)
+                if _recv_exact(c, len(_MAGIC)) != _MAGIC:
+                    raise ConnectionError("not the rendezvous")
+                (n,) = struct.unpack("<I", _recv_exact(c, 4))
+                return _recv_exact(c, n)
         except (ConnectionRefusedError, ConnectionError, socket.timeout, OSError):
             if time.time() > deadline:
                 raise
-            time.sleep(0.05)
+            if i % len(ports) == 0:
+                time.sleep(0.05)
 
 
 def init_comm(handle, rank: int, world: int, addr: str = None, port: int = None):

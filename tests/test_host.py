@@ -6,6 +6,7 @@ import ctypes
 import os
 import re
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -222,3 +223,102 @@ def test_bench_configs_and_reference_arm_plumbing(monkeypatch, capsys):
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2"])
     bench.main()
     assert capsys.readouterr().out == ""
+
+
+def _free_port_block(n):
+    """A base port with n consecutive free ports after it (the rendezvous probes base .. base + n - 1)."""
+    import socket
+    for _ in range(50):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        base = s.getsockname()[1]
+        s.close()
+        socks = []
+        try:
+            for p in range(base, base + n):
+                t = socket.socket()
+                t.bind(("127.0.0.1", p))
+                socks.append(t)
+            return base
+        except OSError:
+            continue
+        finally:
+            for t in socks:
+                t.close()
+    pytest.skip("no block of free ports")
+
+
+@pytest.mark.parametrize("occupied", [0, 2])
+def test_nccl_id_rendezvous_over_localhost(occupied):
+    """parallel.exchange_bytes (the TCP rendezvous that carries the 128-byte NCCL id, no torch): world size 3 over
+    localhost; with the first `occupied` ports of the list taken by a foreign listener that answers garbage, rank 0
+    moves to the next port and the other ranks skip the foreign service (magic + job token in the hello)."""
+    import socket
+    import threading
+    from ldm_tf2_b200 import parallel
+    base = _free_port_block(parallel._PORT_TRIES)
+    foreign, stop = [], threading.Event()
+
+    def babble(srv):
+        srv.settimeout(0.2)
+        while not stop.is_set():
+            try:
+                c, _ = srv.accept()
+            except (socket.timeout, OSError):
+                continue
+            with c:
+                try:
+                    c.sendall(b"HTTP/1.1 400 Bad Request\r\n\r\n")
+                except OSError:
+                    pass
+
+    for p in range(base, base + occupied):
+        s = socket.socket()
+        s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        s.bind(("127.0.0.1", p))
+        s.listen(4)
+        foreign.append(s)
+        threading.Thread(target=babble, args=(s,), daemon=True).start()
+    payload = bytes(range(128))
+    out = {}
+
+    def run(rank):
+        out[rank] = parallel.exchange_bytes(payload if rank == 0 else None, rank, 3, "127.0.0.1", base, timeout=30.0)
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in (2, 1, 0)]   # clients first: they retry until rank 0 listens
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=60)
+    stop.set()
+    for s in foreign:
+        s.close()
+    assert out == {0: payload, 1: payload, 2: payload}
+    assert parallel.exchange_bytes(b"x", 0, 1) == b"x"   # world size 1: no socket at all
+
+
+def test_rendezvous_rejects_another_jobs_token():
+    """Two jobs with neighbouring base ports: a rank of job B that probes job A's port is not served A's id."""
+    import socket
+    import threading
+    from ldm_tf2_b200 import parallel
+    base = _free_port_block(parallel._PORT_TRIES + 1)
+    got = {}
+
+    def job_a(rank):
+        got[("a", rank)] = parallel.exchange_bytes(b"A" * 128 if rank == 0 else None, rank, 2, "127.0.0.1", base, timeout=30.0)
+
+    ta = threading.Thread(target=job_a, args=(0,))
+    ta.start()
+    time.sleep(0.3)   # A's rank 0 listens on `base`
+    # a rank of job B (base port = base - 1 would probe `base` as its second candidate): same address, other token
+    hello_b = parallel._MAGIC + parallel._job_token("127.0.0.1", base - 1, 2)
+    with socket.create_connection(("127.0.0.1", base), timeout=5.0) as c:
+        c.settimeout(5.0)
+        c.sendall(hello_b)
+        assert c.recv(16) == b""   # closed without a payload
+    tb = threading.Thread(target=job_a, args=(1,))
+    tb.start()
+    ta.join(timeout=60)
+    tb.join(timeout=60)
+    assert got == {("a", 0): b"A" * 128, ("a", 1): b"A" * 128}

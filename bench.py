@@ -155,7 +155,7 @@ def cpu_reference(name, steps, warmup):
         O.decode_first_stage(Wv, cfg["autoencoder_vq"], "vq", z[:1])
         t_vq = time.perf_counter() - t0
         per_image = t_kl + t_vq   # one KL decode + one VQ decode (argmin of its rows included)
-        return dict(value=1.0 / per_image, cores=threads, vq_indices=idx,
+        return dict(value=1.0 / per_image, cores=threads, vq_indices=idx, step_ms=per_image * 1e3,
                     sample=f"1 of {c['B']} images: KL decode {t_kl:.2f} s + VQ decode incl. argmin {t_vq:.2f} s "
                            f"(argmin of all {idx.size} rows: {t_idx:.2f} s); NumPy fp32 + OpenBLAS, {threads} threads")
     us = O.unet_spec(cfg["unet"])
@@ -183,7 +183,7 @@ def cpu_reference(name, steps, warmup):
         ts.append(time.perf_counter() - t0)
     t_step = float(np.mean(ts))
     per_image = S * t_step + t_dec
-    return dict(value=1.0 / per_image, cores=threads,
+    return dict(value=1.0 / per_image, cores=threads, step_ms=t_step * 1e3,
                 sample=f"B=1 at {hw}x{hw} latents: {steps} CFG UNet steps ({t_step:.2f} s each) + 1 KL decode "
                        f"({t_dec:.2f} s), extrapolated to {S} steps + decode per image; NumPy fp32 + OpenBLAS, "
                        f"{threads} threads")
@@ -230,10 +230,12 @@ def main():
         r = cpu_reference(name, max(args.steps, 1), min(args.warmup, 1))
         print(json.dumps({
             "impl": "reference", "metric": c["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_ms"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "note": "CPU restatement of the reference (oracle/, NumPy fp32) on a bounded "
-                       "sample of this workload; TensorFlow is not installable here, so kind=port, not the TF2 sampler"},
+                       "sample of this workload; TensorFlow is not installable here, so kind=port, not the TF2 sampler. "
+                       "A step of this arm = the bounded sample (ms_per_step is its measured wall time); value = the "
+                       "workload's metric extrapolated from it (cpu_baseline.sample says how)"},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))

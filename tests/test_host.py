@@ -322,3 +322,31 @@ def test_rendezvous_rejects_another_jobs_token():
     ta.join(timeout=60)
     tb.join(timeout=60)
     assert got == {("a", 0): b"A" * 128, ("a", 1): b"A" * 128}
+
+
+def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
+    """bench.py --impl reference on rank 0: one JSON line with the same metric / unit / config as the CUDA arm,
+    impl = reference, a cpu_baseline describing the run and a zero-copy e2e object; ms_per_step is the measured time of
+    the bounded sample (so steps x ms_per_step fits the run), value the extrapolated metric.  The oracle is stubbed."""
+    import importlib
+    import json
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    calls = []
+
+    def fake(name, steps, warmup):
+        calls.append((name, steps, warmup))
+        return dict(value=0.004, cores=8, step_ms=4500.0, sample="stub")
+
+    monkeypatch.setattr(bench, "cpu_reference", fake)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1"])
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip())
+    assert calls == [("c3", 2, 1)]
+    assert line["impl"] == "reference" and line["metric"] == bench.CONFIGS["c3"]["metric"] and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["value"] == 0.004 and line["ms_per_step"] == 4500.0
+    assert line["cpu_baseline"] == {"value": 0.004, "unit": "images/s", "cores": 8, "kind": "port", "sample": "stub"}
+    assert line["e2e"] == {"value": 0.004, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "configs[2]" in line["config"]["workload"] and "model" not in line["config"]

@@ -19,11 +19,22 @@ not vendored by the reference) in plain Python:
     reports exactly these attribute paths as weight names (`ldm_weight_info`), in flat Keras order,
     which tests/golden/ckpt_keys_small.json pins against the reference's own objects.
 
+  * key "_CHECKPOINTABLE_OBJECT_GRAPH" holds a DT_STRING scalar with the serialized `TrackableObjectGraph`
+    (tensorflow/core/protobuf/trackable_object_graph.proto): one node per tracked object, `children` edges
+    (local attribute name -> node id) and `attributes` (name "VARIABLE_VALUE" -> checkpoint_key).
+    `Checkpoint.restore` matches objects by walking these edges from the root, not by comparing key strings;
+    `restore()` below does the same when the entry is present (a key that differs from the loader's own attribute
+    path -- the saving program reached the object over another edge first -- still resolves), and falls back to
+    the literal attribute-path keys for name-based bundles.  On disk a string tensor is `[varint64 length of
+    every element][masked CRC-32C of the lengths as uint32s][bytes of every element]` (tensor_bundle.cc,
+    WriteStringTensor).
+
 Parity status: no real TensorFlow checkpoint exists in this environment, so the reader is verified
-against this module's writer (both follow the format description above), the CRC-32C known answer,
-and hand-built tables with prefix compression; reading a file written by TensorFlow itself is
-UNPINNED.  The writer emits name-based bundles (`tf.train.load_checkpoint` / this reader); it does not
-write the `_CHECKPOINTABLE_OBJECT_GRAPH` proto `Checkpoint.restore` needs.
+against this module's writer, a second independent TF-style table writer in the tests, the CRC-32C known
+answers and TensorFlow's own masked-CRC routine and compiled protos as shipped in `tensorboard.compat`
+(TrackableObjectGraph, TensorShapeProto, DataType); reading a file written by TensorFlow itself is
+UNPINNED.  The writer emits name-based bundles by default (`tf.train.load_checkpoint` / this reader) and, with
+`object_graph=True`, the `_CHECKPOINTABLE_OBJECT_GRAPH` + `save_counter` entries of an object-based checkpoint.
 """
 import ctypes as C
 import os
@@ -32,6 +43,7 @@ import struct
 import numpy as np
 
 SUFFIX = "/.ATTRIBUTES/VARIABLE_VALUE"
+OBJECT_GRAPH_KEY = "_CHECKPOINTABLE_OBJECT_GRAPH"
 MAGIC = 0xDB4775248B80FB57
 _MASK_DELTA = 0xA282EAD8
 # tensorflow/core/framework/types.proto
@@ -252,10 +264,10 @@ def read_index(prefix, verify=True):
     return header, entries
 
 
-def load_checkpoint(prefix, keys=None, verify=True):
+def load_checkpoint(prefix, keys=None, verify=True, _index=None):
     """Reads tensors of a TF2 checkpoint into NumPy arrays: {key: array}.  `keys` restricts the read
-    (missing ones raise); string-typed entries (the object graph) are skipped."""
-    header, entries = read_index(prefix, verify)
+    (missing ones raise); string-typed entries (the object graph: read_object_graph) are skipped."""
+    header, entries = _index or read_index(prefix, verify)
     want = list(entries) if keys is None else list(keys)
     files, out = {}, {}
     try:
@@ -308,13 +320,21 @@ def _table_block(items, restart_interval):
     return bytes(body)
 
 
-def write_checkpoint(prefix, tensors, block_size=4096, restart_interval=16):
-    """Writes {key: array} as a single-shard TensorBundle (`<prefix>.index`, `.data-00000-of-00001`)."""
+def write_checkpoint(prefix, tensors, block_size=4096, restart_interval=16, strings=None):
+    """Writes {key: array} (and `strings` = {key: bytes}, DT_STRING scalars) as a single-shard TensorBundle
+    (`<prefix>.index`, `.data-00000-of-00001`)."""
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     items = [(b"", b"\x08\x01\x1a\x02\x08\x01")]   # BundleHeaderProto{num_shards: 1, version{producer: 1}}
     offset = 0
+    strings = dict(strings or {})
     with open(prefix + ".data-00000-of-00001", "wb") as f:
-        for key in sorted(tensors, key=lambda s: s.encode()):
+        for key in sorted(list(tensors) + list(strings), key=lambda s: s.encode()):
+            if key in strings:
+                raw, crc = _string_payload([bytes(strings[key])])
+                f.write(raw)
+                items.append((key.encode(), _build_entry(DT_STRING, (), offset, len(raw), crc)))
+                offset += len(raw)
+                continue
             a = np.asarray(tensors[key])
             if a.dtype not in _DT_OF_NP:
                 raise CheckpointError(f"{key}: dtype {a.dtype} not supported")
@@ -349,18 +369,184 @@ def write_checkpoint(prefix, tensors, block_size=4096, restart_interval=16):
         f.write(bytes(out))
 
 
+# ----------------------------------------------------------------------------- object graph
+def _string_tensor(raw, count, stored_crc, verify, what):
+    """DT_STRING payload -> list of bytes.  Checksums as tensor_bundle.cc computes them: the running CRC covers
+    every length as a little-endian uint32 (uint64 above 4 GiB), then the 4 bytes of the masked length checksum,
+    then the string bytes; the entry stores its masked value."""
+    pos, lens = 0, []
+    for _ in range(count):
+        n, pos = _get_varint(raw, pos)
+        lens.append(n)
+    if pos + 4 + sum(lens) != len(raw):
+        raise CheckpointError(f"{what}: string tensor layout does not match its {len(raw)} bytes")
+    c = 0
+    for n in lens:
+        c = _crc32c_py(struct.pack("<I" if n <= 0xFFFFFFFF else "<Q", n), c)
+    if verify and mask_crc(c) != struct.unpack_from("<I", raw, pos)[0]:
+        raise CheckpointError(f"{what}: string length checksum mismatch")
+    c = _crc32c_py(bytes(raw[pos:pos + 4]), c)
+    pos += 4
+    out = []
+    for n in lens:
+        out.append(bytes(raw[pos:pos + n]))
+        c = crc32c(out[-1], c)
+        pos += n
+    if verify and mask_crc(c) != stored_crc:
+        raise CheckpointError(f"{what}: payload checksum mismatch")
+    return out
+
+
+def _string_payload(strings):
+    """Inverse of _string_tensor: (bytes on disk, masked entry checksum)."""
+    lens = b"".join(_put_varint(len(x)) for x in strings)
+    c = 0
+    for x in strings:
+        c = _crc32c_py(struct.pack("<I" if len(x) <= 0xFFFFFFFF else "<Q", len(x)), c)
+    cks = struct.pack("<I", mask_crc(c))
+    c = _crc32c_py(cks, c)
+    for x in strings:
+        c = crc32c(x, c)
+    return lens + cks + b"".join(strings), mask_crc(c)
+
+
+def parse_object_graph(buf):
+    """Serialized TrackableObjectGraph -> list of nodes, node = dict(children={local_name: node_id},
+    attributes={name: checkpoint_key}); node 0 is the root (the tf.train.Checkpoint object)."""
+    nodes = []
+    for f, w, v in _pb_fields(buf):
+        if f != 1 or w != 2:
+            continue
+        node = dict(children={}, attributes={})
+        for f2, w2, v2 in _pb_fields(v):
+            if f2 == 1 and w2 == 2:      # ObjectReference { int32 node_id = 1; string local_name = 2; }
+                nid, name = 0, ""
+                for f3, _, v3 in _pb_fields(v2):
+                    if f3 == 1:
+                        nid = v3
+                    elif f3 == 2:
+                        name = v3.decode()
+                node["children"][name] = nid
+            elif f2 == 2 and w2 == 2:    # SerializedTensor { name = 1; full_name = 2; checkpoint_key = 3; }
+                name, key = "", ""
+                for f3, _, v3 in _pb_fields(v2):
+                    if f3 == 1:
+                        name = v3.decode()
+                    elif f3 == 3:
+                        key = v3.decode()
+                node["attributes"][name] = key
+        nodes.append(node)
+    for n in nodes:
+        for name, nid in n["children"].items():
+            if not 0 <= nid < len(nodes):
+                raise CheckpointError(f"object graph: edge {name!r} points at node {nid} of {len(nodes)}")
+    return nodes
+
+
+def build_object_graph(variable_paths, extra_edges=(), key_of=None):
+    """Serialized TrackableObjectGraph of the object tree the attribute paths describe (root = node 0; every path
+    `a/b/c` becomes edges root -a-> . -b-> . -c-> variable node with a VARIABLE_VALUE attribute), nodes numbered
+    breadth first like TensorFlow's ObjectGraphView.  `extra_edges` = [(parent path, local name, target path)]
+    adds further edges to existing objects (an object that is also reachable under another name); `key_of` maps a
+    variable path to the checkpoint key to record (default: path + SUFFIX)."""
+    tree = {}
+    for path in variable_paths:
+        cur = tree
+        for part in path.split("/"):
+            cur = cur.setdefault(part, {})
+    ids, order, queue = {(): 0}, [()], [((), tree)]
+    while queue:
+        path, sub = queue.pop(0)
+        for name, child in sub.items():
+            ids[path + (name,)] = len(order)
+            order.append(path + (name,))
+            queue.append((path + (name,), child))
+    var_set = {tuple(p.split("/")) for p in variable_paths}
+    edges = {p: [] for p in order}
+    for p in order[1:]:
+        edges[p[:-1]].append((p[-1], ids[p]))
+    for parent, name, target in extra_edges:
+        edges[tuple(parent.split("/")) if parent else ()].append((name, ids[tuple(target.split("/"))]))
+
+    def ld(field, payload):
+        return _put_varint(field << 3 | 2) + _put_varint(len(payload)) + payload
+
+    out = b""
+    for p in order:
+        node = b""
+        for name, nid in edges[p]:
+            node += ld(1, (b"\x08" + _put_varint(nid) if nid else b"") + ld(2, name.encode()))
+        if p in var_set:
+            path = "/".join(p)
+            key = key_of(path) if key_of else path + SUFFIX
+            node += ld(2, ld(1, b"VARIABLE_VALUE") + ld(2, path.encode()) + ld(3, key.encode()))
+        out += ld(1, node)
+    return out
+
+
+def read_object_graph(prefix, verify=True, _index=None):
+    """The checkpoint's TrackableObjectGraph as parse_object_graph returns it, or None for a name-based bundle."""
+    header, entries = _index or read_index(prefix, verify)
+    e = entries.get(OBJECT_GRAPH_KEY)
+    if e is None:
+        return None
+    if e["dtype"] != DT_STRING:
+        raise CheckpointError(f"{OBJECT_GRAPH_KEY}: not a string tensor")
+    name = f"{prefix}.data-{e['shard']:05d}-of-{header['num_shards']:05d}"
+    with open(name, "rb") as f:
+        f.seek(e["offset"])
+        raw = f.read(e["size"])
+    if len(raw) != e["size"]:
+        raise CheckpointError(f"{OBJECT_GRAPH_KEY}: data file too short")
+    count = int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1
+    strings = _string_tensor(raw, count, e["crc"], verify, OBJECT_GRAPH_KEY)
+    return parse_object_graph(strings[0])
+
+
+def resolve_key(nodes, path):
+    """Checkpoint key of the variable at attribute path `a/b/c`: walk the saved graph's edges from the root the way
+    Checkpoint.restore matches objects, then take the node's VARIABLE_VALUE attribute."""
+    cur = 0
+    for i, part in enumerate(path.split("/")):
+        nxt = nodes[cur]["children"].get(part)
+        if nxt is None:
+            raise CheckpointError(f"object graph: no edge {part!r} below {'/'.join(path.split('/')[:i]) or '<root>'} "
+                                  f"(looking for {path})")
+        cur = nxt
+    key = nodes[cur]["attributes"].get("VARIABLE_VALUE")
+    if not key:
+        raise CheckpointError(f"object graph: {path} is not a variable in this checkpoint")
+    return key
+
+
 # ----------------------------------------------------------------------------- model glue
 def variable_keys(handle, model):
     """Checkpoint keys of one model's variables in flat Keras order (works on a describe-only handle)."""
     return [handle.weight_info(model, i)[0] + SUFFIX for i in range(handle.num_weights(model))]
 
 
+def resolve_variable_keys(handle, model, prefix, verify=True, _index=None):
+    """Checkpoint keys of one model's variables in flat Keras order for THIS checkpoint (works on a describe-only
+    handle): through the object graph when the bundle has one, else the literal attribute-path keys."""
+    paths = [handle.weight_info(model, i)[0] for i in range(handle.num_weights(model))]
+    index = _index or read_index(prefix, verify)
+    graph = None
+    try:
+        graph = read_object_graph(prefix, verify, index)
+    except CheckpointError as e:   # the variables are still read, shape-checked and checksummed by key
+        import warnings
+        warnings.warn(f"{prefix}: object graph unreadable ({e}); matching variables by attribute-path key")
+    return [resolve_key(graph, p) for p in paths] if graph else [p + SUFFIX for p in paths]
+
+
 def restore(handle, model, prefix, verify=True):
     """tf.train.Checkpoint(<root>=layer).restore(prefix) for one of the three models
-    (run_ldm_sampler.py:70-75): reads every variable by its attribute-path key, validates shapes and
-    hands the flat list to the library."""
-    keys = variable_keys(handle, model)
-    tensors = load_checkpoint(prefix, keys, verify)
+    (run_ldm_sampler.py:70-75): resolves every variable of the model -- through the checkpoint's object graph
+    when it has one (objects are matched edge by edge from the root, as Checkpoint.restore does), else by the
+    literal attribute-path key -- validates shapes and hands the flat list to the library."""
+    index = read_index(prefix, verify)
+    keys = resolve_variable_keys(handle, model, prefix, verify, index)
+    tensors = load_checkpoint(prefix, keys, verify, index)
     weights = []
     for i, k in enumerate(keys):
         _, shape = handle.weight_info(model, i)
@@ -372,9 +558,16 @@ def restore(handle, model, prefix, verify=True):
     return len(weights)
 
 
-def save(handle_or_names, weights, prefix, model=None):
-    """Writes a flat Keras weight list under the reference's checkpoint keys (name-based bundle)."""
+def save(handle_or_names, weights, prefix, model=None, object_graph=False):
+    """Writes a flat Keras weight list under the reference's checkpoint keys.  object_graph=True adds what
+    `tf.train.Checkpoint(<root>=layer).save` also writes: the `_CHECKPOINTABLE_OBJECT_GRAPH` entry and `save_counter`."""
     keys = variable_keys(handle_or_names, model) if model is not None else list(handle_or_names)
     if len(keys) != len(weights):
         raise CheckpointError(f"{len(keys)} keys for {len(weights)} tensors")
-    write_checkpoint(prefix, {k: np.asarray(w, np.float32) for k, w in zip(keys, weights)})
+    tensors = {k: np.asarray(w, np.float32) for k, w in zip(keys, weights)}
+    strings = None
+    if object_graph:
+        paths = [k[:-len(SUFFIX)] if k.endswith(SUFFIX) else k for k in keys] + ["save_counter"]
+        strings = {OBJECT_GRAPH_KEY: build_object_graph(paths)}
+        tensors["save_counter" + SUFFIX] = np.asarray(1, np.int64)
+    write_checkpoint(prefix, tensors, strings=strings)

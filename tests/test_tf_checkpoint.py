@@ -2,8 +2,10 @@
 
 No TensorFlow-written checkpoint exists in this environment (parity against real TF is unpinned);
 what is pinned: the CRC-32C known answers, the table format against a hand-assembled index with
-prefix-compressed keys and several data blocks, corruption detection, and the variable keys against
-the reference's own objects (tests/golden/ckpt_keys_small.json, made by make_ckpt_keys.py)."""
+prefix-compressed keys and several data blocks, corruption detection, the variable keys against
+the reference's own objects (tests/golden/ckpt_keys_small.json, made by make_ckpt_keys.py), and -- against
+TensorFlow's own code as shipped in tensorboard.compat -- the masked CRC-32C routine, the dtype enum, the
+TensorShapeProto encoding and the TrackableObjectGraph parser / builder (byte-identical to TF's serializer)."""
 import json
 import os
 import struct
@@ -184,10 +186,9 @@ def test_tensorflow_style_object_checkpoint_is_read(tmp_path):
     d = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), -1)
     keys = T.variable_keys(d, d.UNET)
     shapes = [d.weight_info(d.UNET, i)[1] for i in range(d.num_weights(d.UNET))]
-    d.close()
     rng = np.random.default_rng(0)
     tensors = {k: rng.standard_normal(s).astype(np.float32) for k, s in zip(keys, shapes)}
-    graph = b"\x0a\x10fake object graph proto" * 40          # opaque to the reader: a DT_STRING scalar
+    graph = T.build_object_graph([k[:-len(T.SUFFIX)] for k in keys] + ["save_counter"])   # a DT_STRING scalar
     # ---- data file, in key order; a DT_STRING tensor is [varint lengths][masked crc of the lengths][bytes]
     allkeys = sorted([k.encode() for k in tensors] + [b"_CHECKPOINTABLE_OBJECT_GRAPH", b"save_counter" + T.SUFFIX.encode()])
     data = bytearray()
@@ -206,8 +207,13 @@ def test_tensorflow_style_object_checkpoint_is_read(tmp_path):
     for k in allkeys:
         off = len(data)
         if k == b"_CHECKPOINTABLE_OBJECT_GRAPH":
+            # WriteStringTensor: the checksums run over the length as a uint32, not over its varint bytes
             lens = v(len(graph))
-            raw = lens + struct.pack("<I", crc_of(lens)) + graph
+            c_len = T._crc32c_py(struct.pack("<I", len(graph)))
+            cks = struct.pack("<I", (((c_len >> 15) | (c_len << 17)) + 0xA282EAD8) & 0xFFFFFFFF)
+            raw = lens + cks + graph
+            c_all = T._crc32c_py(graph, T._crc32c_py(cks, c_len))
+            string_crc = (((c_all >> 15) | (c_all << 17)) + 0xA282EAD8) & 0xFFFFFFFF
             dtype, shp = 7, ()
         elif k.startswith(b"save_counter"):
             raw = np.int64(1).tobytes()
@@ -218,7 +224,7 @@ def test_tensorflow_style_object_checkpoint_is_read(tmp_path):
             dtype, shp = 1, a.shape
         data += raw
         entry = b"\x08" + v(dtype) + shape_pb(shp) + (b"\x20" + v(off) if off else b"") + b"\x28" + v(len(raw)) + \
-            b"\x35" + struct.pack("<I", crc_of(raw))
+            b"\x35" + struct.pack("<I", string_crc if dtype == 7 else crc_of(raw))
         table.add(k, entry)
     prefix = str(tmp_path / "unet-1")
     open(prefix + ".index", "wb").write(table.finish())
@@ -230,6 +236,8 @@ def test_tensorflow_style_object_checkpoint_is_read(tmp_path):
     got = T.load_checkpoint(prefix, keys)           # exactly what restore() asks for
     for k in keys:
         assert np.array_equal(got[k], tensors[k]), k
+    assert T.resolve_variable_keys(d, d.UNET, prefix) == keys   # through the object graph entry, checksums verified
+    d.close()
     everything = T.load_checkpoint(prefix)          # the string entry is skipped, save_counter is read
     assert "_CHECKPOINTABLE_OBJECT_GRAPH" not in everything
     assert everything["save_counter" + T.SUFFIX] == 1 and everything["save_counter" + T.SUFFIX].dtype == np.int64
@@ -292,3 +300,150 @@ def test_save_and_reload_flat_weight_list(tmp_path):
         assert keys[0] == "autoencoder/_post_quant_conv/kernel" + T.SUFFIX
     finally:
         h.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pins against TensorFlow's own code as shipped inside `tensorboard.compat` (the image has tensorboard, not TF):
+# the masked CRC-32C routine the TF team wrote for record files, and the protobuf classes compiled from TF's
+# trackable_object_graph.proto / tensor_shape.proto / types.proto.
+# ---------------------------------------------------------------------------------------------------------------
+def test_masked_crc_matches_tensorflows_own_routine():
+    tb = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 8, 9, 63, 4096, 5000, 70001):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert T.crc32c(data) == tb.crc32c(data) & 0xFFFFFFFF, n          # table path and SSE4.2 path of the library
+        assert T.mask_crc(T.crc32c(data)) == tb.masked_crc32c(data) & 0xFFFFFFFF, n
+
+
+def test_object_graph_parser_against_tensorflows_compiled_protos():
+    pb = pytest.importorskip("tensorboard.compat.proto.trackable_object_graph_pb2")
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    # dtype enum values of types.proto
+    for name in ("DT_FLOAT", "DT_DOUBLE", "DT_INT32", "DT_UINT8", "DT_STRING", "DT_INT64", "DT_BOOL", "DT_BFLOAT16", "DT_HALF"):
+        assert getattr(T, name) == getattr(types_pb2, name), name
+    # a graph written by TF's proto classes, with the fields the reader must ignore (slot variables of an optimizer,
+    # full_name, has_checkpoint_values, registered_saver) and children listed out of node order
+    g = pb.TrackableObjectGraph()
+    root, unet, conv, kern, bias, ctr, opt = (g.nodes.add() for _ in range(7))
+    root.children.add(node_id=6, local_name="optimizer")
+    root.children.add(node_id=1, local_name="unet")
+    root.children.add(node_id=5, local_name="save_counter")
+    unet.children.add(node_id=2, local_name="_conv_in")
+    conv.children.add(node_id=3, local_name="kernel")
+    conv.children.add(node_id=4, local_name="bias")
+    kern.attributes.add(name="VARIABLE_VALUE", full_name="u_net/conv2d/kernel",
+                        checkpoint_key="unet/_conv_in/kernel/.ATTRIBUTES/VARIABLE_VALUE")
+    bias.attributes.add(name="VARIABLE_VALUE", full_name="u_net/conv2d/bias",
+                        checkpoint_key="unet/_conv_in/bias/.ATTRIBUTES/VARIABLE_VALUE")
+    ctr.attributes.add(name="VARIABLE_VALUE", full_name="save_counter",
+                       checkpoint_key="save_counter/.ATTRIBUTES/VARIABLE_VALUE")
+    opt.slot_variables.add(original_variable_node_id=3, slot_name="m", slot_variable_node_id=3)
+    opt.registered_saver.name = "none"
+    kern.has_checkpoint_values.value = True
+    nodes = T.parse_object_graph(g.SerializeToString())
+    assert len(nodes) == 7
+    assert nodes[0]["children"] == {"optimizer": 6, "unet": 1, "save_counter": 5}
+    assert nodes[2]["children"] == {"kernel": 3, "bias": 4}
+    assert T.resolve_key(nodes, "unet/_conv_in/kernel") == "unet/_conv_in/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert T.resolve_key(nodes, "save_counter") == "save_counter/.ATTRIBUTES/VARIABLE_VALUE"
+    with pytest.raises(T.CheckpointError, match="no edge '_conv_out'"):
+        T.resolve_key(nodes, "unet/_conv_out/kernel")
+    with pytest.raises(T.CheckpointError, match="not a variable"):
+        T.resolve_key(nodes, "unet/_conv_in")
+    # an edge that points outside the node list is refused
+    root.children.add(node_id=99, local_name="dangling")
+    with pytest.raises(T.CheckpointError, match="points at node 99"):
+        T.parse_object_graph(g.SerializeToString())
+    # the other direction: this module's graph builder is byte-identical to TF's serializer for the same message
+    paths = ["unet/_conv_in/kernel", "unet/_conv_in/bias", "unet/_blocks/0/_dense/kernel", "save_counter"]
+    mine = T.build_object_graph(paths)
+    m = pb.TrackableObjectGraph()
+    m.ParseFromString(mine)
+    assert m.SerializeToString() == mine and len(m.nodes) == 10
+    assert [(c.local_name, c.node_id) for c in m.nodes[0].children] == [("unet", 1), ("save_counter", 2)]
+    assert sorted(a.checkpoint_key for n in m.nodes for a in n.attributes) == sorted(p + T.SUFFIX for p in paths)
+    # BundleEntryProto carries a TensorShapeProto: TF's serializer for the nested message, this module's entry parser
+    shp = shape_pb2.TensorShapeProto()
+    for d in (3, 3, 320, 1280):
+        shp.dim.add(size=d)
+    body = shp.SerializeToString()
+    entry = b"\x08\x01" + b"\x12" + bytes([len(body)]) + body + b"\x20\x80\x01" + b"\x28\x10" + b"\x35" + struct.pack("<I", 7)
+    e = T._parse_entry(entry)
+    assert e == dict(dtype=T.DT_FLOAT, shape=(3, 3, 320, 1280), shard=0, offset=128, size=16, crc=7, sliced=False)
+    mine_shape = T._build_entry(T.DT_FLOAT, (3, 3, 320, 1280), 128, 16, 7)
+    assert mine_shape == entry
+
+
+def test_restore_matches_objects_through_the_saved_graph(tmp_path):
+    """Checkpoint.restore matches objects by walking the saved graph's edges, not by comparing key strings.  Here
+    the saving program reached the UNet's first ResBlock over an alias attribute first (`unet/_alias`), so TensorFlow
+    recorded those variables under `unet/_alias/...` keys; the loader asks for them under its own attribute paths
+    and must get the right tensors.  The bundle is the TF-style object checkpoint (graph + save_counter)."""
+    from oracle import ldm_oracle as O
+    cfg = O.TINY_CONFIG
+    d = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), -1)
+    try:
+        paths = [d.weight_info(d.UNET, i)[0] for i in range(d.num_weights(d.UNET))]
+        shapes = [d.weight_info(d.UNET, i)[1] for i in range(d.num_weights(d.UNET))]
+        block = "/".join(next(p for p in paths if p.count("/") >= 3).split("/")[:3])   # e.g. unet/_down_blocks/0
+        aliased = [p for p in paths if p.startswith(block + "/")]
+        assert aliased and len(aliased) < len(paths)
+
+        def key_of(path):
+            if path.startswith(block + "/"):
+                return "unet/_alias" + path[len(block):] + T.SUFFIX
+            return path + T.SUFFIX
+
+        rng = np.random.default_rng(5)
+        tensors = {key_of(p): rng.standard_normal(s).astype(np.float32) for p, s in zip(paths, shapes)}
+        tensors["save_counter" + T.SUFFIX] = np.asarray(1, np.int64)
+        graph = T.build_object_graph(paths + ["save_counter"], extra_edges=[("unet", "_alias", block)], key_of=key_of)
+        prefix = str(tmp_path / "unet-1")
+        T.write_checkpoint(prefix, tensors, block_size=900, strings={T.OBJECT_GRAPH_KEY: graph})
+        nodes = T.read_object_graph(prefix)
+        assert nodes[1]["children"]["_alias"] == nodes[nodes[1]["children"][block.split("/")[1]]]["children"][block.split("/")[2]]
+        keys = T.resolve_variable_keys(d, d.UNET, prefix)
+        assert keys == [key_of(p) for p in paths] and keys != T.variable_keys(d, d.UNET)
+        got = T.load_checkpoint(prefix, keys)
+        assert all(np.array_equal(got[k], tensors[k]) for k in keys)
+        # name-based bundle (no graph entry): the literal attribute-path keys
+        T.save(d, [tensors[key_of(p)] for p in paths], str(tmp_path / "named-1"), model=d.UNET)
+        assert T.read_object_graph(str(tmp_path / "named-1")) is None
+        assert T.resolve_variable_keys(d, d.UNET, str(tmp_path / "named-1")) == T.variable_keys(d, d.UNET)
+        # save(object_graph=True) writes what Checkpoint.save writes; it resolves to the same keys
+        T.save(d, [tensors[key_of(p)] for p in paths], str(tmp_path / "obj-1"), model=d.UNET, object_graph=True)
+        assert T.resolve_variable_keys(d, d.UNET, str(tmp_path / "obj-1")) == T.variable_keys(d, d.UNET)
+        assert T.load_checkpoint(str(tmp_path / "obj-1"))["save_counter" + T.SUFFIX] == 1
+        # a corrupted graph payload: the string checksums catch it; resolve falls back to the literal keys with a warning
+        data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+        off = T.read_index(prefix)[1][T.OBJECT_GRAPH_KEY]["offset"]
+        data[off + 40] ^= 0x01
+        open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+        with pytest.raises(T.CheckpointError, match="checksum"):
+            T.read_object_graph(prefix)
+        with pytest.warns(UserWarning, match="object graph unreadable"):
+            assert T.resolve_variable_keys(d, d.UNET, prefix) == T.variable_keys(d, d.UNET)
+    finally:
+        d.close()
+
+
+def test_string_tensor_layout_and_checksums():
+    """tensor_bundle.cc WriteStringTensor: [varint64 lengths][masked CRC-32C of the lengths as uint32s][bytes]; the
+    entry checksum runs over the uint32 lengths, the 4 checksum bytes and the string bytes (not over the varints)."""
+    strings = [b"", b"a", b"x" * 300]
+    raw, crc = T._string_payload(strings)
+    assert raw[:4] == b"\x00\x01\xac\x02"                       # 0, 1, 300 as varints
+    lens_crc = T._crc32c_py(struct.pack("<III", 0, 1, 300))
+    assert struct.unpack_from("<I", raw, 4)[0] == T.mask_crc(lens_crc)
+    running = T._crc32c_py(b"a" + b"x" * 300, T._crc32c_py(raw[4:8], lens_crc))
+    assert crc == T.mask_crc(running)
+    assert T._string_tensor(raw, 3, crc, True, "t") == strings
+    with pytest.raises(T.CheckpointError, match="layout"):
+        T._string_tensor(raw[:-1], 3, crc, True, "t")
+    bad = bytearray(raw)
+    bad[5] ^= 1
+    with pytest.raises(T.CheckpointError, match="length checksum"):
+        T._string_tensor(bytes(bad), 3, crc, True, "t")
+    assert T._string_tensor(bytes(bad), 3, crc, False, "t") == strings

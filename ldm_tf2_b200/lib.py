@@ -166,6 +166,15 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def want_shape(a, expect, what):
+    """Buffer sizes cannot be seen through the C ABI's raw pointers: the shim checks them.  `expect` is a tuple with
+    None for free dimensions; `a` is a numpy array or a DevPtr."""
+    shape = tuple(a.shape)
+    if len(shape) != len(expect) or any(e is not None and int(e) != int(g) for e, g in zip(expect, shape)):
+        raise LdmError(f"{what}: expected shape [{', '.join('*' if e is None else str(int(e)) for e in expect)}], "
+                       f"got {list(shape)}")
+
+
 PRECISIONS = {"bf16": 0, "fp16": 1, "fp32": 2}   # fp32 = validation mode (UNet on the CUDA cores in fp32)
 DEFAULT_PRECISION = "fp16"
 
@@ -225,6 +234,7 @@ class Handle:
         self._h = C.c_void_p()
         check(self.lib.ldm_create(C.byref(config), device, C.byref(self._h)))
         self._keep = []
+        self._S = 0   # DDIM steps of the configured sampler (configure_sampler)
 
     def close(self):
         if self._h:
@@ -274,12 +284,15 @@ class Handle:
 
     def set_context(self, ctx):
         ctx = f32(ctx)
+        want_shape(ctx, (None, self.config.max_seq_len, self.config.context_dim), "set_context: context")
         check(self.lib.ldm_set_context(self._h, ptr(ctx), ctx.shape[0]))
 
     def unet_forward(self, x, t) -> np.ndarray:
         x = f32(x)
         t = np.ascontiguousarray(t, dtype=np.int32)
+        want_shape(x, (None, None, None, self.config.latent_channels), "unet_forward: x")
         n, hh, ww, _ = x.shape
+        want_shape(t, (n,), "unet_forward: t")
         out = np.empty((n, hh, ww, self.config.out_channels), np.float32)
         check(self.lib.ldm_unet_forward(self._h, ptr(x), ptr(t), n, hh, ww, ptr(out)))
         return out
@@ -287,13 +300,19 @@ class Handle:
     def configure_sampler(self, ddim_t, coeffs):
         ddim_t = np.ascontiguousarray(ddim_t, dtype=np.int32)
         coeffs = f32(coeffs)
-        assert coeffs.shape == (len(ddim_t), 8)
+        want_shape(ddim_t, (None,), "configure_sampler: ddim_t")
+        want_shape(coeffs, (len(ddim_t), 8), "configure_sampler: coefficient table")
         check(self.lib.ldm_configure_sampler(self._h, len(ddim_t), ptr(ddim_t), ptr(coeffs)))
+        self._S = len(ddim_t)
 
     def ddim_step(self, xt, eps2, noise, index, guidance, clip=False, return_x0=False):
         xt, eps2 = f32(xt), f32(eps2)
         noise = None if noise is None else f32(noise)
+        want_shape(xt, (None, None, None, 4), "ddim_step: xt")
         b, hh, ww, _ = xt.shape
+        want_shape(eps2, (2 * b, hh, ww, 4), "ddim_step: eps (uncond rows, then cond rows)")
+        if noise is not None:
+            want_shape(noise, (b, hh, ww, 4), "ddim_step: noise")
         out = np.empty(xt.shape, np.float32)
         x0 = np.empty(xt.shape, np.float32) if return_x0 else None
         check(self.lib.ldm_ddim_step(self._h, ptr(xt), ptr(eps2), ptr(noise), index, float(guidance),
@@ -305,11 +324,17 @@ class Handle:
         """keep_on_device: do not read the final latents back; decode(None, shape=...) consumes them."""
         x_init = f32(x_init)
         noise = None if noise is None else f32(noise)
+        want_shape(x_init, (None, None, None, 4), "sample: x_init")
         b, hh, ww, _ = x_init.shape
+        if noise is not None:   # one slice per DDIM step, indexed by the step index (model_runners.py:466)
+            want_shape(noise, (self._S if self._S else None, b, hh, ww, 4), "sample: noise")
         out = None if keep_on_device else np.empty(x_init.shape, np.float32)
         tr = None
         if trace:
-            n = steps_limit if steps_limit else num_steps
+            n = steps_limit or num_steps or self._S
+            loop = steps_limit or self._S
+            if not n or n < loop:
+                raise LdmError(f"sample: an eps trace of {n} steps is shorter than the loop ({loop} steps)")
             tr = np.empty((n, 2 * b, hh, ww, 4), np.float32)
         check(self.lib.ldm_sample(self._h, ptr(x_init), ptr(noise), b, hh, ww, float(guidance), ptr(out),
                                   ptr(tr), steps_limit, int(use_graph)))
@@ -321,6 +346,7 @@ class Handle:
             b, hh, ww, _ = shape
         else:
             z = f32(z)
+            want_shape(z, (None, None, None, self.config.latent_channels), "decode: latents")
             b, hh, ww, _ = z.shape
         up = 1 << (self.config.ae_num_multipliers - 1)   # Decoder upsamples at every level but the last
         img = np.empty((b, hh * up, ww * up, 3), np.float32)
@@ -331,6 +357,7 @@ class Handle:
     def encode_images(self, images):
         """AutoencoderKL.encode -> (mean, logvar); AutoencoderVQ.encode(only_encode=True) -> latents."""
         images = f32(images)
+        want_shape(images, (None, None, None, 3), "encode_images: images")
         b, hh, ww, _ = images.shape
         f = 1 << (self.config.ae_num_multipliers - 1)
         z = self.config.latent_channels * (2 if self.config.ae_kind == 0 else 1)
@@ -343,14 +370,19 @@ class Handle:
     def get_latents(self, images, noise=None, scale_factor=0.18215):
         images = f32(images)
         noise = None if noise is None else f32(noise)
+        want_shape(images, (None, None, None, 3), "get_latents: images")
         b, hh, ww, _ = images.shape
         f = 1 << (self.config.ae_num_multipliers - 1)
+        if noise is not None:
+            want_shape(noise, (b, hh // f, ww // f, self.config.latent_channels), "get_latents: noise")
         out = np.empty((b, hh // f, ww // f, self.config.latent_channels), np.float32)
         check(self.lib.ldm_get_latents(self._h, ptr(images), ptr(noise), b, hh, ww, float(scale_factor), ptr(out)))
         return out
 
     def vq_argmin(self, z, div=1.0):
         z = f32(z)
+        if not z.shape or z.shape[-1] != 4:
+            raise LdmError(f"vq_argmin: rows of 4-vectors expected, got shape {list(z.shape)}")
         rows = z.size // 4
         idx = np.empty((rows,), np.int64)
         zq = np.empty(z.shape, np.float32)
@@ -382,6 +414,10 @@ class Handle:
 
     def allgather(self, local, count_per_rank: int, out):
         """local / out: numpy arrays or DevPtr; every rank passes count_per_rank floats."""
+        world = getattr(self, "_world", 1)
+        if local.size < count_per_rank or out.size < world * count_per_rank:
+            raise LdmError(f"allgather: {count_per_rank} floats per rank x {world} ranks do not fit the buffers "
+                           f"({local.size} in, {out.size} out)")
         check(self.lib.ldm_allgather_images(self._h, ptr(local), count_per_rank, ptr(out)))
 
     def timing(self):

@@ -350,3 +350,56 @@ def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
     assert line["cpu_baseline"] == {"value": 0.004, "unit": "images/s", "cores": 8, "kind": "port", "sample": "stub"}
     assert line["e2e"] == {"value": 0.004, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[2]" in line["config"]["workload"] and "model" not in line["config"]
+
+
+def test_shim_validates_buffer_shapes(libpath):
+    """The C ABI takes raw pointers + a few sizes, so a buffer of the wrong shape would be read or written out of
+    bounds: the Python shim refuses it before the call.  Runs on a describe-only handle (no GPU): a conforming call
+    gets as far as the library and is refused there ("describe-only"), a non-conforming one never reaches it."""
+    from ldm_tf2_b200 import lib
+    cfg = O.TINY_CONFIG
+    h = lib.Handle(lib.make_config(cfg["cond_stage_model"], cfg["unet"], cfg["autoencoder_kl"], "kl", 8), -1)
+    T, D = h.config.max_seq_len, h.config.context_dim
+    z = lambda *s: np.zeros(s, np.float32)
+    try:
+        bad = [
+            lambda: h.set_context(z(2, T - 1, D)),
+            lambda: h.set_context(z(2, T, D + 8)),
+            lambda: h.set_context(z(T, D)),
+            lambda: h.unet_forward(z(2, 8, 8, 3), np.zeros(2, np.int32)),
+            lambda: h.unet_forward(z(2, 8, 8, 4), np.zeros(3, np.int32)),
+            lambda: h.configure_sampler(np.arange(5), z(4, 8)),
+            lambda: h.configure_sampler(np.arange(5), z(5, 5)),
+            lambda: h.ddim_step(z(2, 8, 8, 4), z(2, 8, 8, 4), None, 0, 5.0),           # eps needs 2B rows
+            lambda: h.ddim_step(z(2, 8, 8, 4), z(4, 8, 8, 4), z(1, 8, 8, 4), 0, 5.0),  # noise of another batch
+            lambda: h.sample(z(2, 8, 8), None, 5.0),
+            lambda: h.sample(z(2, 8, 8, 4), z(2, 8, 8, 4), 5.0),                        # noise without the step axis
+            lambda: h.sample(z(2, 8, 8, 4), None, 5.0, trace=True),                     # trace length unknown
+            lambda: h.decode(z(2, 8, 8, 3)),
+            lambda: h.encode_images(z(1, 64, 64, 4)),
+            lambda: h.get_latents(z(1, 64, 64, 3), noise=z(1, 8, 8, 8)),
+            lambda: h.vq_argmin(z(16, 3)),
+            lambda: h.allgather(z(4), 8, z(8)),
+            lambda: h.encode_text(np.zeros((2, T + 1), np.int64)),
+        ]
+        for i, f in enumerate(bad):
+            with pytest.raises(lib.LdmError) as e:
+                f()
+            assert "describe-only" not in str(e.value), (i, str(e.value))
+        good = [
+            lambda: h.set_context(z(2, T, D)),
+            lambda: h.unet_forward(z(2, 8, 8, 4), np.zeros(2, np.int32)),
+            lambda: h.configure_sampler(np.arange(5), z(5, 8)),
+            lambda: h.ddim_step(z(2, 8, 8, 4), z(4, 8, 8, 4), z(2, 8, 8, 4), 0, 5.0),
+            lambda: h.sample(z(2, 8, 8, 4), z(5, 2, 8, 8, 4), 5.0, trace=True, num_steps=5),
+            lambda: h.decode(z(2, 8, 8, 4)),
+            lambda: h.encode_images(z(1, 64, 64, 3)),
+            lambda: h.get_latents(z(1, 64, 64, 3), noise=z(1, 8, 8, 4)),
+            lambda: h.vq_argmin(z(16, 4)),
+            lambda: h.encode_text(np.zeros((2, T), np.int64)),
+        ]
+        for i, f in enumerate(good):
+            with pytest.raises(lib.LdmError, match="describe-only"):
+                f()
+    finally:
+        h.close()

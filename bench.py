@@ -113,6 +113,16 @@ def workload_text(name, c, world, per_gpu, weak):
             + (", all-gather of the images" if world > 1 else ""))
 
 
+def config_dict(name, c, world, per_gpu, weak, global_b):
+    """The `config` object of the JSON line: the WORKLOAD, identical for the CUDA arm and the reference arm run with
+    the same flags (arm-specific facts -- operand format, how time was taken -- are top-level keys of the line)."""
+    return {"workload": workload_text(name, c, world, per_gpu, weak), "baseline_config_index": c["index"],
+            "global_batch": global_b, "per_gpu_batch": per_gpu,
+            "parallelism": f"dp{world} (sample-sharded weight replicas, no collective inside the loop)",
+            "l2": "not flushed explicitly: every UNet step streams the whole weight set (1.75 GB as 16-bit operands, "
+                  "3.5 GB in fp32) plus activations far larger than the 126 MB L2"}
+
+
 # --------------------------------------------------------------------------------------
 # CPU arm: the NumPy restatement of the reference (oracle/), the only place bench.py runs it
 # --------------------------------------------------------------------------------------
@@ -232,10 +242,12 @@ def main():
             "impl": "reference", "metric": c["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_ms"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU restatement of the reference (oracle/, NumPy fp32) on a bounded "
-                       "sample of this workload; TensorFlow is not installable here, so kind=port, not the TF2 sampler. "
-                       "A step of this arm = the bounded sample (ms_per_step is its measured wall time); value = the "
-                       "workload's metric extrapolated from it (cpu_baseline.sample says how)"},
+            "config": config_dict(name, c, world, per_gpu, weak, global_b),
+            "note": "CPU restatement of the reference (oracle/, NumPy fp32) on a bounded sample of this workload; "
+                    "TensorFlow is not installable here, so kind=port, not the TF2 sampler.  A step of this arm = the "
+                    "bounded sample (ms_per_step is its measured wall time); value = the workload's metric extrapolated "
+                    "from it (cpu_baseline.sample says how)",
+            "timing": "time.perf_counter around each bounded step on the host",
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -441,14 +453,10 @@ def main():
             "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": precision, "data": "synthetic",
-            "config": {"workload": workload, "baseline_config_index": c["index"],
-                       "operands": f"{precision} tensor-core operands, fp32 accumulate and statistics, "
-                                   + ("fp32" if os.environ.get("LDM_B200_STREAM") == "fp32" else "16-bit") + " residual stream between blocks",
-                       "global_batch": global_b, "per_gpu_batch": B,
-                       "parallelism": f"dp{world} (sample-sharded weight replicas, no collective inside the loop)",
-                       "l2": "not flushed explicitly: every UNet step streams 1.75 GB of 16-bit weights plus "
-                             "activations far larger than the 126 MB L2",
-                       "timing": "CUDA events on the library stream (loop, decode, NCCL all-gather), max over ranks"},
+            "config": config_dict(name, c, world, per_gpu, weak, global_b),
+            "operands": f"{precision} tensor-core operands, fp32 accumulate and statistics, "
+                        + ("fp32" if os.environ.get("LDM_B200_STREAM") == "fp32" else "16-bit") + " residual stream between blocks",
+            "timing": "CUDA events on the library stream (loop, decode, NCCL all-gather), max over ranks",
             "wall_ms_per_step": wall_ms / args.steps,
             "model_tflops_per_gpu": value * gflop_per_image / 1e3 / world,
             "e2e": {"value": total_images / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -350,6 +350,36 @@ def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
     assert line["cpu_baseline"] == {"value": 0.004, "unit": "images/s", "cores": 8, "kind": "port", "sample": "stub"}
     assert line["e2e"] == {"value": 0.004, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[2]" in line["config"]["workload"] and "model" not in line["config"]
+    # the reference arm runs "on the CUDA arm's config": the object is the one the CUDA arm prints for the same flags
+    assert line["config"] == bench.config_dict("c3", bench.CONFIGS["c3"], 1, 64, False, 64)
+    assert line["config"]["global_batch"] == 64 and line["config"]["baseline_config_index"] == 2
+
+
+def test_no_undefined_names_in_the_host_code():
+    """bench.py and the package's Python run on the GPU box where a typo only shows at round end: every name a
+    function reads as a global must be a module-level name or a builtin (symtable walk, no execution)."""
+    import builtins
+    import symtable
+    files = ["bench.py", "__graft_entry__.py"] + [os.path.join("ldm_tf2_b200", f) for f in sorted(os.listdir(os.path.join(ROOT, "ldm_tf2_b200"))) if f.endswith(".py")]
+    files += [os.path.join("profiles", f) for f in sorted(os.listdir(os.path.join(ROOT, "profiles"))) if f.endswith(".py")]
+    files += [os.path.join("tests", f) for f in sorted(os.listdir(os.path.join(ROOT, "tests"))) if f.endswith(".py")]
+    for rel in files:
+        src = open(os.path.join(ROOT, rel), encoding="utf-8").read()
+        top = symtable.symtable(src, rel, "exec")
+        known = {s.get_name() for s in top.get_symbols() if s.is_assigned() or s.is_imported() or s.is_namespace()}
+        known |= {"__file__", "__name__", "__doc__"}
+        bad = []
+
+        def walk(t):
+            for s in t.get_symbols():
+                n = s.get_name()
+                if s.is_global() and s.is_referenced() and n not in known and not hasattr(builtins, n):
+                    bad.append((t.get_name(), n))
+            for c in t.get_children():
+                walk(c)
+
+        walk(top)
+        assert not bad, (rel, bad)
 
 
 def test_shim_validates_buffer_shapes(libpath):

@@ -433,3 +433,66 @@ def test_shim_validates_buffer_shapes(libpath):
                 f()
     finally:
         h.close()
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(libpath, tmp_path):
+    """include/ldm_b200.h is the drop-in boundary: it must compile as plain C (what cgo / JNI / ctypes-style bindings
+    see) and a C host must be able to drive the library through it.  No GPU: the program uses a describe-only handle
+    (device -1), walks the UNet's weight table and checks that a compute call is refused with LDM_ERR_INVALID."""
+    import shutil
+    import subprocess
+    from ldm_tf2_b200 import lib
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "ldm_b200.h"
+int main(void) {
+  ldm_config c;
+  memset(&c, 0, sizeof c);
+  c.vocab_size = 30522; c.encoder_stack_size = 2; c.hidden_size = 128; c.text_num_heads = 8; c.size_per_head = 16;
+  c.max_seq_len = 77; c.filter_size = 256;
+  c.model_channels = 64; c.out_channels = 4; c.num_blocks = 2; c.num_channel_mult = 4;
+  c.channel_mult[0] = 1; c.channel_mult[1] = 2; c.channel_mult[2] = 4; c.channel_mult[3] = 4;
+  c.num_heads = 8; c.head_base = 8; c.context_dim = 128;
+  c.ae_kind = 0; c.latent_channels = 4; c.ae_channels = 32; c.ae_num_blocks = 2; c.ae_num_multipliers = 4;
+  c.ae_multipliers[0] = 1; c.ae_multipliers[1] = 2; c.ae_multipliers[2] = 4; c.ae_multipliers[3] = 4;
+  c.vq_vocab_size = 512; c.ae_build_latent_hw = 8; c.precision = 1;
+  ldm_handle* h = NULL;
+  if (ldm_create(&c, -1, &h) != LDM_OK) { printf("create failed: %s\n", ldm_last_error()); return 1; }
+  int n = 0;
+  if (ldm_num_weights(h, 1, &n) != LDM_OK) return 2;
+  const char* name = NULL; int nd = 0; int shape[4];
+  if (ldm_weight_info(h, 1, 0, &name, &nd, shape) != LDM_OK) return 3;
+  printf("sizeof=%zu version=%d unet_weights=%d first=%s ndim=%d shape=%d,%d,%d,%d\n", sizeof(ldm_config), ldm_version(),
+         n, name, nd, shape[0], shape[1], shape[2], shape[3]);
+  int rc = ldm_finalize_weights(h);
+  printf("finalize rc=%d msg=%s\n", rc, ldm_last_error());
+  c.latent_channels = 5;
+  ldm_handle* h2 = NULL;
+  rc = ldm_create(&c, -1, &h2);
+  printf("bad config rc=%d msg=%s\n", rc, ldm_last_error());
+  return ldm_destroy(h) == LDM_OK ? 0 : 4;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(libpath)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-l:libldm_b200.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout.splitlines()
+    assert f"sizeof={C_sizeof_config()}" in out[0] and "version=200" in out[0], out[0]
+    assert "unet_weights=686" in out[0] and "first=unet/_conv_in/kernel ndim=4 shape=3,3,4,64" in out[0], out[0]
+    assert out[1].startswith(f"finalize rc={-1} ") and "describe-only" in out[1]
+    assert out[2].startswith("bad config rc=-1") and "latent_channels" in out[2]
+
+
+def C_sizeof_config():
+    import ctypes
+    from ldm_tf2_b200 import lib
+    return ctypes.sizeof(lib.LdmConfig)

@@ -496,3 +496,39 @@ def C_sizeof_config():
     import ctypes
     from ldm_tf2_b200 import lib
     return ctypes.sizeof(lib.LdmConfig)
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the package imports it (AST walk over every import statement),
+    bench.py imports it only inside cpu_reference (the CPU arm) and __graft_entry__ only inside smoke()."""
+    def imports(path):
+        tree = ast.parse(open(path, encoding="utf-8").read())
+        out = []
+        for fn in ast.walk(tree):
+            scope = fn.name if isinstance(fn, (ast.FunctionDef, ast.AsyncFunctionDef)) else None
+            body = ast.walk(fn) if scope else []
+            for node in body:
+                if isinstance(node, ast.Import):
+                    out += [(scope, a.name) for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    out.append((scope, node.module or ""))
+        top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+        for node in top:
+            if isinstance(node, ast.Import):
+                out += [(None, a.name) for a in node.names]
+            else:
+                out.append((None, node.module or ""))
+        return out
+
+    pkg = os.path.join(ROOT, "ldm_tf2_b200")
+    for f in sorted(os.listdir(pkg)):
+        if f.endswith(".py"):
+            bad = [m for _, m in imports(os.path.join(pkg, f)) if m.split(".")[0] in ("oracle", "torch", "triton", "tensorflow")]
+            # parallel.allgather_images (the gloo variant the CPU tests drive) is the one sanctioned torch import
+            if f == "parallel.py":
+                bad = [m for m in bad if m.split(".")[0] != "torch"]
+            assert not bad, (f, bad)
+    where = {s for s, m in imports(os.path.join(ROOT, "bench.py")) if m.split(".")[0] == "oracle"}
+    assert where == {"cpu_reference"}, where
+    where = {s for s, m in imports(os.path.join(ROOT, "__graft_entry__.py")) if m.split(".")[0] == "oracle"}
+    assert where == {"smoke"}, where

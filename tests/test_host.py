@@ -532,3 +532,37 @@ def test_product_path_never_imports_the_oracle():
     assert where == {"cpu_reference"}, where
     where = {s for s, m in imports(os.path.join(ROOT, "__graft_entry__.py")) if m.split(".")[0] == "oracle"}
     assert where == {"smoke"}, where
+
+
+@pytest.mark.parametrize("total,world", [(8, 2), (5, 2), (7, 4), (3, 8)])
+def test_nccl_gather_host_logic_with_ragged_shards(total, world):
+    """parallel.allgather_images_nccl: shards of unequal size are padded to the largest one for the collective and the
+    padding is cut out again, so every rank ends up with the images in global order.  The handle is a stand-in whose
+    allgather does what ncclAllGather does (rank r's `count` floats land at offset r * count)."""
+    from ldm_tf2_b200 import parallel
+    g = np.random.default_rng(9).standard_normal((total, 4, 4, 3)).astype(np.float32)
+    shards = [parallel.shard_batch(g, r, world) for r in range(world)]
+    maxn = max(s.shape[0] for s in shards)
+    per = 4 * 4 * 3
+
+    class FakeHandle:
+        def __init__(self, rank):
+            self._world, self._rank = world, rank
+
+        def allgather(self, send, count, out):
+            assert count == maxn * per and send.shape[0] == maxn and out.size == world * count
+            assert np.array_equal(send[: shards[self._rank].shape[0]], shards[self._rank])
+            assert not send[shards[self._rank].shape[0]:].any()          # zero padding
+            flat = out.reshape(world, maxn, 4, 4, 3)
+            flat[:] = 0
+            for r, s in enumerate(shards):
+                flat[r, : s.shape[0]] = s
+
+    for r in range(world):
+        if shards[r].shape[0] == 0 and total < world:
+            local = np.zeros((0, 4, 4, 3), np.float32)
+        else:
+            local = shards[r]
+        out = parallel.allgather_images_nccl(FakeHandle(r), local, total)
+        assert out.shape == g.shape and np.array_equal(out, g)
+    assert parallel.gather_plan(total, world, per)[0] == maxn
